@@ -1,0 +1,1343 @@
+// libblues_b200.so — host side of the C ABI declared in include/blues_b200.h.
+// Owns device memory, builds the per-step launch program from the splitting string, captures it into CUDA
+// graphs and replays it without host round-trips.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/blues_b200.h"
+#include "engine.cuh"
+#include "kernels_nb.cuh"
+#include "kernels_bonded.cuh"
+#include "kernels_pme.cuh"
+#include "kernels_integrate.cuh"
+
+static std::string g_create_error;
+
+struct TimedLaunch { int kid; cudaEvent_t e0, e1; };
+
+struct bl_handle {
+    Dev d;
+    IntegratorConsts ic;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    std::vector<void*> allocs;
+    // host copies needed after creation
+    int integrator_kind = 0;
+    std::vector<std::string> splitting;
+    int n_H = 0;
+    double prop_lambda_min = 2.0, prop_lambda_max = -1.0;
+    std::vector<double> lam_s_host, lam_e_host;
+    double temperature = 300.0;
+    // lock-step host mirror of the per-walker program counters
+    int step = 0, lambda_step = 0, first_step = 0;
+    int cursor = 0;               // alchemical slot holding the energy/forces of the current lambda_step
+    bool forces_valid = false;    // f_env / slots match the current positions
+    bool vel_dirty = true;        // cm_acc must be recomputed
+    int* cm_parity = nullptr;     // device int
+    int n_cons_total = 0;
+    // cuFFT
+    cufftHandle plan_r2c = 0, plan_c2r = 0;
+    bool has_fft = false;
+    // graphs
+    bool use_graphs = true;
+    std::map<std::string, cudaGraphExec_t> graphs;
+    // profiling
+    bool profiling = false;
+    std::vector<TimedLaunch> timed;
+    double ktime[BL_NUM_KERNEL_IDS] = {0};
+    long long kcount[BL_NUM_KERNEL_IDS] = {0};
+    unsigned long long launches = 0;
+    bool capturing = false;
+    unsigned long long capture_launches = 0;
+    // scratch
+    double* d_scratch = nullptr;   // [R*4] doubles
+    int* d_iscratch = nullptr;     // [R*2]
+    double4* d_saved = nullptr;    // minimizer
+    int* d_move_atoms = nullptr; float* d_move_masses = nullptr; int move_capacity = 0;
+    std::vector<double> host_tmp;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            h->error = buf_;                                                                       \
+            return BL_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+static T* dalloc(bl_handle* h, size_t n) {
+    void* p = nullptr;
+    if (n == 0) n = 1;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, n * sizeof(T));
+    h->allocs.push_back(p);
+    return static_cast<T*>(p);
+}
+template <typename T>
+static T* dupload(bl_handle* h, const std::vector<T>& v) {
+    T* p = dalloc<T>(h, v.size());
+    if (p && !v.empty()) cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return p;
+}
+
+// ---- launch helper with optional per-kernel event timing -------------------------------------------------
+struct LaunchTimer {
+    bl_handle* h; int kid; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    LaunchTimer(bl_handle* h_, int kid_) : h(h_), kid(kid_) {
+        if (h->capturing) h->capture_launches++; else h->launches++;
+        if (h->profiling && !h->capturing && kid >= 0) {
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0, h->stream);
+        }
+    }
+    ~LaunchTimer() {
+        if (e0) { cudaEventRecord(e1, h->stream); h->timed.push_back({kid, e0, e1}); }
+    }
+};
+static void collect_timings(bl_handle* h) {
+    for (auto& t : h->timed) {
+        float ms = 0.f;
+        cudaEventSynchronize(t.e1);
+        cudaEventElapsedTime(&ms, t.e0, t.e1);
+        h->ktime[t.kid] += ms;
+        h->kcount[t.kid] += 1;
+        cudaEventDestroy(t.e0); cudaEventDestroy(t.e1);
+    }
+    h->timed.clear();
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- force / energy evaluation at the current positions ---------------------------------------------------
+// energy: also accumulate energies; cm_mode: forwarded to k_begin_eval
+static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, int cm_mode) {
+    Dev& d = h->d;
+    cudaStream_t st = h->stream;
+    const int R = d.R, N = d.N;
+    {
+        LaunchTimer t(h, -1);
+        long long nf = (long long)R * 3 * N * (d.n_alch > 0 ? 1 + ALCH_SLOTS : 1);
+        int blocks = std::max(1, std::min(cdiv(nf, 256 * 4), 148 * 8));
+        k_begin_eval<<<blocks, 256, 0, st>>>(d, adv_noise, adv_md, cm_mode, h->cm_parity);
+    }
+    {
+        LaunchTimer t(h, BL_K_NEIGHBOR);
+        k_sort_atoms<<<R, 1024, 0, st>>>(d);
+    }
+    {
+        LaunchTimer t(h, BL_K_NEIGHBOR);
+        k_find_tiles<<<dim3(cdiv(d.nblocks, FT_WARPS), R), FT_WARPS * 32, 0, st>>>(d);
+    }
+    {
+        LaunchTimer t(h, BL_K_PAIR);
+        // grid: a multiple of the SM count; each warp strides over work items
+        const int blocks = 148 * 4;
+        dim3 grid(std::max(1, blocks / std::min(R, 4)), R);
+#define PAIR(M)                                                           \
+        if (energy) k_pair<M, true><<<grid, 256, 0, st>>>(d);             \
+        else k_pair<M, false><<<grid, 256, 0, st>>>(d)
+        if (d.nb_method == 4) { PAIR(NB_PME); }
+        else if (d.nb_method == 2) { PAIR(NB_RF); }
+        else { PAIR(NB_NOCUT); }
+#undef PAIR
+    }
+    {
+        const int nterms = d.n_bonds + d.n_angles + d.n_torsions + d.n_excl + d.n_restraints + d.n_alch_exc;
+        if (nterms > 0) {
+            LaunchTimer t(h, BL_K_BONDED);
+            k_bonded<<<dim3(cdiv(nterms, 128), R), 128, 0, st>>>(d);
+        }
+    }
+    if (d.pme && h->has_fft) {
+        { LaunchTimer t(h, BL_K_PME_SPREAD); k_pme_spread<<<dim3(cdiv(N, 128), R), 128, 0, st>>>(d); }
+        { LaunchTimer t(h, BL_K_PME_SPREAD);
+          k_pme_finish<<<std::max(1, std::min(cdiv((long long)R * d.gsize, 256), 148 * 8)), 256, 0, st>>>(d); }
+        { LaunchTimer t(h, BL_K_FFT); cufftExecR2C(h->plan_r2c, d.grid_r, reinterpret_cast<cufftComplex*>(d.grid_c)); }
+        { LaunchTimer t(h, BL_K_PME_CONVOLVE);
+          if (energy) k_pme_convolve<true><<<dim3(cdiv(d.csize, 256), R), 256, 0, st>>>(d);
+          else k_pme_convolve<false><<<dim3(cdiv(d.csize, 256), R), 256, 0, st>>>(d); }
+        { LaunchTimer t(h, BL_K_FFT); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
+        { LaunchTimer t(h, BL_K_PME_GATHER); k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, st>>>(d); }
+    }
+    if (d.n_alch > 0) {
+        LaunchTimer t(h, BL_K_ALCH);
+        k_alch<<<dim3(cdiv(N, 128), R), 128, 2 * d.n_alch * sizeof(double4), st>>>(d);
+    }
+}
+
+static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a) {
+    LaunchTimer t(h, BL_K_INTEGRATE);
+    k_integrate<<<dim3(cdiv(h->d.n_clusters, 128), h->d.R), 128, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity);
+}
+
+static void enqueue_momentum(bl_handle* h) {
+    if (!h->ic.remove_cm) return;
+    Dev& d = h->d;
+    { LaunchTimer t(h, -1); k_zero_ll<<<1, 64, 0, h->stream>>>(d.cm_acc, (size_t)2 * d.R * 3); }
+    { LaunchTimer t(h, -1); k_momentum<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, h->cm_parity); }
+}
+
+// ---- step-program compilation -----------------------------------------------------------------------------
+struct Launch { bool is_eval; bool energy; int cm_mode; int adv_noise; IntegrateArgs args; bool flip_after; };
+
+// Build the launch list of one pass over the splitting string (blues/integrators.py:192,200 → openmmtools
+// LangevinIntegrator._add_integrator_steps).  cursor: alchemical slot of the current lambda_step.
+static void compile_pass(bl_handle* h, std::vector<Launch>& out, int& cursor, bool h_active, bool last_pass,
+                         bool energy_at_end) {
+    std::vector<Launch> pass;
+    IntegrateArgs cur;
+    memset(&cur, 0, sizeof cur);
+    auto push_op = [&](int kind, int slot) {
+        if (cur.nops >= MAX_OPS) return;
+        cur.ops[cur.nops].kind = kind;
+        cur.ops[cur.nops].slot = slot;
+        cur.nops++;
+    };
+    auto emit_integrate = [&]() {
+        Launch l;
+        memset(&l, 0, sizeof l);
+        l.is_eval = false;
+        l.args = cur;
+        pass.push_back(l);
+        memset(&cur, 0, sizeof cur);
+    };
+    auto emit_eval = [&](bool energy) {
+        Launch l;
+        memset(&l, 0, sizeof l);
+        l.is_eval = true;
+        l.energy = energy;
+        pass.push_back(l);
+        cursor = 0;
+    };
+    push_op(OP_CM, 0);
+    bool x_dirty = false;
+    for (const std::string& tok : h->splitting) {
+        if (tok == "V") {
+            if (x_dirty) { emit_integrate(); emit_eval(false); x_dirty = false; }
+            push_op(OP_V, cursor);
+        } else if (tok == "R") {
+            push_op(OP_R, 0);
+            x_dirty = true;
+        } else if (tok == "O") {
+            push_op(OP_O, 0);
+        } else if (tok == "H") {
+            if (!h_active) continue;
+            if (x_dirty) { emit_integrate(); emit_eval(false); x_dirty = false; }
+            if (cursor + 1 >= ALCH_SLOTS) { emit_integrate(); emit_eval(false); }
+            push_op(OP_H, cursor);
+            cursor++;
+        }
+    }
+    if (x_dirty) { emit_integrate(); emit_eval(energy_at_end && last_pass); x_dirty = false; }
+    else if (energy_at_end && last_pass) {
+        // the last evaluation of this pass must carry energies: mark it
+        for (int k = (int)pass.size() - 1; k >= 0; --k)
+            if (pass[k].is_eval) { pass[k].energy = true; break; }
+    }
+    if (last_pass) push_op(OP_STEP_END, cursor);
+    emit_integrate();      // every pass ends with an INTEGRATE launch (momentum accumulation lives there)
+    // energy_valid for STEP_END: true if the most recent EVAL of the pass carried energies and no H with a
+    // re-evaluation invalidated it — alchemical slot energies are always present, e_env only with `energy`
+    bool last_eval_energy = false;
+    int first_int = -1, last_int = -1;
+    bool eval_between = false;
+    for (size_t k = 0; k < pass.size(); ++k) {
+        if (pass[k].is_eval) { last_eval_energy = pass[k].energy; if (first_int >= 0) eval_between = true; }
+        else { if (first_int < 0) first_int = (int)k; last_int = (int)k; }
+    }
+    pass[last_int].args.energy_valid = last_eval_energy ? 1 : 0;
+    // centre-of-mass momentum plumbing
+    if (h->ic.remove_cm) {
+        bool between = false;
+        for (int k = first_int + 1; k < last_int; ++k) if (pass[k].is_eval) between = true;
+        if (between && first_int != last_int) {
+            for (int k = first_int + 1; k < last_int; ++k) if (pass[k].is_eval) pass[k].cm_mode = 1;
+            pass[last_int].args.accum_cm = 1;
+        } else {
+            pass[last_int].args.accum_cm = 2;
+            pass[last_int].flip_after = true;
+        }
+    }
+    (void)eval_between;
+    for (auto& l : pass) out.push_back(l);
+}
+
+// ---- issuing launches, CUDA-graph caching -------------------------------------------------------------------
+static void issue(bl_handle* h, const std::vector<Launch>& ls, int& pending_noise, int& pending_md) {
+    for (const Launch& l : ls) {
+        if (l.is_eval) {
+            enqueue_eval(h, l.energy, pending_noise, pending_md, l.cm_mode);
+            pending_noise = 0;
+            pending_md = 0;
+        } else {
+            IntegrateArgs a = l.args;
+            a.noise_offset = pending_noise;
+            a.md_offset = pending_md;
+            enqueue_integrate(h, a);
+            for (int k = 0; k < a.nops; ++k) {
+                if (a.ops[k].kind == OP_O) pending_noise++;
+                if (a.ops[k].kind == OP_MD) pending_md++;
+            }
+            if (l.flip_after) {
+                LaunchTimer t(h, -1);
+                k_cm_flip<<<1, 64, 0, h->stream>>>(h->d, h->cm_parity);
+            }
+        }
+    }
+}
+
+struct HostCounters { int pending_noise = 0, pending_md = 0; };
+static HostCounters& counters(bl_handle* h) {
+    static std::map<bl_handle*, HostCounters> m;
+    return m[h];
+}
+
+// run `ls` either directly or through a cached graph keyed by `key`
+static int run_launches(bl_handle* h, const std::string& key, const std::vector<Launch>& ls) {
+    HostCounters& hc = counters(h);
+    if (!h->use_graphs || h->profiling) {
+        issue(h, ls, hc.pending_noise, hc.pending_md);
+        return BL_OK;
+    }
+    char suffix[64];
+    snprintf(suffix, sizeof suffix, "|n%d|m%d", hc.pending_noise, hc.pending_md);
+    const std::string k = key + suffix;
+    auto it = h->graphs.find(k);
+    if (it == h->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        int pn = hc.pending_noise, pm = hc.pending_md;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->capturing = true;
+        h->capture_launches = 0;
+        issue(h, ls, pn, pm);
+        h->capturing = false;
+        CK(cudaStreamEndCapture(h->stream, &graph));
+        cudaGraphExec_t exec = nullptr;
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = h->graphs.emplace(k, exec).first;
+        // remember how many kernels one replay launches
+        h->graphs.emplace(k + "#n", reinterpret_cast<cudaGraphExec_t>((uintptr_t)h->capture_launches));
+    }
+    CK(cudaGraphLaunch(it->second, h->stream));
+    h->launches += (unsigned long long)(uintptr_t)h->graphs[k + "#n"];
+    // advance the host mirror of the pending counters exactly as issue() would
+    for (const Launch& l : ls) {
+        if (l.is_eval) { hc.pending_noise = 0; hc.pending_md = 0; }
+        else for (int q = 0; q < l.args.nops; ++q) {
+            if (l.args.ops[q].kind == OP_O) hc.pending_noise++;
+            if (l.args.ops[q].kind == OP_MD) hc.pending_md++;
+        }
+    }
+    return BL_OK;
+}
+
+static void invalidate_graphs(bl_handle* h) {
+    for (auto& kv : h->graphs)
+        if (kv.first.find("#n") == std::string::npos && kv.second) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+}
+
+static int check_flags(bl_handle* h) {
+    Dev& d = h->d;
+    std::vector<Globals> g(d.R);
+    CK(cudaMemcpyAsync(g.data(), d.g, sizeof(Globals) * d.R, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->profiling) collect_timings(h);
+    for (int r = 0; r < d.R; ++r) {
+        if (g[r].item_overflow) {
+            h->error = "neighbour work-item list overflow";
+            return BL_ERR_CAPACITY;
+        }
+        if (g[r].nan_flag) {
+            char b[96];
+            snprintf(b, sizeof b, "Particle coordinate is nan (walker %d)", r);
+            h->error = b;
+            return BL_ERR_NAN;
+        }
+    }
+    return BL_OK;
+}
+
+// evaluate forces (and energies) at the current positions outside the step program
+static void eval_now(bl_handle* h, bool energy) {
+    HostCounters& hc = counters(h);
+    enqueue_eval(h, energy, hc.pending_noise, hc.pending_md, 0);
+    hc.pending_noise = hc.pending_md = 0;
+    h->forces_valid = true;
+    h->cursor = 0;
+}
+
+// ---- topology preprocessing ---------------------------------------------------------------------------------
+static bool build_clusters(bl_handle* h, const bl_topology* t, std::vector<Cluster>& out) {
+    const int N = t->n_atoms;
+    std::vector<int> parent(N);
+    for (int i = 0; i < N; ++i) parent[i] = i;
+    auto find = [&](int a) { while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; } return a; };
+    for (int k = 0; k < t->n_constraints; ++k) {
+        int a = find(t->constraints[2 * k]), b = find(t->constraints[2 * k + 1]);
+        if (a != b) parent[a] = b;
+    }
+    std::map<int, int> root_to_cluster;
+    std::vector<Cluster> cl;
+    std::vector<int> atom_cluster(N, -1);
+    for (int k = 0; k < t->n_constraints; ++k) {
+        const int i = t->constraints[2 * k], j = t->constraints[2 * k + 1];
+        const int root = find(i);
+        auto it = root_to_cluster.find(root);
+        if (it == root_to_cluster.end()) {
+            Cluster c;
+            memset(&c, 0, sizeof c);
+            cl.push_back(c);
+            it = root_to_cluster.emplace(root, (int)cl.size() - 1).first;
+        }
+        Cluster& c = cl[it->second];
+        int li = -1, lj = -1;
+        for (int q = 0; q < c.natoms; ++q) { if (c.atom[q] == i) li = q; if (c.atom[q] == j) lj = q; }
+        if (li < 0) { if (c.natoms >= MAX_CLUSTER_ATOMS) return false; li = c.natoms; c.atom[c.natoms++] = i; }
+        if (lj < 0) { if (c.natoms >= MAX_CLUSTER_ATOMS) return false; lj = c.natoms; c.atom[c.natoms++] = j; }
+        if (c.ncons >= MAX_CLUSTER_CONS) return false;
+        c.ca[c.ncons] = (signed char)li;
+        c.cb[c.ncons] = (signed char)lj;
+        c.d2[c.ncons] = t->constraint_d[k] * t->constraint_d[k];
+        c.ncons++;
+        atom_cluster[i] = atom_cluster[j] = it->second;
+    }
+    // homogeneous warps: order constrained clusters by (ncons, natoms), then the free atoms
+    std::stable_sort(cl.begin(), cl.end(), [](const Cluster& a, const Cluster& b) {
+        return a.ncons != b.ncons ? a.ncons > b.ncons : a.natoms > b.natoms;
+    });
+    for (int i = 0; i < N; ++i) {
+        if (atom_cluster[i] >= 0) continue;
+        Cluster c;
+        memset(&c, 0, sizeof c);
+        c.natoms = 1;
+        c.atom[0] = i;
+        cl.push_back(c);
+    }
+    out.swap(cl);
+    return true;
+}
+
+static void bspline_moduli_host(int K, std::vector<float>& out) {
+    // M5 at the integer nodes 1..4: 1/24, 11/24, 11/24, 1/24
+    const double data[PME_ORDER] = {0.0, 1.0 / 24, 11.0 / 24, 11.0 / 24, 1.0 / 24};
+    std::vector<double> mod(K);
+    for (int m = 0; m < K; ++m) {
+        double sc = 0, ss = 0;
+        for (int k = 0; k < PME_ORDER; ++k) {
+            double arg = 2.0 * M_PI * m * k / K;
+            sc += data[k] * cos(arg);
+            ss += data[k] * sin(arg);
+        }
+        mod[m] = sc * sc + ss * ss;
+    }
+    for (int m = 0; m < K; ++m)
+        if (mod[m] < 1e-7) mod[m] = 0.5 * (mod[(m - 1 + K) % K] + mod[(m + 1) % K]);
+    out.resize(K);
+    for (int m = 0; m < K; ++m) out[m] = (float)mod[m];
+}
+
+static uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+    auto part = [](uint32_t v) {
+        uint64_t r = v & 0x1fffff;
+        r = (r | r << 32) & 0x1f00000000ffffULL;
+        r = (r | r << 16) & 0x1f0000ff0000ffULL;
+        r = (r | r << 8) & 0x100f00f00f00f00fULL;
+        r = (r | r << 4) & 0x10c30c30c30c30c3ULL;
+        r = (r | r << 2) & 0x1249249249249249ULL;
+        return r;
+    };
+    return (uint32_t)(part(x) | (part(y) << 1) | (part(z) << 2));
+}
+
+static int setup_box(bl_handle* h, const double box[3]) {
+    Dev& d = h->d;
+    double bd[6] = {box[0], box[1], box[2], 0, 0, 0};
+    float bf[6];
+    for (int k = 0; k < 3; ++k) {
+        bd[3 + k] = box[k] > 0 ? 1.0 / box[k] : 0.0;
+        bf[k] = (float)bd[k];
+        bf[3 + k] = (float)bd[3 + k];
+    }
+    CK(cudaMemcpy(d.boxd, bd, sizeof bd, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d.boxf, bf, sizeof bf, cudaMemcpyHostToDevice));
+    return BL_OK;
+}
+
+// cell grid for spatial sorting: ~4 atoms per cell, Morton rank per cell
+static void plan_cells(int N, const double box[3], bool periodic, int nc[3], std::vector<int>& order) {
+    nc[0] = nc[1] = nc[2] = 1;
+    if (periodic && box[0] > 0) {
+        const double V = box[0] * box[1] * box[2];
+        const double edge = cbrt(4.0 * V / std::max(N, 1));
+        for (int k = 0; k < 3; ++k) nc[k] = std::max(1, std::min(128, (int)floor(box[k] / edge)));
+    }
+    const int n = nc[0] * nc[1] * nc[2];
+    std::vector<std::pair<uint32_t, int>> keys(n);
+    for (int x = 0; x < nc[0]; ++x)
+        for (int y = 0; y < nc[1]; ++y)
+            for (int z = 0; z < nc[2]; ++z) {
+                int lin = (x * nc[1] + y) * nc[2] + z;
+                keys[lin] = {morton3(x, y, z), lin};
+            }
+    std::sort(keys.begin(), keys.end());
+    order.assign(n, 0);
+    for (int rnk = 0; rnk < n; ++rnk) order[keys[rnk].second] = rnk;
+}
+
+// ---- C ABI ----------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* bl_version(void) { return "blues_b200 0.1.0 (sm_100a)"; }
+
+const char* bl_last_error(const bl_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int bl_num_replicas(const bl_handle* h) { return h ? h->d.R : 0; }
+int bl_num_atoms(const bl_handle* h) { return h ? h->d.N : 0; }
+uint64_t bl_launch_count(const bl_handle* h) { return h ? h->launches : 0; }
+void* bl_stream(bl_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int bl_destroy(bl_handle* h) {
+    if (!h) return BL_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    invalidate_graphs(h);
+    if (h->has_fft) { cufftDestroy(h->plan_r2c); cufftDestroy(h->plan_c2r); }
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return BL_OK;
+}
+
+int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, bl_handle** out) {
+    if (!t || !out || n_replicas < 1 || t->n_atoms < 1) { g_create_error = "invalid arguments"; return BL_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "no CUDA device available: blues_b200 has no CPU fallback";
+        cudaGetLastError();
+        return BL_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "invalid device index"; return BL_ERR_INVALID; }
+    if (t->nb_method != 0 && t->nb_method != 2 && t->nb_method != 4) { g_create_error = "unsupported nonbonded method"; return BL_ERR_INVALID; }
+    bl_handle* h = new bl_handle();
+    auto fail = [&](int code, const std::string& msg) { g_create_error = msg; bl_destroy(h); return code; };
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(BL_ERR_CUDA, "cudaSetDevice failed");
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(BL_ERR_CUDA, "stream creation failed");
+    Dev& d = h->d;
+    memset(&d, 0, sizeof d);
+    const int N = t->n_atoms, R = n_replicas;
+    d.N = N; d.R = R;
+    d.nblocks = (N + 31) / 32;
+    d.Npad = d.nblocks * 32;
+    d.nb_method = t->nb_method;
+    d.periodic = t->nb_method != 0;
+    d.pme = t->nb_method == 4;
+    if (d.periodic) {
+        const double minbox = std::min(t->box[0], std::min(t->box[1], t->box[2]));
+        if (!(minbox > 0) || t->cutoff * 2.0 > minbox) return fail(BL_ERR_INVALID, "cutoff must be at most half the smallest box edge");
+    }
+    d.cutoffd = t->cutoff; d.alphad = t->ewald_alpha;
+    d.cutoff = (float)t->cutoff; d.cutoff2 = (float)(t->cutoff * t->cutoff);
+    const double skin = d.periodic ? 0.1 * t->cutoff : 0.0;
+    d.list_cutoff2 = d.periodic ? (float)((t->cutoff + skin) * (t->cutoff + skin)) : 3.0e38f;
+    d.skin_half2 = d.periodic ? (float)(0.25 * skin * skin) : 3.0e38f;
+    d.alpha = (float)t->ewald_alpha;
+    if (t->nb_method == 2) {
+        const double eps_rf = 78.3, rc = t->cutoff;
+        d.krf = (float)((1.0 / (rc * rc * rc)) * (eps_rf - 1.0) / (2.0 * eps_rf + 1.0));
+        d.crf = (float)((1.0 / rc) * 3.0 * eps_rf / (2.0 * eps_rf + 1.0));
+    }
+    // per-atom tables
+    std::vector<double> mass(t->mass, t->mass + N), invmass(N);
+    std::vector<float> charge(N);
+    std::vector<float2> sigeps(N);
+    double total_mass = 0, sumq = 0, sumq2 = 0;
+    for (int i = 0; i < N; ++i) {
+        invmass[i] = mass[i] > 0 ? 1.0 / mass[i] : 0.0;
+        total_mass += mass[i];
+        charge[i] = (float)t->charge[i];
+        sumq += t->charge[i];
+        sumq2 += t->charge[i] * t->charge[i];
+        sigeps[i] = make_float2((float)(0.5 * t->sigma[i]), (float)(2.0 * sqrt(t->epsilon[i])));
+    }
+    d.mass = dupload(h, mass); d.invmass = dupload(h, invmass);
+    d.charge = dupload(h, charge); d.sigeps = dupload(h, sigeps);
+    d.sumq = sumq;
+    d.self_energy_coeff = -ONE_4PI_EPS0 * t->ewald_alpha / sqrt(M_PI) * sumq2;
+    d.dispersion_coeff = t->dispersion_coeff;
+    // exclusion windows
+    std::vector<ull> win(N, 0ull);
+    std::vector<unsigned char> hasfar(N, 0);
+    std::vector<long long> far;
+    for (int k = 0; k < t->n_excl; ++k) {
+        int i = t->excl_pairs[2 * k], j = t->excl_pairs[2 * k + 1];
+        if (i < 0 || j < 0 || i >= N || j >= N || i == j) return fail(BL_ERR_INVALID, "bad exclusion pair");
+        int dd = j - i + 32;
+        if (dd >= 0 && dd < 64 && (i - j + 32) >= 0 && (i - j + 32) < 64) {
+            win[i] |= 1ull << dd;
+            win[j] |= 1ull << (i - j + 32);
+        } else {
+            hasfar[i] = hasfar[j] = 1;
+            far.push_back(i < j ? (long long)i * N + j : (long long)j * N + i);
+        }
+    }
+    std::sort(far.begin(), far.end());
+    d.excl_win = dupload(h, win); d.has_far = dupload(h, hasfar);
+    d.far_codes = dupload(h, far); d.n_far = (int)far.size();
+    // bonded tables
+    d.n_bonds = t->n_bonds; d.n_angles = t->n_angles; d.n_torsions = t->n_torsions;
+    d.n_excl = t->n_excl; d.n_restraints = t->n_restraints; d.n_alch_exc = t->n_alch_exc;
+    {
+        std::vector<int2> ix(t->n_bonds); std::vector<double2> p(t->n_bonds);
+        for (int k = 0; k < t->n_bonds; ++k) { ix[k] = make_int2(t->bonds[2 * k], t->bonds[2 * k + 1]); p[k] = make_double2(t->bond_k[k], t->bond_r0[k]); }
+        d.bonds = dupload(h, ix); d.bond_p = dupload(h, p);
+    }
+    {
+        std::vector<int4> ix(t->n_angles); std::vector<double2> p(t->n_angles);
+        for (int k = 0; k < t->n_angles; ++k) { ix[k] = make_int4(t->angles[3 * k], t->angles[3 * k + 1], t->angles[3 * k + 2], 0); p[k] = make_double2(t->angle_k[k], t->angle_t0[k]); }
+        d.angles = dupload(h, ix); d.angle_p = dupload(h, p);
+    }
+    {
+        std::vector<int4> ix(t->n_torsions); std::vector<double4> p(t->n_torsions);
+        for (int k = 0; k < t->n_torsions; ++k) {
+            ix[k] = make_int4(t->torsions[4 * k], t->torsions[4 * k + 1], t->torsions[4 * k + 2], t->torsions[4 * k + 3]);
+            p[k] = make_double4(t->torsion_k[k], (double)t->torsion_n[k], t->torsion_phase[k], 0.0);
+        }
+        d.torsions = dupload(h, ix); d.torsion_p = dupload(h, p);
+    }
+    {
+        std::vector<int2> ix(t->n_excl); std::vector<double4> p(t->n_excl);
+        for (int k = 0; k < t->n_excl; ++k) {
+            int i = t->excl_pairs[2 * k], j = t->excl_pairs[2 * k + 1];
+            ix[k] = make_int2(i, j);
+            p[k] = make_double4(ONE_4PI_EPS0 * t->excl_qq[k], t->excl_sigma[k], t->excl_eps[k],
+                                ONE_4PI_EPS0 * t->charge[i] * t->charge[j]);
+        }
+        d.excl = dupload(h, ix); d.excl_p = dupload(h, p);
+    }
+    {
+        std::vector<int> ix(t->n_restraints); std::vector<double4> p(t->n_restraints);
+        for (int k = 0; k < t->n_restraints; ++k) {
+            ix[k] = t->restraint_atoms[k];
+            p[k] = make_double4(t->restraint_x0[3 * k], t->restraint_x0[3 * k + 1], t->restraint_x0[3 * k + 2], t->restraint_k[k]);
+        }
+        d.restraint_atom = dupload(h, ix); d.restraint_p = dupload(h, p);
+    }
+    // alchemical region
+    d.n_alch = t->n_alch;
+    if (d.n_alch > MAX_ALCH_SMEM) return fail(BL_ERR_INVALID, "too many alchemical atoms");
+    std::vector<unsigned char> is_alch(N, 0);
+    {
+        std::vector<int> at(t->n_alch); std::vector<double4> p(t->n_alch);
+        for (int k = 0; k < t->n_alch; ++k) {
+            at[k] = t->alch_atoms[k];
+            is_alch[at[k]] = 1;
+            p[k] = make_double4(t->alch_charge[k], t->alch_sigma[k], t->alch_eps[k], 0.0);
+        }
+        d.alch_atom = dupload(h, at); d.alch_p = dupload(h, p);
+        d.is_alch = dupload(h, is_alch);
+        std::vector<int2> ix(t->n_alch_exc); std::vector<double4> pe(t->n_alch_exc);
+        for (int k = 0; k < t->n_alch_exc; ++k) {
+            int i = t->alch_exc_pairs[2 * k], j = t->alch_exc_pairs[2 * k + 1];
+            ix[k] = make_int2(i, j);
+            pe[k] = make_double4(ONE_4PI_EPS0 * t->alch_exc_qq[k], t->alch_exc_sigma[k], t->alch_exc_eps[k],
+                                 (is_alch[i] && is_alch[j]) ? 1.0 : 0.0);
+        }
+        d.alch_exc = dupload(h, ix); d.alch_exc_p = dupload(h, pe);
+    }
+    d.sc_alpha = t->softcore_alpha; d.sc_a = t->softcore_a; d.sc_b = t->softcore_b; d.sc_c = t->softcore_c;
+    d.annihilate_sterics = t->annihilate_sterics; d.annihilate_elec = t->annihilate_electrostatics;
+    {
+        std::vector<double> one(2, 1.0);
+        d.lam_s = dupload(h, one); d.lam_e = dupload(h, one); d.n_lambda = 2;
+        h->lam_s_host = one; h->lam_e_host = one;
+    }
+    // clusters
+    std::vector<Cluster> clusters;
+    if (!build_clusters(h, t, clusters)) return fail(BL_ERR_INVALID, "constraint cluster too large (max 5 atoms / 4 constraints per cluster)");
+    // water triangles have 3 constraints among 3 atoms; everything else is a star — both fit
+    d.n_clusters = (int)clusters.size();
+    d.clusters = dupload(h, clusters);
+    h->n_cons_total = t->n_constraints;
+    // dynamic state
+    const size_t RN = (size_t)R * N;
+    d.boxd = dalloc<double>(h, 6); d.boxf = dalloc<float>(h, 6);
+    d.pos = dalloc<double4>(h, RN); d.vel = dalloc<double4>(h, RN);
+    d.posq = dalloc<float4>(h, RN); d.pos_ref = dalloc<float4>(h, RN);
+    d.f_env = dalloc<long long>(h, RN * 3);
+    d.f_alch = dalloc<long long>(h, d.n_alch > 0 ? RN * 3 * ALCH_SLOTS : 1);
+    d.eacc = dalloc<long long>(h, (size_t)R * N_ETERMS);
+    d.alch_acc = dalloc<long long>(h, (size_t)R * ALCH_SLOTS * 3);
+    d.cm_acc = dalloc<long long>(h, (size_t)2 * R * 3);
+    d.heat_acc = dalloc<long long>(h, R);
+    d.g = dalloc<Globals>(h, R);
+    h->cm_parity = dalloc<int>(h, 1);
+    h->d_scratch = dalloc<double>(h, std::max((size_t)R * 4, (size_t)N * 3));
+    h->d_iscratch = dalloc<int>(h, (size_t)R * 2);
+    // neighbour structures
+    std::vector<int> order;
+    plan_cells(N, t->box, d.periodic, d.ncell, order);
+    d.ncells = d.ncell[0] * d.ncell[1] * d.ncell[2];
+    d.cell_order = dupload(h, order);
+    d.cell_count = dalloc<int>(h, (size_t)R * (d.ncells + 1));
+    d.atom_cell = dalloc<int>(h, RN); d.atom_slot = dalloc<int>(h, RN); d.rank = dalloc<int>(h, RN);
+    d.posq_s = dalloc<float4>(h, (size_t)R * d.Npad);
+    d.sigeps_s = dalloc<float2>(h, (size_t)R * d.Npad);
+    d.orig_s = dalloc<int>(h, (size_t)R * d.Npad);
+    d.blk_center = dalloc<float4>(h, (size_t)R * d.nblocks);
+    d.blk_half = dalloc<float4>(h, (size_t)R * d.nblocks);
+    {
+        // capacity: atoms within the list cutoff of a 32-atom block, halved (j >= i), in 128-atom items
+        double per_block = 64;
+        if (d.periodic) {
+            const double V = t->box[0] * t->box[1] * t->box[2];
+            const double rho = N / V;
+            const double edge = cbrt(32.0 / rho), rl = t->cutoff + skin;
+            const double vol = edge * edge * edge + 6 * edge * edge * rl + 3 * M_PI * edge * rl * rl + 4.0 / 3 * M_PI * rl * rl * rl;
+            per_block = std::min((double)N, 0.5 * vol * rho * 2.5 + 128);
+        } else {
+            per_block = N + 128;
+        }
+        long long cap = (long long)d.nblocks * ((long long)(per_block / ITEM_ATOMS) + 2);
+        d.item_capacity = (int)std::min<long long>(std::max<long long>(cap, 64), 1LL << 24);
+    }
+    const size_t RI = (size_t)R * d.item_capacity;
+    d.item_block = dalloc<int>(h, RI); d.item_natoms = dalloc<int>(h, RI); d.item_flags = dalloc<int>(h, RI);
+    d.item_atoms = dalloc<int>(h, RI * ITEM_ATOMS);
+    d.item_excl = dalloc<unsigned int>(h, RI * ITEM_ATOMS);
+    // PME
+    if (d.pme) {
+        d.gx = t->pme_grid[0]; d.gy = t->pme_grid[1]; d.gz = t->pme_grid[2];
+        if (d.gx < PME_ORDER || d.gy < PME_ORDER || d.gz < PME_ORDER) return fail(BL_ERR_INVALID, "PME grid too small");
+        d.gsize = d.gx * d.gy * d.gz;
+        d.csize = d.gx * d.gy * (d.gz / 2 + 1);
+        d.grid_fx = dalloc<long long>(h, (size_t)R * d.gsize);
+        d.grid_r = dalloc<float>(h, (size_t)R * d.gsize);
+        d.grid_c = dalloc<float2>(h, (size_t)R * d.csize);
+        std::vector<float> mx, my, mz;
+        bspline_moduli_host(d.gx, mx); bspline_moduli_host(d.gy, my); bspline_moduli_host(d.gz, mz);
+        d.bmod_x = dupload(h, mx); d.bmod_y = dupload(h, my); d.bmod_z = dupload(h, mz);
+        int n[3] = {d.gx, d.gy, d.gz};
+        if (cufftPlanMany(&h->plan_r2c, 3, n, nullptr, 1, d.gsize, nullptr, 1, d.csize, CUFFT_R2C, R) != CUFFT_SUCCESS ||
+            cufftPlanMany(&h->plan_c2r, 3, n, nullptr, 1, d.csize, nullptr, 1, d.gsize, CUFFT_C2R, R) != CUFFT_SUCCESS)
+            return fail(BL_ERR_CUDA, "cufftPlanMany failed");
+        h->has_fft = true;
+        cufftSetStream(h->plan_r2c, h->stream);
+        cufftSetStream(h->plan_c2r, h->stream);
+    }
+    for (void* p : h->allocs) if (!p) return fail(BL_ERR_CUDA, "device allocation failed");
+    if (setup_box(h, t->box) != BL_OK) return fail(BL_ERR_CUDA, h->error);
+    // integrator defaults
+    memset(&h->ic, 0, sizeof h->ic);
+    h->ic.total_mass = total_mass;
+    h->ic.remove_cm = t->remove_cm && total_mass > 0;
+    h->ic.seed = seed;
+    h->ic.tol = 1e-8;
+    h->ic.kT = 0.0083144720 * 300.0;
+    // initial globals
+    std::vector<Globals> g0(R);
+    memset(g0.data(), 0, sizeof(Globals) * R);
+    for (auto& g : g0) { g.prop = 1; g.rebuild_request = 1; }
+    cudaMemcpy(d.g, g0.data(), sizeof(Globals) * R, cudaMemcpyHostToDevice);
+    // identity ordering so that mirrors can be written before the first rebuild
+    {
+        std::vector<int> rk(RN);
+        for (size_t i = 0; i < RN; ++i) rk[i] = (int)(i % N);
+        cudaMemcpy(d.rank, rk.data(), RN * sizeof(int), cudaMemcpyHostToDevice);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(BL_ERR_CUDA, "device initialisation failed");
+    *out = h;
+    return BL_OK;
+}
+
+int bl_set_seed(bl_handle* h, uint64_t seed) {
+    if (!h) return BL_ERR_INVALID;
+    h->ic.seed = seed;
+    invalidate_graphs(h);
+    return BL_OK;
+}
+
+int bl_use_graphs(bl_handle* h, int on) { if (!h) return BL_ERR_INVALID; h->use_graphs = on != 0; return BL_OK; }
+int bl_set_profiling(bl_handle* h, int on) {
+    if (!h) return BL_ERR_INVALID;
+    cudaStreamSynchronize(h->stream);
+    collect_timings(h);
+    h->profiling = on != 0;
+    if (on) for (int k = 0; k < BL_NUM_KERNEL_IDS; ++k) { h->ktime[k] = 0; h->kcount[k] = 0; }
+    return BL_OK;
+}
+int bl_get_kernel_time(bl_handle* h, int kid, double* total_ms, int64_t* launches) {
+    if (!h || kid < 0 || kid >= BL_NUM_KERNEL_IDS) return BL_ERR_INVALID;
+    cudaStreamSynchronize(h->stream);
+    collect_timings(h);
+    if (total_ms) *total_ms = h->ktime[kid];
+    if (launches) *launches = h->kcount[kid];
+    return BL_OK;
+}
+int bl_synchronize(bl_handle* h) { if (!h) return BL_ERR_INVALID; CK(cudaStreamSynchronize(h->stream)); return BL_OK; }
+
+int bl_set_integrator(bl_handle* h, const bl_integrator_params* p) {
+    if (!h || !p) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    IntegratorConsts& ic = h->ic;
+    h->integrator_kind = p->kind;
+    h->temperature = p->temperature;
+    ic.kT = 0.0083144720036 * p->temperature;   // kB*NA = 1.3806504e-23 * 6.02214179e23 / 1000
+    ic.kT = 1.3806504e-23 * 6.02214179e23 / 1000.0 * p->temperature;
+    ic.gamma = p->friction;
+    ic.dt = p->timestep;
+    ic.tol = p->constraint_tol > 0 ? p->constraint_tol : 1e-8;
+    h->splitting.clear();
+    if (p->kind == BL_INTEGRATOR_NCMC) {
+        std::string s = p->splitting ? p->splitting : "H V R O R V H";
+        size_t pos = 0;
+        while (pos < s.size()) {
+            while (pos < s.size() && s[pos] == ' ') pos++;
+            size_t e = pos;
+            while (e < s.size() && s[e] != ' ') e++;
+            if (e > pos) h->splitting.push_back(s.substr(pos, e - pos));
+            pos = e;
+        }
+        int nV = 0, nR = 0, nO = 0, nH = 0;
+        for (auto& tok : h->splitting) {
+            if (tok == "V") nV++; else if (tok == "R") nR++; else if (tok == "O") nO++; else if (tok == "H") nH++;
+            else { h->error = "unsupported splitting token '" + tok + "' (supported: H V R O)"; return BL_ERR_INVALID; }
+        }
+        if ((int)h->splitting.size() + 2 > MAX_OPS) { h->error = "splitting string too long"; return BL_ERR_INVALID; }
+        h->n_H = nH;
+        ic.hV = nV ? ic.dt / nV : 0; ic.hR = nR ? ic.dt / nR : 0; ic.hO = nO ? ic.dt / nO : 0;
+        ic.a = exp(-ic.gamma * ic.hO);
+        ic.b = sqrt(1.0 - exp(-2.0 * ic.gamma * ic.hO));
+        ic.nsteps = p->nsteps_neq;
+        ic.nprop = std::max(1, p->nprop);
+        ic.n_lambda_steps = p->nsteps_neq * nH;
+        h->prop_lambda_min = p->prop_lambda_min;
+        h->prop_lambda_max = p->prop_lambda_max;
+        const int need = ic.n_lambda_steps + 1;
+        if (p->n_lambda != need || !p->lambda_sterics || !p->lambda_electrostatics) {
+            h->error = "lambda tables must have nsteps_neq * n_H + 1 entries";
+            return BL_ERR_INVALID;
+        }
+        h->lam_s_host.assign(p->lambda_sterics, p->lambda_sterics + need);
+        h->lam_e_host.assign(p->lambda_electrostatics, p->lambda_electrostatics + need);
+        // pad so that slot indices beyond the end stay in range
+        for (int k = 0; k < ALCH_SLOTS; ++k) { h->lam_s_host.push_back(h->lam_s_host[need - 1]); h->lam_e_host.push_back(h->lam_e_host[need - 1]); }
+        h->d.lam_s = dupload(h, h->lam_s_host);
+        h->d.lam_e = dupload(h, h->lam_e_host);
+        h->d.n_lambda = (int)h->lam_s_host.size();
+    } else if (p->kind == BL_INTEGRATOR_LANGEVIN) {
+        ic.md_vscale = exp(-ic.dt * ic.gamma);
+        ic.md_fscale = ic.gamma > 0 ? (1.0 - ic.md_vscale) / ic.gamma : ic.dt;
+        ic.md_nscale = sqrt(ic.kT * (1.0 - ic.md_vscale * ic.md_vscale));
+    } else {
+        h->error = "unknown integrator kind";
+        return BL_ERR_INVALID;
+    }
+    invalidate_graphs(h);
+    h->forces_valid = false;
+    return BL_OK;
+}
+
+// ---- state ---------------------------------------------------------------------------------------------------
+static int upload_vec3(bl_handle* h, double4* dst, int replica, const double* xyz) {
+    Dev& d = h->d;
+    if (replica >= d.R) { h->error = "replica index out of range"; return BL_ERR_INVALID; }
+    std::vector<double4> tmp(d.N);
+    for (int i = 0; i < d.N; ++i) tmp[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
+    const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? d.R : replica + 1;
+    for (int r = r0; r < r1; ++r)
+        CK(cudaMemcpyAsync(dst + (size_t)r * d.N, tmp.data(), sizeof(double4) * d.N, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BL_OK;
+}
+static int download_vec3(bl_handle* h, const double4* src, int replica, double* xyz) {
+    Dev& d = h->d;
+    if (replica < 0 || replica >= d.R) { h->error = "replica index out of range"; return BL_ERR_INVALID; }
+    std::vector<double4> tmp(d.N);
+    CK(cudaMemcpyAsync(tmp.data(), src + (size_t)replica * d.N, sizeof(double4) * d.N, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < d.N; ++i) { xyz[3 * i] = tmp[i].x; xyz[3 * i + 1] = tmp[i].y; xyz[3 * i + 2] = tmp[i].z; }
+    return BL_OK;
+}
+
+static void positions_changed(bl_handle* h) {
+    Dev& d = h->d;
+    LaunchTimer t(h, -1);
+    k_refresh_mirrors<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, 1);
+    h->forces_valid = false;
+}
+
+int bl_set_positions(bl_handle* h, int replica, const double* xyz) {
+    if (!h || !xyz) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    int rc = upload_vec3(h, h->d.pos, replica, xyz);
+    if (rc != BL_OK) return rc;
+    positions_changed(h);
+    return BL_OK;
+}
+int bl_set_velocities(bl_handle* h, int replica, const double* v) {
+    if (!h || !v) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    h->vel_dirty = true;
+    return upload_vec3(h, h->d.vel, replica, v);
+}
+int bl_set_box(bl_handle* h, const double box[3]) {
+    if (!h || !box) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    Dev& d = h->d;
+    if (d.periodic) {
+        const double minbox = std::min(box[0], std::min(box[1], box[2]));
+        if (d.cutoffd * 2.0 > minbox) { h->error = "cutoff must be at most half the smallest box edge"; return BL_ERR_INVALID; }
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = setup_box(h, box);
+    if (rc != BL_OK) return rc;
+    positions_changed(h);
+    return BL_OK;
+}
+int bl_get_box(bl_handle* h, double box[3]) {
+    if (!h || !box) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(box, h->d.boxd, 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return BL_OK;
+}
+int bl_get_positions(bl_handle* h, int replica, double* xyz) {
+    if (!h || !xyz) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    return download_vec3(h, h->d.pos, replica, xyz);
+}
+int bl_get_velocities(bl_handle* h, int replica, double* v) {
+    if (!h || !v) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    return download_vec3(h, h->d.vel, replica, v);
+}
+
+static bool g_env_energy_valid(bl_handle* h);
+
+int bl_get_forces(bl_handle* h, int replica, double* f) {
+    if (!h || !f || replica < 0 || replica >= h->d.R) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    Dev& d = h->d;
+    if (!h->forces_valid) eval_now(h, true);
+    { LaunchTimer t(h, -1); k_export_forces<<<cdiv(d.N, 128), 128, 0, h->stream>>>(d, replica, h->cursor, h->d_scratch); }
+    CK(cudaMemcpyAsync(f, h->d_scratch, sizeof(double) * 3 * d.N, cudaMemcpyDeviceToHost, h->stream));
+    return check_flags(h);
+}
+
+int bl_get_energy(bl_handle* h, double* epot, double* ekin) {
+    if (!h) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    Dev& d = h->d;
+    if (epot) {
+        eval_now(h, true);     // energies are only accumulated on request
+        { LaunchTimer t(h, -1); k_export_energy<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d, h->cursor, h->d_scratch); }
+        CK(cudaMemcpyAsync(epot, h->d_scratch, sizeof(double) * d.R, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    if (ekin) {
+        CK(cudaMemsetAsync(h->d_scratch, 0, sizeof(double) * d.R, h->stream));
+        { LaunchTimer t(h, -1); k_kinetic_energy<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, h->d_scratch); }
+        CK(cudaMemcpyAsync(ekin, h->d_scratch, sizeof(double) * d.R, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return check_flags(h);
+}
+
+int bl_get_energy_terms(bl_handle* h, int replica, double terms[BL_NUM_ENERGY_TERMS]) {
+    if (!h || !terms || replica < 0 || replica >= h->d.R) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    Dev& d = h->d;
+    eval_now(h, true);
+    long long e[N_ETERMS], a[ALCH_SLOTS * 3];
+    double box[3];
+    CK(cudaMemcpyAsync(e, d.eacc + (size_t)replica * N_ETERMS, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(a, d.alch_acc + (size_t)replica * ALCH_SLOTS * 3, sizeof a, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(box, d.boxd, sizeof box, cudaMemcpyDeviceToHost, h->stream));
+    int rc = check_flags(h);
+    if (rc != BL_OK) return rc;
+    for (int k = 0; k < N_ETERMS; ++k) terms[k] = (double)e[k] / ENERGY_SCALE;
+    const double V = d.periodic ? box[0] * box[1] * box[2] : 1.0;
+    terms[E_SELF] = d.pme ? d.self_energy_coeff - ONE_4PI_EPS0 * M_PI * d.sumq * d.sumq / (2.0 * d.alphad * d.alphad * V) : 0.0;
+    terms[E_DISP] = d.periodic ? d.dispersion_coeff / V : 0.0;
+    terms[E_ALCH_STERICS] = (double)a[h->cursor * 3 + 0] / ENERGY_SCALE;
+    terms[E_ALCH_ELEC] = (double)a[h->cursor * 3 + 1] / ENERGY_SCALE;
+    terms[E_ALCH_EXC] = (double)a[h->cursor * 3 + 2] / ENERGY_SCALE;
+    return BL_OK;
+}
+
+int bl_copy_state(bl_handle* dst, const bl_handle* src, int flags) {
+    if (!dst || !src) return BL_ERR_INVALID;
+    bl_handle* h = dst;
+    if (dst->d.N != src->d.N || dst->device != src->device) { h->error = "handles are not compatible"; return BL_ERR_INVALID; }
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(src->stream));
+    const int R = std::min(dst->d.R, src->d.R);
+    const size_t n = sizeof(double4) * (size_t)R * dst->d.N;
+    if (flags & 4) {
+        double box[3];
+        CK(cudaMemcpy(box, src->d.boxd, sizeof box, cudaMemcpyDeviceToHost));
+        int rc = setup_box(h, box);
+        if (rc != BL_OK) return rc;
+    }
+    if (flags & 1) CK(cudaMemcpyAsync(dst->d.pos, src->d.pos, n, cudaMemcpyDeviceToDevice, h->stream));
+    if (flags & 2) { CK(cudaMemcpyAsync(dst->d.vel, src->d.vel, n, cudaMemcpyDeviceToDevice, h->stream)); h->vel_dirty = true; }
+    if (flags & 5) positions_changed(h);
+    return BL_OK;
+}
+
+int bl_velocities_to_temperature(bl_handle* h, double temperature) {
+    if (!h) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    Dev& d = h->d;
+    const double kT = 1.3806504e-23 * 6.02214179e23 / 1000.0 * temperature;
+    { LaunchTimer t(h, -1);
+      k_velocities_to_temperature<<<dim3(cdiv(d.n_clusters, 128), d.R), 128, 0, h->stream>>>(d, kT, h->ic.seed); }
+    { LaunchTimer t(h, -1); k_bump_counter<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d, 0); }
+    h->vel_dirty = true;
+    return BL_OK;
+}
+
+// ---- globals -------------------------------------------------------------------------------------------------
+int bl_get_global(bl_handle* h, int replica, const char* name, double* value) {
+    if (!h || !name || !value || replica < 0 || replica >= h->d.R) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    Globals g;
+    long long heat = 0;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(&g, h->d.g + replica, sizeof g, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&heat, h->d.heat_acc + replica, sizeof heat, cudaMemcpyDeviceToHost));
+    const std::string n = name;
+    const int li = std::min(std::max(g.lambda_step, 0), (int)h->lam_s_host.size() - 1);
+    if (n == "lambda") *value = g.lambda;
+    else if (n == "lambda_step") *value = g.lambda_step;
+    else if (n == "step") *value = g.step;
+    else if (n == "protocol_work") *value = g.protocol_work;
+    else if (n == "shadow_work") *value = g.shadow_work;
+    else if (n == "heat") *value = g.heat + (double)heat / ENERGY_SCALE;
+    else if (n == "first_step") *value = g.first_step;
+    else if (n == "perturbed_pe") *value = g.perturbed_pe;
+    else if (n == "unperturbed_pe") *value = g.unperturbed_pe;
+    else if (n == "prop") *value = g.prop;
+    else if (n == "nprop") *value = h->ic.nprop;
+    else if (n == "prop_lambda_min") *value = h->prop_lambda_min;
+    else if (n == "prop_lambda_max") *value = h->prop_lambda_max;
+    else if (n == "Eold") *value = g.Eold;
+    else if (n == "Enew") *value = g.Enew;
+    else if (n == "debug") *value = g.debug;
+    else if (n == "lambda_sterics") *value = h->lam_s_host[li];
+    else if (n == "lambda_electrostatics") *value = h->lam_e_host[li];
+    else if (n == "n_lambda_steps") *value = h->ic.n_lambda_steps;
+    else if (n == "nsteps") *value = h->ic.nsteps;
+    else if (n == "kT") *value = h->ic.kT;
+    else if (n == "n_rebuilds") *value = (double)g.n_rebuilds;
+    else { h->error = "unknown global variable '" + n + "'"; return BL_ERR_INVALID; }
+    return BL_OK;
+}
+
+int bl_set_global(bl_handle* h, int replica, const char* name, double value) {
+    if (!h || !name || replica >= h->d.R) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<Globals> g(h->d.R);
+    CK(cudaMemcpy(g.data(), h->d.g, sizeof(Globals) * h->d.R, cudaMemcpyDeviceToHost));
+    const std::string n = name;
+    const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? h->d.R : replica + 1;
+    for (int r = r0; r < r1; ++r) {
+        Globals& x = g[r];
+        if (n == "lambda") x.lambda = value;
+        else if (n == "lambda_step") { x.lambda_step = (int)value; h->lambda_step = (int)value; h->forces_valid = false; }
+        else if (n == "step") { x.step = (int)value; h->step = (int)value; }
+        else if (n == "protocol_work") x.protocol_work = value;
+        else if (n == "shadow_work") x.shadow_work = value;
+        else if (n == "heat") x.heat = value;
+        else if (n == "first_step") { x.first_step = (int)value; h->first_step = (int)value; }
+        else if (n == "perturbed_pe") x.perturbed_pe = value;
+        else if (n == "unperturbed_pe") x.unperturbed_pe = value;
+        else if (n == "prop") x.prop = (int)value;
+        else if (n == "Eold") x.Eold = value;
+        else if (n == "Enew") x.Enew = value;
+        else if (n == "debug") x.debug = (int)value;
+        else if (n == "nprop") { h->ic.nprop = std::max(1, (int)value); invalidate_graphs(h); }
+        else if (n == "prop_lambda_min") h->prop_lambda_min = value;
+        else if (n == "prop_lambda_max") h->prop_lambda_max = value;
+        else { h->error = "global variable '" + n + "' cannot be set"; return BL_ERR_INVALID; }
+    }
+    CK(cudaMemcpy(h->d.g, g.data(), sizeof(Globals) * h->d.R, cudaMemcpyHostToDevice));
+    return BL_OK;
+}
+
+int bl_reset_ncmc(bl_handle* h) {
+    if (!h) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<Globals> g(h->d.R);
+    CK(cudaMemcpy(g.data(), h->d.g, sizeof(Globals) * h->d.R, cudaMemcpyDeviceToHost));
+    for (auto& x : g) {
+        x.step = 0; x.lambda = 0.0; x.protocol_work = 0.0; x.shadow_work = 0.0; x.first_step = 0;
+        x.perturbed_pe = 0.0; x.unperturbed_pe = 0.0; x.prop = 1; x.lambda_step = 0; x.e_valid = 0;
+    }
+    CK(cudaMemcpy(h->d.g, g.data(), sizeof(Globals) * h->d.R, cudaMemcpyHostToDevice));
+    h->step = 0; h->lambda_step = 0; h->first_step = 0;
+    h->forces_valid = false;
+    return BL_OK;
+}
+
+// ---- moves -----------------------------------------------------------------------------------------------------
+static int stage_move(bl_handle* h, const bl_move* m) {
+    if (m->n_atoms <= 0 || !m->atoms || !m->masses) { h->error = "move needs atoms and masses"; return BL_ERR_INVALID; }
+    if (m->n_atoms > h->move_capacity) {
+        h->d_move_atoms = dalloc<int>(h, m->n_atoms);
+        h->d_move_masses = dalloc<float>(h, m->n_atoms);
+        h->move_capacity = m->n_atoms;
+    }
+    std::vector<float> mf(m->n_atoms);
+    for (int k = 0; k < m->n_atoms; ++k) mf[k] = (float)m->masses[k];
+    CK(cudaMemcpyAsync(h->d_move_atoms, m->atoms, sizeof(int) * m->n_atoms, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_move_masses, mf.data(), sizeof(float) * m->n_atoms, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return BL_OK;
+}
+static int enqueue_move(bl_handle* h, const bl_move* m) {
+    Dev& d = h->d;
+    if (m->kind == BL_MOVE_ROTATE) {
+        { LaunchTimer t(h, -1); k_move_rotate<<<d.R, 32, 0, h->stream>>>(d, m->n_atoms, h->d_move_atoms, h->d_move_masses, h->ic.seed); }
+        { LaunchTimer t(h, -1); k_bump_counter<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d, 1); }
+    } else {
+        h->error = "unknown move kind";
+        return BL_ERR_INVALID;
+    }
+    positions_changed(h);
+    return BL_OK;
+}
+
+int bl_apply_move(bl_handle* h, const bl_move* m) {
+    if (!h || !m) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    int rc = stage_move(h, m);
+    if (rc != BL_OK) return rc;
+    return enqueue_move(h, m);
+}
+
+// ---- the hot path ----------------------------------------------------------------------------------------------
+static void external_work_eval(bl_handle* h, bool first_only) {
+    eval_now(h, true);
+    LaunchTimer t(h, -1);
+    k_external_work<<<cdiv(h->d.R, 64), 64, 0, h->stream>>>(h->d, 0, first_only ? 1 : 0);
+    h->first_step = 1;
+}
+
+int bl_ncmc_run(bl_handle* h, int n_steps, const bl_move* move) {
+    if (!h || n_steps < 0) return BL_ERR_INVALID;
+    if (h->integrator_kind != BL_INTEGRATOR_NCMC) { h->error = "bl_ncmc_run needs an NCMC integrator"; return BL_ERR_INVALID; }
+    cudaSetDevice(h->device);
+    Dev& d = h->d;
+    const bool has_move = move && move->kind != BL_MOVE_NONE;
+    if (has_move) { int rc = stage_move(h, move); if (rc != BL_OK) return rc; }
+    for (int i = 0; i < n_steps; ++i) {
+        if (h->step >= h->ic.nsteps) break;        // `if step < nsteps` (blues/integrators.py:183)
+        if (h->step == 0) {
+            // reset block (blues/integrators.py:165-172): constrain, zero the work, lambda = 0
+            IntegrateArgs a;
+            memset(&a, 0, sizeof a);
+            a.nops = 1;
+            a.ops[0].kind = OP_CONSTRAIN;
+            enqueue_integrate(h, a);
+            { LaunchTimer t(h, -1); k_reset_protocol<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d); }
+            h->lambda_step = 0;
+            h->forces_valid = false;
+            h->vel_dirty = true;
+        }
+        if (has_move && i == move->step) {
+            if (!h->forces_valid && h->first_step >= 1) {
+                // unperturbed energy unknown at the pre-move coordinates: evaluate it first
+            }
+            int rc = enqueue_move(h, move);
+            if (rc != BL_OK) return rc;
+        }
+        if (h->vel_dirty) { enqueue_momentum(h); h->vel_dirty = false; }
+        if (!h->forces_valid) external_work_eval(h, false);
+        // one integrator step = main pass + optional extra propagation passes
+        const int ls_after = h->lambda_step + h->n_H;
+        const double lam_after = (double)ls_after / (double)h->ic.n_lambda_steps;
+        int n_extra = 0;
+        if (h->ic.nprop > 1 && lam_after > h->prop_lambda_min && lam_after <= h->prop_lambda_max) n_extra = h->ic.nprop - 1;
+        const bool energy_end = (i == n_steps - 1) || (h->step + 1 >= h->ic.nsteps) || (has_move && i + 1 == move->step);
+        std::vector<Launch> ls;
+        int cursor = h->cursor;
+        compile_pass(h, ls, cursor, true, n_extra == 0, energy_end);
+        for (int p = 0; p < n_extra; ++p) compile_pass(h, ls, cursor, false, p == n_extra - 1, energy_end);
+        char key[96];
+        snprintf(key, sizeof key, "ncmc|c%d|e%d|x%d", h->cursor, energy_end ? 1 : 0, n_extra);
+        int rc = run_launches(h, key, ls);
+        if (rc != BL_OK) return rc;
+        h->cursor = cursor;
+        h->step += 1;
+        h->lambda_step = ls_after;
+        h->forces_valid = true;
+    }
+    return check_flags(h);
+}
+
+int bl_md_run(bl_handle* h, int n_steps) {
+    if (!h || n_steps < 0) return BL_ERR_INVALID;
+    if (h->integrator_kind != BL_INTEGRATOR_LANGEVIN) { h->error = "bl_md_run needs a Langevin integrator"; return BL_ERR_INVALID; }
+    cudaSetDevice(h->device);
+    for (int i = 0; i < n_steps; ++i) {
+        if (h->vel_dirty) { enqueue_momentum(h); h->vel_dirty = false; }
+        if (!h->forces_valid) eval_now(h, false);
+        std::vector<Launch> ls(2);
+        memset(&ls[0], 0, sizeof(Launch));
+        memset(&ls[1], 0, sizeof(Launch));
+        ls[0].is_eval = false;
+        ls[0].args.nops = 2;
+        ls[0].args.ops[0].kind = OP_CM;
+        ls[0].args.ops[1].kind = OP_MD;
+        ls[0].args.ops[1].slot = h->cursor;
+        ls[0].args.accum_cm = h->ic.remove_cm ? 2 : 0;
+        ls[1].is_eval = true;
+        ls[1].energy = false;
+        ls[1].cm_mode = h->ic.remove_cm ? 2 : 0;
+        char key[64];
+        snprintf(key, sizeof key, "md|c%d", h->cursor);
+        int rc = run_launches(h, key, ls);
+        if (rc != BL_OK) return rc;
+        h->cursor = 0;
+        h->forces_valid = true;
+    }
+    return check_flags(h);
+}
+
+int bl_accept_reject(bl_handle* h, const double* correction, int32_t* accepted, double* logp, double* log_u) {
+    if (!h || !accepted) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    Dev& d = h->d;
+    double* dcorr = nullptr;
+    if (correction) {
+        dcorr = h->d_scratch + 2 * d.R;
+        CK(cudaMemcpyAsync(dcorr, correction, sizeof(double) * d.R, cudaMemcpyHostToDevice, h->stream));
+    }
+    { LaunchTimer t(h, -1);
+      k_accept<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d, h->ic.kT, dcorr, h->d_iscratch, h->d_scratch, h->d_scratch + d.R, h->ic.seed); }
+    { LaunchTimer t(h, -1); k_bump_counter<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d, 2); }
+    std::vector<double> tmp(2 * d.R);
+    CK(cudaMemcpyAsync(accepted, h->d_iscratch, sizeof(int) * d.R, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(tmp.data(), h->d_scratch, sizeof(double) * 2 * d.R, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (logp) memcpy(logp, tmp.data(), sizeof(double) * d.R);
+    if (log_u) memcpy(log_u, tmp.data() + d.R, sizeof(double) * d.R);
+    return BL_OK;
+}
+
+int bl_minimize(bl_handle* h, int max_iterations, double tolerance) {
+    if (!h) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    Dev& d = h->d;
+    if (max_iterations <= 0) max_iterations = 1000;
+    if (tolerance <= 0) tolerance = 10.0;
+    if (!h->d_saved) h->d_saved = dalloc<double4>(h, (size_t)d.R * d.N);
+    // constrain first, then adaptive steepest descent: accept a trial if the energy went down (step *= 1.2),
+    // otherwise restore and halve the step.  One host round-trip per iteration (not a hot path).
+    {
+        IntegrateArgs a; memset(&a, 0, sizeof a); a.nops = 1; a.ops[0].kind = OP_CONSTRAIN;
+        enqueue_integrate(h, a);
+        positions_changed(h);
+    }
+    std::vector<double> e0(d.R), e1(d.R), step(d.R, 1e-6);
+    std::vector<int> reject(d.R);
+    int rc = bl_get_energy(h, e0.data(), nullptr);
+    if (rc != BL_OK) return rc;
+    double gstep = 1e-5;   // nm per (kJ/mol/nm): displacement = gstep * F, capped at 0.01 nm per atom
+    for (int it = 0; it < max_iterations; ++it) {
+        { LaunchTimer t(h, -1);
+          k_minimize_step<<<dim3(cdiv(d.n_clusters, 128), d.R), 128, 0, h->stream>>>(d, gstep, 0.01, h->ic.tol, h->d_saved); }
+        positions_changed(h);
+        rc = bl_get_energy(h, e1.data(), nullptr);
+        if (rc != BL_OK && rc != BL_ERR_NAN) return rc;
+        bool any_reject = false, all_up = true;
+        for (int r = 0; r < d.R; ++r) {
+            reject[r] = !(e1[r] < e0[r]);
+            if (reject[r]) any_reject = true; else { all_up = false; e0[r] = e1[r]; }
+        }
+        if (any_reject) {
+            CK(cudaMemcpyAsync(h->d_iscratch, reject.data(), sizeof(int) * d.R, cudaMemcpyHostToDevice, h->stream));
+            { LaunchTimer t(h, -1);
+              k_restore_positions<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, h->d_saved, h->d_iscratch); }
+            positions_changed(h);
+            CK(cudaStreamSynchronize(h->stream));
+            // forces must be re-evaluated at the restored coordinates
+            eval_now(h, true);
+        }
+        gstep = all_up ? gstep * 0.5 : gstep * 1.2;
+        if (gstep < 1e-12) break;
+        if (!any_reject && (it % 10) == 9) {
+            CK(cudaMemsetAsync(h->d_scratch, 0, sizeof(double) * d.R, h->stream));
+            { LaunchTimer t(h, -1); k_max_force<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, h->d_scratch); }
+            std::vector<double> f2(d.R);
+            CK(cudaMemcpyAsync(f2.data(), h->d_scratch, sizeof(double) * d.R, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            double worst = 0;
+            for (double v : f2) worst = std::max(worst, sqrt(v));
+            if (worst < tolerance) break;
+        }
+    }
+    // clear a NaN flag possibly raised by rejected trial steps
+    std::vector<Globals> g(d.R);
+    CK(cudaMemcpy(g.data(), d.g, sizeof(Globals) * d.R, cudaMemcpyDeviceToHost));
+    for (auto& x : g) x.nan_flag = 0;
+    CK(cudaMemcpy(d.g, g.data(), sizeof(Globals) * d.R, cudaMemcpyHostToDevice));
+    return BL_OK;
+}
+
+// ---- introspection ----------------------------------------------------------------------------------------------
+int bl_neighbor_pairs(bl_handle* h, int replica, int64_t* codes, size_t capacity, size_t* n_pairs) {
+    if (!h || !n_pairs || replica < 0 || replica >= h->d.R) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    Dev& d = h->d;
+    // force a fresh list at the current coordinates
+    { LaunchTimer t(h, -1); k_refresh_mirrors<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, 1); }
+    eval_now(h, false);
+    long long* dcodes = nullptr;
+    unsigned long long* dn = nullptr;
+    CK(cudaMalloc(&dcodes, sizeof(long long) * std::max<size_t>(capacity, 1)));
+    CK(cudaMalloc(&dn, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(dn, 0, sizeof(unsigned long long), h->stream));
+    { LaunchTimer t(h, -1); k_neighbor_pairs<<<148 * 2, 256, 0, h->stream>>>(d, replica, dcodes, capacity, dn); }
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, dn, sizeof n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *n_pairs = (size_t)n;
+    if (codes && n <= capacity) {
+        CK(cudaMemcpy(codes, dcodes, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+        std::sort(codes, codes + n);
+    }
+    cudaFree(dcodes);
+    cudaFree(dn);
+    return check_flags(h);
+}
+
+int bl_neighbor_stats(bl_handle* h, int replica, int64_t* n_tiles, int64_t* n_rebuilds) {
+    if (!h || replica < 0 || replica >= h->d.R) return BL_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(h->stream));
+    Globals g;
+    CK(cudaMemcpy(&g, h->d.g + replica, sizeof g, cudaMemcpyDeviceToHost));
+    if (n_tiles) *n_tiles = g.n_items;
+    if (n_rebuilds) *n_rebuilds = g.n_rebuilds;
+    return BL_OK;
+}
+
+}  // extern "C"

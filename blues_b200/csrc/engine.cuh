@@ -1,0 +1,123 @@
+// Device-side data layout of one engine handle (R independent walkers of the same N-atom system).
+#pragma once
+#include "common.cuh"
+
+#define MAX_CLUSTER_ATOMS 5
+#define MAX_CLUSTER_CONS 4
+#define TILE_CHUNKS 4                 /* one pair-kernel work item = 1 i-block x up to 4 chunks of 32 j-atoms */
+#define ITEM_ATOMS (TILE_CHUNKS * 32)
+#define N_ETERMS 12
+#define MAX_OPS 16
+#define ALCH_SLOTS 3
+#define MAX_ALCH_SMEM 512             /* alchemical atoms staged in shared memory by k_alch                 */
+
+enum EnergyTerm { E_BOND = 0, E_ANGLE, E_TORSION, E_RESTRAINT, E_PAIR, E_EXCEPT, E_PME, E_SELF, E_DISP,
+                  E_ALCH_STERICS, E_ALCH_ELEC, E_ALCH_EXC };
+
+enum OpKind { OP_NONE = 0, OP_CM, OP_V, OP_R, OP_O, OP_H, OP_MD, OP_CONSTRAIN, OP_STEP_BEGIN, OP_STEP_END };
+
+struct Op { int kind; int slot; };
+
+// Constraint cluster: atoms that share holonomic constraints (water triangle, heavy atom + its hydrogens) or a
+// single unconstrained atom.  One thread integrates one cluster through the whole V/R/O sequence.
+struct Cluster {
+    int natoms, ncons;
+    int atom[MAX_CLUSTER_ATOMS];
+    signed char ca[MAX_CLUSTER_CONS], cb[MAX_CLUSTER_CONS];   // local atom indices of each constraint
+    double d2[MAX_CLUSTER_CONS];                              // squared constraint lengths
+};
+
+// Per-walker integrator globals (the CustomIntegrator global variables of blues/integrators.py:124-145 plus
+// engine bookkeeping).  Doubles so host get/set round-trips are exact.
+struct Globals {
+    double protocol_work, shadow_work, heat, perturbed_pe, unperturbed_pe, Eold, Enew, lambda;
+    double e_env;            // environment (lambda-independent) potential energy at the last energy-enabled evaluation
+    double e_total_prev;     // total potential energy recorded at the end of the last completed step
+    int lambda_step, step, first_step, prop, debug;
+    int alch_base;           // lambda_step for which alchemical slot 0 was evaluated
+    int e_valid;             // e_total_prev is valid
+    int nan_flag;
+    unsigned int noise_counter, vel_counter, move_counter, accept_counter, md_counter;
+    int do_rebuild, rebuild_request;
+    long long n_rebuilds;
+    int n_items, item_overflow;
+};
+
+struct IntegratorConsts {
+    double dt, kT, gamma;
+    double hV, hR, hO;                 // substep lengths dt/n_V, dt/n_R, dt/n_O
+    double a, b;                       // O-step coefficients
+    double md_vscale, md_fscale, md_nscale;
+    double tol;
+    int n_lambda_steps, nsteps, nprop;
+    double total_mass;
+    int remove_cm;
+    uint64_t seed;
+};
+
+struct Dev {
+    int N, Npad, nblocks, R;
+    int periodic, pme, nb_method;
+    // box (device memory so CUDA graphs survive bl_set_box): [0..2] L, [3..5] 1/L as double; floats mirror
+    double* boxd;
+    float* boxf;
+    float cutoff, cutoff2, list_cutoff2, skin_half2, alpha, krf, crf;
+    double cutoffd, alphad;
+    // static per-atom data (original order)
+    double* mass; double* invmass;
+    float* charge; float2* sigeps;          // sigeps: (sigma/2, 2 sqrt(eps)) so sigma_ij = s_i+s_j, 4 eps_ij = e_i e_j
+    ull* excl_win;                          // bit (j - i + 32) set if pair (i, j) is excluded / an exception
+    unsigned char* has_far;                 // atom has exclusions outside the +-32 index window
+    long long* far_codes; int n_far;        // sorted i*N+j (i<j) codes of those far exclusions
+    // dynamic state
+    double4* pos; double4* vel;             // [R*N]
+    float4* posq;                           // [R*N] single-precision mirror (x, y, z, q)
+    float4* pos_ref;                        // [R*N] positions at the last neighbour rebuild
+    long long* f_env;                       // [R][3][N] fixed point
+    long long* f_alch;                      // [ALCH_SLOTS][R][3][N]
+    long long* eacc;                        // [R][N_ETERMS]
+    long long* alch_acc;                    // [R][ALCH_SLOTS][3]  (sterics, electrostatics, exceptions)
+    long long* cm_acc;                      // [R][3] sum of m v
+    long long* heat_acc;                    // [R]
+    Globals* g;                             // [R]
+    // neighbour structures
+    int ncell[3]; int ncells;
+    int* cell_order;                        // [ncells] Morton rank of each cell
+    int* cell_count;                        // [R][ncells+1]
+    int* atom_cell; int* atom_slot;         // [R*N]
+    int* rank;                              // [R*N] position of atom a in the sorted order
+    float4* posq_s; float2* sigeps_s; int* orig_s;   // [R*Npad] sorted copies (pads: NaN position, orig -1)
+    float4* blk_center; float4* blk_half;   // [R*nblocks]
+    int item_capacity;
+    int* item_block; int* item_natoms;      // [R*item_capacity]
+    int* item_flags;                        // bit c: chunk c has exclusions; bit 8: chunk 0 is the block's own atoms
+    int* item_atoms;                        // [R*item_capacity*ITEM_ATOMS] sorted indices, -1 pads
+    unsigned int* item_excl;                // [R*item_capacity*ITEM_ATOMS] per-lane exclusion bits vs the chunk's 32 j
+    // bonded tables
+    int n_bonds, n_angles, n_torsions, n_excl, n_restraints, n_alch_exc;
+    int2* bonds; double2* bond_p;           // (k, r0)
+    int4* angles; double2* angle_p;         // (k, theta0)   (w unused)
+    int4* torsions; double4* torsion_p;     // (k, n, phase, -)
+    int2* excl; double4* excl_p;            // (k_e*qq_exception, sigma, eps, k_e*q_i*q_j)
+    int* restraint_atom; double4* restraint_p;   // (x0, y0, z0, k)
+    int2* alch_exc; double4* alch_exc_p;    // (k_e*qq, sigma, eps, both_alchemical)
+    // alchemical region
+    int n_alch;
+    int* alch_atom; double4* alch_p;        // (q, sigma, eps, -)
+    unsigned char* is_alch;                 // [N]
+    double sc_alpha, sc_a, sc_b, sc_c;
+    int annihilate_sterics, annihilate_elec;
+    double* lam_s; double* lam_e; int n_lambda;       // tables indexed by lambda_step
+    // PME
+    int gx, gy, gz; int gsize; int csize;   // real grid size, complex grid size (gx*gy*(gz/2+1))
+    long long* grid_fx;                     // [R][gsize] fixed point
+    float* grid_r;                          // [R][gsize]
+    float2* grid_c;                         // [R][csize]
+    float* bmod_x; float* bmod_y; float* bmod_z;
+    double self_energy_coeff;               // -k_e alpha/sqrt(pi) sum q^2  (constant)
+    double sumq;
+    double dispersion_coeff;
+    // integrator clusters
+    int n_clusters;
+    Cluster* clusters;
+};

@@ -1,0 +1,560 @@
+// Fused integrator (K8): one thread per constraint cluster runs a whole sequence of Langevin substeps
+// (V / R / O with matrix-SHAKE + exact RATTLE), the H-step work bookkeeping (K9), plus small state kernels (K10/K11).
+#pragma once
+#include "engine.cuh"
+
+struct ClusterState {
+    double x[MAX_CLUSTER_ATOMS][3];
+    double v[MAX_CLUSTER_ATOMS][3];
+    double im[MAX_CLUSTER_ATOMS];
+};
+
+// Solve the n x n system A y = b in place (Gaussian elimination with partial pivoting), n <= MAX_CLUSTER_CONS.
+__device__ __forceinline__ void solve_small(double A[MAX_CLUSTER_CONS][MAX_CLUSTER_CONS], double* b, int n) {
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        double best = fabs(A[c][c]);
+        for (int rr = c + 1; rr < n; ++rr)
+            if (fabs(A[rr][c]) > best) { best = fabs(A[rr][c]); piv = rr; }
+        if (piv != c) {
+            for (int k = 0; k < n; ++k) { double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+            double t = b[c]; b[c] = b[piv]; b[piv] = t;
+        }
+        const double inv = 1.0 / A[c][c];
+        for (int rr = c + 1; rr < n; ++rr) {
+            const double f = A[rr][c] * inv;
+            if (f != 0.0) {
+                for (int k = c; k < n; ++k) A[rr][k] -= f * A[c][k];
+                b[rr] -= f * b[c];
+            }
+        }
+    }
+    for (int c = n - 1; c >= 0; --c) {
+        double s = b[c];
+        for (int k = c + 1; k < n; ++k) s -= A[c][k] * b[k];
+        b[c] = s / A[c][c];
+    }
+}
+
+// coupling coefficient between constraints a and b of a cluster: how a unit multiplier on b moves the
+// separation vector of a (through shared atoms and inverse masses)
+__device__ __forceinline__ double coupling(const Cluster& c, const double* im, int a, int b) {
+    const int ia = c.ca[a], ja = c.cb[a], ib = c.ca[b], jb = c.cb[b];
+    return ((ia == ib) - (ia == jb)) * im[ia] - ((ja == ib) - (ja == jb)) * im[ja];
+}
+
+// RATTLE (exact, linear): remove velocity components along the constraints
+__device__ __forceinline__ void constrain_velocities(const Cluster& c, ClusterState& s) {
+    const int n = c.ncons;
+    if (n == 0) return;
+    double sv[MAX_CLUSTER_CONS][3];
+    double A[MAX_CLUSTER_CONS][MAX_CLUSTER_CONS], rhs[MAX_CLUSTER_CONS];
+    for (int a = 0; a < n; ++a) {
+        const int i = c.ca[a], j = c.cb[a];
+        double dvv = 0.0;
+        for (int k = 0; k < 3; ++k) {
+            sv[a][k] = s.x[i][k] - s.x[j][k];
+            dvv += sv[a][k] * (s.v[i][k] - s.v[j][k]);
+        }
+        rhs[a] = -dvv;
+    }
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b)
+            A[a][b] = coupling(c, s.im, a, b) * (sv[a][0] * sv[b][0] + sv[a][1] * sv[b][1] + sv[a][2] * sv[b][2]);
+    solve_small(A, rhs, n);
+    for (int a = 0; a < n; ++a) {
+        const int i = c.ca[a], j = c.cb[a];
+        for (int k = 0; k < 3; ++k) {
+            const double cc = rhs[a] * sv[a][k];
+            s.v[i][k] += cc * s.im[i];
+            s.v[j][k] -= cc * s.im[j];
+        }
+    }
+}
+
+// matrix SHAKE: move x along the reference directions (xref) until every |x_i - x_j|^2 = d^2
+__device__ __forceinline__ void constrain_positions(const Cluster& c, ClusterState& s,
+                                                    const double xref[MAX_CLUSTER_ATOMS][3], double tol) {
+    const int n = c.ncons;
+    if (n == 0) return;
+    double rr[MAX_CLUSTER_CONS][3];
+    for (int a = 0; a < n; ++a)
+        for (int k = 0; k < 3; ++k) rr[a][k] = xref[c.ca[a]][k] - xref[c.cb[a]][k];
+    for (int it = 0; it < 30; ++it) {
+        double sv[MAX_CLUSTER_CONS][3], diff[MAX_CLUSTER_CONS];
+        double worst = 0.0;
+        for (int a = 0; a < n; ++a) {
+            const int i = c.ca[a], j = c.cb[a];
+            double s2 = 0.0;
+            for (int k = 0; k < 3; ++k) { sv[a][k] = s.x[i][k] - s.x[j][k]; s2 += sv[a][k] * sv[a][k]; }
+            diff[a] = c.d2[a] - s2;
+            worst = fmax(worst, fabs(diff[a]) / c.d2[a]);
+        }
+        if (worst < tol) break;
+        double A[MAX_CLUSTER_CONS][MAX_CLUSTER_CONS];
+        for (int a = 0; a < n; ++a)
+            for (int b = 0; b < n; ++b)
+                A[a][b] = 2.0 * coupling(c, s.im, a, b) * (sv[a][0] * rr[b][0] + sv[a][1] * rr[b][1] + sv[a][2] * rr[b][2]);
+        solve_small(A, diff, n);
+        for (int a = 0; a < n; ++a) {
+            const int i = c.ca[a], j = c.cb[a];
+            for (int k = 0; k < 3; ++k) {
+                const double cc = diff[a] * rr[a][k];
+                s.x[i][k] += cc * s.im[i];
+                s.x[j][k] -= cc * s.im[j];
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ double alch_energy(const Dev& d, int r, int slot) {
+    const long long* a = d.alch_acc + (r * ALCH_SLOTS + slot) * 3;
+    return (double)(a[0] + a[1] + a[2]) * (1.0 / ENERGY_SCALE);
+}
+__device__ __forceinline__ double env_energy(const Dev& d, int r) {
+    long long s = 0;
+    for (int k = 0; k <= E_PME; ++k) s += d.eacc[r * N_ETERMS + k];
+    const double V = d.periodic ? d.boxd[0] * d.boxd[1] * d.boxd[2] : 1.0;
+    double e = (double)s * (1.0 / ENERGY_SCALE);
+    if (d.pme) e += d.self_energy_coeff - ONE_4PI_EPS0 * 3.14159265358979323846 * d.sumq * d.sumq / (2.0 * d.alphad * d.alphad * V);
+    if (d.periodic) e += d.dispersion_coeff / V;
+    return e;
+}
+
+struct IntegrateArgs {
+    int nops;
+    Op ops[MAX_OPS];
+    int accum_cm;       // 0 none, 1 into cm_acc[parity], 2 into cm_acc[1-parity]
+    int energy_valid;   // the preceding force evaluation produced energies (for OP_STEP_END bookkeeping)
+    int noise_offset;   // O / MD ops executed by INTEGRATE launches since the last k_begin_eval
+    int md_offset;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_integrate(Dev d, IntegratorConsts ic, IntegrateArgs args, const int* cm_parity) {
+    const int r = blockIdx.y;
+    const int N = d.N;
+    const int cid = blockIdx.x * blockDim.x + threadIdx.x;
+    Globals& g = d.g[r];
+    const int parity = *cm_parity;
+    double mom[3] = {0.0, 0.0, 0.0};
+    double dheat = 0.0;
+
+    if (cid < d.n_clusters) {
+        const Cluster c = d.clusters[cid];
+        double4* pos = d.pos + (size_t)r * N;
+        double4* vel = d.vel + (size_t)r * N;
+        const long long* fenv = d.f_env + (size_t)r * 3 * N;
+        ClusterState s;
+        double mass[MAX_CLUSTER_ATOMS];
+        for (int k = 0; k < c.natoms; ++k) {
+            const int a = c.atom[k];
+            const double4 p = pos[a], v = vel[a];
+            s.x[k][0] = p.x; s.x[k][1] = p.y; s.x[k][2] = p.z;
+            s.v[k][0] = v.x; s.v[k][1] = v.y; s.v[k][2] = v.z;
+            s.im[k] = d.invmass[a];
+            mass[k] = d.mass[a];
+        }
+        const unsigned int noise0 = g.noise_counter + args.noise_offset, md0 = g.md_counter + args.md_offset;
+        int n_o = 0, n_md = 0;
+        for (int o = 0; o < args.nops; ++o) {
+            const Op op = args.ops[o];
+            switch (op.kind) {
+            case OP_CM: {
+                if (ic.remove_cm) {
+                    const long long* cm = d.cm_acc + ((size_t)parity * d.R + r) * 3;
+                    const double inv = 1.0 / (FORCE_SCALE * ic.total_mass);
+                    const double vx = (double)cm[0] * inv, vy = (double)cm[1] * inv, vz = (double)cm[2] * inv;
+                    for (int k = 0; k < c.natoms; ++k)
+                        if (s.im[k] > 0.0) { s.v[k][0] -= vx; s.v[k][1] -= vy; s.v[k][2] -= vz; }
+                }
+            } break;
+            case OP_V: {
+                const long long* fa = d.n_alch > 0 ? d.f_alch + ((size_t)op.slot * d.R + r) * 3 * N : nullptr;
+                for (int k = 0; k < c.natoms; ++k) {
+                    const int a = c.atom[k];
+                    const double sc = ic.hV * s.im[k] * (1.0 / FORCE_SCALE);
+                    for (int q = 0; q < 3; ++q) {
+                        long long f = fenv[q * N + a];
+                        if (fa) f += fa[q * N + a];
+                        s.v[k][q] += sc * (double)f;
+                    }
+                }
+                constrain_velocities(c, s);
+            } break;
+            case OP_R: {
+                double xref[MAX_CLUSTER_ATOMS][3], x1[MAX_CLUSTER_ATOMS][3];
+                for (int k = 0; k < c.natoms; ++k)
+                    for (int q = 0; q < 3; ++q) {
+                        xref[k][q] = s.x[k][q];
+                        if (s.im[k] > 0.0) s.x[k][q] += ic.hR * s.v[k][q];
+                        x1[k][q] = s.x[k][q];
+                    }
+                constrain_positions(c, s, xref, ic.tol);
+                const double ih = 1.0 / ic.hR;
+                for (int k = 0; k < c.natoms; ++k)
+                    for (int q = 0; q < 3; ++q) s.v[k][q] += (s.x[k][q] - x1[k][q]) * ih;
+                constrain_velocities(c, s);
+            } break;
+            case OP_O: {
+                double ke0 = 0.0, ke1 = 0.0;
+                for (int k = 0; k < c.natoms; ++k) {
+                    ke0 += 0.5 * mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
+                    if (s.im[k] > 0.0) {
+                        double n0, n1, n2;
+                        philox_normal3(ic.seed, STREAM_LANGEVIN, (uint32_t)r, noise0 + n_o, (uint32_t)c.atom[k], n0, n1, n2);
+                        const double sg = ic.b * sqrt(ic.kT * s.im[k]);
+                        s.v[k][0] = ic.a * s.v[k][0] + sg * n0;
+                        s.v[k][1] = ic.a * s.v[k][1] + sg * n1;
+                        s.v[k][2] = ic.a * s.v[k][2] + sg * n2;
+                    }
+                }
+                ++n_o;
+                constrain_velocities(c, s);
+                for (int k = 0; k < c.natoms; ++k)
+                    ke1 += 0.5 * mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
+                dheat += ke1 - ke0;
+            } break;
+            case OP_MD: {
+                // OpenMM LangevinIntegrator: v' = e^{-g dt} v + (1-e^{-g dt})/g f/m + sqrt(kT(1-e^{-2 g dt})/m) xi;
+                // x' = x + dt v'; constrain; v = (x'-x)/dt
+                double xref[MAX_CLUSTER_ATOMS][3];
+                for (int k = 0; k < c.natoms; ++k) {
+                    const int a = c.atom[k];
+                    double n[3] = {0.0, 0.0, 0.0};
+                    if (s.im[k] > 0.0)
+                        philox_normal3(ic.seed, STREAM_MD, (uint32_t)r, md0 + n_md, (uint32_t)a, n[0], n[1], n[2]);
+                    const double sq = ic.md_nscale * sqrt(s.im[k]);
+                    for (int q = 0; q < 3; ++q) {
+                        xref[k][q] = s.x[k][q];
+                        if (s.im[k] > 0.0) {
+                            long long fi = fenv[q * N + a];
+                            if (d.n_alch > 0) fi += d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + a];
+                            const double f = (double)fi * (1.0 / FORCE_SCALE);
+                            s.v[k][q] = ic.md_vscale * s.v[k][q] + ic.md_fscale * s.im[k] * f + sq * n[q];
+                            s.x[k][q] += ic.dt * s.v[k][q];
+                        }
+                    }
+                }
+                ++n_md;
+                constrain_positions(c, s, xref, ic.tol);
+                const double idt = 1.0 / ic.dt;
+                for (int k = 0; k < c.natoms; ++k)
+                    for (int q = 0; q < 3; ++q)
+                        if (s.im[k] > 0.0) s.v[k][q] = (s.x[k][q] - xref[k][q]) * idt;
+            } break;
+            case OP_CONSTRAIN: {
+                double xref[MAX_CLUSTER_ATOMS][3];
+                for (int k = 0; k < c.natoms; ++k)
+                    for (int q = 0; q < 3; ++q) xref[k][q] = s.x[k][q];
+                constrain_positions(c, s, xref, ic.tol);
+                constrain_velocities(c, s);
+            } break;
+            default: break;
+            }
+        }
+        // write back + mirrors + rebuild / NaN checks
+        bool moved = false, bad = false;
+        const float lim = d.skin_half2;
+        for (int k = 0; k < c.natoms; ++k) {
+            const int a = c.atom[k];
+            pos[a] = make_double4(s.x[k][0], s.x[k][1], s.x[k][2], 0.0);
+            vel[a] = make_double4(s.v[k][0], s.v[k][1], s.v[k][2], 0.0);
+            const float4 pf = make_float4((float)s.x[k][0], (float)s.x[k][1], (float)s.x[k][2], d.charge[a]);
+            d.posq[(size_t)r * N + a] = pf;
+            d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * N + a]] = pf;
+            const float4 pr = d.pos_ref[(size_t)r * N + a];
+            const float ddx = pf.x - pr.x, ddy = pf.y - pr.y, ddz = pf.z - pr.z;
+            moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
+            bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
+            for (int q = 0; q < 3; ++q) mom[q] += mass[k] * s.v[k][q];
+        }
+        if (moved) g.rebuild_request = 1;
+        if (bad) g.nan_flag = 1;
+    }
+    if (args.accum_cm && ic.remove_cm) {
+        const int target = args.accum_cm == 1 ? parity : 1 - parity;
+        for (int q = 0; q < 3; ++q) {
+            const double v = warp_sum(mom[q]);
+            if ((threadIdx.x & 31) == 0) fx_add(&d.cm_acc[((size_t)target * d.R + r) * 3 + q], v, FORCE_SCALE);
+        }
+    }
+    {
+        const double v = warp_sum(dheat);
+        if ((threadIdx.x & 31) == 0 && v != 0.0) fx_add(&d.heat_acc[r], v, ENERGY_SCALE);
+    }
+    // scalar bookkeeping of the step program by one thread per walker (K9): H updates and step begin / end.
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int o = 0; o < args.nops; ++o) {
+            const Op op = args.ops[o];
+            if (op.kind == OP_H) {
+                // blues/integrators.py:217-231
+                g.debug += 1;
+                const double e_old = alch_energy(d, r, op.slot), e_new = alch_energy(d, r, op.slot + 1);
+                g.Eold = g.e_env + e_old;
+                g.lambda_step += 1;
+                g.lambda = (double)g.lambda_step / (double)ic.n_lambda_steps;
+                g.Enew = g.e_env + e_new;
+                g.protocol_work += e_new - e_old;
+            } else if (op.kind == OP_STEP_END) {
+                // blues/integrators.py:205-207: unperturbed_pe = energy; step += 1; prop = 1
+                if (args.energy_valid) {
+                    g.e_env = env_energy(d, r);
+                    g.e_total_prev = g.e_env + alch_energy(d, r, op.slot);
+                    g.unperturbed_pe = g.e_total_prev;
+                    g.e_valid = 1;
+                } else {
+                    g.e_valid = 0;
+                }
+                g.step += 1;
+                g.prop = 1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small state kernels
+// ---------------------------------------------------------------------------------------------------------
+// refresh the float mirrors from the double positions (after host writes / moves); request a rebuild
+__global__ void k_refresh_mirrors(Dev d, int request_rebuild) {
+    const int r = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= d.N) return;
+    const double4 p = d.pos[(size_t)r * d.N + a];
+    const float4 pf = make_float4((float)p.x, (float)p.y, (float)p.z, d.charge[a]);
+    d.posq[(size_t)r * d.N + a] = pf;
+    d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * d.N + a]] = pf;
+    if (a == 0 && request_rebuild) d.g[r].rebuild_request = 1;
+}
+
+__global__ void k_momentum(Dev d, const int* cm_parity) {
+    const int r = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double m[3] = {0.0, 0.0, 0.0};
+    if (a < d.N) {
+        const double4 v = d.vel[(size_t)r * d.N + a];
+        const double ms = d.mass[a];
+        m[0] = ms * v.x; m[1] = ms * v.y; m[2] = ms * v.z;
+    }
+    const int p = *cm_parity;
+    for (int q = 0; q < 3; ++q) {
+        const double v = warp_sum(m[q]);
+        if ((threadIdx.x & 31) == 0 && v != 0.0) fx_add(&d.cm_acc[((size_t)p * d.R + r) * 3 + q], v, FORCE_SCALE);
+    }
+}
+
+// zero the consumed centre-of-mass accumulator and flip the parity (single-INTEGRATE passes)
+__global__ void k_cm_flip(Dev d, int* cm_parity) {
+    const int p = *cm_parity;
+    for (int i = threadIdx.x; i < d.R * 3; i += blockDim.x) d.cm_acc[(size_t)p * d.R * 3 + i] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) *cm_parity = p ^ 1;
+}
+
+// total force (environment + alchemical slot) as doubles, and potential energy per walker, for the host
+__global__ void k_export_forces(Dev d, int r, int slot, double* out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= d.N) return;
+    for (int q = 0; q < 3; ++q) {
+        long long f = d.f_env[(size_t)r * 3 * d.N + q * d.N + a];
+        if (d.n_alch > 0) f += d.f_alch[((size_t)slot * d.R + r) * 3 * d.N + q * d.N + a];
+        out[a * 3 + q] = (double)f * (1.0 / FORCE_SCALE);
+    }
+}
+__global__ void k_export_energy(Dev d, int slot, double* out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.R) return;
+    out[r] = env_energy(d, r) + (d.n_alch > 0 ? alch_energy(d, r, slot) : 0.0);
+}
+
+__global__ void k_zero_ll(long long* p, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0;
+}
+
+__global__ void k_kinetic_energy(Dev d, double* out) {
+    const int r = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double ke = 0.0;
+    if (a < d.N) {
+        const double4 v = d.vel[(size_t)r * d.N + a];
+        ke = 0.5 * d.mass[a] * (v.x * v.x + v.y * v.y + v.z * v.z);
+    }
+    ke = warp_sum(ke);
+    if ((threadIdx.x & 31) == 0 && ke != 0.0) atomicAdd(&out[r], ke);
+}
+
+// Maxwell-Boltzmann draw per cluster followed by the velocity constraints (setVelocitiesToTemperature)
+__global__ void __launch_bounds__(128) k_velocities_to_temperature(Dev d, double kT, uint64_t seed) {
+    const int r = blockIdx.y;
+    const int cid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cid >= d.n_clusters) return;
+    const Cluster c = d.clusters[cid];
+    const unsigned int counter = d.g[r].vel_counter;
+    ClusterState s;
+    for (int k = 0; k < c.natoms; ++k) {
+        const int a = c.atom[k];
+        const double4 p = d.pos[(size_t)r * d.N + a];
+        s.x[k][0] = p.x; s.x[k][1] = p.y; s.x[k][2] = p.z;
+        s.im[k] = d.invmass[a];
+        double n0, n1, n2;
+        philox_normal3(seed, STREAM_VELOCITY, (uint32_t)r, counter, (uint32_t)a, n0, n1, n2);
+        const double sg = sqrt(kT * s.im[k]);
+        s.v[k][0] = sg * n0; s.v[k][1] = sg * n1; s.v[k][2] = sg * n2;
+    }
+    constrain_velocities(c, s);
+    for (int k = 0; k < c.natoms; ++k)
+        d.vel[(size_t)r * d.N + c.atom[k]] = make_double4(s.v[k][0], s.v[k][1], s.v[k][2], 0.0);
+}
+
+__global__ void k_bump_counter(Dev d, int which) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.R) return;
+    if (which == 0) d.g[r].vel_counter += 1;
+    else if (which == 1) d.g[r].move_counter += 1;
+    else d.g[r].accept_counter += 1;
+}
+
+// RandomLigandRotationMove.move (blues/moves.py:278-310): one warp per walker.
+// COM in float32 with the supplied masses, Shoemake quaternion from three Philox uniforms, x' = (x-c) R + c.
+__global__ void k_move_rotate(Dev d, int n, const int* atoms, const float* masses, uint64_t seed) {
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x;
+    double4* pos = d.pos + (size_t)r * d.N;
+    float cx = 0.f, cy = 0.f, cz = 0.f, mt = 0.f;
+    // sequential float32 accumulation in atom order (numpy's float32 sum over a short axis is sequential)
+    if (lane == 0) {
+        for (int k = 0; k < n; ++k) {
+            const double4 p = pos[atoms[k]];
+            const float m = masses[k];
+            cx += (float)p.x * m; cy += (float)p.y * m; cz += (float)p.z * m; mt += m;
+        }
+        cx /= mt; cy /= mt; cz /= mt;
+    }
+    cx = __shfl_sync(0xffffffffu, cx, 0);
+    cy = __shfl_sync(0xffffffffu, cy, 0);
+    cz = __shfl_sync(0xffffffffu, cz, 0);
+    Philox4 u = philox4x32_10(0u, d.g[r].move_counter, (uint32_t)r, STREAM_MOVE, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u0 = u01(u.x), u1 = u01(u.y), u2 = u01(u.z);
+    const double s1 = sqrt(1.0 - u0), s2 = sqrt(u0);
+    double sa, ca, sb, cb;
+    sincospi(2.0 * u1, &sa, &ca);
+    sincospi(2.0 * u2, &sb, &cb);
+    const double w = s1 * sa, x = s1 * ca, y = s2 * sb, z = s2 * cb;
+    const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
+                            {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
+                            {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
+    for (int k = lane; k < n; k += 32) {
+        const int a = atoms[k];
+        const double4 p = pos[a];
+        const double px = p.x - (double)cx, py = p.y - (double)cy, pz = p.z - (double)cz;
+        // row vector times R
+        pos[a] = make_double4(px * R[0][0] + py * R[1][0] + pz * R[2][0] + (double)cx,
+                              px * R[0][1] + py * R[1][1] + pz * R[2][1] + (double)cy,
+                              px * R[0][2] + py * R[1][2] + pz * R[2][2] + (double)cz, 0.0);
+    }
+}
+
+// external work after a coordinate change between steps (blues/integrators.py:184-191):
+// protocol_work += perturbed_pe - unperturbed_pe, using the energies of the evaluation that just finished
+__global__ void k_external_work(Dev d, int slot, int first_step_only) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.R) return;
+    Globals& g = d.g[r];
+    g.e_env = env_energy(d, r);
+    const double e = g.e_env + alch_energy(d, r, slot);
+    g.perturbed_pe = e;
+    if (g.first_step < 1 || first_step_only) {
+        g.first_step = 1;
+        g.unperturbed_pe = e;
+    } else if (g.e_valid) {
+        g.protocol_work += e - g.unperturbed_pe;
+    }
+    g.e_total_prev = e;
+    g.unperturbed_pe = e;
+    g.e_valid = 1;
+}
+
+// reset block of the step == 0 branch (blues/integrators.py:165-172) after the energies were evaluated
+__global__ void k_reset_protocol(Dev d) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.R) return;
+    Globals& g = d.g[r];
+    g.protocol_work = 0.0;
+    g.lambda = 0.0;
+    g.lambda_step = 0;
+}
+
+// Metropolis test on the device: accept iff logp + correction > log(u)  (blues/simulation.py:1130-1140)
+__global__ void k_accept(Dev d, double kT, const double* correction, int* accepted, double* logp_out, double* logu_out,
+                         uint64_t seed) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d.R) return;
+    Globals& g = d.g[r];
+    double w = -(g.protocol_work + g.shadow_work) / kT;
+    Philox4 u = philox4x32_10(0u, g.accept_counter, (uint32_t)r, STREAM_ACCEPT, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double lu = log(u01(u.x));
+    if (!isnan(w) && correction) w += correction[r];
+    accepted[r] = (w > lu) ? 1 : 0;
+    logp_out[r] = w;
+    logu_out[r] = lu;
+}
+
+// steepest-descent displacement with a per-atom cap, constraints re-imposed per cluster (bl_minimize)
+__global__ void __launch_bounds__(128) k_minimize_step(Dev d, double step, double maxdisp, double tol, double4* saved) {
+    const int r = blockIdx.y;
+    const int cid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cid >= d.n_clusters) return;
+    const Cluster c = d.clusters[cid];
+    const int N = d.N;
+    double4* pos = d.pos + (size_t)r * N;
+    const long long* fenv = d.f_env + (size_t)r * 3 * N;
+    ClusterState s;
+    double xref[MAX_CLUSTER_ATOMS][3];
+    for (int k = 0; k < c.natoms; ++k) {
+        const int a = c.atom[k];
+        const double4 p = pos[a];
+        saved[(size_t)r * N + a] = p;
+        s.im[k] = d.invmass[a];
+        double f[3];
+        for (int q = 0; q < 3; ++q) f[q] = (double)fenv[q * N + a] * (1.0 / FORCE_SCALE);
+        if (d.n_alch > 0) {
+            const long long* fa = d.f_alch + (size_t)r * 3 * N;
+            for (int q = 0; q < 3; ++q) f[q] += (double)fa[q * N + a] * (1.0 / FORCE_SCALE);
+        }
+        double disp[3] = {step * f[0], step * f[1], step * f[2]};
+        const double dn = sqrt(disp[0] * disp[0] + disp[1] * disp[1] + disp[2] * disp[2]);
+        const double sc = (dn > maxdisp) ? maxdisp / dn : 1.0;
+        const double mob = s.im[k] > 0.0 ? 1.0 : 0.0;
+        xref[k][0] = p.x; xref[k][1] = p.y; xref[k][2] = p.z;
+        s.x[k][0] = p.x + mob * sc * disp[0];
+        s.x[k][1] = p.y + mob * sc * disp[1];
+        s.x[k][2] = p.z + mob * sc * disp[2];
+        s.v[k][0] = s.v[k][1] = s.v[k][2] = 0.0;
+    }
+    constrain_positions(c, s, xref, tol);
+    for (int k = 0; k < c.natoms; ++k) pos[c.atom[k]] = make_double4(s.x[k][0], s.x[k][1], s.x[k][2], 0.0);
+}
+
+__global__ void k_restore_positions(Dev d, const double4* saved, const int* reject) {
+    const int r = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= d.N || !reject[r]) return;
+    d.pos[(size_t)r * d.N + a] = saved[(size_t)r * d.N + a];
+}
+
+__global__ void k_max_force(Dev d, double* out) {
+    const int r = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double f2 = 0.0;
+    if (a < d.N && d.invmass[a] > 0.0) {
+        const long long* fenv = d.f_env + (size_t)r * 3 * d.N;
+        for (int q = 0; q < 3; ++q) {
+            double f = (double)fenv[q * d.N + a] * (1.0 / FORCE_SCALE);
+            if (d.n_alch > 0) f += (double)d.f_alch[(size_t)r * 3 * d.N + q * d.N + a] * (1.0 / FORCE_SCALE);
+            f2 += f * f;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) f2 = fmax(f2, __shfl_xor_sync(0xffffffffu, f2, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long*>(&out[r]), (unsigned long long)__double_as_longlong(f2));
+}

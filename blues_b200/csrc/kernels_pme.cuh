@@ -1,0 +1,171 @@
+// Smooth particle-mesh Ewald reciprocal space (K4 spread, K5 convolution, K6 gather) around cuFFT.
+// Order-5 cardinal B-splines; weight of grid point base+k is M5(frac + 4 - k) (same convention as the oracle).
+#pragma once
+#include "engine.cuh"
+
+// M5 weights and derivatives at fractional offset w in [0,1): out[k] = M5(w + 4 - k), dout[k] = M5'(w + 4 - k)
+__device__ __forceinline__ void bspline5(float w, float* out, float* dout) {
+    // build orders 2..5 by the standard recursion on the array a[k] = M_n(w + k), k = 0..n-1
+    float a[PME_ORDER];
+    a[0] = w; a[1] = 1.0f - w; a[2] = 0.f; a[3] = 0.f; a[4] = 0.f;      // order 2: M2(w), M2(w+1)
+    float da[PME_ORDER];
+#pragma unroll
+    for (int n = 3; n <= PME_ORDER; ++n) {
+        if (n == PME_ORDER) {
+            // derivative of order n from order n-1: M_n'(u) = M_{n-1}(u) - M_{n-1}(u-1)
+            da[0] = a[0];
+#pragma unroll
+            for (int k = 1; k < PME_ORDER - 1; ++k) da[k] = a[k] - a[k - 1];
+            da[PME_ORDER - 1] = -a[PME_ORDER - 2];
+        }
+        const float div = 1.0f / (float)(n - 1);
+        // M_n(u) = [u M_{n-1}(u) + (n-u) M_{n-1}(u-1)] / (n-1), with u = w + k
+#pragma unroll
+        for (int k = n - 1; k >= 0; --k) {
+            float u = w + (float)k;
+            float lo = (k < n - 1) ? a[k] : 0.f;          // M_{n-1}(u)   (zero for u >= n-1)
+            float hi = (k > 0) ? a[k - 1] : 0.f;          // M_{n-1}(u-1)
+            a[k] = div * (u * lo + ((float)n - u) * hi);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PME_ORDER; ++k) {
+        out[k] = a[PME_ORDER - 1 - k];
+        dout[k] = da[PME_ORDER - 1 - k];
+    }
+}
+
+__device__ __forceinline__ void pme_atom_setup(const Dev& d, float4 p, int* base, float* frac) {
+    float fx = p.x * d.boxf[3], fy = p.y * d.boxf[4], fz = p.z * d.boxf[5];
+    fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+    float ux = fx * d.gx, uy = fy * d.gy, uz = fz * d.gz;
+    int ix = (int)ux, iy = (int)uy, iz = (int)uz;
+    frac[0] = ux - ix; frac[1] = uy - iy; frac[2] = uz - iz;
+    base[0] = ix >= d.gx ? ix - d.gx : ix;
+    base[1] = iy >= d.gy ? iy - d.gy : iy;
+    base[2] = iz >= d.gz ? iz - d.gz : iz;
+}
+
+__global__ void __launch_bounds__(128) k_pme_spread(Dev d) {
+    const int r = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= d.N) return;
+    const float4 p = d.posq[(size_t)r * d.N + a];
+    if (p.w == 0.f) return;
+    int base[3];
+    float frac[3];
+    pme_atom_setup(d, p, base, frac);
+    float wx[PME_ORDER], wy[PME_ORDER], wz[PME_ORDER], dw[PME_ORDER];
+    bspline5(frac[0], wx, dw);
+    bspline5(frac[1], wy, dw);
+    bspline5(frac[2], wz, dw);
+    long long* grid = d.grid_fx + (size_t)r * d.gsize;
+#pragma unroll
+    for (int i = 0; i < PME_ORDER; ++i) {
+        int gx = base[0] + i; gx -= gx >= d.gx ? d.gx : 0;
+        const float qx = p.w * wx[i];
+#pragma unroll
+        for (int j = 0; j < PME_ORDER; ++j) {
+            int gy = base[1] + j; gy -= gy >= d.gy ? d.gy : 0;
+            const float qxy = qx * wy[j];
+            long long* row = grid + ((size_t)gx * d.gy + gy) * d.gz;
+#pragma unroll
+            for (int k = 0; k < PME_ORDER; ++k) {
+                int gz = base[2] + k; gz -= gz >= d.gz ? d.gz : 0;
+                atomicAdd(reinterpret_cast<ull*>(&row[gz]),
+                          static_cast<ull>(static_cast<long long>((double)(qxy * wz[k]) * GRID_SCALE)));
+            }
+        }
+    }
+}
+
+// fixed point → float, and reset the fixed-point grid for the next evaluation
+__global__ void k_pme_finish(Dev d) {
+    const size_t n = (size_t)d.R * d.gsize;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        long long v = d.grid_fx[i];
+        d.grid_r[i] = (float)((double)v * (1.0 / GRID_SCALE));
+        d.grid_fx[i] = 0;
+    }
+}
+
+// multiply the transformed charge grid by the influence function; optional energy
+template <bool ENERGY>
+__global__ void __launch_bounds__(256) k_pme_convolve(Dev d) {
+    const int r = blockIdx.y;
+    const int nzc = d.gz / 2 + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (idx < d.csize) {
+        const int kz = idx % nzc;
+        const int ky = (idx / nzc) % d.gy;
+        const int kx = idx / (nzc * d.gy);
+        float2 c = d.grid_c[(size_t)r * d.csize + idx];
+        float eterm = 0.f;
+        if (idx != 0) {
+            const int mx = kx <= d.gx / 2 ? kx : kx - d.gx;
+            const int my = ky <= d.gy / 2 ? ky : ky - d.gy;
+            const float fx = mx * d.boxf[3], fy = my * d.boxf[4], fz = kz * d.boxf[5];
+            const float m2 = fx * fx + fy * fy + fz * fz;
+            const float V = d.boxf[0] * d.boxf[1] * d.boxf[2];
+            const float denom = m2 * d.bmod_x[kx] * d.bmod_y[ky] * d.bmod_z[kz] * 3.14159265358979f * V;
+            const float pi2_over_a2 = 9.8696044010893586f / (d.alpha * d.alpha);
+            eterm = (float)ONE_4PI_EPS0 * expf(-pi2_over_a2 * m2) / denom;
+        }
+        if (ENERGY) {
+            // half-spectrum weights: planes kz = 0 and (even gz) kz = gz/2 count once, all others twice
+            const double w = (kz == 0 || (2 * kz == d.gz)) ? 1.0 : 2.0;
+            e = 0.5 * w * (double)eterm * ((double)c.x * c.x + (double)c.y * c.y);
+        }
+        c.x *= eterm;
+        c.y *= eterm;
+        d.grid_c[(size_t)r * d.csize + idx] = c;
+    }
+    if (ENERGY) {
+        e = warp_sum(e);
+        if ((threadIdx.x & 31) == 0 && e != 0.0) fx_add(&d.eacc[r * N_ETERMS + E_PME], e, ENERGY_SCALE);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pme_gather(Dev d) {
+    const int r = blockIdx.y;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= d.N) return;
+    const float4 p = d.posq[(size_t)r * d.N + a];
+    if (p.w == 0.f) return;
+    int base[3];
+    float frac[3];
+    pme_atom_setup(d, p, base, frac);
+    float wx[PME_ORDER], wy[PME_ORDER], wz[PME_ORDER], dx[PME_ORDER], dy[PME_ORDER], dz[PME_ORDER];
+    bspline5(frac[0], wx, dx);
+    bspline5(frac[1], wy, dy);
+    bspline5(frac[2], wz, dz);
+    const float* grid = d.grid_r + (size_t)r * d.gsize;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll
+    for (int i = 0; i < PME_ORDER; ++i) {
+        int gx = base[0] + i; gx -= gx >= d.gx ? d.gx : 0;
+#pragma unroll
+        for (int j = 0; j < PME_ORDER; ++j) {
+            int gy = base[1] + j; gy -= gy >= d.gy ? d.gy : 0;
+            const float* row = grid + ((size_t)gx * d.gy + gy) * d.gz;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < PME_ORDER; ++k) {
+                int gz = base[2] + k; gz -= gz >= d.gz ? d.gz : 0;
+                const float v = row[gz];
+                s0 += v * wz[k];
+                s1 += v * dz[k];
+            }
+            fx += dx[i] * wy[j] * s0;
+            fy += wx[i] * dy[j] * s0;
+            fz += wx[i] * wy[j] * s1;
+        }
+    }
+    // d.grid_r now holds the (unnormalised) inverse transform of G*S: potential phi = that value
+    const float q = p.w;
+    long long* fenv = d.f_env + (size_t)r * 3 * d.N;
+    fx_addf(&fenv[a], -q * fx * d.gx * d.boxf[3], (float)FORCE_SCALE);
+    fx_addf(&fenv[d.N + a], -q * fy * d.gy * d.boxf[4], (float)FORCE_SCALE);
+    fx_addf(&fenv[2 * d.N + a], -q * fz * d.gz * d.boxf[5], (float)FORCE_SCALE);
+}
