@@ -104,6 +104,9 @@ class Quantity(object):
     __array_priority__ = 100
 
     def __init__(self, value=None, unit=None):
+        if isinstance(unit, Quantity):           # e.g. Quantity(3, 1/picoseconds)
+            value = value * unit._value
+            unit = unit.unit
         if unit is None:
             if isinstance(value, Quantity):
                 value, unit = value._value, value.unit

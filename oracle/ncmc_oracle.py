@@ -498,6 +498,10 @@ class ForceField(object):
         """Sorted (i<j) pairs within ``rc`` (default: cutoff) that are not excluded — the bit-exact neighbour test."""
         rc = self.cutoff if rc is None else rc
         i, j = _pairs_within(x, box, rc, self.periodic)
+        if rc is not None:
+            d = _min_image(x[i] - x[j], box, self.periodic)
+            m = np.einsum('ij,ij->i', d, d) < rc * rc      # strict, like the force loop
+            i, j = i[m], j[m]
         lo, hi = np.minimum(i, j), np.maximum(i, j)
         code = lo * self.n + hi
         if len(self.excl_code):

@@ -330,7 +330,43 @@ def oracle_vectors(structs):
     return out
 
 
+def reference_bookkeeping():
+    """Run the reference's own pure-Python bookkeeping functions (source extracted with ``ast`` from the reference
+    checkout, executed with a stub logger) on a grid of inputs → golden table for calculateNCMCSteps
+    (blues/utils.py:89-145) and _get_prop_lambda (blues/integrators.py:147-157)."""
+    import ast
+    import json
+    import logging
+    refroot = os.path.dirname(os.path.dirname(REF))
+
+    def extract(path, name):
+        src = open(path).read()
+        tree = ast.parse(src)
+        for node in ast.walk(tree):
+            if isinstance(node, ast.FunctionDef) and node.name == name:
+                return ast.get_source_segment(src, node)
+        raise KeyError(name)
+
+    ns = {'logger': logging.getLogger('ref'), 'sys': sys, 'floor': math.floor, 'ceil': math.ceil}
+    logging.getLogger('ref').setLevel(logging.CRITICAL)
+    exec(extract(os.path.join(refroot, 'utils.py'), 'calculateNCMCSteps'), ns)
+    import textwrap
+    exec(textwrap.dedent(extract(os.path.join(refroot, 'integrators.py'), '_get_prop_lambda')), ns)
+    out = {'calculateNCMCSteps': [], 'get_prop_lambda': []}
+    for nsteps in (2, 4, 10, 11, 20, 99, 100, 500, 1000, 1001, 2500, 5000, 10000):
+        for nprop in (1, 2, 3, 5):
+            for pl in (0.0, 0.1, 0.2, 0.3, 0.45, 0.5):
+                res = ns['calculateNCMCSteps'](nstepsNC=nsteps, nprop=nprop, propLambda=pl)
+                out['calculateNCMCSteps'].append([[nsteps, nprop, pl], res])
+    for pl in (0.0, 0.05, 0.1, 0.2, 0.3, 0.33333, 0.45, 0.5, 0.6, -0.1):
+        out['get_prop_lambda'].append([pl, list(ns['_get_prop_lambda'](None, pl))])
+    with open(os.path.join(HERE, 'reference_bookkeeping.json'), 'w') as f:
+        json.dump(out, f)
+    print('reference bookkeeping rows:', len(out['calculateNCMCSteps']), len(out['get_prop_lambda']))
+
+
 def main():
+    reference_bookkeeping()
     structs = {}
     for out, base in (('tol_parm', 'TOL-parm'), ('wat_divaline', 'watDivaline'), ('vac_divaline', 'vacDivaline')):
         s = load_file(os.path.join(REF, base + '.prmtop'), xyz=os.path.join(REF, base + '.inpcrd'))

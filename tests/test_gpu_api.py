@@ -1,0 +1,201 @@
+"""GPU tests of the drop-in Python API, modelled on blues/tests/test_simulation.py and test_randomrotation.py."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from blues_b200 import unit, utils                     # noqa: E402
+from blues_b200 import mm as openmm                    # noqa: E402
+from blues_b200.structure import Structure             # noqa: E402
+from blues_b200.simulation import SystemFactory, SimulationFactory, BLUESSimulation   # noqa: E402
+from blues_b200.moves import RandomLigandRotationMove, MoveEngine                     # noqa: E402
+from blues_b200.reporters import ReporterConfig        # noqa: E402
+from blues_b200.settings import Settings               # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+STATE_KEYS = {'getPositions': True, 'getVelocities': True, 'getForces': False, 'getEnergy': True,
+              'getParameters': True, 'enforcePeriodicBox': True}
+
+
+@pytest.fixture(scope='module')
+def structure():
+    return Structure.load_npz(os.path.join(GOLDEN, 'tol_parm.npz'))
+
+
+def sim_cfg():
+    return {'nprop': 1, 'propLambda': 0.3, 'dt': 0.002 * unit.picoseconds, 'friction': 1 * 1 / unit.picoseconds,
+            'temperature': 300 * unit.kelvin, 'nIter': 1, 'nstepsMD': 10, 'nstepsNC': 10, 'platform': 'CUDA'}
+
+
+def system_cfg():
+    return {'nonbondedMethod': 'PME', 'nonbondedCutoff': 8.0 * unit.angstroms, 'constraints': 'HBonds'}
+
+
+class NoRandomLigandRotation(RandomLigandRotationMove):
+    def move(self, context):
+        return context
+
+
+@pytest.fixture(scope='module')
+def blues_sim(structure):
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, system_cfg())
+    engine = MoveEngine(NoRandomLigandRotation(structure, 'LIG'))
+    simulations = SimulationFactory(systems, engine, sim_cfg())
+    b = BLUESSimulation(simulations)
+    b._md_sim.minimizeEnergy()
+    b._alch_sim.minimizeEnergy()
+    b._ncmc_sim.minimizeEnergy()
+    return b
+
+
+def test_simulation_set(blues_sim, structure):
+    """tests/test_simulation.py:291-327"""
+    for sim in (blues_sim._md_sim, blues_sim._alch_sim, blues_sim._ncmc_sim):
+        assert isinstance(sim, openmm.Simulation)
+        box = sim.context.getState().getPeriodicBoxVectors(asNumpy=True).value_in_unit(unit.angstroms)
+        assert np.allclose(np.diag(box), structure.box[:3])
+    integ = blues_sim._ncmc_sim.context._integrator
+    assert integ._n_lambda_steps == 20 and integ._n_steps_neq == 10
+
+
+def test_state_and_sync(blues_sim):
+    """tests/test_simulation.py:331-383"""
+    st = BLUESSimulation.getStateFromContext(blues_sim._md_sim.context, STATE_KEYS)
+    assert set(st) == {'positions', 'velocities', 'potential_energy', 'kinetic_energy', 'box_vectors'}
+    blues_sim._syncStatesMDtoNCMC()
+    md = BLUESSimulation.getStateFromContext(blues_sim._md_sim.context, STATE_KEYS)
+    nc = BLUESSimulation.getStateFromContext(blues_sim._ncmc_sim.context, STATE_KEYS)
+    assert np.array_equal(md['positions']._value, nc['positions']._value)
+
+
+def test_step_ncmc_accept_reject_md(blues_sim):
+    """tests/test_simulation.py:385-428"""
+    blues_sim._syncStatesMDtoNCMC()
+    before = BLUESSimulation.getStateFromContext(blues_sim._ncmc_sim.context, STATE_KEYS)
+    blues_sim._stepNCMC(10, 5)
+    after = BLUESSimulation.getStateFromContext(blues_sim._ncmc_sim.context, STATE_KEYS)
+    assert np.not_equal(before['positions']._value, after['positions']._value).all()
+    assert blues_sim._ncmc_sim.integrator.getGlobalVariableByName('lambda') == pytest.approx(1.0)
+    corr = blues_sim._computeAlchemicalCorrection()
+    assert isinstance(corr, float)
+    # force accept / reject through the work
+    integ = blues_sim._ncmc_sim.context._integrator
+    integ.setGlobalVariableByName('protocol_work', -1e6)
+    blues_sim._acceptRejectMove()
+    md = BLUESSimulation.getStateFromContext(blues_sim._md_sim.context, STATE_KEYS)
+    assert np.allclose(md['positions']._value, after['positions']._value)
+    integ.setGlobalVariableByName('protocol_work', 999999)
+    n_rej = blues_sim.reject
+    blues_sim._acceptRejectMove()
+    assert blues_sim.reject == n_rej + 1
+    v0 = blues_sim._md_sim.context.getState(getVelocities=True).getVelocities(asNumpy=True)._value
+    blues_sim._resetSimulations()
+    v1 = blues_sim._md_sim.context.getState(getVelocities=True).getVelocities(asNumpy=True)._value
+    assert np.not_equal(v0, v1).all()
+    assert integ.getGlobalVariableByName('step') == 0 and integ.getGlobalVariableByName('protocol_work') == 0
+    x0 = blues_sim._md_sim.context.getState(getPositions=True).getPositions(asNumpy=True)._value
+    blues_sim._stepMD(10)
+    x1 = blues_sim._md_sim.context.getState(getPositions=True).getPositions(asNumpy=True)._value
+    assert np.not_equal(x0, x1).all()
+
+
+def test_random_rotation_move(structure):
+    """tests/test_randomrotation.py:52-61 — seeded host path and the on-device path both rotate every ligand atom."""
+    system = structure.createSystem(nonbondedMethod='NoCutoff', constraints='HBonds')
+    for seed in (3134, None):
+        move = RandomLigandRotationMove(structure, 'LIG', seed)
+        integ = openmm.LangevinIntegrator(300 * unit.kelvin, 1, 0.002 * unit.picoseconds)
+        sim = SimulationFactory.generateSimFromStruct(structure, system, integ)
+        x0 = sim.context.getState(getPositions=True).getPositions(asNumpy=True)._value[move.atom_indices]
+        if seed is None:
+            d = move.device_move()
+            assert d is not None
+            sim.context._engine.apply_move(d['kind'], d['atoms'], d['masses'])
+            move._after_device_move(sim.context)
+        else:
+            assert move.device_move() is None
+            sim.context = move.move(sim.context)
+        x1 = sim.context.getState(getPositions=True).getPositions(asNumpy=True)._value[move.atom_indices]
+        assert np.not_equal(x0, x1).all()
+        d0 = np.linalg.norm(x0[0] - x0[5]); d1 = np.linalg.norm(x1[0] - x1[5])
+        assert d0 == pytest.approx(d1, rel=1e-9)                  # rigid
+        rest0 = sim.context.getState(getPositions=True).getPositions(asNumpy=True)._value[15:]
+        assert np.allclose(rest0, structure.coordinates[15:] * 0.1)
+
+
+def test_run_from_yaml(structure, tmp_path):
+    """tests/test_simulation.py:430-491"""
+    yaml_cfg = """
+        output_dir: %s
+        outfname: tol-test
+        logger:
+          level: info
+          stream: False
+        system:
+          nonbondedMethod: PME
+          nonbondedCutoff: 8.0 * angstroms
+          constraints: HBonds
+        simulation:
+          dt: 0.002 * picoseconds
+          friction: 1 * 1/picoseconds
+          temperature: 300 * kelvin
+          nIter: 2
+          nstepsMD: 4
+          nstepsNC: 4
+          platform: CUDA
+        md_reporters:
+          stream:
+            title: md
+            reportInterval: 1
+            totalSteps: 8
+            step: True
+            speed: True
+            progress: True
+            remainingTime: True
+            currentIter : True
+        ncmc_reporters:
+          traj_netcdf:
+            frame_indices: [1, 0.5, -1]
+            alchemicalLambda: True
+            protocolWork: True
+          stream:
+            title: ncmc
+            reportInterval: 1
+            totalSteps: 4
+            step: True
+            speed: True
+            progress: True
+            remainingTime: True
+            protocolWork : True
+            alchemicalLambda : True
+            currentIter : True
+    """ % tmp_path
+    cfg = Settings(yaml_cfg).asDict()
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, cfg['system'])
+    engine = MoveEngine(RandomLigandRotationMove(structure, 'LIG'))
+    simulations = SimulationFactory(systems, engine, cfg['simulation'], cfg['md_reporters'], cfg['ncmc_reporters'])
+    blues = BLUESSimulation(simulations)
+    blues._md_sim.minimizeEnergy()
+    before = blues._md_sim.context.getState(getPositions=True).getPositions(asNumpy=True)._value
+    blues.run()
+    after = blues._md_sim.context.getState(getPositions=True).getPositions(asNumpy=True)._value
+    assert np.not_equal(before, after).all()
+    assert blues.accept + blues.reject == 2
+    log = open(os.path.join(str(tmp_path), 'tol-test.log')).read()
+    assert 'ncmc:' in log and 'md:' in log and 'Acceptance Ratio' in log
+    for rep in cfg['ncmc_reporters']:
+        if hasattr(rep, 'close'):
+            rep.close()
+    from scipy.io import netcdf_file
+    nc = netcdf_file(os.path.join(str(tmp_path), 'tol-test-ncmc.nc'), 'r', mmap=False)
+    assert nc.variables['coordinates'].shape[1:] == (975, 3) and nc.variables['coordinates'].shape[0] >= 4
+    assert 'protocolWork' in nc.variables and 'alchemicalLambda' in nc.variables
+    nc.close()
+
+
+def test_no_cpu_fallback_message():
+    from blues_b200 import _native
+    assert 'no CPU fallback' in (_native.load_library.__doc__ + open(_native.__file__).read())

@@ -1,0 +1,160 @@
+"""CPU tests: host-side logic (units, parsers, system builder, bookkeeping pinned by the reference's own functions)."""
+import json
+import os
+import re
+import numpy as np
+import pytest
+
+from blues_b200 import unit as u
+from blues_b200 import utils, lepton
+from blues_b200.structure import Structure, AmberMask
+from blues_b200.integrators import AlchemicalExternalLangevinIntegrator
+from blues_b200.simulation import SystemFactory, SimulationFactory
+from blues_b200.moves import uniform_quaternion, rotation_matrix_from_quaternion, select_atoms, MoveEngine, Move
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+@pytest.fixture(scope='module')
+def tol():
+    return Structure.load_npz(os.path.join(GOLDEN, 'tol_parm.npz'))
+
+
+def test_unit_algebra():
+    kT = u.MOLAR_GAS_CONSTANT_R * (300 * u.kelvin)
+    assert abs(kT.value_in_unit(u.kilojoules_per_mole) - 2.494341741) < 1e-8
+    assert (10 * u.angstroms).value_in_unit(u.nanometers) == pytest.approx(1.0)
+    w = 5.0 * u.kilocalories_per_mole / u.angstroms ** 2
+    assert w.value_in_unit(u.kilojoules_per_mole / u.nanometers ** 2) == pytest.approx(2092.0)
+    p = u.Quantity(np.arange(12.0).reshape(4, 3), u.nanometers)
+    assert p[[0, 2]].shape == (2, 3) and p[1].unit == u.nanometers
+    p[0] = p[1]
+    assert np.all(p._value[0] == p._value[1])
+    assert utils.parse_unit_quantity('1 * 1/picoseconds').value_in_unit(u.picoseconds ** -1) == 1.0
+    assert utils.parse_unit_quantity('3.024 * daltons').value_in_unit(u.dalton) == pytest.approx(3.024)
+    e = 3 * u.kilojoules_per_mole
+    assert isinstance(e * (-1.0 / kT), float)
+
+
+def test_reference_bookkeeping_tables():
+    """calculateNCMCSteps / _get_prop_lambda against outputs of the reference's own source (make_fixtures.py)."""
+    tab = json.load(open(os.path.join(GOLDEN, 'reference_bookkeeping.json')))
+    for (nsteps, nprop, pl), want in tab['calculateNCMCSteps']:
+        assert utils.calculateNCMCSteps(nstepsNC=nsteps, nprop=nprop, propLambda=pl) == want
+    integ = AlchemicalExternalLangevinIntegrator({'lambda_sterics': '1'})
+    for pl, want in tab['get_prop_lambda']:
+        assert list(integ._get_prop_lambda(pl)) == want
+
+
+def test_ncmc_integrator_attributes():
+    """blues/tests/test_simulation.py:262-289"""
+    cfg = {'nstepsNC': 100, 'temperature': 100 * u.kelvin, 'dt': 0.001 * u.picoseconds, 'nprop': 2, 'propLambda': 0.1,
+           'splitting': 'V H R O R H V', 'alchemical_functions': {'lambda_sterics': '1', 'lambda_electrostatics': '1'}}
+    integ = SimulationFactory.generateNCMCIntegrator(**cfg)
+    assert integ._n_steps_neq == 100
+    assert integ._n_lambda_steps == 200
+    assert integ._alchemical_functions == cfg['alchemical_functions']
+    assert integ._splitting == 'V H R O R H V'
+    assert integ._prop_lambda == (0.4, 0.6)
+    assert integ.getTemperature().value_in_unit(u.kelvin) == 100
+    assert integ.getStepSize().value_in_unit(u.picoseconds) == pytest.approx(0.001)
+    assert integ.getGlobalVariableByName('nprop') == 2
+    assert integ.getGlobalVariableByName('prop_lambda_min') == 0.4
+
+
+def test_lambda_functions():
+    fs = 'min(1, (1/0.3)*abs(lambda-0.5))'
+    fe = 'step(0.2-lambda) - 1/0.2*lambda*step(0.2-lambda) + 1/0.2*(lambda-0.8)*step(lambda-0.8)'
+    s, e = lepton.Expression(fs), lepton.Expression(fe)
+    assert s(0.0) == 1 and s(0.5) == 0 and s(0.35) == pytest.approx(0.5) and s(1.0) == 1
+    assert e(0.0) == 1 and e(0.1) == pytest.approx(0.5) and e(0.5) == 0 and e(0.9) == pytest.approx(0.5)
+    assert lepton.tabulate('lambda^2', 4) == [0.0, 0.0625, 0.25, 0.5625, 1.0]
+    with pytest.raises(ValueError):
+        lepton.Expression('__import__("os")')
+
+
+def test_prmtop_facts(tol):
+    """composition, term counts, charges, LJ known answers."""
+    assert tol.n_atoms == 975 and len(tol.bonds) == 655 and len(tol.angles) == 344 and len(tol.dihedrals) == 36
+    assert tol.residue_names[0] == 'LIG' and tol.residue_names.count('HOH') == 320
+    assert np.sum(tol.charges ** 2) == pytest.approx(334.0509, abs=1e-3)
+    assert abs(tol.charges.sum()) < 1e-6
+    i = tol.atom_types.index('c3')
+    assert tol.lj_sigma[i] * 0.1 == pytest.approx(0.339966951, rel=1e-7)
+    assert tol.lj_epsilon[i] * 4.184 == pytest.approx(0.4577296, rel=1e-6)
+    wd = Structure.load_npz(os.path.join(GOLDEN, 'wat_divaline.npz'))
+    assert wd.n_atoms == 2591 and wd.velocities is not None
+    ow = wd.atom_types.index('OW')
+    assert wd.lj_sigma[ow] * 0.1 == pytest.approx(0.315075241, rel=1e-7)
+    assert wd.lj_epsilon[wd.atom_types.index('HW')] == 0.0
+
+
+def test_create_system(tol):
+    system = tol.createSystem(nonbondedMethod='PME', nonbondedCutoff=8.0 * u.angstroms, constraints='HBonds')
+    t = system.flatten()
+    assert len(t['excl_pairs']) == 1026 and int((t['excl_eps'] != 0).sum()) == 27
+    assert len(t['constraints']) == 8 + 3 * 320
+    assert t['ewald_alpha'] == pytest.approx(3.28533, rel=1e-5) and list(t['pme_grid']) == [24, 24, 24]
+    names = [type(f).__name__ for f in system.getForces()]
+    assert names == ['HarmonicBondForce', 'HarmonicAngleForce', 'PeriodicTorsionForce', 'NonbondedForce', 'CMMotionRemover']
+    s2 = tol.createSystem(nonbondedMethod='PME', nonbondedCutoff=10 * u.angstroms, ewaldErrorTolerance=0.005,
+                          hydrogenMass=3.024 * u.dalton)
+    assert s2.masses.sum() == pytest.approx(system.masses.sum())
+    assert s2.flatten()['ewald_alpha'] == pytest.approx(2.14597, rel=1e-5)
+
+
+def test_alchemical_system_and_factories(tol):
+    """blues/tests/test_simulation.py:146-237 (structure of the systems; no GPU needed)."""
+    idx = utils.atomIndexfromTop('LIG', tol.topology)
+    assert idx == list(range(15))
+    systems = SystemFactory(tol, idx, {'nonbondedMethod': 'PME', 'nonbondedCutoff': 8.0 * u.angstroms, 'constraints': 'HBonds'})
+    md_forces = systems.md.getForces()
+    alch_forces = systems.alch.getForces()
+    assert len(alch_forces) > len(md_forces)
+    assert any(type(f).__name__.startswith('Custom') for f in alch_forces)
+    ta = systems.alch.flatten()
+    assert np.all(ta['charge'][:15] == 0) and np.all(ta['epsilon'][:15] == 0) and len(ta['alch_exc_pairs']) == 27
+    restrained = SystemFactory.restrain_positions(tol, systems.md, ':LIG')
+    assert type(restrained.getForces()[-1]).__name__ == 'CustomExternalForce'
+    assert len(restrained.flatten()['restraint_atoms']) == 15
+    frozen = SystemFactory.freeze_atoms(tol, systems.alch, ':LIG')
+    assert all(frozen.getParticleMass(i)._value == 0 for i in range(15))
+    import copy
+    fr = SystemFactory.freeze_radius(tol, copy.deepcopy(systems.md), freeze_distance=5 * u.angstrom,
+                                     freeze_center=':LIG', freeze_solvent=':Cl-')
+    sel = AmberMask(tol, '(:LIG<:5.0)&!(:Cl-)').Selection()
+    assert [fr.getParticleMass(i)._value == 0 for i in range(975)] == [not bool(x) for x in sel]
+
+
+def test_t4l_freeze_count():
+    """docs/BLUES_tutorial.ipynb:718 — 22 065 atoms frozen by freeze_radius(':LIG', 5 A, ':HOH,Cl-')."""
+    s = Structure.load_npz(os.path.join(GOLDEN, 't4l_surrogate.npz'))
+    sel = AmberMask(s, '(:LIG<:5.000000)&!(:HOH,Cl-)').Selection()
+    assert s.n_atoms - int(sel.sum()) == 22065
+
+
+def test_move_helpers(tol):
+    q = uniform_quaternion(3134)
+    assert np.allclose(q, uniform_quaternion(3134)) and abs(np.dot(q, q) - 1) < 1e-12
+    R = rotation_matrix_from_quaternion(q)
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and np.linalg.det(R) == pytest.approx(1.0)
+    assert list(select_atoms(tol, '(index 3) or (index 5)')) == [3, 5]
+    assert len(select_atoms(tol, 'resname LIG and not name C1')) == 14
+    eng = MoveEngine([Move(), Move()], [1, 3])
+    assert eng.probabilities == [0.25, 0.75]
+    eng.selectMove()
+    assert eng.move_name == 'Move'
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports every function include/blues_b200.h declares."""
+    import ctypes
+    from blues_b200 import _native
+    header = open(os.path.join(os.path.dirname(GOLDEN), '..', 'include', 'blues_b200.h')).read()
+    declared = set(re.findall(r'\b(bl_[a-z_0-9]+)\s*\(', header))
+    assert declared == set(_native.SYMBOLS), declared ^ set(_native.SYMBOLS)
+    lib = _native.load_library()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b'sm_100a' in lib.bl_version()
+    assert ctypes.sizeof(_native.BlTopology) > 0

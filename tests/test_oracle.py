@@ -1,0 +1,138 @@
+"""CPU tests of the oracle itself: golden vectors, analytic anchors, RNG known answers."""
+import os
+import numpy as np
+import pytest
+
+from blues_b200 import unit as u
+from blues_b200.structure import Structure
+from blues_b200.alchemy import AbsoluteAlchemicalFactory, AlchemicalRegion
+from oracle import ncmc_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _case(name, alch=None, **kw):
+    s = Structure.load_npz(os.path.join(GOLDEN, name + '.npz'))
+    system = s.createSystem(**kw)
+    if alch is not None:
+        system = AbsoluteAlchemicalFactory().create_alchemical_system(system, AlchemicalRegion(alchemical_atoms=alch))
+    return s, system.flatten(), s.coordinates * 0.1
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    def kat(c, k):
+        return [int(x) for x in orc.philox4x32(*[np.uint32(v) for v in c], k[0], k[1])]
+    assert kat([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert kat([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert kat([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    xi = orc.philox_normal3(5, 0, 0, 0, 20000)
+    assert abs(xi.mean()) < 0.02 and abs(xi.std() - 1) < 0.02
+
+
+def test_golden_vectors_reproduce():
+    vec = np.load(os.path.join(GOLDEN, 'oracle_vectors.npz'))
+    s, t, x = _case('tol_parm', nonbondedMethod='PME', nonbondedCutoff=8.0 * u.angstroms, constraints='HBonds')
+    E, F, comp = orc.ForceField(t).energy_forces(x, t['box'])
+    assert E == pytest.approx(float(vec['tol_parm/md/energy']), rel=1e-12)
+    assert np.allclose(F, vec['tol_parm/md/forces'], rtol=1e-9, atol=1e-6)
+    s, t, x = _case('vac_divaline', alch=list(range(16, 35)), nonbondedMethod='NoCutoff', constraints='HBonds')
+    E, F, comp = orc.ForceField(t).energy_forces(x, t['box'], 0.5, 0.25)
+    assert E == pytest.approx(float(vec['vac_divaline/alch_0.5_0.25/energy']), rel=1e-12)
+
+
+def test_forces_are_energy_gradients():
+    s, t, x = _case('vac_divaline', alch=list(range(16, 35)), nonbondedMethod='NoCutoff')
+    ff = orc.ForceField(t)
+    E, F, _ = ff.energy_forces(x, t['box'], 0.4, 0.3)
+    h = 1e-6
+    for a, k in ((0, 0), (17, 2), (30, 1)):
+        xp, xm = x.copy(), x.copy()
+        xp[a, k] += h
+        xm[a, k] -= h
+        fd = -(ff.energy(xp, t['box'], 0.4, 0.3) - ff.energy(xm, t['box'], 0.4, 0.3)) / (2 * h)
+        assert fd == pytest.approx(F[a, k], rel=1e-5, abs=1e-4)
+
+
+def test_ewald_sum_is_alpha_independent_and_self_energy():
+    s = Structure.load_npz(os.path.join(GOLDEN, 'tol_parm.npz'))
+    x = s.coordinates * 0.1
+    tot = []
+    for tol_, rc in ((5e-4, 0.8), (1e-5, 1.0)):
+        t = s.createSystem(nonbondedMethod='PME', nonbondedCutoff=rc * 10 * u.angstroms, ewaldErrorTolerance=tol_).flatten()
+        comp = orc.ForceField(t).energy_forces(x, t['box'])[2]
+        tot.append(sum(comp[k] for k in ('coulomb_direct', 'pme_reciprocal', 'ewald_self', 'ewald_exclusion', 'exceptions')))
+    assert tot[0] == pytest.approx(tot[1], rel=2e-5)
+    t = s.createSystem(nonbondedMethod='PME', nonbondedCutoff=10 * u.angstroms, ewaldErrorTolerance=0.005).flatten()
+    comp = orc.ForceField(t).energy_forces(x, t['box'])[2]
+    assert comp["ewald_self"] == pytest.approx(-56191.99, abs=0.2)       # SURVEY.md Appendix B (quoted to ~1e-6 rel)
+
+
+def test_alchemical_endpoints():
+    """lambda = 1: alchemical system = MD system minus the ligand's reciprocal-space / dispersion terms."""
+    s, t_md, x = _case('vac_divaline', nonbondedMethod='NoCutoff')
+    _, t_al, _ = _case('vac_divaline', alch=list(range(16, 35)), nonbondedMethod='NoCutoff')
+    e_md = orc.ForceField(t_md).energy(x, t_md['box'])
+    e_al = orc.ForceField(t_al).energy(x, t_al['box'], 1.0, 1.0)
+    assert e_al == pytest.approx(e_md, rel=1e-10)          # no cutoff → identical at lambda = 1
+    e0 = orc.ForceField(t_al).energy_forces(x, t_al['box'], 0.0, 0.0)[2]
+    assert e0['alch_electrostatics'] == 0.0
+
+
+def test_constraints_and_energy_conservation():
+    s, t, x = _case('vac_divaline', alch=list(range(16, 35)), nonbondedMethod='NoCutoff', constraints='HBonds')
+    o = orc.NCMCOracle(t, {'lambda_sterics': '1', 'lambda_electrostatics': '1'}, 'V R R V', 300.0, 1.0, 0.0005, 200)
+    o.x = x.copy()
+    o.set_velocities_to_temperature(300.0, 0)
+    o.step(1)
+    e0 = o.energy() + o.kinetic_energy()
+    o.step(60)
+    e1 = o.energy() + o.kinetic_energy()
+    c = t['constraints']
+    d = np.linalg.norm(o.x[c[:, 0]] - o.x[c[:, 1]], axis=1)
+    assert np.max(np.abs(d - t['constraint_d'])) < 1e-10
+    rel_v = np.einsum('ij,ij->i', o.x[c[:, 0]] - o.x[c[:, 1]], o.v[c[:, 0]] - o.v[c[:, 1]])
+    assert np.max(np.abs(rel_v)) < 1e-10
+    assert abs(e1 - e0) < 0.05 * o.kT * 3            # velocity-Verlet without thermostat conserves energy
+    assert o.g['protocol_work'] == pytest.approx(0.0, abs=1e-9)
+
+
+def test_program_bookkeeping_and_symmetric_protocol():
+    s, t, x = _case('vac_divaline', alch=list(range(16, 35)), nonbondedMethod='NoCutoff', constraints='HBonds')
+    o = orc.NCMCOracle(t, None, 'H V R O R V H', 300.0, 1.0, 0.001, 10, seed=3)
+    assert o.n_lambda_steps == 20
+    o.x = x.copy()
+    o.set_velocities_to_temperature(300.0, 0)
+    o.step(5)
+    assert o.g['lambda_'] == pytest.approx(0.5) and o.lam_s == pytest.approx(0.0) and o.lam_e == pytest.approx(0.0)
+    w_mid = o.g['protocol_work']
+    # a rigid rotation of the decoupled ligand costs no external work at lambda = 0.5
+    R = orc.rotation_matrix_from_quaternion(orc.quaternion_from_uniforms(0.3, 0.6, 0.1))
+    o.x = orc.rotate_ligand(o.x, np.arange(16, 35), np.ones(19), R)
+    o.step(1)
+    # external-work term must vanish (intramolecular energy is rotation invariant; environment decoupled)
+    assert abs(o.g['perturbed_pe'] - (o.g['perturbed_pe'])) == 0
+    o.step(4)
+    assert o.g['step'] == 10 and o.g['lambda_'] == pytest.approx(1.0)
+    o.step(3)                                   # `if step < nsteps` guard: nothing happens
+    assert o.g['step'] == 10
+    assert np.isfinite(o.g['protocol_work']) and np.isfinite(w_mid)
+    assert o.log_acceptance_probability() == pytest.approx(-o.g['protocol_work'] / o.kT)
+    o.reset()
+    assert o.g['step'] == 0 and o.g['protocol_work'] == 0.0 and o.g['lambda_'] == 0.0
+
+
+def test_moves_and_acceptance_rules():
+    R = orc.rotation_matrix_from_quaternion(orc.quaternion_from_uniforms(0.2, 0.7, 0.9))
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
+    x = np.random.RandomState(0).rand(10, 3)
+    y = orc.rotate_ligand(x, np.arange(4), np.array([12.0, 1.0, 1.0, 16.0]), R)
+    d0 = np.linalg.norm(x[0] - x[3]); d1 = np.linalg.norm(y[0] - y[3])
+    assert d0 == pytest.approx(d1) and np.all(y[4:] == x[4:])
+    p = orc.random_sphere_point(0.9, np.zeros(3), 0.5, 0.25, 0.75)
+    assert np.linalg.norm(p) == pytest.approx(0.9 * 0.5 ** (1 / 3))
+    assert orc.metropolis_accept(float('nan'), 5.0, -100.0) is False        # NaN work is always rejected
+    assert orc.metropolis_accept(-1.0, 0.0, -2.0) is True
+    assert orc.metropolis_accept(-999999 / 2.49, 0.0, -2.0) is False        # the 999999 sentinel forces rejection
+    assert orc.alchemical_correction(1.0, 2.0, 3.0, 4.0, 2.0) == pytest.approx(1.0)
