@@ -126,6 +126,53 @@ def _p(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 
 
+def build_topology(topo):
+    """Flat dictionary (``System.flatten()``) → (BlTopology, keep-alive dict of the numpy buffers it points to)."""
+    keep = {}
+
+    def dp(key, dtype=np.float64):
+        keep[key] = _arr(topo[key], dtype)
+        return _p(keep[key], C.c_double if dtype == np.float64 else C.c_int32)
+
+    t = BlTopology()
+    t.n_atoms = int(topo['n_atoms'])
+    t.mass, t.charge, t.sigma, t.epsilon = dp('mass'), dp('charge'), dp('sigma'), dp('epsilon')
+    t.n_bonds = len(topo['bonds'])
+    t.bonds, t.bond_k, t.bond_r0 = dp('bonds', np.int32), dp('bond_k'), dp('bond_r0')
+    t.n_angles = len(topo['angles'])
+    t.angles, t.angle_k, t.angle_t0 = dp('angles', np.int32), dp('angle_k'), dp('angle_t0')
+    t.n_torsions = len(topo['torsions'])
+    t.torsions, t.torsion_k, t.torsion_n, t.torsion_phase = (dp('torsions', np.int32), dp('torsion_k'),
+                                                             dp('torsion_n', np.int32), dp('torsion_phase'))
+    t.n_excl = len(topo['excl_pairs'])
+    t.excl_pairs, t.excl_qq, t.excl_sigma, t.excl_eps = (dp('excl_pairs', np.int32), dp('excl_qq'),
+                                                         dp('excl_sigma'), dp('excl_eps'))
+    t.n_constraints = len(topo['constraints'])
+    t.constraints, t.constraint_d = dp('constraints', np.int32), dp('constraint_d')
+    for k in range(3):
+        t.box[k] = float(topo['box'][k])
+        t.pme_grid[k] = int(topo['pme_grid'][k])
+    t.nb_method = int(topo['nb_method'])
+    t.cutoff = float(topo['cutoff'])
+    t.ewald_alpha = float(topo['ewald_alpha'])
+    t.dispersion_coeff = float(topo['dispersion_coeff'])
+    t.remove_cm = int(topo['remove_cm'])
+    t.n_restraints = len(topo['restraint_atoms'])
+    t.restraint_atoms, t.restraint_k, t.restraint_x0 = (dp('restraint_atoms', np.int32), dp('restraint_k'),
+                                                        dp('restraint_x0'))
+    t.n_alch = len(topo['alch_atoms'])
+    t.alch_atoms, t.alch_charge, t.alch_sigma, t.alch_eps = (dp('alch_atoms', np.int32), dp('alch_charge'),
+                                                             dp('alch_sigma'), dp('alch_eps'))
+    t.n_alch_exc = len(topo['alch_exc_pairs'])
+    t.alch_exc_pairs, t.alch_exc_qq, t.alch_exc_sigma, t.alch_exc_eps = (
+        dp('alch_exc_pairs', np.int32), dp('alch_exc_qq'), dp('alch_exc_sigma'), dp('alch_exc_eps'))
+    t.softcore_alpha, t.softcore_a = float(topo['softcore_alpha']), float(topo['softcore_a'])
+    t.softcore_b, t.softcore_c = float(topo['softcore_b']), float(topo['softcore_c'])
+    t.annihilate_sterics = int(topo['annihilate_sterics'])
+    t.annihilate_electrostatics = int(topo['annihilate_electrostatics'])
+    return t, keep
+
+
 class Engine(object):
     """One native handle: R independent walkers of one flattened system on one GPU."""
 
@@ -134,48 +181,7 @@ class Engine(object):
         self.topo = topo
         self.n_atoms = int(topo['n_atoms'])
         self.n_replicas = int(n_replicas)
-        keep = self._keep = {}
-
-        def dp(key, dtype=np.float64):
-            keep[key] = _arr(topo[key], dtype)
-            return _p(keep[key], C.c_double if dtype == np.float64 else C.c_int32)
-
-        t = BlTopology()
-        t.n_atoms = self.n_atoms
-        t.mass, t.charge, t.sigma, t.epsilon = dp('mass'), dp('charge'), dp('sigma'), dp('epsilon')
-        t.n_bonds = len(topo['bonds'])
-        t.bonds, t.bond_k, t.bond_r0 = dp('bonds', np.int32), dp('bond_k'), dp('bond_r0')
-        t.n_angles = len(topo['angles'])
-        t.angles, t.angle_k, t.angle_t0 = dp('angles', np.int32), dp('angle_k'), dp('angle_t0')
-        t.n_torsions = len(topo['torsions'])
-        t.torsions, t.torsion_k, t.torsion_n, t.torsion_phase = (dp('torsions', np.int32), dp('torsion_k'),
-                                                                 dp('torsion_n', np.int32), dp('torsion_phase'))
-        t.n_excl = len(topo['excl_pairs'])
-        t.excl_pairs, t.excl_qq, t.excl_sigma, t.excl_eps = (dp('excl_pairs', np.int32), dp('excl_qq'),
-                                                             dp('excl_sigma'), dp('excl_eps'))
-        t.n_constraints = len(topo['constraints'])
-        t.constraints, t.constraint_d = dp('constraints', np.int32), dp('constraint_d')
-        for k in range(3):
-            t.box[k] = float(topo['box'][k])
-            t.pme_grid[k] = int(topo['pme_grid'][k])
-        t.nb_method = int(topo['nb_method'])
-        t.cutoff = float(topo['cutoff'])
-        t.ewald_alpha = float(topo['ewald_alpha'])
-        t.dispersion_coeff = float(topo['dispersion_coeff'])
-        t.remove_cm = int(topo['remove_cm'])
-        t.n_restraints = len(topo['restraint_atoms'])
-        t.restraint_atoms, t.restraint_k, t.restraint_x0 = (dp('restraint_atoms', np.int32), dp('restraint_k'),
-                                                            dp('restraint_x0'))
-        t.n_alch = len(topo['alch_atoms'])
-        t.alch_atoms, t.alch_charge, t.alch_sigma, t.alch_eps = (dp('alch_atoms', np.int32), dp('alch_charge'),
-                                                                 dp('alch_sigma'), dp('alch_eps'))
-        t.n_alch_exc = len(topo['alch_exc_pairs'])
-        t.alch_exc_pairs, t.alch_exc_qq, t.alch_exc_sigma, t.alch_exc_eps = (
-            dp('alch_exc_pairs', np.int32), dp('alch_exc_qq'), dp('alch_exc_sigma'), dp('alch_exc_eps'))
-        t.softcore_alpha, t.softcore_a = float(topo['softcore_alpha']), float(topo['softcore_a'])
-        t.softcore_b, t.softcore_c = float(topo['softcore_b']), float(topo['softcore_c'])
-        t.annihilate_sterics = int(topo['annihilate_sterics'])
-        t.annihilate_electrostatics = int(topo['annihilate_electrostatics'])
+        t, self._keep = build_topology(topo)
         h = _H()
         rc = self.lib.bl_create(C.byref(t), int(device), self.n_replicas, C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(h))
         if rc != 0:

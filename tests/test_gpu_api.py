@@ -86,10 +86,19 @@ def test_step_ncmc_accept_reject_md(blues_sim):
     blues_sim._acceptRejectMove()
     md = BLUESSimulation.getStateFromContext(blues_sim._md_sim.context, STATE_KEYS)
     assert np.allclose(md['positions']._value, after['positions']._value)
+    # next iteration: a move carrying the 999999 sentinel is rejected and the MD state is left untouched
+    blues_sim._resetSimulations()
+    blues_sim._syncStatesMDtoNCMC()
+    blues_sim._stepNCMC(10, 5)
     integ.setGlobalVariableByName('protocol_work', 999999)
     n_rej = blues_sim.reject
+    md_before = BLUESSimulation.getStateFromContext(blues_sim._md_sim.context, STATE_KEYS)
     blues_sim._acceptRejectMove()
     assert blues_sim.reject == n_rej + 1
+    md_after = BLUESSimulation.getStateFromContext(blues_sim._md_sim.context, STATE_KEYS)
+    assert np.array_equal(md_before['positions']._value, md_after['positions']._value)
+    nc_after = BLUESSimulation.getStateFromContext(blues_sim._ncmc_sim.context, STATE_KEYS)
+    assert np.not_equal(md_after['positions']._value, nc_after['positions']._value).any()
     v0 = blues_sim._md_sim.context.getState(getVelocities=True).getVelocities(asNumpy=True)._value
     blues_sim._resetSimulations()
     v1 = blues_sim._md_sim.context.getState(getVelocities=True).getVelocities(asNumpy=True)._value
