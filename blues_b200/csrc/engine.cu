@@ -63,6 +63,7 @@ struct bl_handle {
     double4* d_saved = nullptr;    // minimizer
     int* d_move_atoms = nullptr; float* d_move_masses = nullptr; int move_capacity = 0;
     std::vector<double> host_tmp;
+    double4* pinned = nullptr;     // pinned staging for state uploads / downloads ([N] double4)
 };
 
 #define CK(call)                                                                                   \
@@ -517,6 +518,7 @@ int bl_destroy(bl_handle* h) {
     invalidate_graphs(h);
     if (h->has_fft) { cufftDestroy(h->plan_r2c); cufftDestroy(h->plan_c2r); }
     for (void* p : h->allocs) cudaFree(p);
+    if (h->pinned) cudaFreeHost(h->pinned);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return BL_OK;
@@ -576,6 +578,9 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     }
     d.mass = dupload(h, mass); d.invmass = dupload(h, invmass);
     d.charge = dupload(h, charge); d.sigeps = dupload(h, sigeps);
+    d.charge_d = dupload(h, std::vector<double>(t->charge, t->charge + N));
+    d.sigma_d = dupload(h, std::vector<double>(t->sigma, t->sigma + N));
+    d.eps_d = dupload(h, std::vector<double>(t->epsilon, t->epsilon + N));
     d.sumq = sumq;
     d.self_energy_coeff = -ONE_4PI_EPS0 * t->ewald_alpha / sqrt(M_PI) * sumq2;
     d.dispersion_coeff = t->dispersion_coeff;
@@ -856,19 +861,22 @@ int bl_set_integrator(bl_handle* h, const bl_integrator_params* p) {
 static int upload_vec3(bl_handle* h, double4* dst, int replica, const double* xyz) {
     Dev& d = h->d;
     if (replica >= d.R) { h->error = "replica index out of range"; return BL_ERR_INVALID; }
-    std::vector<double4> tmp(d.N);
+    if (!h->pinned) CK(cudaMallocHost(&h->pinned, sizeof(double4) * d.N));
+    CK(cudaStreamSynchronize(h->stream));
+    double4* tmp = h->pinned;
     for (int i = 0; i < d.N; ++i) tmp[i] = make_double4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0);
     const int r0 = replica < 0 ? 0 : replica, r1 = replica < 0 ? d.R : replica + 1;
     for (int r = r0; r < r1; ++r)
-        CK(cudaMemcpyAsync(dst + (size_t)r * d.N, tmp.data(), sizeof(double4) * d.N, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dst + (size_t)r * d.N, tmp, sizeof(double4) * d.N, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return BL_OK;
 }
 static int download_vec3(bl_handle* h, const double4* src, int replica, double* xyz) {
     Dev& d = h->d;
     if (replica < 0 || replica >= d.R) { h->error = "replica index out of range"; return BL_ERR_INVALID; }
-    std::vector<double4> tmp(d.N);
-    CK(cudaMemcpyAsync(tmp.data(), src + (size_t)replica * d.N, sizeof(double4) * d.N, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->pinned) CK(cudaMallocHost(&h->pinned, sizeof(double4) * d.N));
+    double4* tmp = h->pinned;
+    CK(cudaMemcpyAsync(tmp, src + (size_t)replica * d.N, sizeof(double4) * d.N, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < d.N; ++i) { xyz[3 * i] = tmp[i].x; xyz[3 * i + 1] = tmp[i].y; xyz[3 * i + 2] = tmp[i].z; }
     return BL_OK;

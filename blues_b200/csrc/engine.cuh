@@ -65,6 +65,7 @@ struct Dev {
     double cutoffd, alphad;
     // static per-atom data (original order)
     double* mass; double* invmass;
+    double* charge_d; double* sigma_d; double* eps_d;   // double-precision parameters for the alchemical kernel
     float* charge; float2* sigeps;          // sigeps: (sigma/2, 2 sqrt(eps)) so sigma_ij = s_i+s_j, 4 eps_ij = e_i e_j
     ull* excl_win;                          // bit (j - i + 32) set if pair (i, j) is excluded / an exception
     unsigned char* has_far;                 // atom has exclusions outside the +-32 index window

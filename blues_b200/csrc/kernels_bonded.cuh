@@ -237,10 +237,9 @@ __global__ void __launch_bounds__(128) k_alch(Dev d) {
     const bool j_alch = active ? d.is_alch[j] : false;
     double qj = 0.0, sigj = 0.0, epsj = 0.0;
     if (active && !j_alch) {
-        qj = (double)d.charge[j];
-        float2 se = d.sigeps[j];
-        sigj = 2.0 * (double)se.x;
-        epsj = 0.25 * (double)se.y * (double)se.y;
+        qj = d.charge_d[j];
+        sigj = d.sigma_d[j];
+        epsj = d.eps_d[j];
     }
     const ull wj = active ? d.excl_win[j] : 0ull;
     const bool farj = active ? d.has_far[j] : false;
