@@ -27,6 +27,8 @@ struct bl_handle {
     IntegratorConsts ic;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;   // reciprocal-space branch, forked from / joined to `stream` inside every evaluation
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string error;
     std::vector<void*> allocs;
     // host copies needed after creation
@@ -63,6 +65,7 @@ struct bl_handle {
     double4* d_saved = nullptr;    // minimizer
     int* d_move_atoms = nullptr; float* d_move_masses = nullptr; int move_capacity = 0;
     std::vector<double> host_tmp;
+    double skin = 0.0; int cell_capacity = 0;
     double4* pinned = nullptr;     // pinned staging for state uploads / downloads ([N] double4)
 };
 
@@ -95,16 +98,16 @@ static T* dupload(bl_handle* h, const std::vector<T>& v) {
 
 // ---- launch helper with optional per-kernel event timing -------------------------------------------------
 struct LaunchTimer {
-    bl_handle* h; int kid; cudaEvent_t e0 = nullptr, e1 = nullptr;
-    LaunchTimer(bl_handle* h_, int kid_) : h(h_), kid(kid_) {
+    bl_handle* h; int kid; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    LaunchTimer(bl_handle* h_, int kid_, cudaStream_t st_ = nullptr) : h(h_), kid(kid_), st(st_ ? st_ : h_->stream) {
         if (h->capturing) h->capture_launches++; else h->launches++;
         if (h->profiling && !h->capturing && kid >= 0) {
             cudaEventCreate(&e0); cudaEventCreate(&e1);
-            cudaEventRecord(e0, h->stream);
+            cudaEventRecord(e0, st);
         }
     }
     ~LaunchTimer() {
-        if (e0) { cudaEventRecord(e1, h->stream); h->timed.push_back({kid, e0, e1}); }
+        if (e0) { cudaEventRecord(e1, st); h->timed.push_back({kid, e0, e1}); }
     }
 };
 static void collect_timings(bl_handle* h) {
@@ -133,22 +136,44 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         int blocks = std::max(1, std::min(cdiv(nf, 256 * 4), 148 * 8));
         k_begin_eval<<<blocks, 256, 0, st>>>(d, adv_noise, adv_md, cm_mode, h->cm_parity);
     }
-    {
-        LaunchTimer t(h, BL_K_NEIGHBOR);
-        k_sort_atoms<<<R, 1024, 0, st>>>(d);
+    const bool fork = d.pme && h->has_fft;
+    if (fork) {
+        // reciprocal space needs only the positions: run it on the second stream, concurrently with the neighbour
+        // search, the pair kernel, the bonded terms and the alchemical kernel; joined before returning
+        cudaStream_t s2 = h->stream2;
+        cudaEventRecord(h->ev_fork, st);
+        cudaStreamWaitEvent(s2, h->ev_fork, 0);
+        { LaunchTimer t(h, BL_K_PME_SPREAD, s2); k_pme_spread<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
+        { LaunchTimer t(h, BL_K_PME_SPREAD, s2);
+          k_pme_finish<<<std::max(1, std::min(cdiv((long long)R * d.gsize, 256), 148 * 8)), 256, 0, s2>>>(d); }
+        { LaunchTimer t(h, BL_K_FFT, s2); cufftExecR2C(h->plan_r2c, d.grid_r, reinterpret_cast<cufftComplex*>(d.grid_c)); }
+        { LaunchTimer t(h, BL_K_PME_CONVOLVE, s2);
+          if (energy) k_pme_convolve<true><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d);
+          else k_pme_convolve<false><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d); }
+        { LaunchTimer t(h, BL_K_FFT, s2); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
+        { LaunchTimer t(h, BL_K_PME_GATHER, s2); k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
+        cudaEventRecord(h->ev_join, s2);
     }
     {
         LaunchTimer t(h, BL_K_NEIGHBOR);
-        k_find_tiles<<<dim3(cdiv(d.nblocks, FT_WARPS), R), FT_WARPS * 32, 0, st>>>(d);
+        const int smem_cells = (d.ncells + 1) * (int)sizeof(int) <= 40 * 1024 ? 1 : 0;
+        k_sort_atoms<<<R, 1024, smem_cells ? (d.ncells + 1) * sizeof(int) : 0, st>>>(d, smem_cells);
+    }
+    {
+        LaunchTimer t(h, BL_K_NEIGHBOR);
+        k_build_list<<<dim3(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R), NL_BLOCK, 0, st>>>(d);
+    }
+    if (d.n_alch > 0) {
+        { LaunchTimer t(h, BL_K_NEIGHBOR); k_alch_reset<<<cdiv(R * d.n_alch, 128), 128, 0, st>>>(d); }
+        { LaunchTimer t(h, BL_K_NEIGHBOR);
+          k_alch_list<<<dim3(cdiv(N, 128), R), 128, d.n_alch * sizeof(float4), st>>>(d); }
     }
     {
         LaunchTimer t(h, BL_K_PAIR);
-        // grid: a multiple of the SM count; each warp strides over work items
-        const int blocks = 148 * 4;
-        dim3 grid(std::max(1, blocks / std::min(R, 4)), R);
-#define PAIR(M)                                                           \
-        if (energy) k_pair<M, true><<<grid, 256, 0, st>>>(d);             \
-        else k_pair<M, false><<<grid, 256, 0, st>>>(d)
+        dim3 grid(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R);
+#define PAIR(M)                                                               \
+        if (energy) k_pair<M, true><<<grid, NL_BLOCK, 0, st>>>(d);            \
+        else k_pair<M, false><<<grid, NL_BLOCK, 0, st>>>(d)
         if (d.nb_method == 4) { PAIR(NB_PME); }
         else if (d.nb_method == 2) { PAIR(NB_RF); }
         else { PAIR(NB_NOCUT); }
@@ -161,26 +186,16 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
             k_bonded<<<dim3(cdiv(nterms, 128), R), 128, 0, st>>>(d);
         }
     }
-    if (d.pme && h->has_fft) {
-        { LaunchTimer t(h, BL_K_PME_SPREAD); k_pme_spread<<<dim3(cdiv(N, 128), R), 128, 0, st>>>(d); }
-        { LaunchTimer t(h, BL_K_PME_SPREAD);
-          k_pme_finish<<<std::max(1, std::min(cdiv((long long)R * d.gsize, 256), 148 * 8)), 256, 0, st>>>(d); }
-        { LaunchTimer t(h, BL_K_FFT); cufftExecR2C(h->plan_r2c, d.grid_r, reinterpret_cast<cufftComplex*>(d.grid_c)); }
-        { LaunchTimer t(h, BL_K_PME_CONVOLVE);
-          if (energy) k_pme_convolve<true><<<dim3(cdiv(d.csize, 256), R), 256, 0, st>>>(d);
-          else k_pme_convolve<false><<<dim3(cdiv(d.csize, 256), R), 256, 0, st>>>(d); }
-        { LaunchTimer t(h, BL_K_FFT); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
-        { LaunchTimer t(h, BL_K_PME_GATHER); k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, st>>>(d); }
-    }
     if (d.n_alch > 0) {
         LaunchTimer t(h, BL_K_ALCH);
-        k_alch<<<dim3(cdiv(N, 128), R), 128, 2 * d.n_alch * sizeof(double4), st>>>(d);
+        k_alch<<<dim3(cdiv(d.alch_cap, 128), d.n_alch, R), 128, 0, st>>>(d);
     }
+    if (fork) cudaStreamWaitEvent(st, h->ev_join, 0);
 }
 
 static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a) {
     LaunchTimer t(h, BL_K_INTEGRATE);
-    k_integrate<<<dim3(cdiv(h->d.n_clusters, 128), h->d.R), 128, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity);
+    k_integrate<<<dim3(cdiv(h->d.n_clusters, 64), h->d.R), 64, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity);
 }
 
 static void enqueue_momentum(bl_handle* h) {
@@ -416,9 +431,48 @@ static bool build_clusters(bl_handle* h, const bl_topology* t, std::vector<Clust
         c.ncons++;
         atom_cluster[i] = atom_cluster[j] = it->second;
     }
-    // homogeneous warps: order constrained clusters by (ncons, natoms), then the free atoms
+    // canonical layouts: star (every constraint touches one hub atom → hub first, constraint a = (0, a+1)) or
+    // water triangle ((0,1),(0,2),(1,2)); anything else takes the generic path
+    for (Cluster& c : cl) {
+        c.shape = 2;
+        int hub = -1;
+        for (int k = 0; k < c.natoms && hub < 0; ++k) {
+            bool all = true;
+            for (int a = 0; a < c.ncons; ++a) if (c.ca[a] != k && c.cb[a] != k) all = false;
+            if (all) hub = k;
+        }
+        if (hub >= 0 && c.natoms == c.ncons + 1) {
+            Cluster n = c;
+            n.atom[0] = c.atom[hub];
+            for (int a = 0; a < c.ncons; ++a) {
+                const int other = c.ca[a] == hub ? c.cb[a] : c.ca[a];
+                n.atom[a + 1] = c.atom[other];
+                n.ca[a] = 0; n.cb[a] = (signed char)(a + 1);
+                n.d2[a] = c.d2[a];
+            }
+            n.shape = 0;
+            c = n;
+        } else if (c.natoms == 3 && c.ncons == 3) {
+            Cluster n = c;
+            double d01 = -1, d02 = -1, d12 = -1;
+            for (int a = 0; a < 3; ++a) {
+                const int lo = std::min(c.ca[a], c.cb[a]), hi = std::max(c.ca[a], c.cb[a]);
+                if (lo == 0 && hi == 1) d01 = c.d2[a];
+                if (lo == 0 && hi == 2) d02 = c.d2[a];
+                if (lo == 1 && hi == 2) d12 = c.d2[a];
+            }
+            if (d01 > 0 && d02 > 0 && d12 > 0) {
+                n.ca[0] = 0; n.cb[0] = 1; n.d2[0] = d01;
+                n.ca[1] = 0; n.cb[1] = 2; n.d2[1] = d02;
+                n.ca[2] = 1; n.cb[2] = 2; n.d2[2] = d12;
+                n.shape = 1;
+                c = n;
+            }
+        }
+    }
+    // homogeneous warps: order constrained clusters by (shape, ncons), then the free atoms
     std::stable_sort(cl.begin(), cl.end(), [](const Cluster& a, const Cluster& b) {
-        return a.ncons != b.ncons ? a.ncons > b.ncons : a.natoms > b.natoms;
+        return a.shape != b.shape ? a.shape > b.shape : a.ncons > b.ncons;
     });
     for (int i = 0; i < N; ++i) {
         if (atom_cluster[i] >= 0) continue;
@@ -478,14 +532,11 @@ static int setup_box(bl_handle* h, const double box[3]) {
     return BL_OK;
 }
 
-// cell grid for spatial sorting: ~4 atoms per cell, Morton rank per cell
-static void plan_cells(int N, const double box[3], bool periodic, int nc[3], std::vector<int>& order) {
+// cell grid for the neighbour search: cell edge >= list cutoff / 2 (so +-2 cells cover it), Morton rank per cell
+static void plan_cells(const double box[3], bool periodic, double list_cutoff, int nc[3], std::vector<int>& order) {
     nc[0] = nc[1] = nc[2] = 1;
-    if (periodic && box[0] > 0) {
-        const double V = box[0] * box[1] * box[2];
-        const double edge = cbrt(4.0 * V / std::max(N, 1));
-        for (int k = 0; k < 3; ++k) nc[k] = std::max(1, std::min(128, (int)floor(box[k] / edge)));
-    }
+    if (periodic && box[0] > 0)
+        for (int k = 0; k < 3; ++k) nc[k] = std::max(1, std::min(256, (int)floor(box[k] / (0.5 * list_cutoff))));
     const int n = nc[0] * nc[1] * nc[2];
     std::vector<std::pair<uint32_t, int>> keys(n);
     for (int x = 0; x < nc[0]; ++x)
@@ -496,7 +547,29 @@ static void plan_cells(int N, const double box[3], bool periodic, int nc[3], std
             }
     std::sort(keys.begin(), keys.end());
     order.assign(n, 0);
-    for (int rnk = 0; rnk < n; ++rnk) order[keys[rnk].second] = rnk;
+    for (int rnk = 0; rnk < n; ++rnk) order[rnk] = rnk;      // row-major cell order (z-columns contiguous)
+}
+
+// (re)plan the cell grid for a box; cell tables are reallocated when the cell count grows
+static int setup_cells(bl_handle* h, const double box[3]) {
+    Dev& d = h->d;
+    std::vector<int> order;
+    int nc[3];
+    plan_cells(box, d.periodic, d.cutoffd + h->skin, nc, order);
+    const int n = nc[0] * nc[1] * nc[2];
+    if (n > h->cell_capacity) {
+        h->cell_capacity = n + n / 4 + 8;
+        d.cell_order = dalloc<int>(h, h->cell_capacity);
+        d.cell_start = dalloc<int>(h, (size_t)d.R * (h->cell_capacity + 1));
+        d.cell_cursor = dalloc<int>(h, (size_t)d.R * (h->cell_capacity + 1));
+        if (!d.cell_order || !d.cell_start || !d.cell_cursor) { h->error = "device allocation failed"; return BL_ERR_CUDA; }
+        invalidate_graphs(h);          // kernels captured the old pointers by value
+    }
+    if (n != d.ncells) invalidate_graphs(h);
+    d.ncell[0] = nc[0]; d.ncell[1] = nc[1]; d.ncell[2] = nc[2];
+    d.ncells = n;
+    CK(cudaMemcpy(d.cell_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    return BL_OK;
 }
 
 // ---- C ABI ----------------------------------------------------------------------------------------------------
@@ -520,6 +593,9 @@ int bl_destroy(bl_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return BL_OK;
 }
@@ -538,7 +614,11 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     auto fail = [&](int code, const std::string& msg) { g_create_error = msg; bl_destroy(h); return code; };
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess) return fail(BL_ERR_CUDA, "cudaSetDevice failed");
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(BL_ERR_CUDA, "stream creation failed");
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
+        return fail(BL_ERR_CUDA, "stream creation failed");
     Dev& d = h->d;
     memset(&d, 0, sizeof d);
     const int N = t->n_atoms, R = n_replicas;
@@ -554,7 +634,8 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     }
     d.cutoffd = t->cutoff; d.alphad = t->ewald_alpha;
     d.cutoff = (float)t->cutoff; d.cutoff2 = (float)(t->cutoff * t->cutoff);
-    const double skin = d.periodic ? 0.1 * t->cutoff : 0.0;
+    double skin = d.periodic ? 0.1 * t->cutoff : 0.0;
+    if (d.periodic && getenv("BLUES_B200_SKIN")) skin = std::max(0.01, atof(getenv("BLUES_B200_SKIN")));
     d.list_cutoff2 = d.periodic ? (float)((t->cutoff + skin) * (t->cutoff + skin)) : 3.0e38f;
     d.skin_half2 = d.periodic ? (float)(0.25 * skin * skin) : 3.0e38f;
     d.alpha = (float)t->ewald_alpha;
@@ -664,6 +745,9 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         }
         d.alch_exc = dupload(h, ix); d.alch_exc_p = dupload(h, pe);
     }
+    d.alch_cap = std::min(N, 2048);
+    d.alch_count = dalloc<int>(h, (size_t)R * std::max(1, d.n_alch));
+    d.alch_list = dalloc<int>(h, (size_t)R * std::max(1, d.n_alch) * d.alch_cap);
     d.sc_alpha = t->softcore_alpha; d.sc_a = t->softcore_a; d.sc_b = t->softcore_b; d.sc_c = t->softcore_c;
     d.annihilate_sterics = t->annihilate_sterics; d.annihilate_elec = t->annihilate_electrostatics;
     {
@@ -694,36 +778,26 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     h->d_scratch = dalloc<double>(h, std::max((size_t)R * 4, (size_t)N * 3));
     h->d_iscratch = dalloc<int>(h, (size_t)R * 2);
     // neighbour structures
-    std::vector<int> order;
-    plan_cells(N, t->box, d.periodic, d.ncell, order);
-    d.ncells = d.ncell[0] * d.ncell[1] * d.ncell[2];
-    d.cell_order = dupload(h, order);
-    d.cell_count = dalloc<int>(h, (size_t)R * (d.ncells + 1));
-    d.atom_cell = dalloc<int>(h, RN); d.atom_slot = dalloc<int>(h, RN); d.rank = dalloc<int>(h, RN);
+    h->skin = skin;
+    {
+        int rc = setup_cells(h, t->box);
+        if (rc != BL_OK) return fail(rc, h->error);
+    }
+    d.atom_cell = dalloc<int>(h, RN); d.rank = dalloc<int>(h, RN);
     d.posq_s = dalloc<float4>(h, (size_t)R * d.Npad);
     d.sigeps_s = dalloc<float2>(h, (size_t)R * d.Npad);
     d.orig_s = dalloc<int>(h, (size_t)R * d.Npad);
-    d.blk_center = dalloc<float4>(h, (size_t)R * d.nblocks);
-    d.blk_half = dalloc<float4>(h, (size_t)R * d.nblocks);
     {
-        // capacity: atoms within the list cutoff of a 32-atom block, halved (j >= i), in 128-atom items
-        double per_block = 64;
+        // list capacity per atom: 1.5 x the mean number of atoms inside the list-cutoff sphere (+ margin)
+        long long M = N;
         if (d.periodic) {
-            const double V = t->box[0] * t->box[1] * t->box[2];
-            const double rho = N / V;
-            const double edge = cbrt(32.0 / rho), rl = t->cutoff + skin;
-            const double vol = edge * edge * edge + 6 * edge * edge * rl + 3 * M_PI * edge * rl * rl + 4.0 / 3 * M_PI * rl * rl * rl;
-            per_block = std::min((double)N, 0.5 * vol * rho * 2.5 + 128);
-        } else {
-            per_block = N + 128;
+            const double V = t->box[0] * t->box[1] * t->box[2], rl = t->cutoff + skin;
+            M = std::min<long long>(N, (long long)(1.5 * 4.0 / 3.0 * M_PI * rl * rl * rl * N / V) + 96);
         }
-        long long cap = (long long)d.nblocks * ((long long)(per_block / ITEM_ATOMS) + 2);
-        d.item_capacity = (int)std::min<long long>(std::max<long long>(cap, 64), 1LL << 24);
+        d.nl_M = (int)((M + 7) / 8 * 8);
     }
-    const size_t RI = (size_t)R * d.item_capacity;
-    d.item_block = dalloc<int>(h, RI); d.item_natoms = dalloc<int>(h, RI); d.item_flags = dalloc<int>(h, RI);
-    d.item_atoms = dalloc<int>(h, RI * ITEM_ATOMS);
-    d.item_excl = dalloc<unsigned int>(h, RI * ITEM_ATOMS);
+    d.nl_count = dalloc<int>(h, (size_t)R * d.Npad);
+    d.nl_list = dalloc<int>(h, (size_t)R * d.Npad * d.nl_M);
     // PME
     if (d.pme) {
         d.gx = t->pme_grid[0]; d.gy = t->pme_grid[1]; d.gz = t->pme_grid[2];
@@ -741,8 +815,8 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
             cufftPlanMany(&h->plan_c2r, 3, n, nullptr, 1, d.csize, nullptr, 1, d.gsize, CUFFT_C2R, R) != CUFFT_SUCCESS)
             return fail(BL_ERR_CUDA, "cufftPlanMany failed");
         h->has_fft = true;
-        cufftSetStream(h->plan_r2c, h->stream);
-        cufftSetStream(h->plan_c2r, h->stream);
+        cufftSetStream(h->plan_r2c, h->stream2);
+        cufftSetStream(h->plan_c2r, h->stream2);
     }
     for (void* p : h->allocs) if (!p) return fail(BL_ERR_CUDA, "device allocation failed");
     if (setup_box(h, t->box) != BL_OK) return fail(BL_ERR_CUDA, h->error);
@@ -914,6 +988,7 @@ int bl_set_box(bl_handle* h, const double box[3]) {
     CK(cudaStreamSynchronize(h->stream));
     int rc = setup_box(h, box);
     if (rc != BL_OK) return rc;
+    if (d.periodic) { rc = setup_cells(h, box); if (rc != BL_OK) return rc; }
     positions_changed(h);
     return BL_OK;
 }
@@ -1000,6 +1075,7 @@ int bl_copy_state(bl_handle* dst, const bl_handle* src, int flags) {
         CK(cudaMemcpy(box, src->d.boxd, sizeof box, cudaMemcpyDeviceToHost));
         int rc = setup_box(h, box);
         if (rc != BL_OK) return rc;
+        if (h->d.periodic) { rc = setup_cells(h, box); if (rc != BL_OK) return rc; }
     }
     if (flags & 1) CK(cudaMemcpyAsync(dst->d.pos, src->d.pos, n, cudaMemcpyDeviceToDevice, h->stream));
     if (flags & 2) { CK(cudaMemcpyAsync(dst->d.vel, src->d.vel, n, cudaMemcpyDeviceToDevice, h->stream)); h->vel_dirty = true; }
@@ -1323,7 +1399,7 @@ int bl_neighbor_pairs(bl_handle* h, int replica, int64_t* codes, size_t capacity
     CK(cudaMalloc(&dcodes, sizeof(long long) * std::max<size_t>(capacity, 1)));
     CK(cudaMalloc(&dn, sizeof(unsigned long long)));
     CK(cudaMemsetAsync(dn, 0, sizeof(unsigned long long), h->stream));
-    { LaunchTimer t(h, -1); k_neighbor_pairs<<<148 * 2, 256, 0, h->stream>>>(d, replica, dcodes, capacity, dn); }
+    { LaunchTimer t(h, -1); k_neighbor_pairs<<<148 * 4, 128, 0, h->stream>>>(d, replica, dcodes, capacity, dn); }
     unsigned long long n = 0;
     CK(cudaMemcpyAsync(&n, dn, sizeof n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1343,7 +1419,7 @@ int bl_neighbor_stats(bl_handle* h, int replica, int64_t* n_tiles, int64_t* n_re
     CK(cudaStreamSynchronize(h->stream));
     Globals g;
     CK(cudaMemcpy(&g, h->d.g + replica, sizeof g, cudaMemcpyDeviceToHost));
-    if (n_tiles) *n_tiles = g.n_items;
+    if (n_tiles) *n_tiles = (int64_t)h->d.nl_M;
     if (n_rebuilds) *n_rebuilds = g.n_rebuilds;
     return BL_OK;
 }

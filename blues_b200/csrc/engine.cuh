@@ -4,8 +4,6 @@
 
 #define MAX_CLUSTER_ATOMS 5
 #define MAX_CLUSTER_CONS 4
-#define TILE_CHUNKS 4                 /* one pair-kernel work item = 1 i-block x up to 4 chunks of 32 j-atoms */
-#define ITEM_ATOMS (TILE_CHUNKS * 32)
 #define N_ETERMS 12
 #define MAX_OPS 16
 #define ALCH_SLOTS 3
@@ -22,6 +20,7 @@ struct Op { int kind; int slot; };
 // single unconstrained atom.  One thread integrates one cluster through the whole V/R/O sequence.
 struct Cluster {
     int natoms, ncons;
+    int shape;                                                // 0 star around atom 0, 1 water triangle, 2 generic
     int atom[MAX_CLUSTER_ATOMS];
     signed char ca[MAX_CLUSTER_CONS], cb[MAX_CLUSTER_CONS];   // local atom indices of each constraint
     double d2[MAX_CLUSTER_CONS];                              // squared constraint lengths
@@ -40,7 +39,7 @@ struct Globals {
     unsigned int noise_counter, vel_counter, move_counter, accept_counter, md_counter;
     int do_rebuild, rebuild_request;
     long long n_rebuilds;
-    int n_items, item_overflow;
+    int item_overflow;        // a neighbour list ran out of capacity
 };
 
 struct IntegratorConsts {
@@ -81,19 +80,16 @@ struct Dev {
     long long* cm_acc;                      // [R][3] sum of m v
     long long* heat_acc;                    // [R]
     Globals* g;                             // [R]
-    // neighbour structures
+    // neighbour structures: Morton-ranked cells (edge >= list cutoff / 2), sorted mirrors, Verlet lists
     int ncell[3]; int ncells;
     int* cell_order;                        // [ncells] Morton rank of each cell
-    int* cell_count;                        // [R][ncells+1]
-    int* atom_cell; int* atom_slot;         // [R*N]
+    int* cell_start; int* cell_cursor;      // [R][ncells+1] first sorted slot of every cell (+ scatter cursor)
+    int* atom_cell;                         // [R*N]
     int* rank;                              // [R*N] position of atom a in the sorted order
     float4* posq_s; float2* sigeps_s; int* orig_s;   // [R*Npad] sorted copies (pads: NaN position, orig -1)
-    float4* blk_center; float4* blk_half;   // [R*nblocks]
-    int item_capacity;
-    int* item_block; int* item_natoms;      // [R*item_capacity]
-    int* item_flags;                        // bit c: chunk c has exclusions; bit 8: chunk 0 is the block's own atoms
-    int* item_atoms;                        // [R*item_capacity*ITEM_ATOMS] sorted indices, -1 pads
-    unsigned int* item_excl;                // [R*item_capacity*ITEM_ATOMS] per-lane exclusion bits vs the chunk's 32 j
+    int nl_M;                               // list capacity per atom
+    int* nl_count;                          // [R*Npad]
+    int* nl_list;                           // [R*Npad][nl_M] sorted indices of the neighbours within the list cutoff
     // bonded tables
     int n_bonds, n_angles, n_torsions, n_excl, n_restraints, n_alch_exc;
     int2* bonds; double2* bond_p;           // (k, r0)
@@ -106,6 +102,7 @@ struct Dev {
     int n_alch;
     int* alch_atom; double4* alch_p;        // (q, sigma, eps, -)
     unsigned char* is_alch;                 // [N]
+    int alch_cap; int* alch_count; int* alch_list;   // per-alchemical-atom neighbour lists: [R][n_alch], [R][n_alch][alch_cap]
     double sc_alpha, sc_a, sc_b, sc_c;
     int annihilate_sterics, annihilate_elec;
     double* lam_s; double* lam_e; int n_lambda;       // tables indexed by lambda_step

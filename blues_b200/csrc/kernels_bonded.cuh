@@ -203,76 +203,103 @@ __global__ void __launch_bounds__(128) k_bonded(Dev d) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_alch: alchemical-region pairs.  Thread j (any atom) x every alchemical atom i staged in shared memory;
-// evaluates the softcore sterics and lambda-scaled direct-space electrostatics at ALCH_SLOTS consecutive
-// lambda_step values in one pass (energies for Enew-Eold, forces for the V steps that follow).
+// Alchemical-region pairs (K3).  k_alch_list runs with the neighbour rebuild: for every alchemical atom it
+// compacts (warp ballot) the atoms within the list cutoff that are not excluded into a per-alchemical-atom list.
+// k_alch then evaluates one pair per thread at ALCH_SLOTS consecutive lambda_step values in one pass (energies
+// for Enew - Eold, forces for the V steps that follow), reducing the force on the alchemical atom over the warp.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_alch(Dev d) {
+__global__ void __launch_bounds__(128) k_alch_list(Dev d) {
     const int r = blockIdx.y;
+    if (!d.g[r].do_rebuild) return;
     const int N = d.N, na = d.n_alch;
-    extern __shared__ double4 s_alch[];          // [na] position (w = q), then [na] (sigma, eps, orig index, -)
-    double4* s_pos = s_alch;
-    double4* s_par = s_alch + na;
-    const double4* pos = d.pos + (size_t)r * N;
+    extern __shared__ float4 s_apos[];           // [na] alchemical positions (w = orig index as float bits)
+    const float4* posq = d.posq + (size_t)r * N;
     for (int k = threadIdx.x; k < na; k += blockDim.x) {
-        int a = d.alch_atom[k];
-        double4 p = pos[a];
-        double4 q = d.alch_p[k];
-        p.w = q.x;
-        s_pos[k] = p;
-        s_par[k] = make_double4(q.y, q.z, (double)a, 0.0);
+        const int a = d.alch_atom[k];
+        float4 p = posq[a];
+        p.w = __int_as_float(a);
+        s_apos[k] = p;
     }
     __syncthreads();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool active = j < N;
-    const int base = d.g[r].lambda_step;
-    double ls[ALCH_SLOTS], le[ALCH_SLOTS];
-    for (int s = 0; s < ALCH_SLOTS; ++s) {
-        int li = min(base + s, d.n_lambda - 1);
-        ls[s] = d.lam_s[li];
-        le[s] = d.lam_e[li];
-    }
-    double4 pj = active ? pos[j] : make_double4(0, 0, 0, 0);
+    const float4 pj = active ? posq[j] : make_float4(0.f, 0.f, 0.f, 0.f);
     const bool j_alch = active ? d.is_alch[j] : false;
-    double qj = 0.0, sigj = 0.0, epsj = 0.0;
-    if (active && !j_alch) {
-        qj = d.charge_d[j];
-        sigj = d.sigma_d[j];
-        epsj = d.eps_d[j];
-    }
     const ull wj = active ? d.excl_win[j] : 0ull;
     const bool farj = active ? d.has_far[j] : false;
-    double fj[ALCH_SLOTS][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    double e_st[ALCH_SLOTS] = {0, 0, 0}, e_el[ALCH_SLOTS] = {0, 0, 0};
-    const double cut2 = d.periodic ? d.cutoffd * d.cutoffd : 1e300;
+    const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
     for (int k = 0; k < na; ++k) {
-        const double4 pi = s_pos[k];
-        const double4 par = s_par[k];
-        const int i = (int)par.z;
+        const float4 pi = s_apos[k];
+        const int i = __float_as_int(pi.w);
         bool ok = active && i != j;
-        if (ok && j_alch) ok = i < j;          // alchemical-alchemical pairs once
+        if (ok && j_alch) ok = i < j;            // alchemical-alchemical pairs once, owned by the lower index
+        float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+        if (d.periodic) {
+            dx -= bx * rintf(dx * ibx);
+            dy -= by * rintf(dy * iby);
+            dz -= bz * rintf(dz * ibz);
+        }
+        ok = ok && (dx * dx + dy * dy + dz * dz) < d.list_cutoff2;
+        if (ok) ok = !pair_excluded(d, j, wj, farj, i, d.has_far[i]);
+        const unsigned int m = __ballot_sync(0xffffffffu, ok);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&d.alch_count[r * na + k], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (ok) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < d.alch_cap) d.alch_list[((size_t)r * na + k) * d.alch_cap + slot] = j;
+                else d.g[r].item_overflow = 1;
+            }
+        }
+    }
+}
+
+__global__ void k_alch_reset(Dev d) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d.R * d.n_alch) return;
+    if (d.g[idx / d.n_alch].do_rebuild) d.alch_count[idx] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_alch(Dev d) {
+    const int r = blockIdx.z, k = blockIdx.y;
+    const int N = d.N, na = d.n_alch;
+    const int count = min(d.alch_count[r * na + k], d.alch_cap);
+    if ((int)(blockIdx.x * blockDim.x) >= count) return;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool active = p < count;
+    const double4* pos = d.pos + (size_t)r * N;
+    const int i = d.alch_atom[k];
+    const double4 par_i = d.alch_p[k];           // (q, sigma, eps)
+    const double4 pi = pos[i];
+    const int base = d.g[r].lambda_step;
+    double fi[ALCH_SLOTS][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double e_st[ALCH_SLOTS] = {0, 0, 0}, e_el[ALCH_SLOTS] = {0, 0, 0};
+    if (active) {
+        const int j = d.alch_list[((size_t)r * na + k) * d.alch_cap + p];
+        const double4 pj = pos[j];
         double3 dv = make_double3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
         min_image(d, dv);
         const double r2 = d3dot(dv, dv);
-        ok = ok && r2 < cut2;
-        if (ok) ok = !pair_excluded(d, j, wj, farj, i, d.has_far[i]);
-        double fi[ALCH_SLOTS][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        if (ok) {
-            double sj = sigj, ej = epsj, qjj = qj;
-            if (j_alch) {   // parameters of an alchemical j come from the alchemical table
+        const double cut2 = d.periodic ? d.cutoffd * d.cutoffd : 1e300;
+        if (r2 < cut2) {
+            const bool j_alch = d.is_alch[j];
+            double qj = d.charge_d[j], sj = d.sigma_d[j], ej = d.eps_d[j];
+            if (j_alch) {
                 for (int m = 0; m < na; ++m)
-                    if ((int)s_par[m].z == j) { sj = s_par[m].x; ej = s_par[m].y; qjj = s_pos[m].w; }
+                    if (d.alch_atom[m] == j) { const double4 q = d.alch_p[m]; qj = q.x; sj = q.y; ej = q.z; }
             }
             const double rr = sqrt(r2);
-            const double sig = 0.5 * (par.x + sj);
-            const double eps = sqrt(par.y * ej);
-            const double kqq = ONE_4PI_EPS0 * pi.w * qjj;
+            const double sig = 0.5 * (par_i.y + sj);
+            const double eps = sqrt(par_i.z * ej);
+            const double kqq = ONE_4PI_EPS0 * par_i.x * qj;
             double ec = 0.0, fc = 0.0;   // unit-lambda electrostatic energy and force/r
             if (kqq != 0.0) {
                 if (d.pme) {
-                    double ar = d.alphad * rr;
-                    double erc = erfc(ar);
+                    const double ar = d.alphad * rr;
+                    const double erc = erfc(ar);
                     ec = kqq * erc / rr;
                     fc = kqq * (erc / rr + TWO_OVER_SQRT_PI * d.alphad * exp(-ar * ar)) / r2;
                 } else if (d.nb_method == 2) {
@@ -284,36 +311,27 @@ __global__ void __launch_bounds__(128) k_alch(Dev d) {
                 }
             }
             for (int s = 0; s < ALCH_SLOTS; ++s) {
-                const double lss = (j_alch && !d.annihilate_sterics) ? 1.0 : ls[s];
-                const double les = (j_alch && !d.annihilate_elec) ? 1.0 : le[s];
+                const int li = min(base + s, d.n_lambda - 1);
+                const double lss = (j_alch && !d.annihilate_sterics) ? 1.0 : d.lam_s[li];
+                const double les = (j_alch && !d.annihilate_elec) ? 1.0 : d.lam_e[li];
                 double fr = 0.0;
-                if (eps > 0.0) e_st[s] += softcore_lj(rr, sig, eps, lss, d.sc_alpha, d.sc_a, d.sc_b, d.sc_c, fr);
-                e_el[s] += les * ec;
+                if (eps > 0.0) e_st[s] = softcore_lj(rr, sig, eps, lss, d.sc_alpha, d.sc_a, d.sc_b, d.sc_c, fr);
+                e_el[s] = les * ec;
                 fr += les * fc;
                 fi[s][0] = dv.x * fr; fi[s][1] = dv.y * fr; fi[s][2] = dv.z * fr;
-                fj[s][0] -= fi[s][0]; fj[s][1] -= fi[s][1]; fj[s][2] -= fi[s][2];
-            }
-        }
-        // force on alchemical atom i: reduce over the warp, one atomic per warp
-        if (__any_sync(0xffffffffu, ok)) {
-            for (int s = 0; s < ALCH_SLOTS; ++s) {
-                double fx = warp_sum(fi[s][0]), fy = warp_sum(fi[s][1]), fz = warp_sum(fi[s][2]);
-                if (lane == 0) {
-                    long long* fa = d.f_alch + ((size_t)s * d.R + r) * 3 * N;
-                    add_force(fa, N, i, make_double3(fx, fy, fz));
-                }
+                long long* fa = d.f_alch + ((size_t)s * d.R + r) * 3 * N;
+                add_force(fa, N, j, make_double3(-fi[s][0], -fi[s][1], -fi[s][2]));
             }
         }
     }
     for (int s = 0; s < ALCH_SLOTS; ++s) {
-        if (active && (fj[s][0] != 0.0 || fj[s][1] != 0.0 || fj[s][2] != 0.0)) {
+        const double fx = warp_sum(fi[s][0]), fy = warp_sum(fi[s][1]), fz = warp_sum(fi[s][2]);
+        const double a = warp_sum(e_st[s]), b = warp_sum(e_el[s]);
+        if (lane == 0) {
             long long* fa = d.f_alch + ((size_t)s * d.R + r) * 3 * N;
-            add_force(fa, N, j, make_double3(fj[s][0], fj[s][1], fj[s][2]));
-        }
-        double a = warp_sum(e_st[s]), b = warp_sum(e_el[s]);
-        if (lane == 0 && (a != 0.0 || b != 0.0)) {
-            fx_add(&d.alch_acc[(r * ALCH_SLOTS + s) * 3 + 0], a, ENERGY_SCALE);
-            fx_add(&d.alch_acc[(r * ALCH_SLOTS + s) * 3 + 1], b, ENERGY_SCALE);
+            if (fx != 0.0 || fy != 0.0 || fz != 0.0) add_force(fa, N, i, make_double3(fx, fy, fz));
+            if (a != 0.0) fx_add(&d.alch_acc[(r * ALCH_SLOTS + s) * 3 + 0], a, ENERGY_SCALE);
+            if (b != 0.0) fx_add(&d.alch_acc[(r * ALCH_SLOTS + s) * 3 + 1], b, ENERGY_SCALE);
         }
     }
 }

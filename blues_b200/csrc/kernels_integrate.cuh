@@ -3,6 +3,16 @@
 #pragma once
 #include "engine.cuh"
 
+// single-precision mirror of a position, wrapped into the primary cell (the neighbour search relies on it)
+__device__ __forceinline__ float4 wrapped_mirror(const Dev& d, double x, double y, double z, float q) {
+    if (d.periodic) {
+        x -= d.boxd[0] * floor(x * d.boxd[3]);
+        y -= d.boxd[1] * floor(y * d.boxd[4]);
+        z -= d.boxd[2] * floor(z * d.boxd[5]);
+    }
+    return make_float4((float)x, (float)y, (float)z, q);
+}
+
 struct ClusterState {
     double x[MAX_CLUSTER_ATOMS][3];
     double v[MAX_CLUSTER_ATOMS][3];
@@ -131,143 +141,421 @@ struct IntegrateArgs {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_integrate(Dev d, IntegratorConsts ic, IntegrateArgs args, const int* cm_parity) {
-    const int r = blockIdx.y;
+// Register-resident cluster integrator.  SHAPE_STAR: constraints (0,1)..(0,NC) around atom 0 (X-H groups, free
+// atoms with NC = 0); SHAPE_TRI: the rigid-water triangle (0,1),(0,2),(1,2).  All loops have compile-time bounds
+// so x/v/… live in registers (no local-memory traffic), unlike the generic fallback further down.
+// ---------------------------------------------------------------------------------------------------------
+#define SHAPE_STAR 0
+#define SHAPE_TRI 1
+#define SHAPE_GENERIC 2
+
+template <int SHAPE> __device__ __forceinline__ constexpr int con_a(int a) { return SHAPE == SHAPE_TRI ? (a == 2 ? 1 : 0) : 0; }
+template <int SHAPE> __device__ __forceinline__ constexpr int con_b(int a) { return SHAPE == SHAPE_TRI ? (a == 0 ? 1 : 2) : a + 1; }
+
+template <int NC>
+__device__ __forceinline__ void solve_fixed(double (&A)[NC > 0 ? NC : 1][NC > 0 ? NC : 1], double (&b)[NC > 0 ? NC : 1]) {
+    // symmetric-positive-definite-like systems (Gram matrices weighted by inverse masses): no pivoting needed
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const double inv = 1.0 / A[c][c];
+#pragma unroll
+        for (int rr = c + 1; rr < NC; ++rr) {
+            const double f = A[rr][c] * inv;
+#pragma unroll
+            for (int k = c + 1; k < NC; ++k) A[rr][k] -= f * A[c][k];
+            b[rr] -= f * b[c];
+        }
+    }
+#pragma unroll
+    for (int c = NC - 1; c >= 0; --c) {
+        double sum = b[c];
+#pragma unroll
+        for (int k = c + 1; k < NC; ++k) sum -= A[c][k] * b[k];
+        b[c] = sum / A[c][c];
+    }
+}
+
+template <int NA, int NC, int SHAPE>
+struct FixedCluster {
+    static constexpr int NCC = NC > 0 ? NC : 1;
+    double x[NA][3], v[NA][3], im[NA], mass[NA];
+    double d2[NCC];
+
+    __device__ __forceinline__ double coup(int a, int b) const {
+        const int ia = con_a<SHAPE>(a), ja = con_b<SHAPE>(a), ib = con_a<SHAPE>(b), jb = con_b<SHAPE>(b);
+        return ((ia == ib) - (ia == jb)) * im[ia] - ((ja == ib) - (ja == jb)) * im[ja];
+    }
+
+    __device__ __forceinline__ void rattle() {
+        if (NC == 0) return;
+        double sv[NCC][3], A[NCC][NCC], rhs[NCC];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+            const int i = con_a<SHAPE>(a), j = con_b<SHAPE>(a);
+            double dvv = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sv[a][k] = x[i][k] - x[j][k]; dvv += sv[a][k] * (v[i][k] - v[j][k]); }
+            rhs[a] = -dvv;
+        }
+#pragma unroll
+        for (int a = 0; a < NC; ++a)
+#pragma unroll
+            for (int b = 0; b < NC; ++b)
+                A[a][b] = coup(a, b) * (sv[a][0] * sv[b][0] + sv[a][1] * sv[b][1] + sv[a][2] * sv[b][2]);
+        solve_fixed<NC>(A, rhs);
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+            const int i = con_a<SHAPE>(a), j = con_b<SHAPE>(a);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double cc = rhs[a] * sv[a][k];
+                v[i][k] += cc * im[i];
+                v[j][k] -= cc * im[j];
+            }
+        }
+    }
+
+    __device__ __forceinline__ void shake(const double (&xref)[NA][3], double tol) {
+        if (NC == 0) return;
+        double rr[NCC][3];
+#pragma unroll
+        for (int a = 0; a < NC; ++a)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rr[a][k] = xref[con_a<SHAPE>(a)][k] - xref[con_b<SHAPE>(a)][k];
+        for (int it = 0; it < 30; ++it) {
+            double sv[NCC][3], diff[NCC], worst = 0.0;
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+                const int i = con_a<SHAPE>(a), j = con_b<SHAPE>(a);
+                double s2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { sv[a][k] = x[i][k] - x[j][k]; s2 += sv[a][k] * sv[a][k]; }
+                diff[a] = d2[a] - s2;
+                worst = fmax(worst, fabs(diff[a]) / d2[a]);
+            }
+            if (worst < tol) break;
+            double A[NCC][NCC];
+#pragma unroll
+            for (int a = 0; a < NC; ++a)
+#pragma unroll
+                for (int b = 0; b < NC; ++b)
+                    A[a][b] = 2.0 * coup(a, b) * (sv[a][0] * rr[b][0] + sv[a][1] * rr[b][1] + sv[a][2] * rr[b][2]);
+            solve_fixed<NC>(A, diff);
+#pragma unroll
+            for (int a = 0; a < NC; ++a) {
+                const int i = con_a<SHAPE>(a), j = con_b<SHAPE>(a);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double cc = diff[a] * rr[a][k];
+                    x[i][k] += cc * im[i];
+                    x[j][k] -= cc * im[j];
+                }
+            }
+        }
+    }
+};
+
+// Runs the op list on one cluster; returns momentum / heat contributions and rebuild / NaN flags through refs.
+template <int NA, int NC, int SHAPE>
+__device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts& ic, const IntegrateArgs& args,
+                                            const Cluster& c, int r, int parity, unsigned int noise0, unsigned int md0,
+                                            double (&mom)[3], double& dheat, bool& moved, bool& bad) {
     const int N = d.N;
+    double4* pos = d.pos + (size_t)r * N;
+    double4* vel = d.vel + (size_t)r * N;
+    const long long* fenv = d.f_env + (size_t)r * 3 * N;
+    FixedCluster<NA, NC, SHAPE> s;
+    int atom[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        const int a = c.atom[k];
+        atom[k] = a;
+        const double4 p = pos[a], v = vel[a];
+        s.x[k][0] = p.x; s.x[k][1] = p.y; s.x[k][2] = p.z;
+        s.v[k][0] = v.x; s.v[k][1] = v.y; s.v[k][2] = v.z;
+        s.im[k] = d.invmass[a];
+        s.mass[k] = d.mass[a];
+    }
+#pragma unroll
+    for (int a = 0; a < NC; ++a) s.d2[a] = c.d2[a];
+    int n_o = 0, n_md = 0;
+    for (int o = 0; o < args.nops; ++o) {
+        const Op op = args.ops[o];
+        if (op.kind == OP_CM) {
+            if (ic.remove_cm) {
+                const long long* cm = d.cm_acc + ((size_t)parity * d.R + r) * 3;
+                const double inv = 1.0 / (FORCE_SCALE * ic.total_mass);
+                const double vx = (double)cm[0] * inv, vy = (double)cm[1] * inv, vz = (double)cm[2] * inv;
+#pragma unroll
+                for (int k = 0; k < NA; ++k)
+                    if (s.im[k] > 0.0) { s.v[k][0] -= vx; s.v[k][1] -= vy; s.v[k][2] -= vz; }
+            }
+        } else if (op.kind == OP_V) {
+            const long long* fa = d.n_alch > 0 ? d.f_alch + ((size_t)op.slot * d.R + r) * 3 * N : nullptr;
+#pragma unroll
+            for (int k = 0; k < NA; ++k) {
+                const double sc = ic.hV * s.im[k] * (1.0 / FORCE_SCALE);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    long long f = fenv[q * N + atom[k]];
+                    if (fa) f += fa[q * N + atom[k]];
+                    s.v[k][q] += sc * (double)f;
+                }
+            }
+            s.rattle();
+        } else if (op.kind == OP_R) {
+            double xref[NA][3], x1[NA][3];
+#pragma unroll
+            for (int k = 0; k < NA; ++k)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    xref[k][q] = s.x[k][q];
+                    if (s.im[k] > 0.0) s.x[k][q] += ic.hR * s.v[k][q];
+                    x1[k][q] = s.x[k][q];
+                }
+            s.shake(xref, ic.tol);
+            const double ih = 1.0 / ic.hR;
+#pragma unroll
+            for (int k = 0; k < NA; ++k)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) s.v[k][q] += (s.x[k][q] - x1[k][q]) * ih;
+            s.rattle();
+        } else if (op.kind == OP_O) {
+            double ke0 = 0.0, ke1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < NA; ++k) {
+                ke0 += 0.5 * s.mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
+                if (s.im[k] > 0.0) {
+                    double n0, n1, n2;
+                    philox_normal3(ic.seed, STREAM_LANGEVIN, (uint32_t)r, noise0 + n_o, (uint32_t)atom[k], n0, n1, n2);
+                    const double sg = ic.b * sqrt(ic.kT * s.im[k]);
+                    s.v[k][0] = ic.a * s.v[k][0] + sg * n0;
+                    s.v[k][1] = ic.a * s.v[k][1] + sg * n1;
+                    s.v[k][2] = ic.a * s.v[k][2] + sg * n2;
+                }
+            }
+            ++n_o;
+            s.rattle();
+#pragma unroll
+            for (int k = 0; k < NA; ++k)
+                ke1 += 0.5 * s.mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
+            dheat += ke1 - ke0;
+        } else if (op.kind == OP_MD) {
+            double xref[NA][3];
+#pragma unroll
+            for (int k = 0; k < NA; ++k) {
+                double n[3] = {0.0, 0.0, 0.0};
+                if (s.im[k] > 0.0)
+                    philox_normal3(ic.seed, STREAM_MD, (uint32_t)r, md0 + n_md, (uint32_t)atom[k], n[0], n[1], n[2]);
+                const double sq = ic.md_nscale * sqrt(s.im[k]);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    xref[k][q] = s.x[k][q];
+                    if (s.im[k] > 0.0) {
+                        long long fi = fenv[q * N + atom[k]];
+                        if (d.n_alch > 0) fi += d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + atom[k]];
+                        const double f = (double)fi * (1.0 / FORCE_SCALE);
+                        s.v[k][q] = ic.md_vscale * s.v[k][q] + ic.md_fscale * s.im[k] * f + sq * n[q];
+                        s.x[k][q] += ic.dt * s.v[k][q];
+                    }
+                }
+            }
+            ++n_md;
+            s.shake(xref, ic.tol);
+            const double idt = 1.0 / ic.dt;
+#pragma unroll
+            for (int k = 0; k < NA; ++k)
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (s.im[k] > 0.0) s.v[k][q] = (s.x[k][q] - xref[k][q]) * idt;
+        } else if (op.kind == OP_CONSTRAIN) {
+            double xref[NA][3];
+#pragma unroll
+            for (int k = 0; k < NA; ++k)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) xref[k][q] = s.x[k][q];
+            s.shake(xref, ic.tol);
+            s.rattle();
+        }
+    }
+    const float lim = d.skin_half2;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        const int a = atom[k];
+        pos[a] = make_double4(s.x[k][0], s.x[k][1], s.x[k][2], 0.0);
+        vel[a] = make_double4(s.v[k][0], s.v[k][1], s.v[k][2], 0.0);
+        const float4 pf = wrapped_mirror(d, s.x[k][0], s.x[k][1], s.x[k][2], d.charge[a]);
+        d.posq[(size_t)r * N + a] = pf;
+        d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * N + a]] = pf;
+        const float4 pr = d.pos_ref[(size_t)r * N + a];
+        float ddx = pf.x - pr.x, ddy = pf.y - pr.y, ddz = pf.z - pr.z;
+        if (d.periodic) {
+            ddx -= d.boxf[0] * rintf(ddx * d.boxf[3]);
+            ddy -= d.boxf[1] * rintf(ddy * d.boxf[4]);
+            ddz -= d.boxf[2] * rintf(ddz * d.boxf[5]);
+        }
+        moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
+        bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
+#pragma unroll
+        for (int q = 0; q < 3; ++q) mom[q] += s.mass[k] * s.v[k][q];
+    }
+}
+
+// generic fallback (dynamic indexing, local memory): clusters that are neither stars nor water triangles
+__device__ __noinline__ void run_cluster_generic(const Dev& d, const IntegratorConsts& ic, const IntegrateArgs& args,
+                                                 const Cluster& c, int r, int parity, unsigned int noise0,
+                                                 unsigned int md0, double (&mom)[3], double& dheat, bool& moved, bool& bad) {
+    const int N = d.N;
+    double4* pos = d.pos + (size_t)r * N;
+    double4* vel = d.vel + (size_t)r * N;
+    const long long* fenv = d.f_env + (size_t)r * 3 * N;
+    ClusterState s;
+    double mass[MAX_CLUSTER_ATOMS];
+    for (int k = 0; k < c.natoms; ++k) {
+        const int a = c.atom[k];
+        const double4 p = pos[a], v = vel[a];
+        s.x[k][0] = p.x; s.x[k][1] = p.y; s.x[k][2] = p.z;
+        s.v[k][0] = v.x; s.v[k][1] = v.y; s.v[k][2] = v.z;
+        s.im[k] = d.invmass[a];
+        mass[k] = d.mass[a];
+    }
+    int n_o = 0, n_md = 0;
+    for (int o = 0; o < args.nops; ++o) {
+        const Op op = args.ops[o];
+        switch (op.kind) {
+        case OP_CM: {
+            if (ic.remove_cm) {
+                const long long* cm = d.cm_acc + ((size_t)parity * d.R + r) * 3;
+                const double inv = 1.0 / (FORCE_SCALE * ic.total_mass);
+                const double vx = (double)cm[0] * inv, vy = (double)cm[1] * inv, vz = (double)cm[2] * inv;
+                for (int k = 0; k < c.natoms; ++k)
+                    if (s.im[k] > 0.0) { s.v[k][0] -= vx; s.v[k][1] -= vy; s.v[k][2] -= vz; }
+            }
+        } break;
+        case OP_V: {
+            const long long* fa = d.n_alch > 0 ? d.f_alch + ((size_t)op.slot * d.R + r) * 3 * N : nullptr;
+            for (int k = 0; k < c.natoms; ++k) {
+                const int a = c.atom[k];
+                const double sc = ic.hV * s.im[k] * (1.0 / FORCE_SCALE);
+                for (int q = 0; q < 3; ++q) {
+                    long long f = fenv[q * N + a];
+                    if (fa) f += fa[q * N + a];
+                    s.v[k][q] += sc * (double)f;
+                }
+            }
+            constrain_velocities(c, s);
+        } break;
+        case OP_R: {
+            double xref[MAX_CLUSTER_ATOMS][3], x1[MAX_CLUSTER_ATOMS][3];
+            for (int k = 0; k < c.natoms; ++k)
+                for (int q = 0; q < 3; ++q) {
+                    xref[k][q] = s.x[k][q];
+                    if (s.im[k] > 0.0) s.x[k][q] += ic.hR * s.v[k][q];
+                    x1[k][q] = s.x[k][q];
+                }
+            constrain_positions(c, s, xref, ic.tol);
+            const double ih = 1.0 / ic.hR;
+            for (int k = 0; k < c.natoms; ++k)
+                for (int q = 0; q < 3; ++q) s.v[k][q] += (s.x[k][q] - x1[k][q]) * ih;
+            constrain_velocities(c, s);
+        } break;
+        case OP_O: {
+            double ke0 = 0.0, ke1 = 0.0;
+            for (int k = 0; k < c.natoms; ++k) {
+                ke0 += 0.5 * mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
+                if (s.im[k] > 0.0) {
+                    double n0, n1, n2;
+                    philox_normal3(ic.seed, STREAM_LANGEVIN, (uint32_t)r, noise0 + n_o, (uint32_t)c.atom[k], n0, n1, n2);
+                    const double sg = ic.b * sqrt(ic.kT * s.im[k]);
+                    s.v[k][0] = ic.a * s.v[k][0] + sg * n0;
+                    s.v[k][1] = ic.a * s.v[k][1] + sg * n1;
+                    s.v[k][2] = ic.a * s.v[k][2] + sg * n2;
+                }
+            }
+            ++n_o;
+            constrain_velocities(c, s);
+            for (int k = 0; k < c.natoms; ++k)
+                ke1 += 0.5 * mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
+            dheat += ke1 - ke0;
+        } break;
+        case OP_MD: {
+            double xref[MAX_CLUSTER_ATOMS][3];
+            for (int k = 0; k < c.natoms; ++k) {
+                const int a = c.atom[k];
+                double n[3] = {0.0, 0.0, 0.0};
+                if (s.im[k] > 0.0)
+                    philox_normal3(ic.seed, STREAM_MD, (uint32_t)r, md0 + n_md, (uint32_t)a, n[0], n[1], n[2]);
+                const double sq = ic.md_nscale * sqrt(s.im[k]);
+                for (int q = 0; q < 3; ++q) {
+                    xref[k][q] = s.x[k][q];
+                    if (s.im[k] > 0.0) {
+                        long long fi = fenv[q * N + a];
+                        if (d.n_alch > 0) fi += d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + a];
+                        const double f = (double)fi * (1.0 / FORCE_SCALE);
+                        s.v[k][q] = ic.md_vscale * s.v[k][q] + ic.md_fscale * s.im[k] * f + sq * n[q];
+                        s.x[k][q] += ic.dt * s.v[k][q];
+                    }
+                }
+            }
+            ++n_md;
+            constrain_positions(c, s, xref, ic.tol);
+            const double idt = 1.0 / ic.dt;
+            for (int k = 0; k < c.natoms; ++k)
+                for (int q = 0; q < 3; ++q)
+                    if (s.im[k] > 0.0) s.v[k][q] = (s.x[k][q] - xref[k][q]) * idt;
+        } break;
+        case OP_CONSTRAIN: {
+            double xref[MAX_CLUSTER_ATOMS][3];
+            for (int k = 0; k < c.natoms; ++k)
+                for (int q = 0; q < 3; ++q) xref[k][q] = s.x[k][q];
+            constrain_positions(c, s, xref, ic.tol);
+            constrain_velocities(c, s);
+        } break;
+        default: break;
+        }
+    }
+    const float lim = d.skin_half2;
+    for (int k = 0; k < c.natoms; ++k) {
+        const int a = c.atom[k];
+        pos[a] = make_double4(s.x[k][0], s.x[k][1], s.x[k][2], 0.0);
+        vel[a] = make_double4(s.v[k][0], s.v[k][1], s.v[k][2], 0.0);
+        const float4 pf = wrapped_mirror(d, s.x[k][0], s.x[k][1], s.x[k][2], d.charge[a]);
+        d.posq[(size_t)r * N + a] = pf;
+        d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * N + a]] = pf;
+        const float4 pr = d.pos_ref[(size_t)r * N + a];
+        float ddx = pf.x - pr.x, ddy = pf.y - pr.y, ddz = pf.z - pr.z;
+        if (d.periodic) {
+            ddx -= d.boxf[0] * rintf(ddx * d.boxf[3]);
+            ddy -= d.boxf[1] * rintf(ddy * d.boxf[4]);
+            ddz -= d.boxf[2] * rintf(ddz * d.boxf[5]);
+        }
+        moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
+        bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
+        for (int q = 0; q < 3; ++q) mom[q] += mass[k] * s.v[k][q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_integrate(Dev d, IntegratorConsts ic, IntegrateArgs args, const int* cm_parity) {
+    const int r = blockIdx.y;
     const int cid = blockIdx.x * blockDim.x + threadIdx.x;
     Globals& g = d.g[r];
     const int parity = *cm_parity;
     double mom[3] = {0.0, 0.0, 0.0};
     double dheat = 0.0;
-
+    bool moved = false, bad = false;
     if (cid < d.n_clusters) {
         const Cluster c = d.clusters[cid];
-        double4* pos = d.pos + (size_t)r * N;
-        double4* vel = d.vel + (size_t)r * N;
-        const long long* fenv = d.f_env + (size_t)r * 3 * N;
-        ClusterState s;
-        double mass[MAX_CLUSTER_ATOMS];
-        for (int k = 0; k < c.natoms; ++k) {
-            const int a = c.atom[k];
-            const double4 p = pos[a], v = vel[a];
-            s.x[k][0] = p.x; s.x[k][1] = p.y; s.x[k][2] = p.z;
-            s.v[k][0] = v.x; s.v[k][1] = v.y; s.v[k][2] = v.z;
-            s.im[k] = d.invmass[a];
-            mass[k] = d.mass[a];
-        }
         const unsigned int noise0 = g.noise_counter + args.noise_offset, md0 = g.md_counter + args.md_offset;
-        int n_o = 0, n_md = 0;
-        for (int o = 0; o < args.nops; ++o) {
-            const Op op = args.ops[o];
-            switch (op.kind) {
-            case OP_CM: {
-                if (ic.remove_cm) {
-                    const long long* cm = d.cm_acc + ((size_t)parity * d.R + r) * 3;
-                    const double inv = 1.0 / (FORCE_SCALE * ic.total_mass);
-                    const double vx = (double)cm[0] * inv, vy = (double)cm[1] * inv, vz = (double)cm[2] * inv;
-                    for (int k = 0; k < c.natoms; ++k)
-                        if (s.im[k] > 0.0) { s.v[k][0] -= vx; s.v[k][1] -= vy; s.v[k][2] -= vz; }
-                }
-            } break;
-            case OP_V: {
-                const long long* fa = d.n_alch > 0 ? d.f_alch + ((size_t)op.slot * d.R + r) * 3 * N : nullptr;
-                for (int k = 0; k < c.natoms; ++k) {
-                    const int a = c.atom[k];
-                    const double sc = ic.hV * s.im[k] * (1.0 / FORCE_SCALE);
-                    for (int q = 0; q < 3; ++q) {
-                        long long f = fenv[q * N + a];
-                        if (fa) f += fa[q * N + a];
-                        s.v[k][q] += sc * (double)f;
-                    }
-                }
-                constrain_velocities(c, s);
-            } break;
-            case OP_R: {
-                double xref[MAX_CLUSTER_ATOMS][3], x1[MAX_CLUSTER_ATOMS][3];
-                for (int k = 0; k < c.natoms; ++k)
-                    for (int q = 0; q < 3; ++q) {
-                        xref[k][q] = s.x[k][q];
-                        if (s.im[k] > 0.0) s.x[k][q] += ic.hR * s.v[k][q];
-                        x1[k][q] = s.x[k][q];
-                    }
-                constrain_positions(c, s, xref, ic.tol);
-                const double ih = 1.0 / ic.hR;
-                for (int k = 0; k < c.natoms; ++k)
-                    for (int q = 0; q < 3; ++q) s.v[k][q] += (s.x[k][q] - x1[k][q]) * ih;
-                constrain_velocities(c, s);
-            } break;
-            case OP_O: {
-                double ke0 = 0.0, ke1 = 0.0;
-                for (int k = 0; k < c.natoms; ++k) {
-                    ke0 += 0.5 * mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
-                    if (s.im[k] > 0.0) {
-                        double n0, n1, n2;
-                        philox_normal3(ic.seed, STREAM_LANGEVIN, (uint32_t)r, noise0 + n_o, (uint32_t)c.atom[k], n0, n1, n2);
-                        const double sg = ic.b * sqrt(ic.kT * s.im[k]);
-                        s.v[k][0] = ic.a * s.v[k][0] + sg * n0;
-                        s.v[k][1] = ic.a * s.v[k][1] + sg * n1;
-                        s.v[k][2] = ic.a * s.v[k][2] + sg * n2;
-                    }
-                }
-                ++n_o;
-                constrain_velocities(c, s);
-                for (int k = 0; k < c.natoms; ++k)
-                    ke1 += 0.5 * mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
-                dheat += ke1 - ke0;
-            } break;
-            case OP_MD: {
-                // OpenMM LangevinIntegrator: v' = e^{-g dt} v + (1-e^{-g dt})/g f/m + sqrt(kT(1-e^{-2 g dt})/m) xi;
-                // x' = x + dt v'; constrain; v = (x'-x)/dt
-                double xref[MAX_CLUSTER_ATOMS][3];
-                for (int k = 0; k < c.natoms; ++k) {
-                    const int a = c.atom[k];
-                    double n[3] = {0.0, 0.0, 0.0};
-                    if (s.im[k] > 0.0)
-                        philox_normal3(ic.seed, STREAM_MD, (uint32_t)r, md0 + n_md, (uint32_t)a, n[0], n[1], n[2]);
-                    const double sq = ic.md_nscale * sqrt(s.im[k]);
-                    for (int q = 0; q < 3; ++q) {
-                        xref[k][q] = s.x[k][q];
-                        if (s.im[k] > 0.0) {
-                            long long fi = fenv[q * N + a];
-                            if (d.n_alch > 0) fi += d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + a];
-                            const double f = (double)fi * (1.0 / FORCE_SCALE);
-                            s.v[k][q] = ic.md_vscale * s.v[k][q] + ic.md_fscale * s.im[k] * f + sq * n[q];
-                            s.x[k][q] += ic.dt * s.v[k][q];
-                        }
-                    }
-                }
-                ++n_md;
-                constrain_positions(c, s, xref, ic.tol);
-                const double idt = 1.0 / ic.dt;
-                for (int k = 0; k < c.natoms; ++k)
-                    for (int q = 0; q < 3; ++q)
-                        if (s.im[k] > 0.0) s.v[k][q] = (s.x[k][q] - xref[k][q]) * idt;
-            } break;
-            case OP_CONSTRAIN: {
-                double xref[MAX_CLUSTER_ATOMS][3];
-                for (int k = 0; k < c.natoms; ++k)
-                    for (int q = 0; q < 3; ++q) xref[k][q] = s.x[k][q];
-                constrain_positions(c, s, xref, ic.tol);
-                constrain_velocities(c, s);
-            } break;
-            default: break;
-            }
-        }
-        // write back + mirrors + rebuild / NaN checks
-        bool moved = false, bad = false;
-        const float lim = d.skin_half2;
-        for (int k = 0; k < c.natoms; ++k) {
-            const int a = c.atom[k];
-            pos[a] = make_double4(s.x[k][0], s.x[k][1], s.x[k][2], 0.0);
-            vel[a] = make_double4(s.v[k][0], s.v[k][1], s.v[k][2], 0.0);
-            const float4 pf = make_float4((float)s.x[k][0], (float)s.x[k][1], (float)s.x[k][2], d.charge[a]);
-            d.posq[(size_t)r * N + a] = pf;
-            d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * N + a]] = pf;
-            const float4 pr = d.pos_ref[(size_t)r * N + a];
-            const float ddx = pf.x - pr.x, ddy = pf.y - pr.y, ddz = pf.z - pr.z;
-            moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
-            bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
-            for (int q = 0; q < 3; ++q) mom[q] += mass[k] * s.v[k][q];
+        const int key = c.shape * 16 + c.ncons;
+        switch (key) {
+        case SHAPE_STAR * 16 + 0: run_cluster<1, 0, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_STAR * 16 + 1: run_cluster<2, 1, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_STAR * 16 + 2: run_cluster<3, 2, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_STAR * 16 + 3: run_cluster<4, 3, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_STAR * 16 + 4: run_cluster<5, 4, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_TRI * 16 + 3: run_cluster<3, 3, SHAPE_TRI>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        default: run_cluster_generic(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
         }
         if (moved) g.rebuild_request = 1;
         if (bad) g.nan_flag = 1;
@@ -283,7 +571,7 @@ __global__ void __launch_bounds__(128) k_integrate(Dev d, IntegratorConsts ic, I
         const double v = warp_sum(dheat);
         if ((threadIdx.x & 31) == 0 && v != 0.0) fx_add(&d.heat_acc[r], v, ENERGY_SCALE);
     }
-    // scalar bookkeeping of the step program by one thread per walker (K9): H updates and step begin / end.
+    // scalar bookkeeping of the step program by one thread per walker (K9): H updates and step end.
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (int o = 0; o < args.nops; ++o) {
             const Op op = args.ops[o];
@@ -322,7 +610,7 @@ __global__ void k_refresh_mirrors(Dev d, int request_rebuild) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= d.N) return;
     const double4 p = d.pos[(size_t)r * d.N + a];
-    const float4 pf = make_float4((float)p.x, (float)p.y, (float)p.z, d.charge[a]);
+    const float4 pf = wrapped_mirror(d, p.x, p.y, p.z, d.charge[a]);
     d.posq[(size_t)r * d.N + a] = pf;
     d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * d.N + a]] = pf;
     if (a == 0 && request_rebuild) d.g[r].rebuild_request = 1;
