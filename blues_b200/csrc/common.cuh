@@ -71,15 +71,20 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
 
 __host__ __device__ __forceinline__ double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 
-// three standard normals for (seed, stream, replica, counter, index) — Box–Muller in double
-__device__ __forceinline__ void philox_normal3(uint64_t seed, uint32_t stream, uint32_t replica, uint32_t counter,
-                                               uint32_t index, double& n0, double& n1, double& n2) {
+// three standard normals for (seed, stream, replica, counter, index) — Box–Muller in double.
+// Deliberately not inlined: the double-precision log / sincospi expansions are ~1k instructions and the integrator
+// calls this once per atom and thermostat op; inlining them everywhere overflows the instruction cache.
+__device__ __noinline__ double3 philox_normal3v(uint64_t seed, uint32_t stream, uint32_t replica, uint32_t counter,
+                                                uint32_t index) {
     Philox4 r = philox4x32_10(index, counter, replica, stream, (uint32_t)seed, (uint32_t)(seed >> 32));
     double r0 = sqrt(-2.0 * log(u01(r.x)));
     double r1 = sqrt(-2.0 * log(u01(r.z)));
     double s, c;
     sincospi(2.0 * u01(r.y), &s, &c);
-    n0 = r0 * c;
-    n1 = r0 * s;
-    n2 = r1 * cospi(2.0 * u01(r.w));
+    return make_double3(r0 * c, r0 * s, r1 * cospi(2.0 * u01(r.w)));
+}
+__device__ __forceinline__ void philox_normal3(uint64_t seed, uint32_t stream, uint32_t replica, uint32_t counter,
+                                               uint32_t index, double& n0, double& n1, double& n2) {
+    const double3 v = philox_normal3v(seed, stream, replica, counter, index);
+    n0 = v.x; n1 = v.y; n2 = v.z;
 }

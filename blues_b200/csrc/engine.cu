@@ -45,6 +45,7 @@ struct bl_handle {
     bool vel_dirty = true;        // cm_acc must be recomputed
     int* cm_parity = nullptr;     // device int
     int n_cons_total = 0;
+    int n_generic = 0;            // clusters handled by the dynamic-index fallback kernel (sorted first)
     // cuFFT
     cufftHandle plan_r2c = 0, plan_c2r = 0;
     bool has_fft = false;
@@ -136,16 +137,19 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         int blocks = std::max(1, std::min(cdiv(nf, 256 * 4), 148 * 8));
         k_begin_eval<<<blocks, 256, 0, st>>>(d, adv_noise, adv_md, cm_mode, h->cm_parity);
     }
+    {
+        LaunchTimer t(h, BL_K_NEIGHBOR);
+        k_sort_atoms<<<dim3(SORT_CTAS, R), 1024, 0, st>>>(d);
+    }
     const bool fork = d.pme && h->has_fft;
     if (fork) {
-        // reciprocal space needs only the positions: run it on the second stream, concurrently with the neighbour
-        // search, the pair kernel, the bonded terms and the alchemical kernel; joined before returning
+        // reciprocal space needs only the (cell-sorted) positions: run it on the second stream, concurrently with the
+        // list build / prune, the pair kernel, the bonded terms and the alchemical kernel; joined before returning
         cudaStream_t s2 = h->stream2;
         cudaEventRecord(h->ev_fork, st);
         cudaStreamWaitEvent(s2, h->ev_fork, 0);
-        { LaunchTimer t(h, BL_K_PME_SPREAD, s2); k_pme_spread<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
         { LaunchTimer t(h, BL_K_PME_SPREAD, s2);
-          k_pme_finish<<<std::max(1, std::min(cdiv((long long)R * d.gsize, 256), 148 * 8)), 256, 0, s2>>>(d); }
+          k_pme_spread<<<dim3(d.gx, R), 256, d.gy * d.gz * sizeof(int), s2>>>(d); }
         { LaunchTimer t(h, BL_K_FFT, s2); cufftExecR2C(h->plan_r2c, d.grid_r, reinterpret_cast<cufftComplex*>(d.grid_c)); }
         { LaunchTimer t(h, BL_K_PME_CONVOLVE, s2);
           if (energy) k_pme_convolve<true><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d);
@@ -156,12 +160,15 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     }
     {
         LaunchTimer t(h, BL_K_NEIGHBOR);
-        const int smem_cells = (d.ncells + 1) * (int)sizeof(int) <= 40 * 1024 ? 1 : 0;
-        k_sort_atoms<<<R, 1024, smem_cells ? (d.ncells + 1) * sizeof(int) : 0, st>>>(d, smem_cells);
+        dim3 grid(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R);
+        if (d.nl_u16) k_build_list<unsigned short><<<grid, NL_BLOCK, 0, st>>>(d);
+        else k_build_list<int><<<grid, NL_BLOCK, 0, st>>>(d);
     }
     {
         LaunchTimer t(h, BL_K_NEIGHBOR);
-        k_build_list<<<dim3(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R), NL_BLOCK, 0, st>>>(d);
+        dim3 grid(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R);
+        if (d.nl_u16) k_prune_list<unsigned short><<<grid, NL_BLOCK, 0, st>>>(d);
+        else k_prune_list<int><<<grid, NL_BLOCK, 0, st>>>(d);
     }
     if (d.n_alch > 0) {
         { LaunchTimer t(h, BL_K_NEIGHBOR); k_alch_reset<<<cdiv(R * d.n_alch, 128), 128, 0, st>>>(d); }
@@ -171,12 +178,14 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     {
         LaunchTimer t(h, BL_K_PAIR);
         dim3 grid(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R);
-#define PAIR(M)                                                               \
-        if (energy) k_pair<M, true><<<grid, NL_BLOCK, 0, st>>>(d);            \
-        else k_pair<M, false><<<grid, NL_BLOCK, 0, st>>>(d)
+#define PAIR2(M, E)                                                           \
+        if (d.nl_u16) k_pair<M, E, unsigned short><<<grid, NL_BLOCK, 0, st>>>(d); \
+        else k_pair<M, E, int><<<grid, NL_BLOCK, 0, st>>>(d)
+#define PAIR(M) if (energy) { PAIR2(M, true); } else { PAIR2(M, false); }
         if (d.nb_method == 4) { PAIR(NB_PME); }
         else if (d.nb_method == 2) { PAIR(NB_RF); }
         else { PAIR(NB_NOCUT); }
+#undef PAIR2
 #undef PAIR
     }
     {
@@ -194,6 +203,11 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
 }
 
 static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a) {
+    if (h->n_generic > 0) {
+        // generic clusters are sorted first; they must not also run the bookkeeping ops of the main kernel
+        LaunchTimer t(h, BL_K_INTEGRATE);
+        k_integrate_generic<<<dim3(cdiv(h->n_generic, 64), h->d.R), 64, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity, h->n_generic);
+    }
     LaunchTimer t(h, BL_K_INTEGRATE);
     k_integrate<<<dim3(cdiv(h->d.n_clusters, 64), h->d.R), 64, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity);
 }
@@ -471,6 +485,7 @@ static bool build_clusters(bl_handle* h, const bl_topology* t, std::vector<Clust
         }
     }
     // homogeneous warps: order constrained clusters by (shape, ncons), then the free atoms
+    for (Cluster& c : cl) if (c.shape == 0 && c.ncons > 3) c.shape = 2;      // stars with > 3 constraints: generic path
     std::stable_sort(cl.begin(), cl.end(), [](const Cluster& a, const Cluster& b) {
         return a.shape != b.shape ? a.shape > b.shape : a.ncons > b.ncons;
     });
@@ -636,6 +651,10 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     d.cutoff = (float)t->cutoff; d.cutoff2 = (float)(t->cutoff * t->cutoff);
     double skin = d.periodic ? 0.1 * t->cutoff : 0.0;
     if (d.periodic && getenv("BLUES_B200_SKIN")) skin = std::max(0.01, atof(getenv("BLUES_B200_SKIN")));
+    double skin_outer = d.periodic ? std::max(skin * 3.5, 0.35 * t->cutoff) : 0.0;
+    if (d.periodic && getenv("BLUES_B200_SKIN_OUTER")) skin_outer = std::max(skin * 1.5, atof(getenv("BLUES_B200_SKIN_OUTER")));
+    d.outer_cutoff2 = d.periodic ? (float)((t->cutoff + skin_outer) * (t->cutoff + skin_outer)) : 3.0e38f;
+    d.outer_half2 = d.periodic ? (float)(0.25 * (skin_outer - skin) * (skin_outer - skin)) : 3.0e38f;
     d.list_cutoff2 = d.periodic ? (float)((t->cutoff + skin) * (t->cutoff + skin)) : 3.0e38f;
     d.skin_half2 = d.periodic ? (float)(0.25 * skin * skin) : 3.0e38f;
     d.alpha = (float)t->ewald_alpha;
@@ -760,6 +779,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (!build_clusters(h, t, clusters)) return fail(BL_ERR_INVALID, "constraint cluster too large (max 5 atoms / 4 constraints per cluster)");
     // water triangles have 3 constraints among 3 atoms; everything else is a star — both fit
     d.n_clusters = (int)clusters.size();
+    for (const Cluster& c : clusters) if (c.shape == 2 || (c.shape == 0 && c.ncons > 3)) h->n_generic++;
     d.clusters = dupload(h, clusters);
     h->n_cons_total = t->n_constraints;
     // dynamic state
@@ -778,7 +798,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     h->d_scratch = dalloc<double>(h, std::max((size_t)R * 4, (size_t)N * 3));
     h->d_iscratch = dalloc<int>(h, (size_t)R * 2);
     // neighbour structures
-    h->skin = skin;
+    h->skin = skin_outer;     // the cell grid serves the outer list
     {
         int rc = setup_cells(h, t->box);
         if (rc != BL_OK) return fail(rc, h->error);
@@ -797,14 +817,31 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         d.nl_M = (int)((M + 7) / 8 * 8);
     }
     d.nl_count = dalloc<int>(h, (size_t)R * d.Npad);
-    d.nl_list = dalloc<int>(h, (size_t)R * d.Npad * d.nl_M);
+    d.nl_u16 = d.Npad < 65536 ? 1 : 0;
+    d.nl_list = dalloc<unsigned char>(h, (size_t)R * d.Npad * d.nl_M * (d.nl_u16 ? 2 : 4));
+    {
+        long long M = N;
+        if (d.periodic) {
+            const double V = t->box[0] * t->box[1] * t->box[2], rl = t->cutoff + skin_outer;
+            M = std::min<long long>(N, (long long)(1.5 * 4.0 / 3.0 * M_PI * rl * rl * rl * N / V) + 96);
+        }
+        d.nlo_M = (int)((M + 7) / 8 * 8);
+    }
+    d.nlo_count = dalloc<int>(h, (size_t)R * d.Npad);
+    d.nlo_list = dalloc<unsigned char>(h, (size_t)R * d.Npad * d.nlo_M * (d.nl_u16 ? 2 : 4));
+    d.pos_ref_outer = dalloc<float4>(h, RN);
     // PME
     if (d.pme) {
         d.gx = t->pme_grid[0]; d.gy = t->pme_grid[1]; d.gz = t->pme_grid[2];
         if (d.gx < PME_ORDER || d.gy < PME_ORDER || d.gz < PME_ORDER) return fail(BL_ERR_INVALID, "PME grid too small");
         d.gsize = d.gx * d.gy * d.gz;
         d.csize = d.gx * d.gy * (d.gz / 2 + 1);
-        d.grid_fx = dalloc<long long>(h, (size_t)R * d.gsize);
+        {
+            const size_t plane_bytes = (size_t)d.gy * d.gz * sizeof(int);
+            if (plane_bytes > 200 * 1024) return fail(BL_ERR_INVALID, "PME grid plane does not fit in shared memory");
+            if (plane_bytes > 48 * 1024)
+                cudaFuncSetAttribute(k_pme_spread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes);
+        }
         d.grid_r = dalloc<float>(h, (size_t)R * d.gsize);
         d.grid_c = dalloc<float2>(h, (size_t)R * d.csize);
         std::vector<float> mx, my, mz;
@@ -830,7 +867,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     // initial globals
     std::vector<Globals> g0(R);
     memset(g0.data(), 0, sizeof(Globals) * R);
-    for (auto& g : g0) { g.prop = 1; g.rebuild_request = 1; }
+    for (auto& g : g0) { g.prop = 1; g.rebuild_request = 2; g.prune_request = 1; }
     cudaMemcpy(d.g, g0.data(), sizeof(Globals) * R, cudaMemcpyHostToDevice);
     // identity ordering so that mirrors can be written before the first rebuild
     {
@@ -1399,7 +1436,9 @@ int bl_neighbor_pairs(bl_handle* h, int replica, int64_t* codes, size_t capacity
     CK(cudaMalloc(&dcodes, sizeof(long long) * std::max<size_t>(capacity, 1)));
     CK(cudaMalloc(&dn, sizeof(unsigned long long)));
     CK(cudaMemsetAsync(dn, 0, sizeof(unsigned long long), h->stream));
-    { LaunchTimer t(h, -1); k_neighbor_pairs<<<148 * 4, 128, 0, h->stream>>>(d, replica, dcodes, capacity, dn); }
+    { LaunchTimer t(h, -1);
+      if (d.nl_u16) k_neighbor_pairs<unsigned short><<<148 * 4, 128, 0, h->stream>>>(d, replica, dcodes, capacity, dn);
+      else k_neighbor_pairs<int><<<148 * 4, 128, 0, h->stream>>>(d, replica, dcodes, capacity, dn); }
     unsigned long long n = 0;
     CK(cudaMemcpyAsync(&n, dn, sizeof n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

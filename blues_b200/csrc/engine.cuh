@@ -37,7 +37,8 @@ struct Globals {
     int e_valid;             // e_total_prev is valid
     int nan_flag;
     unsigned int noise_counter, vel_counter, move_counter, accept_counter, md_counter;
-    int do_rebuild, rebuild_request;
+    int do_rebuild, rebuild_request;   // outer list (cell search)
+    int do_prune, prune_request;       // inner list (prune of the outer list)
     long long n_rebuilds;
     int item_overflow;        // a neighbour list ran out of capacity
 };
@@ -87,9 +88,13 @@ struct Dev {
     int* atom_cell;                         // [R*N]
     int* rank;                              // [R*N] position of atom a in the sorted order
     float4* posq_s; float2* sigeps_s; int* orig_s;   // [R*Npad] sorted copies (pads: NaN position, orig -1)
-    int nl_M;                               // list capacity per atom
+    int nlo_M; int* nlo_count; void* nlo_list;   // outer list (cutoff + outer skin), rebuilt with the cell search
+    float4* pos_ref_outer;                  // [R*N] positions at the last outer rebuild
+    float outer_cutoff2, outer_half2;       // squared outer list cutoff; squared displacement budget of the outer list
+    int nl_M;                               // inner list capacity per atom
     int* nl_count;                          // [R*Npad]
-    int* nl_list;                           // [R*Npad][nl_M] sorted indices of the neighbours within the list cutoff
+    void* nl_list;                          // [R*Npad][nl_M] sorted indices of the neighbours within the list cutoff
+    int nl_u16;                             // indices stored as uint16 (Npad < 65536) to halve the list traffic
     // bonded tables
     int n_bonds, n_angles, n_torsions, n_excl, n_restraints, n_alch_exc;
     int2* bonds; double2* bond_p;           // (k, r0)
@@ -108,7 +113,6 @@ struct Dev {
     double* lam_s; double* lam_e; int n_lambda;       // tables indexed by lambda_step
     // PME
     int gx, gy, gz; int gsize; int csize;   // real grid size, complex grid size (gx*gy*(gz/2+1))
-    long long* grid_fx;                     // [R][gsize] fixed point
     float* grid_r;                          // [R][gsize]
     float2* grid_c;                         // [R][csize]
     float* bmod_x; float* bmod_y; float* bmod_z;

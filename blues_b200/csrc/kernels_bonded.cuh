@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128) k_bonded(Dev d) {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_alch_list(Dev d) {
     const int r = blockIdx.y;
-    if (!d.g[r].do_rebuild) return;
+    if (!d.g[r].do_prune) return;
     const int N = d.N, na = d.n_alch;
     extern __shared__ float4 s_apos[];           // [na] alchemical positions (w = orig index as float bits)
     const float4* posq = d.posq + (size_t)r * N;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(128) k_alch_list(Dev d) {
 __global__ void k_alch_reset(Dev d) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= d.R * d.n_alch) return;
-    if (d.g[idx / d.n_alch].do_rebuild) d.alch_count[idx] = 0;
+    if (d.g[idx / d.n_alch].do_prune) d.alch_count[idx] = 0;
 }
 
 __global__ void __launch_bounds__(128) k_alch(Dev d) {

@@ -259,7 +259,7 @@ struct FixedCluster {
 template <int NA, int NC, int SHAPE>
 __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts& ic, const IntegrateArgs& args,
                                             const Cluster& c, int r, int parity, unsigned int noise0, unsigned int md0,
-                                            double (&mom)[3], double& dheat, bool& moved, bool& bad) {
+                                            double (&mom)[3], double& dheat, bool& moved, bool& bad, bool& moved_outer) {
     const int N = d.N;
     double4* pos = d.pos + (size_t)r * N;
     double4* vel = d.vel + (size_t)r * N;
@@ -279,8 +279,14 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
 #pragma unroll
     for (int a = 0; a < NC; ++a) s.d2[a] = c.d2[a];
     int n_o = 0, n_md = 0;
+    double xref[NA][3], x1[NA][3];
+    // every op = [update] -> optional SHAKE -> [velocity fix-up] -> optional RATTLE, so that the constraint solvers
+    // are instantiated once per cluster shape (keeps the kernel small enough for the instruction cache)
     for (int o = 0; o < args.nops; ++o) {
         const Op op = args.ops[o];
+        bool do_shake = false, do_rattle = false;
+        int post = 0;
+        double ke0 = 0.0;
         if (op.kind == OP_CM) {
             if (ic.remove_cm) {
                 const long long* cm = d.cm_acc + ((size_t)parity * d.R + r) * 3;
@@ -302,9 +308,8 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                     s.v[k][q] += sc * (double)f;
                 }
             }
-            s.rattle();
+            do_rattle = true;
         } else if (op.kind == OP_R) {
-            double xref[NA][3], x1[NA][3];
 #pragma unroll
             for (int k = 0; k < NA; ++k)
 #pragma unroll
@@ -313,15 +318,9 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                     if (s.im[k] > 0.0) s.x[k][q] += ic.hR * s.v[k][q];
                     x1[k][q] = s.x[k][q];
                 }
-            s.shake(xref, ic.tol);
-            const double ih = 1.0 / ic.hR;
-#pragma unroll
-            for (int k = 0; k < NA; ++k)
-#pragma unroll
-                for (int q = 0; q < 3; ++q) s.v[k][q] += (s.x[k][q] - x1[k][q]) * ih;
-            s.rattle();
+            do_shake = do_rattle = true;
+            post = 1;
         } else if (op.kind == OP_O) {
-            double ke0 = 0.0, ke1 = 0.0;
 #pragma unroll
             for (int k = 0; k < NA; ++k) {
                 ke0 += 0.5 * s.mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
@@ -335,13 +334,9 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                 }
             }
             ++n_o;
-            s.rattle();
-#pragma unroll
-            for (int k = 0; k < NA; ++k)
-                ke1 += 0.5 * s.mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
-            dheat += ke1 - ke0;
+            do_rattle = true;
+            post = 3;
         } else if (op.kind == OP_MD) {
-            double xref[NA][3];
 #pragma unroll
             for (int k = 0; k < NA; ++k) {
                 double n[3] = {0.0, 0.0, 0.0};
@@ -361,21 +356,37 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                 }
             }
             ++n_md;
-            s.shake(xref, ic.tol);
+            do_shake = true;
+            post = 2;
+        } else if (op.kind == OP_CONSTRAIN) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) xref[k][q] = s.x[k][q];
+            do_shake = do_rattle = true;
+        }
+        if (do_shake) s.shake(xref, ic.tol);
+        if (post == 1) {
+            const double ih = 1.0 / ic.hR;
+#pragma unroll
+            for (int k = 0; k < NA; ++k)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) s.v[k][q] += (s.x[k][q] - x1[k][q]) * ih;
+        } else if (post == 2) {
             const double idt = 1.0 / ic.dt;
 #pragma unroll
             for (int k = 0; k < NA; ++k)
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     if (s.im[k] > 0.0) s.v[k][q] = (s.x[k][q] - xref[k][q]) * idt;
-        } else if (op.kind == OP_CONSTRAIN) {
-            double xref[NA][3];
+        }
+        if (do_rattle) s.rattle();
+        if (post == 3) {
+            double ke1 = 0.0;
 #pragma unroll
             for (int k = 0; k < NA; ++k)
-#pragma unroll
-                for (int q = 0; q < 3; ++q) xref[k][q] = s.x[k][q];
-            s.shake(xref, ic.tol);
-            s.rattle();
+                ke1 += 0.5 * s.mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
+            dheat += ke1 - ke0;
         }
     }
     const float lim = d.skin_half2;
@@ -389,12 +400,19 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
         d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * N + a]] = pf;
         const float4 pr = d.pos_ref[(size_t)r * N + a];
         float ddx = pf.x - pr.x, ddy = pf.y - pr.y, ddz = pf.z - pr.z;
+        const float4 po = d.pos_ref_outer[(size_t)r * N + a];
+        float ox = pf.x - po.x, oy = pf.y - po.y, oz = pf.z - po.z;
         if (d.periodic) {
             ddx -= d.boxf[0] * rintf(ddx * d.boxf[3]);
             ddy -= d.boxf[1] * rintf(ddy * d.boxf[4]);
             ddz -= d.boxf[2] * rintf(ddz * d.boxf[5]);
+            ox -= d.boxf[0] * rintf(ox * d.boxf[3]);
+            oy -= d.boxf[1] * rintf(oy * d.boxf[4]);
+            oz -= d.boxf[2] * rintf(oz * d.boxf[5]);
         }
         moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
+        bad = bad || false;
+        moved_outer = moved_outer || (ox * ox + oy * oy + oz * oz > d.outer_half2);
         bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
 #pragma unroll
         for (int q = 0; q < 3; ++q) mom[q] += s.mass[k] * s.v[k][q];
@@ -402,9 +420,9 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
 }
 
 // generic fallback (dynamic indexing, local memory): clusters that are neither stars nor water triangles
-__device__ __noinline__ void run_cluster_generic(const Dev& d, const IntegratorConsts& ic, const IntegrateArgs& args,
+__device__ __forceinline__ void run_cluster_generic(const Dev& d, const IntegratorConsts& ic, const IntegrateArgs& args,
                                                  const Cluster& c, int r, int parity, unsigned int noise0,
-                                                 unsigned int md0, double (&mom)[3], double& dheat, bool& moved, bool& bad) {
+                                                 unsigned int md0, double (&mom)[3], double& dheat, bool& moved, bool& bad, bool& moved_outer) {
     const int N = d.N;
     double4* pos = d.pos + (size_t)r * N;
     double4* vel = d.vel + (size_t)r * N;
@@ -524,12 +542,19 @@ __device__ __noinline__ void run_cluster_generic(const Dev& d, const IntegratorC
         d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * N + a]] = pf;
         const float4 pr = d.pos_ref[(size_t)r * N + a];
         float ddx = pf.x - pr.x, ddy = pf.y - pr.y, ddz = pf.z - pr.z;
+        const float4 po = d.pos_ref_outer[(size_t)r * N + a];
+        float ox = pf.x - po.x, oy = pf.y - po.y, oz = pf.z - po.z;
         if (d.periodic) {
             ddx -= d.boxf[0] * rintf(ddx * d.boxf[3]);
             ddy -= d.boxf[1] * rintf(ddy * d.boxf[4]);
             ddz -= d.boxf[2] * rintf(ddz * d.boxf[5]);
+            ox -= d.boxf[0] * rintf(ox * d.boxf[3]);
+            oy -= d.boxf[1] * rintf(oy * d.boxf[4]);
+            oz -= d.boxf[2] * rintf(oz * d.boxf[5]);
         }
         moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
+        bad = bad || false;
+        moved_outer = moved_outer || (ox * ox + oy * oy + oz * oz > d.outer_half2);
         bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
         for (int q = 0; q < 3; ++q) mom[q] += mass[k] * s.v[k][q];
     }
@@ -543,21 +568,21 @@ __global__ void __launch_bounds__(64) k_integrate(Dev d, IntegratorConsts ic, In
     const int parity = *cm_parity;
     double mom[3] = {0.0, 0.0, 0.0};
     double dheat = 0.0;
-    bool moved = false, bad = false;
+    bool moved = false, bad = false, moved_outer = false;
     if (cid < d.n_clusters) {
         const Cluster c = d.clusters[cid];
         const unsigned int noise0 = g.noise_counter + args.noise_offset, md0 = g.md_counter + args.md_offset;
         const int key = c.shape * 16 + c.ncons;
         switch (key) {
-        case SHAPE_STAR * 16 + 0: run_cluster<1, 0, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
-        case SHAPE_STAR * 16 + 1: run_cluster<2, 1, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
-        case SHAPE_STAR * 16 + 2: run_cluster<3, 2, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
-        case SHAPE_STAR * 16 + 3: run_cluster<4, 3, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
-        case SHAPE_STAR * 16 + 4: run_cluster<5, 4, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
-        case SHAPE_TRI * 16 + 3: run_cluster<3, 3, SHAPE_TRI>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
-        default: run_cluster_generic(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_STAR * 16 + 0: run_cluster<1, 0, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
+        case SHAPE_STAR * 16 + 1: run_cluster<2, 1, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
+        case SHAPE_STAR * 16 + 2: run_cluster<3, 2, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
+        case SHAPE_STAR * 16 + 3: run_cluster<4, 3, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
+        case SHAPE_TRI * 16 + 3: run_cluster<3, 3, SHAPE_TRI>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
+        default: break;      // generic clusters are integrated by k_integrate_generic
         }
-        if (moved) g.rebuild_request = 1;
+        if (moved) g.prune_request = 1;
+        if (moved_outer && g.rebuild_request == 0) g.rebuild_request = 1;
         if (bad) g.nan_flag = 1;
     }
     if (args.accum_cm && ic.remove_cm) {
@@ -601,6 +626,36 @@ __global__ void __launch_bounds__(64) k_integrate(Dev d, IntegratorConsts ic, In
     }
 }
 
+// clusters that are neither stars (<= 3 constraints) nor water triangles: dynamic-index fallback, own kernel so that
+// its stack frame and code do not burden the main integrator
+__global__ void __launch_bounds__(64) k_integrate_generic(Dev d, IntegratorConsts ic, IntegrateArgs args, const int* cm_parity,
+                                                         int n_generic) {
+    const int r = blockIdx.y;
+    const int cid = blockIdx.x * blockDim.x + threadIdx.x;
+    Globals& g = d.g[r];
+    const int parity = *cm_parity;
+    double mom[3] = {0.0, 0.0, 0.0};
+    double dheat = 0.0;
+    bool moved = false, bad = false, moved_outer = false;
+    if (cid < n_generic) {
+        const Cluster c = d.clusters[cid];
+        const unsigned int noise0 = g.noise_counter + args.noise_offset, md0 = g.md_counter + args.md_offset;
+        run_cluster_generic(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer);
+        if (moved) g.prune_request = 1;
+        if (moved_outer && g.rebuild_request == 0) g.rebuild_request = 1;
+        if (bad) g.nan_flag = 1;
+    }
+    if (args.accum_cm && ic.remove_cm) {
+        const int target = args.accum_cm == 1 ? parity : 1 - parity;
+        for (int q = 0; q < 3; ++q) {
+            const double v = warp_sum(mom[q]);
+            if ((threadIdx.x & 31) == 0) fx_add(&d.cm_acc[((size_t)target * d.R + r) * 3 + q], v, FORCE_SCALE);
+        }
+    }
+    const double v = warp_sum(dheat);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) fx_add(&d.heat_acc[r], v, ENERGY_SCALE);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // small state kernels
 // ---------------------------------------------------------------------------------------------------------
@@ -613,7 +668,7 @@ __global__ void k_refresh_mirrors(Dev d, int request_rebuild) {
     const float4 pf = wrapped_mirror(d, p.x, p.y, p.z, d.charge[a]);
     d.posq[(size_t)r * d.N + a] = pf;
     d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * d.N + a]] = pf;
-    if (a == 0 && request_rebuild) d.g[r].rebuild_request = 1;
+    if (a == 0 && request_rebuild) { d.g[r].rebuild_request = 2; d.g[r].prune_request = 1; }
 }
 
 __global__ void k_momentum(Dev d, const int* cm_parity) {

@@ -1,5 +1,6 @@
 // Neighbour-list construction (K1) and the tiled direct-space pair kernel (K2).
 #pragma once
+#include <cooperative_groups.h>
 #include "engine.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
@@ -18,8 +19,12 @@ __global__ void k_begin_eval(Dev d, int advance_noise, int advance_md, int cm_mo
         for (int i = threadIdx.x; i < d.R * ALCH_SLOTS * 3; i += blockDim.x) d.alch_acc[i] = 0;
         for (int i = threadIdx.x; i < d.R; i += blockDim.x) {
             Globals& g = d.g[i];
-            g.do_rebuild = g.rebuild_request;
+            // an inner-list refresh is due when some atom moved > inner skin / 2 since the last prune; it becomes a
+            // full rebuild when, at that moment, some atom sits > (outer - inner skin) / 2 away from the outer reference
+            g.do_rebuild = g.rebuild_request == 2 || (g.prune_request && g.rebuild_request);
+            g.do_prune = g.prune_request || g.do_rebuild;
             g.rebuild_request = 0;
+            g.prune_request = 0;
             g.noise_counter += advance_noise;
             g.md_counter += advance_md;
         }
@@ -47,23 +52,27 @@ __device__ __forceinline__ void atom_cell_coords(const Dev& d, float4 p, int& cx
     cz = max(0, min((int)(wrap01(p.z * d.boxf[5]) * d.ncell[2]), d.ncell[2] - 1));
 }
 
-__global__ void __launch_bounds__(1024) k_sort_atoms(Dev d, int smem_cells) {
-    const int r = blockIdx.x;
+#define SORT_CTAS 8
+__global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort_atoms(Dev d) {
+    // one thread-block cluster (8 CTAs, hardware cluster barrier) per walker
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = blockIdx.y;
     Globals& g = d.g[r];
-    if (!g.do_rebuild) return;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    if (!g.do_rebuild) return;                 // uniform over the cluster
+    const int cta = (int)cluster.block_rank();
+    const int tid = cta * blockDim.x + threadIdx.x, nt = SORT_CTAS * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int N = d.N, Npad = d.Npad, ncells = d.ncells;
-    extern __shared__ int s_cells[];            // [ncells + 1] counters / cursors when they fit in shared memory
     int* start = d.cell_start + (size_t)r * (ncells + 1);
-    int* cursor = smem_cells ? s_cells : d.cell_cursor + (size_t)r * (ncells + 1);
+    int* cursor = d.cell_cursor + (size_t)r * (ncells + 1);
     int* acell = d.atom_cell + (size_t)r * N;
     const float4* posq = d.posq + (size_t)r * N;
     int* orig_s = d.orig_s + (size_t)r * Npad;
     __shared__ int s_part[1024];
 
     for (int c = tid; c <= ncells; c += nt) cursor[c] = 0;
-    __syncthreads();
+    cluster.sync();
     for (int a = tid; a < N; a += nt) {
         int cell = 0;
         if (d.periodic) {
@@ -74,27 +83,30 @@ __global__ void __launch_bounds__(1024) k_sort_atoms(Dev d, int smem_cells) {
         acell[a] = cell;
         atomicAdd(&cursor[cell], 1);
     }
-    __syncthreads();
-    // exclusive scan of the per-cell counts
-    const int per = (ncells + nt - 1) / nt;
-    const int c0 = min(tid * per, ncells), c1 = min(c0 + per, ncells);
-    int sum = 0;
-    for (int c = c0; c < c1; ++c) sum += cursor[c];
-    s_part[tid] = sum;
-    __syncthreads();
-    for (int off = 1; off < nt; off <<= 1) {
-        int v = (tid >= off) ? s_part[tid - off] : 0;
+    cluster.sync();
+    if (cta == 0) {
+        // exclusive scan of the per-cell counts by the first CTA
+        const int t = threadIdx.x, n1 = blockDim.x;
+        const int per = (ncells + n1 - 1) / n1;
+        const int c0 = min(t * per, ncells), c1 = min(c0 + per, ncells);
+        int sum = 0;
+        for (int c = c0; c < c1; ++c) sum += cursor[c];
+        s_part[t] = sum;
         __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
+        for (int off = 1; off < n1; off <<= 1) {
+            int v = (t >= off) ? s_part[t - off] : 0;
+            __syncthreads();
+            s_part[t] += v;
+            __syncthreads();
+        }
+        int run = s_part[t] - sum;
+        for (int c = c0; c < c1; ++c) { int v = cursor[c]; start[c] = run; cursor[c] = run; run += v; }
+        if (t == n1 - 1) start[ncells] = N;
     }
-    int run = s_part[tid] - sum;
-    for (int c = c0; c < c1; ++c) { int v = cursor[c]; start[c] = run; cursor[c] = run; run += v; }
-    if (tid == nt - 1) start[ncells] = N;
-    __syncthreads();
+    cluster.sync();
     // scatter (arbitrary order inside a cell) ...
     for (int a = tid; a < N; a += nt) orig_s[atomicAdd(&cursor[acell[a]], 1)] = a;
-    __syncthreads();
+    cluster.sync();
     // ... then order every cell's segment by topology index: one warp per cell, rank by counting smaller keys
     for (int c = warp; c < ncells; c += nwarps) {
         const int s0 = start[c], n = start[c + 1] - s0;
@@ -120,11 +132,11 @@ __global__ void __launch_bounds__(1024) k_sort_atoms(Dev d, int smem_cells) {
             }
         }
     }
-    __syncthreads();
+    cluster.sync();
     int* rank = d.rank + (size_t)r * N;
     float4* posq_s = d.posq_s + (size_t)r * Npad;
     float2* sigeps_s = d.sigeps_s + (size_t)r * Npad;
-    float4* pos_ref = d.pos_ref + (size_t)r * N;
+    float4* pos_ref = d.pos_ref_outer + (size_t)r * N;
     for (int s = tid; s < N; s += nt) {
         const int a = orig_s[s];
         rank[a] = s;
@@ -173,7 +185,7 @@ __device__ __forceinline__ bool pair_excluded(const Dev& d, int oi, ull wi, bool
 // ---------------------------------------------------------------------------------------------------------
 #define NL_LANES 8
 #define NL_BLOCK 128
-
+template <typename IDX>
 __global__ void __launch_bounds__(NL_BLOCK) k_build_list(Dev d) {
     const int r = blockIdx.y;
     Globals& g = d.g[r];
@@ -188,7 +200,7 @@ __global__ void __launch_bounds__(NL_BLOCK) k_build_list(Dev d) {
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
     const int* __restrict__ orig_s = d.orig_s + (size_t)r * Npad;
     const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
-    int* list = d.nl_list + ((size_t)r * Npad + i) * d.nl_M;
+    IDX* list = reinterpret_cast<IDX*>(d.nlo_list) + ((size_t)r * Npad + i) * d.nlo_M;
     int cnt = 0;
     if (i < N) {
         const float4 pi = posq_s[i];
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(NL_BLOCK) k_build_list(Dev d) {
         const ull wi = d.excl_win[oi];
         const bool fari = d.has_far[oi];
         const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
-        const float cut2 = d.list_cutoff2;
+        const float cut2 = d.outer_cutoff2;
         const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
         // positions in the sorted mirror are wrapped into the box, so a periodic image is a per-cell constant shift;
         // dimensions with fewer than 5 cells are scanned completely and use the rint() minimum image instead
@@ -240,16 +252,72 @@ __global__ void __launch_bounds__(NL_BLOCK) k_build_list(Dev d) {
                         const unsigned int m = (__ballot_sync(submask, ok) & submask) >> gshift;
                         if (ok) {
                             const int slot = cnt + __popc(m & ((1u << part) - 1u));
-                            if (slot < d.nl_M) list[slot] = s;
+                            if (slot < d.nlo_M) list[slot] = (IDX)s;
                         }
                         cnt += __popc(m);
                     }
                 }
             }
         }
-        if (cnt > d.nl_M) { g.item_overflow = 1; cnt = d.nl_M; }
+        if (cnt > d.nlo_M) { g.item_overflow = 1; cnt = d.nlo_M; }
     }
-    if (part == 0) d.nl_count[(size_t)r * Npad + i] = cnt;
+    if (part == 0) d.nlo_count[(size_t)r * Npad + i] = cnt;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// k_prune_list: refresh the inner Verlet list (cutoff + inner skin) from the outer one (cutoff + outer skin) at the
+// current coordinates: NL_LANES lanes per atom stream the outer list (coalesced), keep the entries inside the inner
+// list cutoff with ordered sub-warp ballot compaction, and record the reference positions of the inner list.
+// Runs every few steps; the expensive cell search (k_sort_atoms + k_build_list) only every ~10-20 steps.
+// ---------------------------------------------------------------------------------------------------------
+template <typename IDX>
+__global__ void __launch_bounds__(NL_BLOCK) k_prune_list(Dev d) {
+    const int r = blockIdx.y;
+    Globals& g = d.g[r];
+    if (!g.do_prune) return;
+    const int lane = threadIdx.x & 31;
+    const int part = lane & (NL_LANES - 1);
+    const int gshift = lane & ~(NL_LANES - 1);
+    const unsigned int submask = ((1u << NL_LANES) - 1u) << gshift;
+    const int i = (blockIdx.x * NL_BLOCK + threadIdx.x) / NL_LANES;
+    const int N = d.N, Npad = d.Npad;
+    if (i >= Npad) return;
+    const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
+    const IDX* __restrict__ outer = reinterpret_cast<const IDX*>(d.nlo_list) + ((size_t)r * Npad + i) * d.nlo_M;
+    IDX* inner = reinterpret_cast<IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M;
+    const int n_outer = i < N ? d.nlo_count[(size_t)r * Npad + i] : 0;
+    const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
+    const float cut2 = d.list_cutoff2;
+    const float4 pi = posq_s[i];
+    int cnt = 0;
+    for (int base = 0; base < n_outer; base += NL_LANES) {
+        const int k = base + part;
+        bool ok = k < n_outer;
+        int s = 0;
+        if (ok) {
+            s = (int)outer[k];
+            const float4 pj = posq_s[s];
+            float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+            if (d.periodic) {
+                dx -= bx * rintf(dx * ibx);
+                dy -= by * rintf(dy * iby);
+                dz -= bz * rintf(dz * ibz);
+            }
+            ok = (dx * dx + dy * dy + dz * dz) < cut2;
+        }
+        const unsigned int m = (__ballot_sync(submask, ok) & submask) >> gshift;
+        if (ok) {
+            const int slot = cnt + __popc(m & ((1u << part) - 1u));
+            if (slot < d.nl_M) inner[slot] = (IDX)s;
+        }
+        cnt += __popc(m);
+    }
+    if (cnt > d.nl_M) { g.item_overflow = 1; cnt = d.nl_M; }
+    if (part == 0) {
+        d.nl_count[(size_t)r * Npad + i] = cnt;
+        if (i < N) d.pos_ref[(size_t)r * N + d.orig_s[(size_t)r * Npad + i]] = pi;     // inner-list reference positions
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -268,7 +336,7 @@ __device__ __forceinline__ float erfc_times(float ar, float expar) {
     return (0.254829592f + (-0.284496736f + (1.421413741f + (-1.453152027f + 1.061405429f * t) * t) * t) * t) * t * expar;
 }
 
-template <int METHOD, bool ENERGY>
+template <int METHOD, bool ENERGY, typename IDX>
 __global__ void __launch_bounds__(NL_BLOCK) k_pair(Dev d) {
     const int r = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -278,7 +346,7 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair(Dev d) {
     if (i >= Npad) return;
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
     const float2* __restrict__ sigeps_s = d.sigeps_s + (size_t)r * Npad;
-    const int* __restrict__ list = d.nl_list + ((size_t)r * Npad + i) * d.nl_M;
+    const IDX* __restrict__ list = reinterpret_cast<const IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M;
     const int cnt = d.nl_count[(size_t)r * Npad + i];
     const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2];
     const float ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
@@ -288,9 +356,9 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair(Dev d) {
     const float2 se_i = sigeps_s[i];
     const float qi = pi.w * (float)ONE_4PI_EPS0;
     float fx = 0.f, fy = 0.f, fz = 0.f, etot = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = part; k < cnt; k += NL_LANES) {
-        const int s = list[k];
+        const int s = (int)list[k];
         const float4 pj = posq_s[s];
         const float2 se_j = sigeps_s[s];
         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
@@ -350,6 +418,7 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair(Dev d) {
 // ---------------------------------------------------------------------------------------------------------
 // k_neighbor_pairs: enumerate (for tests) the non-excluded pairs within the cutoff found through the Verlet list.
 // ---------------------------------------------------------------------------------------------------------
+template <typename IDX>
 __global__ void k_neighbor_pairs(Dev d, int r, long long* codes, unsigned long long capacity, unsigned long long* n_out) {
     const int Npad = d.Npad;
     const float4* posq_s = d.posq_s + (size_t)r * Npad;
@@ -360,10 +429,10 @@ __global__ void k_neighbor_pairs(Dev d, int r, long long* codes, unsigned long l
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
         const float4 pi = posq_s[i];
         const int oi = orig_s[i];
-        const int* list = d.nl_list + ((size_t)r * Npad + i) * d.nl_M;
+        const IDX* list = reinterpret_cast<const IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M;
         const int cnt = d.nl_count[(size_t)r * Npad + i];
         for (int k = 0; k < cnt; ++k) {
-            const int s = list[k];
+            const int s = (int)list[k];
             const int oj = orig_s[s];
             if (oj < oi) continue;                       // full list: report each pair once
             const float4 pj = posq_s[s];

@@ -46,47 +46,61 @@ __device__ __forceinline__ void pme_atom_setup(const Dev& d, float4 p, int* base
     base[2] = iz >= d.gz ? iz - d.gz : iz;
 }
 
-__global__ void __launch_bounds__(128) k_pme_spread(Dev d) {
-    const int r = blockIdx.y;
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= d.N) return;
-    const float4 p = d.posq[(size_t)r * d.N + a];
-    if (p.w == 0.f) return;
-    int base[3];
-    float frac[3];
-    pme_atom_setup(d, p, base, frac);
-    float wx[PME_ORDER], wy[PME_ORDER], wz[PME_ORDER], dw[PME_ORDER];
-    bspline5(frac[0], wx, dw);
-    bspline5(frac[1], wy, dw);
-    bspline5(frac[2], wz, dw);
-    long long* grid = d.grid_fx + (size_t)r * d.gsize;
+// k_pme_spread: one CTA per x-plane of the charge grid (and walker).  The plane (gy x gz points) lives in shared
+// memory as 32-bit fixed point; the CTA walks the atoms whose order-5 stencil can touch the plane — a contiguous run
+// of the cell-sorted mirror, because cells are ordered with x slowest — and accumulates with shared-memory integer
+// atomics (order independent → deterministic).  The finished plane is written once, as float: no global atomics,
+// no separate conversion pass.
+#define SPREAD_SCALE 8388608.0f            /* 2^23 */
+__global__ void __launch_bounds__(256) k_pme_spread(Dev d) {
+    extern __shared__ int s_plane[];            // [gy * gz]
+    const int r = blockIdx.y, plane = blockIdx.x;
+    const int npts = d.gy * d.gz;
+    for (int k = threadIdx.x; k < npts; k += blockDim.x) s_plane[k] = 0;
+    __syncthreads();
+    const float4* __restrict__ posq_s = d.posq_s + (size_t)r * d.Npad;
+    const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
+    const int ncx = d.ncell[0], col = d.ncell[1] * d.ncell[2];
+    // atoms with base_x in [plane-4, plane]: fractional x in [(plane-4)/gx, (plane+1)/gx); one cell of margin each
+    // side because the sorted order is only refreshed with the outer neighbour list
+    int cxa = (int)floorf((float)(plane - 4) / d.gx * ncx) - 1;
+    int cxb = (int)floorf((float)(plane + 1) / d.gx * ncx) + 1;
+    if (cxb - cxa + 1 >= ncx) { cxa = 0; cxb = ncx - 1; }
+    for (int cxr = cxa; cxr <= cxb; ++cxr) {
+        const int cx = ((cxr % ncx) + ncx) % ncx;
+        const int s0 = start[cx * col], s1 = start[(cx + 1) * col];
+        for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+            const float4 p = posq_s[s];
+            if (p.w == 0.f) continue;
+            int base[3];
+            float frac[3];
+            pme_atom_setup(d, p, base, frac);
+            int i = plane - base[0];
+            if (i < 0) i += d.gx;
+            if (i >= PME_ORDER) continue;
+            float wx[PME_ORDER], wy[PME_ORDER], wz[PME_ORDER], dw[PME_ORDER];
+            bspline5(frac[0], wx, dw);
+            bspline5(frac[1], wy, dw);
+            bspline5(frac[2], wz, dw);
+            float qx = 0.f;
 #pragma unroll
-    for (int i = 0; i < PME_ORDER; ++i) {
-        int gx = base[0] + i; gx -= gx >= d.gx ? d.gx : 0;
-        const float qx = p.w * wx[i];
+            for (int k = 0; k < PME_ORDER; ++k) qx = (k == i) ? p.w * wx[k] : qx;
+            qx *= SPREAD_SCALE;
 #pragma unroll
-        for (int j = 0; j < PME_ORDER; ++j) {
-            int gy = base[1] + j; gy -= gy >= d.gy ? d.gy : 0;
-            const float qxy = qx * wy[j];
-            long long* row = grid + ((size_t)gx * d.gy + gy) * d.gz;
+            for (int j = 0; j < PME_ORDER; ++j) {
+                int gy = base[1] + j; gy -= gy >= d.gy ? d.gy : 0;
+                const float qxy = qx * wy[j];
 #pragma unroll
-            for (int k = 0; k < PME_ORDER; ++k) {
-                int gz = base[2] + k; gz -= gz >= d.gz ? d.gz : 0;
-                atomicAdd(reinterpret_cast<ull*>(&row[gz]),
-                          static_cast<ull>(static_cast<long long>((double)(qxy * wz[k]) * GRID_SCALE)));
+                for (int k = 0; k < PME_ORDER; ++k) {
+                    int gz = base[2] + k; gz -= gz >= d.gz ? d.gz : 0;
+                    atomicAdd(&s_plane[gy * d.gz + gz], __float2int_rn(qxy * wz[k]));
+                }
             }
         }
     }
-}
-
-// fixed point → float, and reset the fixed-point grid for the next evaluation
-__global__ void k_pme_finish(Dev d) {
-    const size_t n = (size_t)d.R * d.gsize;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        long long v = d.grid_fx[i];
-        d.grid_r[i] = (float)((double)v * (1.0 / GRID_SCALE));
-        d.grid_fx[i] = 0;
-    }
+    __syncthreads();
+    float* out = d.grid_r + (size_t)r * d.gsize + (size_t)plane * npts;
+    for (int k = threadIdx.x; k < npts; k += blockDim.x) out[k] = (float)s_plane[k] * (1.0f / SPREAD_SCALE);
 }
 
 // multiply the transformed charge grid by the influence function; optional energy
