@@ -220,12 +220,10 @@ def main():
     d2h = (nbytes + 8 + 4 + 16) * R / K
 
     # ---- statistics gather (the only collective; outside the data path) ------------------------------------------
-    stats = torch.tensor([[w, float(a)] for w, a in zip(works, acc)], device='cuda', dtype=torch.float64)
-    if world > 1:
-        gathered = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)
-        stats = torch.cat(gathered)
-    stats = stats.cpu().numpy()
+    from blues_b200 import parallel
+    local_ids = [rank + world * r for r in range(R)]           # walker w lives on rank w % world
+    gathered = parallel.gather_walker_stats(local_ids, works, logp, acc, device='cuda')
+    stats = np.stack([gathered['work_kT'], gathered['accepted'].astype(float)], axis=1)
 
     if rank != 0:
         if world > 1:

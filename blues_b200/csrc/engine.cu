@@ -28,7 +28,8 @@ struct bl_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // reciprocal-space branch, forked from / joined to `stream` inside every evaluation
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream3 = nullptr, stream4 = nullptr;   // bonded branch, alchemical branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
     std::string error;
     std::vector<void*> allocs;
     // host copies needed after creation
@@ -141,15 +142,19 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         LaunchTimer t(h, BL_K_NEIGHBOR);
         k_sort_atoms<<<dim3(SORT_CTAS, R), 1024, 0, st>>>(d);
     }
-    const bool fork = d.pme && h->has_fft;
-    if (fork) {
-        // reciprocal space needs only the (cell-sorted) positions: run it on the second stream, concurrently with the
-        // list build / prune, the pair kernel, the bonded terms and the alchemical kernel; joined before returning
-        cudaStream_t s2 = h->stream2;
-        cudaEventRecord(h->ev_fork, st);
+    // Fork: everything below depends only on the (cell-sorted) positions, not on each other.  Branches: reciprocal
+    // space (stream2), bonded terms (stream3), alchemical lists + kernel (stream4); the main stream keeps the list
+    // build / prune and the pair kernel.  All branches accumulate into the same fixed-point buffers with atomics.
+    const bool pme = d.pme && h->has_fft;
+    const int nterms = d.n_bonds + d.n_angles + d.n_torsions + d.n_excl + d.n_restraints + d.n_alch_exc;
+    cudaEventRecord(h->ev_fork, st);
+    if (pme) {
+        cudaStream_t s2 = h->profiling ? st : h->stream2;
+        cufftSetStream(h->plan_r2c, s2);
+        cufftSetStream(h->plan_c2r, s2);
         cudaStreamWaitEvent(s2, h->ev_fork, 0);
         { LaunchTimer t(h, BL_K_PME_SPREAD, s2);
-          k_pme_spread<<<dim3(d.gx, R), 256, d.gy * d.gz * sizeof(int), s2>>>(d); }
+          k_pme_spread<<<dim3(d.gx, SPREAD_YSPLIT, R), 256, (d.gy / SPREAD_YSPLIT + 1) * d.gz * sizeof(int), s2>>>(d); }
         { LaunchTimer t(h, BL_K_FFT, s2); cufftExecR2C(h->plan_r2c, d.grid_r, reinterpret_cast<cufftComplex*>(d.grid_c)); }
         { LaunchTimer t(h, BL_K_PME_CONVOLVE, s2);
           if (energy) k_pme_convolve<true><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d);
@@ -158,22 +163,32 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         { LaunchTimer t(h, BL_K_PME_GATHER, s2); k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
         cudaEventRecord(h->ev_join, s2);
     }
-    {
-        LaunchTimer t(h, BL_K_NEIGHBOR);
-        dim3 grid(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R);
-        if (d.nl_u16) k_build_list<unsigned short><<<grid, NL_BLOCK, 0, st>>>(d);
-        else k_build_list<int><<<grid, NL_BLOCK, 0, st>>>(d);
-    }
-    {
-        LaunchTimer t(h, BL_K_NEIGHBOR);
-        dim3 grid(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R);
-        if (d.nl_u16) k_prune_list<unsigned short><<<grid, NL_BLOCK, 0, st>>>(d);
-        else k_prune_list<int><<<grid, NL_BLOCK, 0, st>>>(d);
+    if (nterms > 0) {
+        cudaStream_t s3 = h->profiling ? st : h->stream3;
+        cudaStreamWaitEvent(s3, h->ev_fork, 0);
+        { LaunchTimer t(h, BL_K_BONDED, s3); k_bonded<<<dim3(cdiv(nterms, 128), R), 128, 0, s3>>>(d); }
+        cudaEventRecord(h->ev_join3, s3);
     }
     if (d.n_alch > 0) {
-        { LaunchTimer t(h, BL_K_NEIGHBOR); k_alch_reset<<<cdiv(R * d.n_alch, 128), 128, 0, st>>>(d); }
-        { LaunchTimer t(h, BL_K_NEIGHBOR);
-          k_alch_list<<<dim3(cdiv(N, 128), R), 128, d.n_alch * sizeof(float4), st>>>(d); }
+        cudaStream_t s4 = h->profiling ? st : h->stream4;
+        cudaStreamWaitEvent(s4, h->ev_fork, 0);
+        { LaunchTimer t(h, BL_K_NEIGHBOR, s4); k_alch_reset<<<cdiv(R * d.n_alch, 128), 128, 0, s4>>>(d); }
+        { LaunchTimer t(h, BL_K_NEIGHBOR, s4);
+          k_alch_list<<<dim3(cdiv(N, 128), R), 128, d.n_alch * sizeof(float4), s4>>>(d); }
+        { LaunchTimer t(h, BL_K_ALCH, s4); k_alch<<<dim3(cdiv(d.alch_cap, 128), d.n_alch, R), 128, 0, s4>>>(d); }
+        cudaEventRecord(h->ev_join4, s4);
+    }
+    {
+        LaunchTimer t(h, BL_K_NEIGHBOR);
+        dim3 grid(cdiv(d.Npad, 4), R);                     // one warp per atom, 4 warps per CTA
+        if (d.nl_u16) k_build_list<unsigned short><<<grid, 128, 0, st>>>(d);
+        else k_build_list<int><<<grid, 128, 0, st>>>(d);
+    }
+    {
+        LaunchTimer t(h, BL_K_NEIGHBOR);
+        dim3 grid(cdiv(d.Npad, 4), R);
+        if (d.nl_u16) k_prune_list<unsigned short><<<grid, 128, 0, st>>>(d);
+        else k_prune_list<int><<<grid, 128, 0, st>>>(d);
     }
     {
         LaunchTimer t(h, BL_K_PAIR);
@@ -188,21 +203,22 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
 #undef PAIR2
 #undef PAIR
     }
-    {
-        const int nterms = d.n_bonds + d.n_angles + d.n_torsions + d.n_excl + d.n_restraints + d.n_alch_exc;
-        if (nterms > 0) {
-            LaunchTimer t(h, BL_K_BONDED);
-            k_bonded<<<dim3(cdiv(nterms, 128), R), 128, 0, st>>>(d);
-        }
-    }
-    if (d.n_alch > 0) {
-        LaunchTimer t(h, BL_K_ALCH);
-        k_alch<<<dim3(cdiv(d.alch_cap, 128), d.n_alch, R), 128, 0, st>>>(d);
-    }
-    if (fork) cudaStreamWaitEvent(st, h->ev_join, 0);
+    if (pme) cudaStreamWaitEvent(st, h->ev_join, 0);
+    if (nterms > 0) cudaStreamWaitEvent(st, h->ev_join3, 0);
+    if (d.n_alch > 0) cudaStreamWaitEvent(st, h->ev_join4, 0);
 }
 
 static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a) {
+    int n_o = 0, n_md = 0;
+    for (int k = 0; k < a.nops; ++k) { if (a.ops[k].kind == OP_O) n_o++; if (a.ops[k].kind == OP_MD) n_md++; }
+    if (n_o > 0) {
+        LaunchTimer t(h, BL_K_INTEGRATE);
+        k_noise<<<dim3(cdiv((long long)h->d.N * n_o, 128), h->d.R), 128, 0, h->stream>>>(h->d, h->ic, STREAM_LANGEVIN, n_o, a.noise_offset);
+    }
+    if (n_md > 0) {
+        LaunchTimer t(h, BL_K_INTEGRATE);
+        k_noise<<<dim3(cdiv((long long)h->d.N * n_md, 128), h->d.R), 128, 0, h->stream>>>(h->d, h->ic, STREAM_MD, n_md, a.md_offset);
+    }
     if (h->n_generic > 0) {
         // generic clusters are sorted first; they must not also run the bookkeeping ops of the main kernel
         LaunchTimer t(h, BL_K_INTEGRATE);
@@ -609,6 +625,10 @@ int bl_destroy(bl_handle* h) {
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
+    if (h->stream4) cudaStreamDestroy(h->stream4);
+    if (h->ev_join3) cudaEventDestroy(h->ev_join3);
+    if (h->ev_join4) cudaEventDestroy(h->ev_join4);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
@@ -631,6 +651,10 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (cudaSetDevice(device) != cudaSuccess) return fail(BL_ERR_CUDA, "cudaSetDevice failed");
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
         return fail(BL_ERR_CUDA, "stream creation failed");
@@ -794,6 +818,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     d.cm_acc = dalloc<long long>(h, (size_t)2 * R * 3);
     d.heat_acc = dalloc<long long>(h, R);
     d.g = dalloc<Globals>(h, R);
+    d.noise = dalloc<double>(h, (size_t)R * MAX_NOISE_SETS * N * 3);
     h->cm_parity = dalloc<int>(h, 1);
     h->d_scratch = dalloc<double>(h, std::max((size_t)R * 4, (size_t)N * 3));
     h->d_iscratch = dalloc<int>(h, (size_t)R * 2);
@@ -837,7 +862,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         d.gsize = d.gx * d.gy * d.gz;
         d.csize = d.gx * d.gy * (d.gz / 2 + 1);
         {
-            const size_t plane_bytes = (size_t)d.gy * d.gz * sizeof(int);
+            const size_t plane_bytes = (size_t)(d.gy / SPREAD_YSPLIT + 1) * d.gz * sizeof(int);
             if (plane_bytes > 200 * 1024) return fail(BL_ERR_INVALID, "PME grid plane does not fit in shared memory");
             if (plane_bytes > 48 * 1024)
                 cudaFuncSetAttribute(k_pme_spread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes);
@@ -934,6 +959,7 @@ int bl_set_integrator(bl_handle* h, const bl_integrator_params* p) {
             else { h->error = "unsupported splitting token '" + tok + "' (supported: H V R O)"; return BL_ERR_INVALID; }
         }
         if ((int)h->splitting.size() + 2 > MAX_OPS) { h->error = "splitting string too long"; return BL_ERR_INVALID; }
+        if (nO > MAX_NOISE_SETS) { h->error = "too many O steps in the splitting"; return BL_ERR_INVALID; }
         h->n_H = nH;
         ic.hV = nV ? ic.dt / nV : 0; ic.hR = nR ? ic.dt / nR : 0; ic.hO = nO ? ic.dt / nO : 0;
         ic.a = exp(-ic.gamma * ic.hO);

@@ -7,6 +7,7 @@
 #define N_ETERMS 12
 #define MAX_OPS 16
 #define ALCH_SLOTS 3
+#define MAX_NOISE_SETS 4              /* thermostat ops (O / MD) per INTEGRATE launch */
 #define MAX_ALCH_SMEM 512             /* alchemical atoms staged in shared memory by k_alch                 */
 
 enum EnergyTerm { E_BOND = 0, E_ANGLE, E_TORSION, E_RESTRAINT, E_PAIR, E_EXCEPT, E_PME, E_SELF, E_DISP,
@@ -81,6 +82,7 @@ struct Dev {
     long long* cm_acc;                      // [R][3] sum of m v
     long long* heat_acc;                    // [R]
     Globals* g;                             // [R]
+    double* noise;                          // [R][MAX_NOISE_SETS][N][3] standard normals for the next INTEGRATE launch
     // neighbour structures: Morton-ranked cells (edge >= list cutoff / 2), sorted mirrors, Verlet lists
     int ncell[3]; int ncells;
     int* cell_order;                        // [ncells] Morton rank of each cell

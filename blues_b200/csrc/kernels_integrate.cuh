@@ -325,8 +325,8 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
             for (int k = 0; k < NA; ++k) {
                 ke0 += 0.5 * s.mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
                 if (s.im[k] > 0.0) {
-                    double n0, n1, n2;
-                    philox_normal3(ic.seed, STREAM_LANGEVIN, (uint32_t)r, noise0 + n_o, (uint32_t)atom[k], n0, n1, n2);
+                    const double* nz = d.noise + (((size_t)r * MAX_NOISE_SETS + n_o) * N + atom[k]) * 3;
+                    const double n0 = nz[0], n1 = nz[1], n2 = nz[2];
                     const double sg = ic.b * sqrt(ic.kT * s.im[k]);
                     s.v[k][0] = ic.a * s.v[k][0] + sg * n0;
                     s.v[k][1] = ic.a * s.v[k][1] + sg * n1;
@@ -340,8 +340,10 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
 #pragma unroll
             for (int k = 0; k < NA; ++k) {
                 double n[3] = {0.0, 0.0, 0.0};
-                if (s.im[k] > 0.0)
-                    philox_normal3(ic.seed, STREAM_MD, (uint32_t)r, md0 + n_md, (uint32_t)atom[k], n[0], n[1], n[2]);
+                if (s.im[k] > 0.0) {
+                    const double* nz = d.noise + (((size_t)r * MAX_NOISE_SETS + n_md) * N + atom[k]) * 3;
+                    n[0] = nz[0]; n[1] = nz[1]; n[2] = nz[2];
+                }
                 const double sq = ic.md_nscale * sqrt(s.im[k]);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
@@ -654,6 +656,22 @@ __global__ void __launch_bounds__(64) k_integrate_generic(Dev d, IntegratorConst
     }
     const double v = warp_sum(dheat);
     if ((threadIdx.x & 31) == 0 && v != 0.0) fx_add(&d.heat_acc[r], v, ENERGY_SCALE);
+}
+
+// Thermostat noise for the next INTEGRATE launch: one thread per (atom, set).  Same Philox counters the fused
+// integrator used to evaluate inline; hoisted out so that 1k-instruction Box-Muller chains run 22k-wide instead of
+// serially inside each cluster thread.
+__global__ void __launch_bounds__(128) k_noise(Dev d, IntegratorConsts ic, unsigned int stream_id, int n_sets, int offset) {
+    const int r = blockIdx.y;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d.N * n_sets) return;
+    const int set = idx / d.N, a = idx - set * d.N;
+    if (d.invmass[a] <= 0.0) return;
+    const Globals& g = d.g[r];
+    const unsigned int counter = (stream_id == STREAM_MD ? g.md_counter : g.noise_counter) + offset + set;
+    const double3 v = philox_normal3v(ic.seed, stream_id, (uint32_t)r, counter, (uint32_t)a);
+    double* out = d.noise + (((size_t)r * MAX_NOISE_SETS + set) * d.N + a) * 3;
+    out[0] = v.x; out[1] = v.y; out[2] = v.z;
 }
 
 // ---------------------------------------------------------------------------------------------------------

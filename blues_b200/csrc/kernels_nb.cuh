@@ -186,23 +186,23 @@ __device__ __forceinline__ bool pair_excluded(const Dev& d, int oi, ull wi, bool
 #define NL_LANES 8
 #define NL_BLOCK 128
 template <typename IDX>
-__global__ void __launch_bounds__(NL_BLOCK) k_build_list(Dev d) {
+__global__ void __launch_bounds__(128) k_build_list(Dev d) {
+    // One warp per atom; the 32 lanes test 32 candidates of a cell column per iteration (coalesced loads from the
+    // cell-sorted mirror) and append the survivors in order with a warp ballot + popc prefix.  Columns (and cells of
+    // a column) that cannot reach the list cutoff are skipped from the atom's distance to the column.
     const int r = blockIdx.y;
     Globals& g = d.g[r];
     if (!g.do_rebuild) return;
     const int lane = threadIdx.x & 31;
-    const int part = lane & (NL_LANES - 1);
-    const int gshift = lane & ~(NL_LANES - 1);
-    const unsigned int submask = ((1u << NL_LANES) - 1u) << gshift;
-    const int i = (blockIdx.x * NL_BLOCK + threadIdx.x) / NL_LANES;       // sorted index of this group's atom
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);    // sorted index of this warp's atom
     const int N = d.N, Npad = d.Npad;
     if (i >= Npad) return;
-    const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
-    const int* __restrict__ orig_s = d.orig_s + (size_t)r * Npad;
-    const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
-    IDX* list = reinterpret_cast<IDX*>(d.nlo_list) + ((size_t)r * Npad + i) * d.nlo_M;
     int cnt = 0;
     if (i < N) {
+        const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
+        const int* __restrict__ orig_s = d.orig_s + (size_t)r * Npad;
+        const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
+        IDX* list = reinterpret_cast<IDX*>(d.nlo_list) + ((size_t)r * Npad + i) * d.nlo_M;
         const float4 pi = posq_s[i];
         const int oi = orig_s[i];
         const ull wi = d.excl_win[oi];
@@ -210,48 +210,65 @@ __global__ void __launch_bounds__(NL_BLOCK) k_build_list(Dev d) {
         const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
         const float cut2 = d.outer_cutoff2;
         const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
-        // positions in the sorted mirror are wrapped into the box, so a periodic image is a per-cell constant shift;
-        // dimensions with fewer than 5 cells are scanned completely and use the rint() minimum image instead
+        const float ex = bx / ncx, ey = by / ncy, ez = bz / ncz;          // cell edges
+        // dimensions with fewer than 5 cells are scanned completely with the rint() minimum image
         const bool rx = d.periodic && ncx < 5, ry = d.periodic && ncy < 5, rz = d.periodic && ncz < 5;
         int cx = 0, cy = 0, cz = 0;
         if (d.periodic) atom_cell_coords(d, pi, cx, cy, cz);
-        const int nsx = min(5, ncx), nsy = min(5, ncy);
-        for (int ox = 0; ox < nsx; ++ox) {
-            int ax = ox;
-            float px = pi.x;
-            if (ncx >= 5) { ax = cx - 2 + ox; if (ax < 0) { ax += ncx; px += bx; } else if (ax >= ncx) { ax -= ncx; px -= bx; } }
-            for (int oy = 0; oy < nsy; ++oy) {
-                int ay = oy;
-                float py = pi.y;
-                if (ncy >= 5) { ay = cy - 2 + oy; if (ay < 0) { ay += ncy; py += by; } else if (ay >= ncy) { ay -= ncy; py -= by; } }
+        const int x0 = (rx || !d.periodic) ? 0 : cx - 2, x1 = (rx || !d.periodic) ? ncx - 1 : cx + 2;
+        const int y0 = (ry || !d.periodic) ? 0 : cy - 2, y1 = (ry || !d.periodic) ? ncy - 1 : cy + 2;
+        for (int rxc = x0; rxc <= x1; ++rxc) {
+            int ax = rxc;
+            float sx = 0.f, dxc = 0.f;
+            if (d.periodic && !rx) {
+                if (ax < 0) { ax += ncx; sx = -bx; } else if (ax >= ncx) { ax -= ncx; sx = bx; }
+                dxc = fmaxf(0.f, fmaxf(rxc * ex - pi.x, pi.x - (rxc + 1) * ex));      // gap between atom and column slab
+            }
+            for (int ryc = y0; ryc <= y1; ++ryc) {
+                int ay = ryc;
+                float sy = 0.f, dyc = 0.f;
+                if (d.periodic && !ry) {
+                    if (ay < 0) { ay += ncy; sy = -by; } else if (ay >= ncy) { ay -= ncy; sy = by; }
+                    dyc = fmaxf(0.f, fmaxf(ryc * ey - pi.y, pi.y - (ryc + 1) * ey));
+                }
+                const float rem2 = cut2 - dxc * dxc - dyc * dyc;
+                if (rem2 <= 0.f) continue;                                            // column out of reach
+                int z0 = 0, z1 = ncz - 1;
+                if (d.periodic && !rz) {
+                    const float zr = sqrtf(rem2);
+                    z0 = max(cz - 2, (int)floorf((pi.z - zr) / ez));
+                    z1 = min(cz + 2, (int)floorf((pi.z + zr) / ez));
+                }
                 const int row = (ax * ncy + ay) * ncz;
-                // z-column: up to two contiguous runs of cells (the second one is the periodic wrap)
-                int zlo = ncz >= 5 ? cz - 2 : 0, zhi = ncz >= 5 ? cz + 2 : ncz - 1;
                 for (int seg = 0; seg < 3; ++seg) {
                     int a0, a1;
-                    float pz = pi.z;
-                    if (seg == 0) { a0 = max(zlo, 0); a1 = min(zhi, ncz - 1); }
-                    else if (seg == 1) { if (zlo >= 0) continue; a0 = zlo + ncz; a1 = ncz - 1; pz += bz; }
-                    else { if (zhi < ncz) continue; a0 = 0; a1 = zhi - ncz; pz -= bz; }
+                    float sz = 0.f;
+                    if (seg == 0) { a0 = max(z0, 0); a1 = min(z1, ncz - 1); }
+                    else if (seg == 1) { if (z0 >= 0) continue; a0 = z0 + ncz; a1 = ncz - 1; sz = -bz; }
+                    else { if (z1 < ncz) continue; a0 = 0; a1 = z1 - ncz; sz = bz; }
+                    if (a0 > a1) continue;
                     const int s0 = start[row + a0], s1 = start[row + a1 + 1];
-                    for (int base = s0; base < s1; base += NL_LANES) {
-                        const int s = base + part;
+                    for (int base = s0; base < s1; base += 32) {
+                        const int s = base + lane;
                         bool ok = s < s1 && s != i;
                         if (ok) {
                             const float4 pj = posq_s[s];
-                            float dx = px - pj.x, dy = py - pj.y, dz = pz - pj.z;
+                            float dx = pi.x - (pj.x + sx), dy = pi.y - (pj.y + sy), dz = pi.z - (pj.z + sz);
                             if (rx) dx -= bx * rintf(dx * ibx);
                             if (ry) dy -= by * rintf(dy * iby);
                             if (rz) dz -= bz * rintf(dz * ibz);
                             ok = (dx * dx + dy * dy + dz * dz) < cut2;
                             if (ok) {
+                                // exclusions: partners within +-32 topology indices sit in the 64-bit window mask
                                 const int oj = orig_s[s];
-                                ok = !pair_excluded(d, oi, wi, fari, oj, d.has_far[oj]);
+                                const unsigned int dd = (unsigned int)(oj - oi + 32);
+                                if (dd < 64u) ok = !((wi >> dd) & 1ull);
+                                else if (fari) ok = !pair_excluded(d, oi, wi, true, oj, d.has_far[oj]);   // rare
                             }
                         }
-                        const unsigned int m = (__ballot_sync(submask, ok) & submask) >> gshift;
+                        const unsigned int m = __ballot_sync(0xffffffffu, ok);
                         if (ok) {
-                            const int slot = cnt + __popc(m & ((1u << part) - 1u));
+                            const int slot = cnt + __popc(m & ((1u << lane) - 1u));
                             if (slot < d.nlo_M) list[slot] = (IDX)s;
                         }
                         cnt += __popc(m);
@@ -261,26 +278,22 @@ __global__ void __launch_bounds__(NL_BLOCK) k_build_list(Dev d) {
         }
         if (cnt > d.nlo_M) { g.item_overflow = 1; cnt = d.nlo_M; }
     }
-    if (part == 0) d.nlo_count[(size_t)r * Npad + i] = cnt;
+    if (lane == 0) d.nlo_count[(size_t)r * Npad + i] = cnt;
 }
-
 
 // ---------------------------------------------------------------------------------------------------------
 // k_prune_list: refresh the inner Verlet list (cutoff + inner skin) from the outer one (cutoff + outer skin) at the
-// current coordinates: NL_LANES lanes per atom stream the outer list (coalesced), keep the entries inside the inner
-// list cutoff with ordered sub-warp ballot compaction, and record the reference positions of the inner list.
+// current coordinates: one warp per atom streams the outer list (coalesced), keeps the entries inside the inner list
+// cutoff with ordered ballot compaction, and records the reference positions of the inner list.
 // Runs every few steps; the expensive cell search (k_sort_atoms + k_build_list) only every ~10-20 steps.
 // ---------------------------------------------------------------------------------------------------------
 template <typename IDX>
-__global__ void __launch_bounds__(NL_BLOCK) k_prune_list(Dev d) {
+__global__ void __launch_bounds__(128) k_prune_list(Dev d) {
     const int r = blockIdx.y;
     Globals& g = d.g[r];
     if (!g.do_prune) return;
     const int lane = threadIdx.x & 31;
-    const int part = lane & (NL_LANES - 1);
-    const int gshift = lane & ~(NL_LANES - 1);
-    const unsigned int submask = ((1u << NL_LANES) - 1u) << gshift;
-    const int i = (blockIdx.x * NL_BLOCK + threadIdx.x) / NL_LANES;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int N = d.N, Npad = d.Npad;
     if (i >= Npad) return;
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
@@ -291,8 +304,8 @@ __global__ void __launch_bounds__(NL_BLOCK) k_prune_list(Dev d) {
     const float cut2 = d.list_cutoff2;
     const float4 pi = posq_s[i];
     int cnt = 0;
-    for (int base = 0; base < n_outer; base += NL_LANES) {
-        const int k = base + part;
+    for (int base = 0; base < n_outer; base += 32) {
+        const int k = base + lane;
         bool ok = k < n_outer;
         int s = 0;
         if (ok) {
@@ -306,15 +319,15 @@ __global__ void __launch_bounds__(NL_BLOCK) k_prune_list(Dev d) {
             }
             ok = (dx * dx + dy * dy + dz * dz) < cut2;
         }
-        const unsigned int m = (__ballot_sync(submask, ok) & submask) >> gshift;
+        const unsigned int m = __ballot_sync(0xffffffffu, ok);
         if (ok) {
-            const int slot = cnt + __popc(m & ((1u << part) - 1u));
+            const int slot = cnt + __popc(m & ((1u << lane) - 1u));
             if (slot < d.nl_M) inner[slot] = (IDX)s;
         }
         cnt += __popc(m);
     }
     if (cnt > d.nl_M) { g.item_overflow = 1; cnt = d.nl_M; }
-    if (part == 0) {
+    if (lane == 0) {
         d.nl_count[(size_t)r * Npad + i] = cnt;
         if (i < N) d.pos_ref[(size_t)r * N + d.orig_s[(size_t)r * Npad + i]] = pi;     // inner-list reference positions
     }

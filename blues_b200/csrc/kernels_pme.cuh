@@ -52,10 +52,12 @@ __device__ __forceinline__ void pme_atom_setup(const Dev& d, float4 p, int* base
 // atomics (order independent → deterministic).  The finished plane is written once, as float: no global atomics,
 // no separate conversion pass.
 #define SPREAD_SCALE 8388608.0f            /* 2^23 */
+#define SPREAD_YSPLIT 4                    /* CTAs per x-plane: each owns a band of y-rows */
 __global__ void __launch_bounds__(256) k_pme_spread(Dev d) {
-    extern __shared__ int s_plane[];            // [gy * gz]
-    const int r = blockIdx.y, plane = blockIdx.x;
-    const int npts = d.gy * d.gz;
+    extern __shared__ int s_plane[];            // [rows * gz]
+    const int r = blockIdx.z, plane = blockIdx.x, part = blockIdx.y;
+    const int ya = part * d.gy / SPREAD_YSPLIT, yb = (part + 1) * d.gy / SPREAD_YSPLIT;   // rows [ya, yb)
+    const int npts = (yb - ya) * d.gz;
     for (int k = threadIdx.x; k < npts; k += blockDim.x) s_plane[k] = 0;
     __syncthreads();
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * d.Npad;
@@ -78,6 +80,16 @@ __global__ void __launch_bounds__(256) k_pme_spread(Dev d) {
             int i = plane - base[0];
             if (i < 0) i += d.gx;
             if (i >= PME_ORDER) continue;
+            // y-rows of the stencil that fall into this CTA's band
+            int jrow[PME_ORDER];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < PME_ORDER; ++j) {
+                int gy = base[1] + j; gy -= gy >= d.gy ? d.gy : 0;
+                jrow[j] = (gy >= ya && gy < yb) ? gy - ya : -1;
+                any = any || jrow[j] >= 0;
+            }
+            if (!any) continue;
             float wx[PME_ORDER], wy[PME_ORDER], wz[PME_ORDER], dw[PME_ORDER];
             bspline5(frac[0], wx, dw);
             bspline5(frac[1], wy, dw);
@@ -88,18 +100,18 @@ __global__ void __launch_bounds__(256) k_pme_spread(Dev d) {
             qx *= SPREAD_SCALE;
 #pragma unroll
             for (int j = 0; j < PME_ORDER; ++j) {
-                int gy = base[1] + j; gy -= gy >= d.gy ? d.gy : 0;
+                if (jrow[j] < 0) continue;
                 const float qxy = qx * wy[j];
 #pragma unroll
                 for (int k = 0; k < PME_ORDER; ++k) {
                     int gz = base[2] + k; gz -= gz >= d.gz ? d.gz : 0;
-                    atomicAdd(&s_plane[gy * d.gz + gz], __float2int_rn(qxy * wz[k]));
+                    atomicAdd(&s_plane[jrow[j] * d.gz + gz], __float2int_rn(qxy * wz[k]));
                 }
             }
         }
     }
     __syncthreads();
-    float* out = d.grid_r + (size_t)r * d.gsize + (size_t)plane * npts;
+    float* out = d.grid_r + (size_t)r * d.gsize + ((size_t)plane * d.gy + ya) * d.gz;
     for (int k = threadIdx.x; k < npts; k += blockDim.x) out[k] = (float)s_plane[k] * (1.0f / SPREAD_SCALE);
 }
 
