@@ -365,8 +365,45 @@ def reference_bookkeeping():
     print('reference bookkeeping rows:', len(out['calculateNCMCSteps']), len(out['get_prop_lambda']))
 
 
+def ethylene_fixture():
+    """blues/tests/data/ethylene_system.xml + ethylene_structure.pdb → ethylene.json (the reference's only known-answer
+    system, tests/test_ethylene.py)."""
+    import json
+    import xml.etree.ElementTree as ET
+    root = ET.parse(os.path.join(REF, 'ethylene_system.xml')).getroot()
+    out = {'mass': [float(p.get('mass')) for p in root.find('Particles')],
+           'constraints': [[int(c.get('p1')), int(c.get('p2')), float(c.get('d'))] for c in root.find('Constraints')]}
+    for f in root.find('Forces'):
+        t = f.get('type')
+        if t == 'HarmonicBondForce':
+            out['bonds'] = [[int(b.get('p1')), int(b.get('p2')), float(b.get('d')), float(b.get('k'))] for b in f.find('Bonds')]
+        elif t == 'HarmonicAngleForce':
+            out['angles'] = [[int(a.get('p1')), int(a.get('p2')), int(a.get('p3')), float(a.get('a')), float(a.get('k'))]
+                             for a in f.find('Angles')]
+        elif t == 'PeriodicTorsionForce':
+            out['torsions'] = [[int(x.get('p1')), int(x.get('p2')), int(x.get('p3')), int(x.get('p4')),
+                                int(x.get('periodicity')), float(x.get('phase')), float(x.get('k'))] for x in f.find('Torsions')]
+        elif t == 'CustomNonbondedForce':
+            out['custom_nonbonded'] = {'energy': f.get('energy'), 'method': int(f.get('method')),
+                                       'params': [[float(p.get('param1')), float(p.get('param2')), float(p.get('param3'))]
+                                                  for p in f.find('Particles')],
+                                       'set1': [int(p.get('index')) for p in f.find('InteractionGroups')[0].find('Set1')],
+                                       'set2': [int(p.get('index')) for p in f.find('InteractionGroups')[0].find('Set2')]}
+        elif t == 'CustomCentroidBondForce':
+            groups = [[int(p.get('p')) for p in g] for g in f.find('Groups')]
+            out['centroid_bond'] = {'energy': f.get('energy'), 'groups': groups, 'k': float(f.find('Bonds')[0].get('param1'))}
+    pdb = load_pdb(os.path.join(REF, 'ethylene_structure.pdb'))
+    out['positions_nm'] = (pdb.coordinates * 0.1).tolist()
+    out['atomic_numbers'] = pdb.atomic_numbers.tolist()
+    out['residue_names'] = pdb.residue_names
+    with open(os.path.join(HERE, 'ethylene.json'), 'w') as fh:
+        json.dump(out, fh)
+    print('ethylene fixture:', len(out['mass']), 'particles')
+
+
 def main():
     reference_bookkeeping()
+    ethylene_fixture()
     structs = {}
     for out, base in (('tol_parm', 'TOL-parm'), ('wat_divaline', 'watDivaline'), ('vac_divaline', 'vacDivaline')):
         s = load_file(os.path.join(REF, base + '.prmtop'), xyz=os.path.join(REF, base + '.inpcrd'))
