@@ -328,4 +328,15 @@ def main():
 
 
 if __name__ == '__main__':
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (e.g. NCCL's version banner) go to stderr
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _out = os.fdopen(_real_stdout, 'w')
+    _print = print
+
+    def print(*a, **k):          # noqa: A001  (only the final JSON line is printed through this)
+        k.setdefault('file', _out)
+        _print(*a, **k)
+        _out.flush()
+
     main()
