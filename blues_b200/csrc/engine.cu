@@ -180,9 +180,9 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     }
     {
         LaunchTimer t(h, BL_K_NEIGHBOR);
-        dim3 grid(cdiv(d.Npad, 4), R);                     // one warp per atom, 4 warps per CTA
-        if (d.nl_u16) k_build_list<unsigned short><<<grid, 128, 0, st>>>(d);
-        else k_build_list<int><<<grid, 128, 0, st>>>(d);
+        dim3 grid(cdiv(d.Npad, BUILD_GROUP * BUILD_WARPS), R);      // one warp per 8 consecutive sorted atoms
+        if (d.nl_u16) k_build_list<unsigned short><<<grid, 32 * BUILD_WARPS, 0, st>>>(d);
+        else k_build_list<int><<<grid, 32 * BUILD_WARPS, 0, st>>>(d);
     }
     {
         LaunchTimer t(h, BL_K_NEIGHBOR);
@@ -845,15 +845,18 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     d.nl_u16 = d.Npad < 65536 ? 1 : 0;
     d.nl_list = dalloc<unsigned char>(h, (size_t)R * d.Npad * d.nl_M * (d.nl_u16 ? 2 : 4));
     {
+        // the outer list of an atom is BUILD_SUB sub-rows (one per candidate subset of k_build_list); capacity per
+        // sub-row: 1.5 x the mean share of the outer-cutoff sphere (+ margin), a multiple of the 32-entry flush
         long long M = N;
         if (d.periodic) {
             const double V = t->box[0] * t->box[1] * t->box[2], rl = t->cutoff + skin_outer;
             M = std::min<long long>(N, (long long)(1.5 * 4.0 / 3.0 * M_PI * rl * rl * rl * N / V) + 96);
         }
-        d.nlo_M = (int)((M + 7) / 8 * 8);
+        const long long Mq = (M + BUILD_SUB - 1) / BUILD_SUB + 64;
+        d.nlo_M = (int)((Mq + 31) / 32 * 32);
     }
-    d.nlo_count = dalloc<int>(h, (size_t)R * d.Npad);
-    d.nlo_list = dalloc<unsigned char>(h, (size_t)R * d.Npad * d.nlo_M * (d.nl_u16 ? 2 : 4));
+    d.nlo_count = dalloc<int>(h, (size_t)R * d.Npad * BUILD_SUB);
+    d.nlo_list = dalloc<unsigned char>(h, (size_t)R * d.Npad * BUILD_SUB * d.nlo_M * (d.nl_u16 ? 2 : 4));
     d.pos_ref_outer = dalloc<float4>(h, RN);
     // PME
     if (d.pme) {
@@ -1454,9 +1457,12 @@ int bl_neighbor_pairs(bl_handle* h, int replica, int64_t* codes, size_t capacity
     if (!h || !n_pairs || replica < 0 || replica >= h->d.R) return BL_ERR_INVALID;
     cudaSetDevice(h->device);
     Dev& d = h->d;
-    // force a fresh list at the current coordinates
-    { LaunchTimer t(h, -1); k_refresh_mirrors<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, 1); }
-    eval_now(h, false);
+    // coordinates changed by the host since the last evaluation: build a fresh list.  Otherwise report the list the
+    // last evaluation used (tests use this to check the skin / prune / rebuild logic after dynamics).
+    if (!h->forces_valid) {
+        { LaunchTimer t(h, -1); k_refresh_mirrors<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, 1); }
+        eval_now(h, false);
+    }
     long long* dcodes = nullptr;
     unsigned long long* dn = nullptr;
     CK(cudaMalloc(&dcodes, sizeof(long long) * std::max<size_t>(capacity, 1)));

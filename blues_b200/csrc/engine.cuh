@@ -90,7 +90,7 @@ struct Dev {
     int* atom_cell;                         // [R*N]
     int* rank;                              // [R*N] position of atom a in the sorted order
     float4* posq_s; float2* sigeps_s; int* orig_s;   // [R*Npad] sorted copies (pads: NaN position, orig -1)
-    int nlo_M; int* nlo_count; void* nlo_list;   // outer list (cutoff + outer skin), rebuilt with the cell search
+    int nlo_M; int* nlo_count; void* nlo_list;   // outer list (cutoff + outer skin): [R*Npad][4 sub-rows][nlo_M], counts [R*Npad][4]
     float4* pos_ref_outer;                  // [R*N] positions at the last outer rebuild
     float outer_cutoff2, outer_half2;       // squared outer list cutoff; squared displacement budget of the outer list
     int nl_M;                               // inner list capacity per atom

@@ -154,24 +154,25 @@ template <int SHAPE> __device__ __forceinline__ constexpr int con_b(int a) { ret
 
 template <int NC>
 __device__ __forceinline__ void solve_fixed(double (&A)[NC > 0 ? NC : 1][NC > 0 ? NC : 1], double (&b)[NC > 0 ? NC : 1]) {
-    // symmetric-positive-definite-like systems (Gram matrices weighted by inverse masses): no pivoting needed
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        const double inv = 1.0 / A[c][c];
-#pragma unroll
-        for (int rr = c + 1; rr < NC; ++rr) {
-            const double f = A[rr][c] * inv;
-#pragma unroll
-            for (int k = c + 1; k < NC; ++k) A[rr][k] -= f * A[c][k];
-            b[rr] -= f * b[c];
-        }
-    }
-#pragma unroll
-    for (int c = NC - 1; c >= 0; --c) {
-        double sum = b[c];
-#pragma unroll
-        for (int k = c + 1; k < NC; ++k) sum -= A[c][k] * b[k];
-        b[c] = sum / A[c][c];
+    // closed-form solution (adjugate / determinant) of the 1x1, 2x2 and 3x3 constraint systems: ONE division and a
+    // shallow dependency chain.  The integrator runs one cluster per thread with few warps per SM, so its run time is
+    // the latency of this chain; Gaussian elimination (six dependent double divisions) was most of it.
+    if (NC == 1) {
+        b[0] = b[0] / A[0][0];
+    } else if (NC == 2) {
+        const double inv = 1.0 / (A[0][0] * A[1][1] - A[0][1] * A[1][0]);
+        const double x0 = (b[0] * A[1][1] - A[0][1] * b[1]) * inv;
+        const double x1 = (A[0][0] * b[1] - A[1][0] * b[0]) * inv;
+        b[0] = x0; b[1] = x1;
+    } else if (NC == 3) {
+        const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+        const double c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
+        const double c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+        const double inv = 1.0 / (A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02);
+        const double x0 = b[0] * c00 + b[1] * (A[0][2] * A[2][1] - A[0][1] * A[2][2]) + b[2] * (A[0][1] * A[1][2] - A[0][2] * A[1][1]);
+        const double x1 = b[0] * c01 + b[1] * (A[0][0] * A[2][2] - A[0][2] * A[2][0]) + b[2] * (A[0][2] * A[1][0] - A[0][0] * A[1][2]);
+        const double x2 = b[0] * c02 + b[1] * (A[0][1] * A[2][0] - A[0][0] * A[2][1]) + b[2] * (A[0][0] * A[1][1] - A[0][1] * A[1][0]);
+        b[0] = x0 * inv; b[1] = x1 * inv; b[2] = x2 * inv;
     }
 }
 
@@ -223,7 +224,7 @@ struct FixedCluster {
 #pragma unroll
             for (int k = 0; k < 3; ++k) rr[a][k] = xref[con_a<SHAPE>(a)][k] - xref[con_b<SHAPE>(a)][k];
         for (int it = 0; it < 30; ++it) {
-            double sv[NCC][3], diff[NCC], worst = 0.0;
+            double sv[NCC][3], diff[NCC], worst = -1.0e300;
 #pragma unroll
             for (int a = 0; a < NC; ++a) {
                 const int i = con_a<SHAPE>(a), j = con_b<SHAPE>(a);
@@ -231,9 +232,9 @@ struct FixedCluster {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { sv[a][k] = x[i][k] - x[j][k]; s2 += sv[a][k] * sv[a][k]; }
                 diff[a] = d2[a] - s2;
-                worst = fmax(worst, fabs(diff[a]) / d2[a]);
+                worst = fmax(worst, fabs(diff[a]) - tol * d2[a]);        // |diff| / d2 < tol without the division
             }
-            if (worst < tol) break;
+            if (worst < 0.0) break;
             double A[NCC][NCC];
 #pragma unroll
             for (int a = 0; a < NC; ++a)
@@ -326,11 +327,10 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                 ke0 += 0.5 * s.mass[k] * (s.v[k][0] * s.v[k][0] + s.v[k][1] * s.v[k][1] + s.v[k][2] * s.v[k][2]);
                 if (s.im[k] > 0.0) {
                     const double* nz = d.noise + (((size_t)r * MAX_NOISE_SETS + n_o) * N + atom[k]) * 3;
-                    const double n0 = nz[0], n1 = nz[1], n2 = nz[2];
-                    const double sg = ic.b * sqrt(ic.kT * s.im[k]);
-                    s.v[k][0] = ic.a * s.v[k][0] + sg * n0;
-                    s.v[k][1] = ic.a * s.v[k][1] + sg * n1;
-                    s.v[k][2] = ic.a * s.v[k][2] + sg * n2;
+                    // k_noise stores the kicks already scaled by b sqrt(kT / m)
+                    s.v[k][0] = ic.a * s.v[k][0] + nz[0];
+                    s.v[k][1] = ic.a * s.v[k][1] + nz[1];
+                    s.v[k][2] = ic.a * s.v[k][2] + nz[2];
                 }
             }
             ++n_o;
@@ -344,7 +344,6 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                     const double* nz = d.noise + (((size_t)r * MAX_NOISE_SETS + n_md) * N + atom[k]) * 3;
                     n[0] = nz[0]; n[1] = nz[1]; n[2] = nz[2];
                 }
-                const double sq = ic.md_nscale * sqrt(s.im[k]);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     xref[k][q] = s.x[k][q];
@@ -352,7 +351,7 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                         long long fi = fenv[q * N + atom[k]];
                         if (d.n_alch > 0) fi += d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + atom[k]];
                         const double f = (double)fi * (1.0 / FORCE_SCALE);
-                        s.v[k][q] = ic.md_vscale * s.v[k][q] + ic.md_fscale * s.im[k] * f + sq * n[q];
+                        s.v[k][q] = ic.md_vscale * s.v[k][q] + ic.md_fscale * s.im[k] * f + n[q];   // pre-scaled kick
                         s.x[k][q] += ic.dt * s.v[k][q];
                     }
                 }
@@ -670,8 +669,11 @@ __global__ void __launch_bounds__(128) k_noise(Dev d, IntegratorConsts ic, unsig
     const Globals& g = d.g[r];
     const unsigned int counter = (stream_id == STREAM_MD ? g.md_counter : g.noise_counter) + offset + set;
     const double3 v = philox_normal3v(ic.seed, stream_id, (uint32_t)r, counter, (uint32_t)a);
+    // stored already scaled: b sqrt(kT / m) for the O step, md_nscale sqrt(1 / m) for the MD leg
+    const double im = d.invmass[a];
+    const double sc = stream_id == STREAM_MD ? ic.md_nscale * sqrt(im) : ic.b * sqrt(ic.kT * im);
     double* out = d.noise + (((size_t)r * MAX_NOISE_SETS + set) * d.N + a) * 3;
-    out[0] = v.x; out[1] = v.y; out[2] = v.z;
+    out[0] = sc * v.x; out[1] = sc * v.y; out[2] = sc * v.z;
 }
 
 // ---------------------------------------------------------------------------------------------------------

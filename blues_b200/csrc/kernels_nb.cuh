@@ -178,107 +178,254 @@ __device__ __forceinline__ bool pair_excluded(const Dev& d, int oi, ull wi, bool
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_build_list: Verlet list with skin.  NL_LANES lanes cooperate on one atom: they stride over the candidates of
-// the (up to) 5x5x5 neighbouring cells, test distance + exclusions, and append the survivors with sub-warp
-// ballot compaction, so the list of an atom is ordered (cell scan order, topology order inside a cell).
-// Full list (i sees j and j sees i): the pair kernel needs no j-side force scatter and no exclusion test.
+// k_build_list: outer Verlet list (cutoff + outer skin) by cell search.  Full list (i sees j and j sees i): the pair
+// kernel needs no j-side force scatter and no exclusion test.
+//
+// One warp owns BUILD_GROUP = 8 consecutive atoms of the cell-sorted order (a compact group: one cell, sometimes two);
+// lane = (atom a = lane & 7, candidate subset q = lane >> 3).  The warp walks the cell columns around the group's
+// bounding box; candidates are staged 32 at a time in shared memory, already shifted to the periodic image that can
+// be in range, and in iteration t lane (a, q) tests candidate 8 q + t against atom a: one LDS and ~12 ALU instructions
+// per 32 distance tests, no per-candidate global load.  Exclusions are only looked at in chunks that hold a candidate
+// whose topology index is near the group's (warp-uniform test), i.e. almost never.  Survivors go to a per-lane ring in
+// shared memory (bank-skewed) that the whole warp flushes 32 entries at a time, so global stores stay coalesced.
+// An atom's outer list is therefore stored as BUILD_SUB = 4 sub-rows (one per candidate subset); scan order is fixed,
+// hence so is the order of every sub-row (reproducible float sums downstream).
 // ---------------------------------------------------------------------------------------------------------
 #define NL_LANES 8
 #define NL_BLOCK 128
+#define BUILD_WARPS 4
+#define BUILD_RING 64
+#define BUILD_GROUP 8
+#define BUILD_SUB 4
+
+__device__ __forceinline__ void sts_u32(unsigned int addr, unsigned int v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 template <typename IDX>
-__global__ void __launch_bounds__(128) k_build_list(Dev d) {
-    // One warp per atom; the 32 lanes test 32 candidates of a cell column per iteration (coalesced loads from the
-    // cell-sorted mirror) and append the survivors in order with a warp ballot + popc prefix.  Columns (and cells of
-    // a column) that cannot reach the list cutoff are skipped from the atom's distance to the column.
-    const int r = blockIdx.y;
-    Globals& g = d.g[r];
-    if (!g.do_rebuild) return;
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);    // sorted index of this warp's atom
-    const int N = d.N, Npad = d.Npad;
-    if (i >= Npad) return;
-    int cnt = 0;
-    if (i < N) {
-        const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
-        const int* __restrict__ orig_s = d.orig_s + (size_t)r * Npad;
-        const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
-        IDX* list = reinterpret_cast<IDX*>(d.nlo_list) + ((size_t)r * Npad + i) * d.nlo_M;
-        const float4 pi = posq_s[i];
-        const int oi = orig_s[i];
-        const ull wi = d.excl_win[oi];
-        const bool fari = d.has_far[oi];
-        const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
-        const float cut2 = d.outer_cutoff2;
-        const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
-        const float ex = bx / ncx, ey = by / ncy, ez = bz / ncz;          // cell edges
-        // dimensions with fewer than 5 cells are scanned completely with the rint() minimum image
-        const bool rx = d.periodic && ncx < 5, ry = d.periodic && ncy < 5, rz = d.periodic && ncz < 5;
-        int cx = 0, cy = 0, cz = 0;
-        if (d.periodic) atom_cell_coords(d, pi, cx, cy, cz);
-        const int x0 = (rx || !d.periodic) ? 0 : cx - 2, x1 = (rx || !d.periodic) ? ncx - 1 : cx + 2;
-        const int y0 = (ry || !d.periodic) ? 0 : cy - 2, y1 = (ry || !d.periodic) ? ncy - 1 : cy + 2;
-        for (int rxc = x0; rxc <= x1; ++rxc) {
-            int ax = rxc;
-            float sx = 0.f, dxc = 0.f;
-            if (d.periodic && !rx) {
-                if (ax < 0) { ax += ncx; sx = -bx; } else if (ax >= ncx) { ax -= ncx; sx = bx; }
-                dxc = fmaxf(0.f, fmaxf(rxc * ex - pi.x, pi.x - (rxc + 1) * ex));      // gap between atom and column slab
+__device__ __forceinline__ void build_flush(IDX* __restrict__ rows, int Mq, const unsigned int* ring, int lane,
+                                            int cnt, int& flushed) {
+    // rows: sub-row 0 of the group's first atom; lane L = (atom L & 7, subset L >> 3) owns sub-row (L & 7) * 4 + (L >> 3)
+    unsigned int full = __ballot_sync(0xffffffffu, cnt - flushed >= 32);
+    while (full) {
+        const int L = __ffs(full) - 1;
+        full &= full - 1;
+        const int cL = __shfl_sync(0xffffffffu, flushed, L);
+        const unsigned int v = ring[L * BUILD_RING + ((cL + lane + L) & (BUILD_RING - 1))];
+        if (cL < Mq) rows[(size_t)((L & (BUILD_GROUP - 1)) * BUILD_SUB + (L >> 3)) * Mq + cL + lane] = (IDX)v;   // Mq % 32 == 0
+        if (lane == L) flushed += 32;
+    }
+}
+
+template <bool RINT, typename IDX>
+__device__ __forceinline__ void build_scan_run(const Dev& d, const float4* __restrict__ posq_s, const int* __restrict__ orig_s,
+                                               int s0, int s1, float sx, float sy, float sz, bool rx, bool ry, bool rz,
+                                               float4* cand, unsigned int* ring, IDX* rows, int lane, float4 pi, int oi,
+                                               ull wi, bool fari, bool anyfar, const int (&og)[BUILD_GROUP],
+                                               const unsigned int (&osp)[BUILD_GROUP], int& cnt, int& flushed) {
+    const float cut2 = d.outer_cutoff2;
+    const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
+    const float qnan = __int_as_float(0x7fc00000);
+    const int q = lane >> 3;
+    unsigned int* myring = ring + lane * BUILD_RING;
+    const unsigned int ring_addr = (unsigned int)__cvta_generic_to_shared(myring), lane4 = 4u * lane;
+    for (int base = s0; base < s1; base += 32) {
+        bool near = false;
+        {
+            const int s = base + lane;
+            float4 c = make_float4(qnan, qnan, qnan, 0.f);
+            if (s < s1) {
+                c = posq_s[s];
+                c.x += sx; c.y += sy; c.z += sz;
+                const int oj = orig_s[s];
+                c.w = __int_as_float(oj);
+#pragma unroll
+                for (int k = 0; k < BUILD_GROUP; ++k)               // inside the exclusion window of a group atom
+                    near = near || (unsigned int)(oj - og[k]) <= osp[k];
             }
-            for (int ryc = y0; ryc <= y1; ++ryc) {
-                int ay = ryc;
-                float sy = 0.f, dyc = 0.f;
-                if (d.periodic && !ry) {
-                    if (ay < 0) { ay += ncy; sy = -by; } else if (ay >= ncy) { ay -= ncy; sy = by; }
-                    dyc = fmaxf(0.f, fmaxf(ryc * ey - pi.y, pi.y - (ryc + 1) * ey));
+            __syncwarp();
+            cand[lane + (lane >> 3)] = c;                           // 8-candidate pieces, padded: conflict-free LDS
+            __syncwarp();
+        }
+        const bool check = anyfar || __any_sync(0xffffffffu, near);   // warp-uniform
+        if (!check) {
+            // fast path: no candidate of this chunk can be excluded from (or be) an atom of the group.  All eight
+            // candidates are loaded and measured before the first ring store, so the eight chains overlap.
+            float r2v[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float4 c = cand[q * 9 + t];                  // candidate 8 q + t
+                float dx = c.x - pi.x, dy = c.y - pi.y, dz = c.z - pi.z;
+                if (RINT) {
+                    if (rx) dx -= bx * rintf(dx * ibx);
+                    if (ry) dy -= by * rintf(dy * iby);
+                    if (rz) dz -= bz * rintf(dz * ibz);
                 }
-                const float rem2 = cut2 - dxc * dxc - dyc * dyc;
-                if (rem2 <= 0.f) continue;                                            // column out of reach
-                int z0 = 0, z1 = ncz - 1;
-                if (d.periodic && !rz) {
-                    const float zr = sqrtf(rem2);
-                    z0 = max(cz - 2, (int)floorf((pi.z - zr) / ez));
-                    z1 = min(cz + 2, (int)floorf((pi.z + zr) / ez));
+                r2v[t] = dx * dx + dy * dy + dz * dz;
+            }
+            const unsigned int vq = (unsigned int)(base + 8 * q);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (r2v[t] < cut2) {                               // NaN (padding) compares false
+                    // ring slot (cnt + lane) & 63 of this lane's 256-byte aligned ring
+                    sts_u32(ring_addr | ((((unsigned int)cnt << 2) + lane4) & 0xFFu), vq + t);
+                    ++cnt;
                 }
-                const int row = (ax * ncy + ay) * ncz;
-                for (int seg = 0; seg < 3; ++seg) {
-                    int a0, a1;
-                    float sz = 0.f;
-                    if (seg == 0) { a0 = max(z0, 0); a1 = min(z1, ncz - 1); }
-                    else if (seg == 1) { if (z0 >= 0) continue; a0 = z0 + ncz; a1 = ncz - 1; sz = -bz; }
-                    else { if (z1 < ncz) continue; a0 = 0; a1 = z1 - ncz; sz = bz; }
-                    if (a0 > a1) continue;
-                    const int s0 = start[row + a0], s1 = start[row + a1 + 1];
-                    for (int base = s0; base < s1; base += 32) {
-                        const int s = base + lane;
-                        bool ok = s < s1 && s != i;
-                        if (ok) {
-                            const float4 pj = posq_s[s];
-                            float dx = pi.x - (pj.x + sx), dy = pi.y - (pj.y + sy), dz = pi.z - (pj.z + sz);
-                            if (rx) dx -= bx * rintf(dx * ibx);
-                            if (ry) dy -= by * rintf(dy * iby);
-                            if (rz) dz -= bz * rintf(dz * ibz);
-                            ok = (dx * dx + dy * dy + dz * dz) < cut2;
-                            if (ok) {
-                                // exclusions: partners within +-32 topology indices sit in the 64-bit window mask
-                                const int oj = orig_s[s];
-                                const unsigned int dd = (unsigned int)(oj - oi + 32);
-                                if (dd < 64u) ok = !((wi >> dd) & 1ull);
-                                else if (fari) ok = !pair_excluded(d, oi, wi, true, oj, d.has_far[oj]);   // rare
-                            }
-                        }
-                        const unsigned int m = __ballot_sync(0xffffffffu, ok);
-                        if (ok) {
-                            const int slot = cnt + __popc(m & ((1u << lane) - 1u));
-                            if (slot < d.nlo_M) list[slot] = (IDX)s;
-                        }
-                        cnt += __popc(m);
+            }
+        } else {
+#pragma unroll 1
+            for (int t = 0; t < 8; ++t) {
+                const float4 c = cand[q * 9 + t];
+                float dx = c.x - pi.x, dy = c.y - pi.y, dz = c.z - pi.z;
+                if (RINT) {
+                    if (rx) dx -= bx * rintf(dx * ibx);
+                    if (ry) dy -= by * rintf(dy * iby);
+                    if (rz) dz -= bz * rintf(dz * ibz);
+                }
+                if (dx * dx + dy * dy + dz * dz < cut2) {
+                    const int oj = __float_as_int(c.w);
+                    const unsigned int dd = (unsigned int)(oj - oi + 32);
+                    bool ok = true;
+                    if (dd < 64u) ok = !((wi >> dd) & 1ull);           // includes the atom itself (bit 32)
+                    else if (fari) ok = !pair_excluded(d, oi, wi, true, oj, d.has_far[oj]);   // rare
+                    if (ok) {
+                        myring[(cnt + lane) & (BUILD_RING - 1)] = (unsigned int)(base + 8 * q + t);
+                        ++cnt;
                     }
                 }
             }
         }
-        if (cnt > d.nlo_M) { g.item_overflow = 1; cnt = d.nlo_M; }
+        __syncwarp();
+        build_flush<IDX>(rows, d.nlo_M, ring, lane, cnt, flushed);
     }
-    if (lane == 0) d.nlo_count[(size_t)r * Npad + i] = cnt;
+}
+
+template <bool RINT, typename IDX>
+__device__ __forceinline__ void build_scan_cells(const Dev& d, const float4* __restrict__ posq_s, const int* __restrict__ orig_s,
+                                              const int* __restrict__ start, bool rx, bool ry, bool rz, int x0, int x1,
+                                              int y0, int y1, int za, int zb, float lox, float hix, float loy, float hiy,
+                                              float loz, float hiz, float4* cand, unsigned int* ring, IDX* rows, int lane,
+                                              float4 pi, int oi, ull wi, bool fari, bool anyfar,
+                                              const int (&og)[BUILD_GROUP], const unsigned int (&osp)[BUILD_GROUP], int& cnt,
+                                              int& flushed) {
+    const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2];
+    const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
+    const float ex = bx / ncx, ey = by / ncy, ez = bz / ncz;
+    const float cut2 = d.outer_cutoff2;
+    for (int rxc = x0; rxc <= x1; ++rxc) {
+        int ax = rxc;
+        float sx = 0.f, dxc = 0.f;
+        if (!rx) {
+            if (ax < 0) { ax += ncx; sx = -bx; } else if (ax >= ncx) { ax -= ncx; sx = bx; }
+            dxc = fmaxf(0.f, fmaxf(rxc * ex - hix, lox - (rxc + 1) * ex));   // gap between the group and the slab
+        }
+        for (int ryc = y0; ryc <= y1; ++ryc) {
+            int ay = ryc;
+            float sy = 0.f, dyc = 0.f;
+            if (!ry) {
+                if (ay < 0) { ay += ncy; sy = -by; } else if (ay >= ncy) { ay -= ncy; sy = by; }
+                dyc = fmaxf(0.f, fmaxf(ryc * ey - hiy, loy - (ryc + 1) * ey));
+            }
+            const float rem2 = cut2 - dxc * dxc - dyc * dyc;
+            if (rem2 <= 0.f) continue;                                        // column out of reach
+            int z0 = 0, z1 = ncz - 1;
+            if (!rz) {
+                const float zr = sqrtf(rem2);
+                z0 = max(za - 2, (int)floorf((loz - zr) / ez));
+                z1 = min(zb + 2, (int)floorf((hiz + zr) / ez));
+            }
+            const int row = (ax * ncy + ay) * ncz;
+#pragma unroll 1
+            for (int seg = 0; seg < 3; ++seg) {
+                int a0, a1;
+                float sz = 0.f;
+                if (seg == 0) { a0 = max(z0, 0); a1 = min(z1, ncz - 1); }
+                else if (seg == 1) { if (z0 >= 0) continue; a0 = z0 + ncz; a1 = ncz - 1; sz = -bz; }
+                else { if (z1 < ncz) continue; a0 = 0; a1 = z1 - ncz; sz = bz; }
+                if (a0 > a1) continue;
+                const int s0 = start[row + a0], s1 = start[row + a1 + 1];
+                build_scan_run<RINT, IDX>(d, posq_s, orig_s, s0, s1, sx, sy, sz, rx, ry, rz, cand, ring, rows, lane,
+                                          pi, oi, wi, fari, anyfar, og, osp, cnt, flushed);
+            }
+        }
+    }
+}
+
+template <typename IDX>
+__global__ void __launch_bounds__(BUILD_WARPS * 32) k_build_list(Dev d) {
+    const int r = blockIdx.y;
+    Globals& g = d.g[r];
+    if (!g.do_rebuild) return;
+    __shared__ float4 s_cand[BUILD_WARPS][36];                   // 4 pieces of 8 candidates + 1 pad each
+    __shared__ __align__(256) unsigned int s_ring[BUILD_WARPS][32 * BUILD_RING];    // per lane: 64 entries = 256 B
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i0 = (blockIdx.x * BUILD_WARPS + w) * BUILD_GROUP, i = i0 + (lane & (BUILD_GROUP - 1));
+    const int N = d.N, Npad = d.Npad;
+    if (i0 >= Npad) return;
+    int* counts = d.nlo_count + ((size_t)r * Npad + i0) * BUILD_SUB;        // [atom of the group][subset]
+    if (i0 >= N) { counts[(lane & (BUILD_GROUP - 1)) * BUILD_SUB + (lane >> 3)] = 0; return; }
+    const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
+    const int* __restrict__ orig_s = d.orig_s + (size_t)r * Npad;
+    const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
+    IDX* rows = reinterpret_cast<IDX*>(d.nlo_list) + ((size_t)r * Npad + i0) * BUILD_SUB * d.nlo_M;
+    float4* cand = s_cand[w];
+    unsigned int* ring = s_ring[w];
+    const bool valid = i < N;
+    const float4 pi = posq_s[i];                                 // padding rows hold NaN: never in range
+    const int o0 = __shfl_sync(0xffffffffu, valid ? orig_s[i] : 0, 0);      // lane 0 is always a real atom
+    const int oi = valid ? orig_s[i] : o0;
+    const ull wi = valid ? (d.excl_win[oi] | (1ull << 32)) : 0ull;
+    const bool fari = valid ? d.has_far[oi] : false;
+    const bool anyfar = __any_sync(0xffffffffu, fari);
+    // exclusion window of every atom of the group as [og, og + osp] in topology indices (waters: their own molecule)
+    int og[BUILD_GROUP];
+    unsigned int osp[BUILD_GROUP];
+    {
+        const int below = valid ? 32 - (__ffsll((long long)wi) - 1) : 0, above = valid ? 31 - __clzll((long long)wi) : 0;
+#pragma unroll
+        for (int k = 0; k < BUILD_GROUP; ++k) {
+            og[k] = __shfl_sync(0xffffffffu, oi - below, k);
+            osp[k] = (unsigned int)__shfl_sync(0xffffffffu, below + above, k);
+        }
+    }
+    int cnt = 0, flushed = 0;
+    if (!d.periodic) {
+        build_scan_run<false, IDX>(d, posq_s, orig_s, 0, N, 0.f, 0.f, 0.f, false, false, false, cand, ring, rows, lane,
+                                   pi, oi, wi, fari, anyfar, og, osp, cnt, flushed);
+    } else {
+        const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
+        // bounding box of the group, in cells and in space (padding lanes copy lane 0)
+        const float l0x = __shfl_sync(0xffffffffu, pi.x, 0), l0y = __shfl_sync(0xffffffffu, pi.y, 0);
+        const float l0z = __shfl_sync(0xffffffffu, pi.z, 0);
+        const float4 p0 = valid ? pi : make_float4(l0x, l0y, l0z, 0.f);
+        int cx, cy, cz;
+        atom_cell_coords(d, p0, cx, cy, cz);
+        const int xa = __reduce_min_sync(0xffffffffu, cx), xb = __reduce_max_sync(0xffffffffu, cx);
+        const int ya = __reduce_min_sync(0xffffffffu, cy), yb = __reduce_max_sync(0xffffffffu, cy);
+        const int za = __reduce_min_sync(0xffffffffu, cz), zb = __reduce_max_sync(0xffffffffu, cz);
+        const float lox = warp_min(p0.x), hix = warp_max(p0.x), loy = warp_min(p0.y), hiy = warp_max(p0.y);
+        const float loz = warp_min(p0.z), hiz = warp_max(p0.z);
+        // a dimension whose scan range would cover a cell twice is scanned once, with the rint() minimum image
+        const bool rx = xb - xa + 5 > ncx, ry = yb - ya + 5 > ncy, rz = zb - za + 5 > ncz;
+        const int x0 = rx ? 0 : xa - 2, x1 = rx ? ncx - 1 : xb + 2;
+        const int y0 = ry ? 0 : ya - 2, y1 = ry ? ncy - 1 : yb + 2;
+        if (rx || ry || rz)
+            build_scan_cells<true, IDX>(d, posq_s, orig_s, start, rx, ry, rz, x0, x1, y0, y1, za, zb, lox, hix, loy, hiy,
+                                        loz, hiz, cand, ring, rows, lane, pi, oi, wi, fari, anyfar, og, osp, cnt, flushed);
+        else
+            build_scan_cells<false, IDX>(d, posq_s, orig_s, start, false, false, false, x0, x1, y0, y1, za, zb, lox, hix,
+                                         loy, hiy, loz, hiz, cand, ring, rows, lane, pi, oi, wi, fari, anyfar, og, osp, cnt, flushed);
+    }
+    // drain the rings: the warp writes each lane's remaining (< 32) entries
+    __syncwarp();
+    for (int L = 0; L < 32; ++L) {
+        const int cL = __shfl_sync(0xffffffffu, flushed, L), nL = __shfl_sync(0xffffffffu, cnt, L) - cL;
+        if (lane < nL && cL + lane < d.nlo_M)
+            rows[(size_t)((L & (BUILD_GROUP - 1)) * BUILD_SUB + (L >> 3)) * d.nlo_M + cL + lane] =
+                (IDX)ring[L * BUILD_RING + ((cL + lane + L) & (BUILD_RING - 1))];
+    }
+    if (cnt > d.nlo_M) { g.item_overflow = 1; cnt = d.nlo_M; }
+    counts[(lane & (BUILD_GROUP - 1)) * BUILD_SUB + (lane >> 3)] = cnt;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -297,34 +444,42 @@ __global__ void __launch_bounds__(128) k_prune_list(Dev d) {
     const int N = d.N, Npad = d.Npad;
     if (i >= Npad) return;
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
-    const IDX* __restrict__ outer = reinterpret_cast<const IDX*>(d.nlo_list) + ((size_t)r * Npad + i) * d.nlo_M;
+    const IDX* __restrict__ outer_rows = reinterpret_cast<const IDX*>(d.nlo_list) + ((size_t)r * Npad + i) * BUILD_SUB * d.nlo_M;
     IDX* inner = reinterpret_cast<IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M;
-    const int n_outer = i < N ? d.nlo_count[(size_t)r * Npad + i] : 0;
     const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
     const float cut2 = d.list_cutoff2;
     const float4 pi = posq_s[i];
     int cnt = 0;
-    for (int base = 0; base < n_outer; base += 32) {
-        const int k = base + lane;
-        bool ok = k < n_outer;
-        int s = 0;
-        if (ok) {
-            s = (int)outer[k];
-            const float4 pj = posq_s[s];
-            float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+    for (int sub = 0; sub < BUILD_SUB; ++sub) {
+        const IDX* __restrict__ outer = outer_rows + (size_t)sub * d.nlo_M;
+        const int n_outer = i < N ? d.nlo_count[((size_t)r * Npad + i) * BUILD_SUB + sub] : 0;
+        // two chunks of 32 entries per iteration: twice the gathers in flight (the kernel is latency bound)
+        for (int base = 0; base < n_outer; base += 64) {
+            const int k0 = base + lane, k1 = k0 + 32;
+            bool ok0 = k0 < n_outer, ok1 = k1 < n_outer;
+            const int s0 = ok0 ? (int)outer[k0] : i, s1 = ok1 ? (int)outer[k1] : i;
+            const float4 pj0 = posq_s[s0], pj1 = posq_s[s1];
+            float dx0 = pi.x - pj0.x, dy0 = pi.y - pj0.y, dz0 = pi.z - pj0.z;
+            float dx1 = pi.x - pj1.x, dy1 = pi.y - pj1.y, dz1 = pi.z - pj1.z;
             if (d.periodic) {
-                dx -= bx * rintf(dx * ibx);
-                dy -= by * rintf(dy * iby);
-                dz -= bz * rintf(dz * ibz);
+                dx0 -= bx * rintf(dx0 * ibx); dy0 -= by * rintf(dy0 * iby); dz0 -= bz * rintf(dz0 * ibz);
+                dx1 -= bx * rintf(dx1 * ibx); dy1 -= by * rintf(dy1 * iby); dz1 -= bz * rintf(dz1 * ibz);
             }
-            ok = (dx * dx + dy * dy + dz * dz) < cut2;
+            ok0 = ok0 && (dx0 * dx0 + dy0 * dy0 + dz0 * dz0) < cut2;
+            ok1 = ok1 && (dx1 * dx1 + dy1 * dy1 + dz1 * dz1) < cut2;
+            const unsigned int m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
+            const unsigned int below = (1u << lane) - 1u;
+            if (ok0) {
+                const int slot = cnt + __popc(m0 & below);
+                if (slot < d.nl_M) inner[slot] = (IDX)s0;
+            }
+            cnt += __popc(m0);
+            if (ok1) {
+                const int slot = cnt + __popc(m1 & below);
+                if (slot < d.nl_M) inner[slot] = (IDX)s1;
+            }
+            cnt += __popc(m1);
         }
-        const unsigned int m = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-            const int slot = cnt + __popc(m & ((1u << lane) - 1u));
-            if (slot < d.nl_M) inner[slot] = (IDX)s;
-        }
-        cnt += __popc(m);
     }
     if (cnt > d.nl_M) { g.item_overflow = 1; cnt = d.nl_M; }
     if (lane == 0) {
@@ -381,31 +536,32 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair(Dev d) {
             dz -= bz * rintf(dz * ibz);
         }
         const float r2 = dx * dx + dy * dy + dz * dz;
-        if (r2 < cut2) {
-            const float invr = rsqrtf(r2);
-            const float invr2 = invr * invr;
-            const float sig = se_i.x + se_j.x;
-            const float s2 = sig * sig * invr2;
-            const float s6 = s2 * s2 * s2;
-            const float eps4 = se_i.y * se_j.y;
-            float de = eps4 * (12.0f * s6 * s6 - 6.0f * s6);
-            const float qq = qi * pj.w;
-            if (METHOD == NB_PME) {
-                const float ar = alpha * r2 * invr;
-                const float ex = __expf(-ar * ar);
-                const float ec = erfc_times(ar, ex);
-                de += qq * invr * (ec + (float)TWO_OVER_SQRT_PI * ar * ex);
-                if (ENERGY) etot += eps4 * (s6 * s6 - s6) + qq * invr * ec;
-            } else if (METHOD == NB_RF) {
-                de += qq * (invr - 2.0f * krf * r2);
-                if (ENERGY) etot += eps4 * (s6 * s6 - s6) + qq * (invr + krf * r2 - crf);
-            } else {
-                de += qq * invr;
-                if (ENERGY) etot += eps4 * (s6 * s6 - s6) + qq * invr;
-            }
-            de *= invr2;
-            fx += dx * de; fy += dy * de; fz += dz * de;
+        // branch-free: entries in the skin shell are computed and masked, so the loads of the unrolled iterations
+        // are issued together instead of behind a divergent branch
+        const float in = r2 < cut2 ? 1.0f : 0.0f;
+        const float invr = rsqrtf(r2);
+        const float invr2 = invr * invr;
+        const float sig = se_i.x + se_j.x;
+        const float s2 = sig * sig * invr2;
+        const float s6 = s2 * s2 * s2;
+        const float eps4 = se_i.y * se_j.y * in;
+        float de = eps4 * (12.0f * s6 * s6 - 6.0f * s6);
+        const float qq = qi * pj.w * in;
+        if (METHOD == NB_PME) {
+            const float ar = alpha * r2 * invr;
+            const float ex = __expf(-ar * ar);
+            const float ec = erfc_times(ar, ex);
+            de += qq * invr * (ec + (float)TWO_OVER_SQRT_PI * ar * ex);
+            if (ENERGY) etot += eps4 * (s6 * s6 - s6) + qq * invr * ec;
+        } else if (METHOD == NB_RF) {
+            de += qq * (invr - 2.0f * krf * r2);
+            if (ENERGY) etot += eps4 * (s6 * s6 - s6) + qq * (invr + krf * r2 - crf) ;
+        } else {
+            de += qq * invr;
+            if (ENERGY) etot += eps4 * (s6 * s6 - s6) + qq * invr;
         }
+        de *= invr2;
+        fx += dx * de; fy += dy * de; fz += dz * de;
     }
     // combine the NL_LANES partial sums (fixed xor tree → deterministic)
 #pragma unroll

@@ -378,7 +378,10 @@ class System(object):
         ra, rk, rx = [], [], []
         for f in self.forces:
             if isinstance(f, CustomExternalForce) and 'periodicdistance' in f.energy:
-                k = f.global_params.get('k', 0.0)
+                # the coefficient is the global parameter multiplying periodicdistance(...)^2, whatever its name
+                # ('k_restr' in blues/simulation.py:346-348)
+                name = f.energy.split('*')[0].strip()
+                k = f.global_params.get(name, next(iter(f.global_params.values()), 0.0))
                 for a, p in zip(f.atoms, f.params):
                     ra.append(a)
                     rk.append(k)

@@ -144,6 +144,42 @@ def compare_neighbors(name, verbose=False, **overrides):
                 duplicates=len(codes) - len(np.unique(codes)))
 
 
+def compare_neighbors_dynamic(name, steps=60, n_replicas=2, dt=0.004, minimize=0, verbose=False, **overrides):
+    """After `steps` of hot dynamics (several prunes and cell-search rebuilds) the list the last evaluation used must
+    still hold every non-excluded pair inside the cutoff at the current coordinates, for every walker."""
+    from oracle.ncmc_oracle import ForceField
+    s, system, topo, x = load_case(name, True, **overrides)
+    ls, le = lambda_tables(5000)
+    eng = _native.Engine(topo, n_replicas=n_replicas, seed=3)
+    eng.set_ncmc_integrator(300.0, 1.0, dt, 'H V R O R V H', 5000, 1, 0.2, 0.8, ls, le)
+    eng.set_positions(x)
+    if minimize:
+        eng.minimize(minimize, 10.0)
+    eng.velocities_to_temperature(300.0)
+    eng.ncmc_run(steps)
+    ff = ForceField(topo)
+    out = []
+    for r in range(n_replicas):
+        xr = eng.get_positions(r)
+        codes = eng.neighbor_pairs(r)
+        ref = ff.neighbor_pairs(xr, topo['box'])
+        only_e, only_o = np.setdiff1d(codes, ref), np.setdiff1d(ref, codes)
+        n = topo['n_atoms']
+        edge = 0.0
+        if len(only_e) + len(only_o):
+            c = np.concatenate([only_e, only_o])
+            d = xr[c // n] - xr[c % n]
+            if topo['nb_method'] != 0:
+                d -= topo['box'] * np.round(d / topo['box'])
+            edge = float(np.max(np.abs(np.linalg.norm(d, axis=1) - topo['cutoff'])))
+        out.append(dict(n_engine=len(codes), n_oracle=len(ref), only_engine=len(only_e), only_oracle=len(only_o), edge=edge,
+                        duplicates=len(codes) - len(np.unique(codes)), rebuilds=eng.neighbor_stats(r)[1]))
+        if verbose:
+            print('--- dynamic neighbours %s walker %d:' % (name, r), out[-1])
+    eng.close()
+    return out
+
+
 def make_ncmc_pair(name, nsteps=10, dt=0.002, splitting='H V R O R V H', nprop=1, prop_lambda=0.3, seed=7,
                    temperature=300.0, n_replicas=1, minimize=False, **overrides):
     """Engine and oracle initialised identically for step-for-step comparisons."""

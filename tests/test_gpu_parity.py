@@ -48,6 +48,17 @@ def test_neighbour_and_exclusion_sets_bit_exact(name):
     assert out['n_engine'] == out['n_oracle'] or out['edge'] < 5e-7
 
 
+@pytest.mark.parametrize('name,kw', [('wat_divaline', dict(steps=80, dt=0.002)),
+                                     ('t4l_surrogate', dict(steps=60, dt=0.004, minimize=60))])
+def test_neighbour_sets_stay_exact_through_prunes_and_rebuilds(name, kw):
+    # dual Verlet lists: inner list pruned from the outer one every few steps, cell search every ~10; after hot dynamics
+    # the list in use must still contain every pair inside the cutoff, for every walker of a batched context
+    for out in gc.compare_neighbors_dynamic(name, n_replicas=2, **kw):
+        assert out['rebuilds'] >= 3, out
+        assert out['duplicates'] == 0
+        assert out['only_engine'] + out['only_oracle'] == 0 or out['edge'] < 5e-6, out
+
+
 @pytest.mark.parametrize('name,kw', [('vac_divaline', {}), ('tol_parm', dict(minimize=True)),
                                      ('vac_divaline', dict(splitting='V H R O R H V')),
                                      ('vac_divaline', dict(splitting='R V O H O V R', nsteps=8)),

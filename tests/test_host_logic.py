@@ -116,7 +116,9 @@ def test_alchemical_system_and_factories(tol):
     assert np.all(ta['charge'][:15] == 0) and np.all(ta['epsilon'][:15] == 0) and len(ta['alch_exc_pairs']) == 27
     restrained = SystemFactory.restrain_positions(tol, systems.md, ':LIG')
     assert type(restrained.getForces()[-1]).__name__ == 'CustomExternalForce'
-    assert len(restrained.flatten()['restraint_atoms']) == 15
+    flat = restrained.flatten()
+    assert len(flat['restraint_atoms']) == 15
+    assert np.all(flat['restraint_k'] == 5.0)          # 'k_restr' global parameter reaches the engine tables
     frozen = SystemFactory.freeze_atoms(tol, systems.alch, ':LIG')
     assert all(frozen.getParticleMass(i)._value == 0 for i in range(15))
     import copy
