@@ -68,6 +68,7 @@ struct bl_handle {
     int* d_move_atoms = nullptr; float* d_move_masses = nullptr; int move_capacity = 0;
     std::vector<double> host_tmp;
     double skin = 0.0; int cell_capacity = 0;
+    int build_cq = 0, build_ctas = 0;
     double4* pinned = nullptr;     // pinned staging for state uploads / downloads ([N] double4)
 };
 
@@ -128,7 +129,7 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 
 // ---- force / energy evaluation at the current positions ---------------------------------------------------
 // energy: also accumulate energies; cm_mode: forwarded to k_begin_eval
-static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, int cm_mode) {
+static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, int cm_mode, int prefetch_noise = 0) {
     Dev& d = h->d;
     cudaStream_t st = h->stream;
     const int R = d.R, N = d.N;
@@ -163,10 +164,16 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         { LaunchTimer t(h, BL_K_PME_GATHER, s2); k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
         cudaEventRecord(h->ev_join, s2);
     }
-    if (nterms > 0) {
+    if (nterms > 0 || prefetch_noise > 0) {
         cudaStream_t s3 = h->profiling ? st : h->stream3;
         cudaStreamWaitEvent(s3, h->ev_fork, 0);
-        { LaunchTimer t(h, BL_K_BONDED, s3); k_bonded<<<dim3(cdiv(nterms, 128), R), 128, 0, s3>>>(d); }
+        if (nterms > 0) { LaunchTimer t(h, BL_K_BONDED, s3); k_bonded<<<dim3(cdiv(nterms, 128), R), 128, 0, s3>>>(d); }
+        if (prefetch_noise > 0) {
+            // thermostat kicks of the next INTEGRATE launch with O steps: k_begin_eval above has advanced the noise
+            // counter past everything consumed so far, so sets 0.. at offset 0 are exactly what that launch will read
+            LaunchTimer t(h, BL_K_INTEGRATE, s3);
+            k_noise<<<dim3(cdiv((long long)N * prefetch_noise, 128), R), 128, 0, s3>>>(d, h->ic, STREAM_LANGEVIN, prefetch_noise, 0);
+        }
         cudaEventRecord(h->ev_join3, s3);
     }
     if (d.n_alch > 0) {
@@ -180,15 +187,10 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     }
     {
         LaunchTimer t(h, BL_K_NEIGHBOR);
-        dim3 grid(cdiv(d.Npad, BUILD_GROUP * BUILD_WARPS), R);      // one warp per 8 consecutive sorted atoms
-        if (d.nl_u16) k_build_list<unsigned short><<<grid, 32 * BUILD_WARPS, 0, st>>>(d);
-        else k_build_list<int><<<grid, 32 * BUILD_WARPS, 0, st>>>(d);
-    }
-    {
-        LaunchTimer t(h, BL_K_NEIGHBOR);
-        dim3 grid(cdiv(d.Npad, 4), R);
-        if (d.nl_u16) k_prune_list<unsigned short><<<grid, 128, 0, st>>>(d);
-        else k_prune_list<int><<<grid, 128, 0, st>>>(d);
+        dim3 grid(h->build_ctas);                          // persistent single-warp CTAs shared by all walkers
+        const size_t smem = build_smem_bytes(h->build_cq, d.nl_u16 ? 2 : 4);
+        if (d.nl_u16) k_build_list<unsigned short><<<grid, 32, smem, st>>>(d, h->build_cq);
+        else k_build_list<int><<<grid, 32, smem, st>>>(d, h->build_cq);
     }
     {
         LaunchTimer t(h, BL_K_PAIR);
@@ -204,14 +206,14 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
 #undef PAIR
     }
     if (pme) cudaStreamWaitEvent(st, h->ev_join, 0);
-    if (nterms > 0) cudaStreamWaitEvent(st, h->ev_join3, 0);
+    if (nterms > 0 || prefetch_noise > 0) cudaStreamWaitEvent(st, h->ev_join3, 0);
     if (d.n_alch > 0) cudaStreamWaitEvent(st, h->ev_join4, 0);
 }
 
-static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a) {
+static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a, bool noise_prefetched) {
     int n_o = 0, n_md = 0;
     for (int k = 0; k < a.nops; ++k) { if (a.ops[k].kind == OP_O) n_o++; if (a.ops[k].kind == OP_MD) n_md++; }
-    if (n_o > 0) {
+    if (n_o > 0 && !noise_prefetched) {
         LaunchTimer t(h, BL_K_INTEGRATE);
         k_noise<<<dim3(cdiv((long long)h->d.N * n_o, 128), h->d.R), 128, 0, h->stream>>>(h->d, h->ic, STREAM_LANGEVIN, n_o, a.noise_offset);
     }
@@ -321,22 +323,58 @@ static void compile_pass(bl_handle* h, std::vector<Launch>& out, int& cursor, bo
 }
 
 // ---- issuing launches, CUDA-graph caching -------------------------------------------------------------------
-static void issue(bl_handle* h, const std::vector<Launch>& ls, int& pending_noise, int& pending_md) {
-    for (const Launch& l : ls) {
+struct HostCounters {
+    int pending_noise = 0, pending_md = 0;
+    int noise_ready = 0;      // thermostat noise sets prefetched by the last evaluation, valid at offset 0
+};
+static std::map<bl_handle*, HostCounters>& counter_map() {
+    static std::map<bl_handle*, HostCounters> m;
+    return m;
+}
+static HostCounters& counters(bl_handle* h) { return counter_map()[h]; }
+
+static int count_ops(const IntegrateArgs& a, int kind) {
+    int n = 0;
+    for (int k = 0; k < a.nops; ++k) n += a.ops[k].kind == kind;
+    return n;
+}
+
+// O steps of the first noise-consuming INTEGRATE launch after evaluation `k` (wrapping to the start of the list: a step
+// program repeats), or 0 if another evaluation or an MD step comes first.  A wrong guess costs nothing: the consumer
+// checks hc.noise_ready and falls back to generating its noise inline.
+static int noise_lookahead(const std::vector<Launch>& ls, size_t k) {
+    for (size_t j = 1; j <= ls.size(); ++j) {
+        const Launch& l = ls[(k + j) % ls.size()];
+        if (l.is_eval) return 0;
+        if (count_ops(l.args, OP_MD) > 0) return 0;
+        const int n_o = count_ops(l.args, OP_O);
+        if (n_o > 0) return n_o;
+    }
+    return 0;
+}
+
+// Enqueue the launches (dry = false) or only replay their host-side bookkeeping (dry = true, after a graph launch).
+static void issue(bl_handle* h, const std::vector<Launch>& ls, HostCounters& hc, bool dry = false) {
+    for (size_t k = 0; k < ls.size(); ++k) {
+        const Launch& l = ls[k];
         if (l.is_eval) {
-            enqueue_eval(h, l.energy, pending_noise, pending_md, l.cm_mode);
-            pending_noise = 0;
-            pending_md = 0;
+            if (hc.pending_noise != 0 || hc.pending_md != 0) hc.noise_ready = 0;    // counters move: stale
+            const int prefetch = hc.noise_ready > 0 ? 0 : noise_lookahead(ls, k);
+            if (!dry) enqueue_eval(h, l.energy, hc.pending_noise, hc.pending_md, l.cm_mode, prefetch);
+            if (prefetch > 0) hc.noise_ready = prefetch;
+            hc.pending_noise = 0;
+            hc.pending_md = 0;
         } else {
             IntegrateArgs a = l.args;
-            a.noise_offset = pending_noise;
-            a.md_offset = pending_md;
-            enqueue_integrate(h, a);
-            for (int k = 0; k < a.nops; ++k) {
-                if (a.ops[k].kind == OP_O) pending_noise++;
-                if (a.ops[k].kind == OP_MD) pending_md++;
-            }
-            if (l.flip_after) {
+            a.noise_offset = hc.pending_noise;
+            a.md_offset = hc.pending_md;
+            const int n_o = count_ops(a, OP_O), n_md = count_ops(a, OP_MD);
+            const bool prefetched = n_o > 0 && n_md == 0 && hc.pending_noise == 0 && hc.noise_ready >= n_o;
+            if (!dry) enqueue_integrate(h, a, prefetched);
+            if (n_o > 0 || n_md > 0) hc.noise_ready = 0;        // consumed, or overwritten by the inline kernels
+            hc.pending_noise += n_o;
+            hc.pending_md += n_md;
+            if (l.flip_after && !dry) {
                 LaunchTimer t(h, -1);
                 k_cm_flip<<<1, 64, 0, h->stream>>>(h->d, h->cm_parity);
             }
@@ -344,30 +382,24 @@ static void issue(bl_handle* h, const std::vector<Launch>& ls, int& pending_nois
     }
 }
 
-struct HostCounters { int pending_noise = 0, pending_md = 0; };
-static HostCounters& counters(bl_handle* h) {
-    static std::map<bl_handle*, HostCounters> m;
-    return m[h];
-}
-
 // run `ls` either directly or through a cached graph keyed by `key`
 static int run_launches(bl_handle* h, const std::string& key, const std::vector<Launch>& ls) {
     HostCounters& hc = counters(h);
     if (!h->use_graphs || h->profiling) {
-        issue(h, ls, hc.pending_noise, hc.pending_md);
+        issue(h, ls, hc);
         return BL_OK;
     }
     char suffix[64];
-    snprintf(suffix, sizeof suffix, "|n%d|m%d", hc.pending_noise, hc.pending_md);
+    snprintf(suffix, sizeof suffix, "|n%d|m%d|p%d", hc.pending_noise, hc.pending_md, hc.noise_ready);
     const std::string k = key + suffix;
     auto it = h->graphs.find(k);
     if (it == h->graphs.end()) {
         cudaGraph_t graph = nullptr;
-        int pn = hc.pending_noise, pm = hc.pending_md;
+        HostCounters tmp = hc;
         CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
         h->capturing = true;
         h->capture_launches = 0;
-        issue(h, ls, pn, pm);
+        issue(h, ls, tmp);
         h->capturing = false;
         CK(cudaStreamEndCapture(h->stream, &graph));
         cudaGraphExec_t exec = nullptr;
@@ -379,14 +411,7 @@ static int run_launches(bl_handle* h, const std::string& key, const std::vector<
     }
     CK(cudaGraphLaunch(it->second, h->stream));
     h->launches += (unsigned long long)(uintptr_t)h->graphs[k + "#n"];
-    // advance the host mirror of the pending counters exactly as issue() would
-    for (const Launch& l : ls) {
-        if (l.is_eval) { hc.pending_noise = 0; hc.pending_md = 0; }
-        else for (int q = 0; q < l.args.nops; ++q) {
-            if (l.args.ops[q].kind == OP_O) hc.pending_noise++;
-            if (l.args.ops[q].kind == OP_MD) hc.pending_md++;
-        }
-    }
+    issue(h, ls, hc, true);      // advance the host mirror of the counters exactly as the captured launches did
     return BL_OK;
 }
 
@@ -420,6 +445,7 @@ static int check_flags(bl_handle* h) {
 // evaluate forces (and energies) at the current positions outside the step program
 static void eval_now(bl_handle* h, bool energy) {
     HostCounters& hc = counters(h);
+    if (hc.pending_noise != 0 || hc.pending_md != 0) hc.noise_ready = 0;
     enqueue_eval(h, energy, hc.pending_noise, hc.pending_md, 0);
     hc.pending_noise = hc.pending_md = 0;
     h->forces_valid = true;
@@ -593,7 +619,9 @@ static int setup_cells(bl_handle* h, const double box[3]) {
         d.cell_order = dalloc<int>(h, h->cell_capacity);
         d.cell_start = dalloc<int>(h, (size_t)d.R * (h->cell_capacity + 1));
         d.cell_cursor = dalloc<int>(h, (size_t)d.R * (h->cell_capacity + 1));
-        if (!d.cell_order || !d.cell_start || !d.cell_cursor) { h->error = "device allocation failed"; return BL_ERR_CUDA; }
+        d.group_capacity = d.Npad / BUILD_GROUP + h->cell_capacity + 8;
+        d.group_first = dalloc<int>(h, (size_t)d.R * d.group_capacity);
+        if (!d.cell_order || !d.cell_start || !d.cell_cursor || !d.group_first) { h->error = "device allocation failed"; return BL_ERR_CUDA; }
         invalidate_graphs(h);          // kernels captured the old pointers by value
     }
     if (n != d.ncells) invalidate_graphs(h);
@@ -617,6 +645,7 @@ void* bl_stream(bl_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int bl_destroy(bl_handle* h) {
     if (!h) return BL_OK;
+    counter_map().erase(h);
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     invalidate_graphs(h);
@@ -646,6 +675,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (device < 0 || device >= ndev) { g_create_error = "invalid device index"; return BL_ERR_INVALID; }
     if (t->nb_method != 0 && t->nb_method != 2 && t->nb_method != 4) { g_create_error = "unsupported nonbonded method"; return BL_ERR_INVALID; }
     bl_handle* h = new bl_handle();
+    counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping
     auto fail = [&](int code, const std::string& msg) { g_create_error = msg; bl_destroy(h); return code; };
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess) return fail(BL_ERR_CUDA, "cudaSetDevice failed");
@@ -673,12 +703,9 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     }
     d.cutoffd = t->cutoff; d.alphad = t->ewald_alpha;
     d.cutoff = (float)t->cutoff; d.cutoff2 = (float)(t->cutoff * t->cutoff);
-    double skin = d.periodic ? 0.1 * t->cutoff : 0.0;
+    // Verlet skin: 0.14 x cutoff balances list rebuilds (every ~6 steps at 4 fs) against extra pair work (measured)
+    double skin = d.periodic ? 0.14 * t->cutoff : 0.0;
     if (d.periodic && getenv("BLUES_B200_SKIN")) skin = std::max(0.01, atof(getenv("BLUES_B200_SKIN")));
-    double skin_outer = d.periodic ? std::max(skin * 3.5, 0.35 * t->cutoff) : 0.0;
-    if (d.periodic && getenv("BLUES_B200_SKIN_OUTER")) skin_outer = std::max(skin * 1.5, atof(getenv("BLUES_B200_SKIN_OUTER")));
-    d.outer_cutoff2 = d.periodic ? (float)((t->cutoff + skin_outer) * (t->cutoff + skin_outer)) : 3.0e38f;
-    d.outer_half2 = d.periodic ? (float)(0.25 * (skin_outer - skin) * (skin_outer - skin)) : 3.0e38f;
     d.list_cutoff2 = d.periodic ? (float)((t->cutoff + skin) * (t->cutoff + skin)) : 3.0e38f;
     d.skin_half2 = d.periodic ? (float)(0.25 * skin * skin) : 3.0e38f;
     d.alpha = (float)t->ewald_alpha;
@@ -823,7 +850,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     h->d_scratch = dalloc<double>(h, std::max((size_t)R * 4, (size_t)N * 3));
     h->d_iscratch = dalloc<int>(h, (size_t)R * 2);
     // neighbour structures
-    h->skin = skin_outer;     // the cell grid serves the outer list
+    h->skin = skin;           // the cell grid serves the list cutoff (cutoff + skin)
     {
         int rc = setup_cells(h, t->box);
         if (rc != BL_OK) return fail(rc, h->error);
@@ -833,7 +860,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     d.sigeps_s = dalloc<float2>(h, (size_t)R * d.Npad);
     d.orig_s = dalloc<int>(h, (size_t)R * d.Npad);
     {
-        // list capacity per atom: 1.5 x the mean number of atoms inside the list-cutoff sphere (+ margin)
+        // row capacity per atom: 1.5 x the mean number of atoms inside the list-cutoff sphere (+ margin)
         long long M = N;
         if (d.periodic) {
             const double V = t->box[0] * t->box[1] * t->box[2], rl = t->cutoff + skin;
@@ -841,23 +868,27 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         }
         d.nl_M = (int)((M + 7) / 8 * 8);
     }
-    d.nl_count = dalloc<int>(h, (size_t)R * d.Npad);
     d.nl_u16 = d.Npad < 65536 ? 1 : 0;
+    d.nl_count = dalloc<int>(h, (size_t)R * d.Npad);
     d.nl_list = dalloc<unsigned char>(h, (size_t)R * d.Npad * d.nl_M * (d.nl_u16 ? 2 : 4));
     {
-        // the outer list of an atom is BUILD_SUB sub-rows (one per candidate subset of k_build_list); capacity per
-        // sub-row: 1.5 x the mean share of the outer-cutoff sphere (+ margin), a multiple of the 32-entry flush
-        long long M = N;
-        if (d.periodic) {
-            const double V = t->box[0] * t->box[1] * t->box[2], rl = t->cutoff + skin_outer;
-            M = std::min<long long>(N, (long long)(1.5 * 4.0 / 3.0 * M_PI * rl * rl * rl * N / V) + 96);
+        // k_build_list: per-lane sub-list capacity (a quarter of a row + margin), its shared memory and the number of
+        // persistent single-warp CTAs that fit on the device
+        h->build_cq = d.nl_M / 4 + 48;
+        const size_t smem = build_smem_bytes(h->build_cq, d.nl_u16 ? 2 : 4);
+        if (smem > 200 * 1024) return fail(BL_ERR_CAPACITY, "neighbour list rows do not fit the builder's shared memory");
+        int per_sm = 0, n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        if (d.nl_u16) {
+            cudaFuncSetAttribute(k_build_list<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_build_list<unsigned short>, 32, smem);
+        } else {
+            cudaFuncSetAttribute(k_build_list<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_build_list<int>, 32, smem);
         }
-        const long long Mq = (M + BUILD_SUB - 1) / BUILD_SUB + 64;
-        d.nlo_M = (int)((Mq + 31) / 32 * 32);
+        per_sm = std::max(1, per_sm);
+        h->build_ctas = std::max(32, std::min(R * (cdiv(d.Npad, BUILD_GROUP) + 64), per_sm * n_sm));
     }
-    d.nlo_count = dalloc<int>(h, (size_t)R * d.Npad * BUILD_SUB);
-    d.nlo_list = dalloc<unsigned char>(h, (size_t)R * d.Npad * BUILD_SUB * d.nlo_M * (d.nl_u16 ? 2 : 4));
-    d.pos_ref_outer = dalloc<float4>(h, RN);
     // PME
     if (d.pme) {
         d.gx = t->pme_grid[0]; d.gy = t->pme_grid[1]; d.gz = t->pme_grid[2];
@@ -911,6 +942,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
 int bl_set_seed(bl_handle* h, uint64_t seed) {
     if (!h) return BL_ERR_INVALID;
     h->ic.seed = seed;
+    counters(h).noise_ready = 0;
     invalidate_graphs(h);
     return BL_OK;
 }
@@ -993,6 +1025,7 @@ int bl_set_integrator(bl_handle* h, const bl_integrator_params* p) {
         return BL_ERR_INVALID;
     }
     invalidate_graphs(h);
+    counters(h).noise_ready = 0;
     h->forces_valid = false;
     return BL_OK;
 }
@@ -1305,7 +1338,7 @@ int bl_ncmc_run(bl_handle* h, int n_steps, const bl_move* move) {
             memset(&a, 0, sizeof a);
             a.nops = 1;
             a.ops[0].kind = OP_CONSTRAIN;
-            enqueue_integrate(h, a);
+            enqueue_integrate(h, a, false);
             { LaunchTimer t(h, -1); k_reset_protocol<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d); }
             h->lambda_step = 0;
             h->forces_valid = false;
@@ -1403,7 +1436,7 @@ int bl_minimize(bl_handle* h, int max_iterations, double tolerance) {
     // otherwise restore and halve the step.  One host round-trip per iteration (not a hot path).
     {
         IntegrateArgs a; memset(&a, 0, sizeof a); a.nops = 1; a.ops[0].kind = OP_CONSTRAIN;
-        enqueue_integrate(h, a);
+        enqueue_integrate(h, a, false);
         positions_changed(h);
     }
     std::vector<double> e0(d.R), e1(d.R), step(d.R, 1e-6);

@@ -38,10 +38,11 @@ struct Globals {
     int e_valid;             // e_total_prev is valid
     int nan_flag;
     unsigned int noise_counter, vel_counter, move_counter, accept_counter, md_counter;
-    int do_rebuild, rebuild_request;   // outer list (cell search)
-    int do_prune, prune_request;       // inner list (prune of the outer list)
+    int do_rebuild, rebuild_request;   // Verlet list rebuild latched for this evaluation / requested by the host (2)
+    int do_prune, prune_request;       // alchemical list follows do_rebuild / some atom moved > skin / 2
     long long n_rebuilds;
     int item_overflow;        // a neighbour list ran out of capacity
+    int n_groups, build_cursor;   // k_build_list work queue: groups of <= 8 sorted atoms, next group to fetch
 };
 
 struct IntegratorConsts {
@@ -88,14 +89,12 @@ struct Dev {
     int* cell_order;                        // [ncells] Morton rank of each cell
     int* cell_start; int* cell_cursor;      // [R][ncells+1] first sorted slot of every cell (+ scatter cursor)
     int* atom_cell;                         // [R*N]
+    int* group_first; int group_capacity;   // [R][group_capacity] (first sorted index << 4 | atoms) of every build group
     int* rank;                              // [R*N] position of atom a in the sorted order
     float4* posq_s; float2* sigeps_s; int* orig_s;   // [R*Npad] sorted copies (pads: NaN position, orig -1)
-    int nlo_M; int* nlo_count; void* nlo_list;   // outer list (cutoff + outer skin): [R*Npad][4 sub-rows][nlo_M], counts [R*Npad][4]
-    float4* pos_ref_outer;                  // [R*N] positions at the last outer rebuild
-    float outer_cutoff2, outer_half2;       // squared outer list cutoff; squared displacement budget of the outer list
-    int nl_M;                               // inner list capacity per atom
+    int nl_M;                               // capacity of one row of the Verlet list
     int* nl_count;                          // [R*Npad]
-    void* nl_list;                          // [R*Npad][nl_M] sorted indices of the neighbours within the list cutoff
+    void* nl_list;                          // [R*Npad][nl_M] sorted indices of the neighbours within cutoff + skin
     int nl_u16;                             // indices stored as uint16 (Npad < 65536) to halve the list traffic
     // bonded tables
     int n_bonds, n_angles, n_torsions, n_excl, n_restraints, n_alch_exc;

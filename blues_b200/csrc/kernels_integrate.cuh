@@ -401,19 +401,12 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
         d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * N + a]] = pf;
         const float4 pr = d.pos_ref[(size_t)r * N + a];
         float ddx = pf.x - pr.x, ddy = pf.y - pr.y, ddz = pf.z - pr.z;
-        const float4 po = d.pos_ref_outer[(size_t)r * N + a];
-        float ox = pf.x - po.x, oy = pf.y - po.y, oz = pf.z - po.z;
         if (d.periodic) {
             ddx -= d.boxf[0] * rintf(ddx * d.boxf[3]);
             ddy -= d.boxf[1] * rintf(ddy * d.boxf[4]);
             ddz -= d.boxf[2] * rintf(ddz * d.boxf[5]);
-            ox -= d.boxf[0] * rintf(ox * d.boxf[3]);
-            oy -= d.boxf[1] * rintf(oy * d.boxf[4]);
-            oz -= d.boxf[2] * rintf(oz * d.boxf[5]);
         }
         moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
-        bad = bad || false;
-        moved_outer = moved_outer || (ox * ox + oy * oy + oz * oz > d.outer_half2);
         bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
 #pragma unroll
         for (int q = 0; q < 3; ++q) mom[q] += s.mass[k] * s.v[k][q];
@@ -543,19 +536,12 @@ __device__ __forceinline__ void run_cluster_generic(const Dev& d, const Integrat
         d.posq_s[(size_t)r * d.Npad + d.rank[(size_t)r * N + a]] = pf;
         const float4 pr = d.pos_ref[(size_t)r * N + a];
         float ddx = pf.x - pr.x, ddy = pf.y - pr.y, ddz = pf.z - pr.z;
-        const float4 po = d.pos_ref_outer[(size_t)r * N + a];
-        float ox = pf.x - po.x, oy = pf.y - po.y, oz = pf.z - po.z;
         if (d.periodic) {
             ddx -= d.boxf[0] * rintf(ddx * d.boxf[3]);
             ddy -= d.boxf[1] * rintf(ddy * d.boxf[4]);
             ddz -= d.boxf[2] * rintf(ddz * d.boxf[5]);
-            ox -= d.boxf[0] * rintf(ox * d.boxf[3]);
-            oy -= d.boxf[1] * rintf(oy * d.boxf[4]);
-            oz -= d.boxf[2] * rintf(oz * d.boxf[5]);
         }
         moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
-        bad = bad || false;
-        moved_outer = moved_outer || (ox * ox + oy * oy + oz * oz > d.outer_half2);
         bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
         for (int q = 0; q < 3; ++q) mom[q] += mass[k] * s.v[k][q];
     }
@@ -583,7 +569,6 @@ __global__ void __launch_bounds__(64) k_integrate(Dev d, IntegratorConsts ic, In
         default: break;      // generic clusters are integrated by k_integrate_generic
         }
         if (moved) g.prune_request = 1;
-        if (moved_outer && g.rebuild_request == 0) g.rebuild_request = 1;
         if (bad) g.nan_flag = 1;
     }
     if (args.accum_cm && ic.remove_cm) {
@@ -643,7 +628,6 @@ __global__ void __launch_bounds__(64) k_integrate_generic(Dev d, IntegratorConst
         const unsigned int noise0 = g.noise_counter + args.noise_offset, md0 = g.md_counter + args.md_offset;
         run_cluster_generic(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer);
         if (moved) g.prune_request = 1;
-        if (moved_outer && g.rebuild_request == 0) g.rebuild_request = 1;
         if (bad) g.nan_flag = 1;
     }
     if (args.accum_cm && ic.remove_cm) {

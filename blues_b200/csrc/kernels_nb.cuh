@@ -19,10 +19,10 @@ __global__ void k_begin_eval(Dev d, int advance_noise, int advance_md, int cm_mo
         for (int i = threadIdx.x; i < d.R * ALCH_SLOTS * 3; i += blockDim.x) d.alch_acc[i] = 0;
         for (int i = threadIdx.x; i < d.R; i += blockDim.x) {
             Globals& g = d.g[i];
-            // an inner-list refresh is due when some atom moved > inner skin / 2 since the last prune; it becomes a
-            // full rebuild when, at that moment, some atom sits > (outer - inner skin) / 2 away from the outer reference
-            g.do_rebuild = g.rebuild_request == 2 || (g.prune_request && g.rebuild_request);
-            g.do_prune = g.prune_request || g.do_rebuild;
+            // the Verlet list is rebuilt (cell sort + search) when some atom moved > skin / 2 since the last build,
+            // or on request (host wrote coordinates, box changed)
+            g.do_rebuild = g.rebuild_request == 2 || g.prune_request;
+            g.do_prune = g.do_rebuild;                        // the alchemical pair list follows the same schedule
             g.rebuild_request = 0;
             g.prune_request = 0;
             g.noise_counter += advance_noise;
@@ -53,6 +53,7 @@ __device__ __forceinline__ void atom_cell_coords(const Dev& d, float4 p, int& cx
 }
 
 #define SORT_CTAS 8
+#define BUILD_GROUP 8          /* atoms per k_build_list work group */
 __global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort_atoms(Dev d) {
     // one thread-block cluster (8 CTAs, hardware cluster barrier) per walker
     namespace cg = cooperative_groups;
@@ -136,7 +137,7 @@ __global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort
     int* rank = d.rank + (size_t)r * N;
     float4* posq_s = d.posq_s + (size_t)r * Npad;
     float2* sigeps_s = d.sigeps_s + (size_t)r * Npad;
-    float4* pos_ref = d.pos_ref_outer + (size_t)r * N;
+    float4* pos_ref = d.pos_ref + (size_t)r * N;          // reference positions of the displacement test
     for (int s = tid; s < N; s += nt) {
         const int a = orig_s[s];
         rank[a] = s;
@@ -154,6 +155,33 @@ __global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort
     if (tid == 0) {
         g.item_overflow = 0;
         g.n_rebuilds += 1;
+        g.build_cursor = 0;
+    }
+    if (cta == SORT_CTAS - 1) {
+        // groups of <= BUILD_GROUP consecutive sorted atoms that never straddle a cell column (k_build_list works on
+        // one group per warp; a group confined to a column has a compact search region)
+        const int t = threadIdx.x, n1 = blockDim.x;
+        const int ncols = d.periodic ? d.ncell[0] * d.ncell[1] : 1, ncz = d.periodic ? d.ncell[2] : 1;
+        const int per = (ncols + n1 - 1) / n1;
+        const int c0 = min(t * per, ncols), c1 = min(c0 + per, ncols);
+        int sum = 0;
+        for (int c = c0; c < c1; ++c) sum += (start[(c + 1) * ncz] - start[c * ncz] + BUILD_GROUP - 1) / BUILD_GROUP;
+        __syncthreads();                       // s_part was last read before the previous cluster barrier
+        s_part[t] = sum;
+        __syncthreads();
+        for (int off = 1; off < n1; off <<= 1) {
+            int v = (t >= off) ? s_part[t - off] : 0;
+            __syncthreads();
+            s_part[t] += v;
+            __syncthreads();
+        }
+        int run = s_part[t] - sum;
+        int* groups = d.group_first + (size_t)r * d.group_capacity;
+        for (int c = c0; c < c1; ++c) {
+            const int s0 = start[c * ncz], n = start[(c + 1) * ncz] - s0;
+            for (int k = 0; k < n; k += BUILD_GROUP) groups[run++] = (s0 + k) * 16 + min(BUILD_GROUP, n - k);
+        }
+        if (t == n1 - 1) g.n_groups = s_part[t];
     }
 }
 
@@ -178,79 +206,72 @@ __device__ __forceinline__ bool pair_excluded(const Dev& d, int oi, ull wi, bool
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// k_build_list: outer Verlet list (cutoff + outer skin) by cell search.  Full list (i sees j and j sees i): the pair
-// kernel needs no j-side force scatter and no exclusion test.
+// k_build_list: Verlet list (cutoff + skin) by cell search.  Full list (i sees j and j sees i): the pair kernel needs
+// no j-side force scatter and no exclusion test.
 //
-// One warp owns BUILD_GROUP = 8 consecutive atoms of the cell-sorted order (a compact group: one cell, sometimes two);
-// lane = (atom a = lane & 7, candidate subset q = lane >> 3).  The warp walks the cell columns around the group's
-// bounding box; candidates are staged 32 at a time in shared memory, already shifted to the periodic image that can
-// be in range, and in iteration t lane (a, q) tests candidate 8 q + t against atom a: one LDS and ~12 ALU instructions
-// per 32 distance tests, no per-candidate global load.  Exclusions are only looked at in chunks that hold a candidate
-// whose topology index is near the group's (warp-uniform test), i.e. almost never.  Survivors go to a per-lane ring in
-// shared memory (bank-skewed) that the whole warp flushes 32 entries at a time, so global stores stay coalesced.
-// An atom's outer list is therefore stored as BUILD_SUB = 4 sub-rows (one per candidate subset); scan order is fixed,
-// hence so is the order of every sub-row (reproducible float sums downstream).
+// Persistent single-warp CTAs fetch groups of <= 8 consecutive cell-sorted atoms (never straddling a cell column) from
+// a work counter.  Lane = (atom a = lane & 7, candidate subset q = lane >> 3).  The warp walks the cell columns around
+// the group's bounding box; candidates are staged 32 at a time in shared memory, already shifted to the periodic image
+// that can be in range (the next chunk's loads are in flight meanwhile), and in iteration t lane (a, q) tests candidate
+// 8 q + t against atom a: one LDS and ~10 ALU instructions per 32 distance tests.  Exclusions are only looked at in
+// chunks that hold a candidate inside the exclusion window of a group atom (warp-uniform test), i.e. almost never.
+// Survivors are appended to per-lane sub-lists in shared memory; when the group is done the warp concatenates the four
+// sub-lists of every atom into its row with coalesced stores.  Scan order is fixed, hence so is the order of every
+// row (reproducible float sums downstream), whichever warp happens to process the group.
 // ---------------------------------------------------------------------------------------------------------
 #define NL_LANES 8
 #define NL_BLOCK 128
-#define BUILD_WARPS 4
-#define BUILD_RING 64
-#define BUILD_GROUP 8
-#define BUILD_SUB 4
+#define BUILD_SLACK 8       /* a chunk appends at most 8 entries per lane between two capacity checks */
 
-__device__ __forceinline__ void sts_u32(unsigned int addr, unsigned int v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+__device__ __forceinline__ void sts_idx(unsigned int addr, unsigned short v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
-
-template <typename IDX>
-__device__ __forceinline__ void build_flush(IDX* __restrict__ rows, int Mq, const unsigned int* ring, int lane,
-                                            int cnt, int& flushed) {
-    // rows: sub-row 0 of the group's first atom; lane L = (atom L & 7, subset L >> 3) owns sub-row (L & 7) * 4 + (L >> 3)
-    unsigned int full = __ballot_sync(0xffffffffu, cnt - flushed >= 32);
-    while (full) {
-        const int L = __ffs(full) - 1;
-        full &= full - 1;
-        const int cL = __shfl_sync(0xffffffffu, flushed, L);
-        const unsigned int v = ring[L * BUILD_RING + ((cL + lane + L) & (BUILD_RING - 1))];
-        if (cL < Mq) rows[(size_t)((L & (BUILD_GROUP - 1)) * BUILD_SUB + (L >> 3)) * Mq + cL + lane] = (IDX)v;   // Mq % 32 == 0
-        if (lane == L) flushed += 32;
-    }
+__device__ __forceinline__ void sts_idx(unsigned int addr, int v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 template <bool RINT, typename IDX>
 __device__ __forceinline__ void build_scan_run(const Dev& d, const float4* __restrict__ posq_s, const int* __restrict__ orig_s,
                                                int s0, int s1, float sx, float sy, float sz, bool rx, bool ry, bool rz,
-                                               float4* cand, unsigned int* ring, IDX* rows, int lane, float4 pi, int oi,
-                                               ull wi, bool fari, bool anyfar, const int (&og)[BUILD_GROUP],
-                                               const unsigned int (&osp)[BUILD_GROUP], int& cnt, int& flushed) {
-    const float cut2 = d.outer_cutoff2;
+                                               float4* cand, IDX* mysub, int cq, int lane, float4 pi, int oi, ull wi,
+                                               bool fari, bool anyfar, const int (&og)[BUILD_GROUP],
+                                               const unsigned int (&osp)[BUILD_GROUP], int& cnt, bool& overflow) {
+    const float cut2 = d.list_cutoff2;
     const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
     const float qnan = __int_as_float(0x7fc00000);
     const int q = lane >> 3;
-    unsigned int* myring = ring + lane * BUILD_RING;
-    const unsigned int ring_addr = (unsigned int)__cvta_generic_to_shared(myring), lane4 = 4u * lane;
+    const unsigned int sub_addr = (unsigned int)__cvta_generic_to_shared(mysub);
+    // software pipeline: the candidate of the next chunk is requested before the current chunk is processed
+    float4 cnext = make_float4(qnan, qnan, qnan, 0.f);
+    int ojnext = 0;
+    if (s0 + lane < s1) { cnext = posq_s[s0 + lane]; ojnext = orig_s[s0 + lane]; }
     for (int base = s0; base < s1; base += 32) {
         bool near = false;
         {
-            const int s = base + lane;
-            float4 c = make_float4(qnan, qnan, qnan, 0.f);
-            if (s < s1) {
-                c = posq_s[s];
+            float4 c = cnext;
+            const int oj = ojnext;
+            const bool have = base + lane < s1;
+            const int sn = base + 32 + lane;
+            if (sn < s1) { cnext = posq_s[sn]; ojnext = orig_s[sn]; }
+            if (have) {
                 c.x += sx; c.y += sy; c.z += sz;
-                const int oj = orig_s[s];
                 c.w = __int_as_float(oj);
 #pragma unroll
                 for (int k = 0; k < BUILD_GROUP; ++k)               // inside the exclusion window of a group atom
                     near = near || (unsigned int)(oj - og[k]) <= osp[k];
+            } else {
+                c = make_float4(qnan, qnan, qnan, 0.f);
             }
             __syncwarp();
             cand[lane + (lane >> 3)] = c;                           // 8-candidate pieces, padded: conflict-free LDS
             __syncwarp();
         }
         const bool check = anyfar || __any_sync(0xffffffffu, near);   // warp-uniform
+        unsigned int wp = sub_addr + (unsigned int)cnt * (unsigned int)sizeof(IDX);     // shared-space byte address
         if (!check) {
             // fast path: no candidate of this chunk can be excluded from (or be) an atom of the group.  All eight
-            // candidates are loaded and measured before the first ring store, so the eight chains overlap.
+            // candidates are loaded and measured before the first store, so the eight chains overlap; every store is
+            // unconditional and only the write pointer advance is predicated.
             float r2v[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
@@ -263,14 +284,11 @@ __device__ __forceinline__ void build_scan_run(const Dev& d, const float4* __res
                 }
                 r2v[t] = dx * dx + dy * dy + dz * dz;
             }
-            const unsigned int vq = (unsigned int)(base + 8 * q);
+            const int vq = base + 8 * q;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                if (r2v[t] < cut2) {                               // NaN (padding) compares false
-                    // ring slot (cnt + lane) & 63 of this lane's 256-byte aligned ring
-                    sts_u32(ring_addr | ((((unsigned int)cnt << 2) + lane4) & 0xFFu), vq + t);
-                    ++cnt;
-                }
+                sts_idx(wp, (IDX)(vq + t));
+                wp += r2v[t] < cut2 ? (unsigned int)sizeof(IDX) : 0u;   // NaN (padding) compares false
             }
         } else {
 #pragma unroll 1
@@ -288,15 +306,12 @@ __device__ __forceinline__ void build_scan_run(const Dev& d, const float4* __res
                     bool ok = true;
                     if (dd < 64u) ok = !((wi >> dd) & 1ull);           // includes the atom itself (bit 32)
                     else if (fari) ok = !pair_excluded(d, oi, wi, true, oj, d.has_far[oj]);   // rare
-                    if (ok) {
-                        myring[(cnt + lane) & (BUILD_RING - 1)] = (unsigned int)(base + 8 * q + t);
-                        ++cnt;
-                    }
+                    if (ok) { sts_idx(wp, (IDX)(base + 8 * q + t)); wp += (unsigned int)sizeof(IDX); }
                 }
             }
         }
-        __syncwarp();
-        build_flush<IDX>(rows, d.nlo_M, ring, lane, cnt, flushed);
+        cnt = (int)((wp - sub_addr) / (unsigned int)sizeof(IDX));
+        if (cnt > cq) { overflow = true; cnt = cq; }               // the sub-list has BUILD_SLACK spare slots
     }
 }
 
@@ -304,14 +319,14 @@ template <bool RINT, typename IDX>
 __device__ __forceinline__ void build_scan_cells(const Dev& d, const float4* __restrict__ posq_s, const int* __restrict__ orig_s,
                                               const int* __restrict__ start, bool rx, bool ry, bool rz, int x0, int x1,
                                               int y0, int y1, int za, int zb, float lox, float hix, float loy, float hiy,
-                                              float loz, float hiz, float4* cand, unsigned int* ring, IDX* rows, int lane,
+                                              float loz, float hiz, float4* cand, IDX* mysub, int cq, int lane,
                                               float4 pi, int oi, ull wi, bool fari, bool anyfar,
                                               const int (&og)[BUILD_GROUP], const unsigned int (&osp)[BUILD_GROUP], int& cnt,
-                                              int& flushed) {
+                                              bool& overflow) {
     const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2];
     const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
     const float ex = bx / ncx, ey = by / ncy, ez = bz / ncz;
-    const float cut2 = d.outer_cutoff2;
+    const float cut2 = d.list_cutoff2;
     for (int rxc = x0; rxc <= x1; ++rxc) {
         int ax = rxc;
         float sx = 0.f, dxc = 0.f;
@@ -344,147 +359,122 @@ __device__ __forceinline__ void build_scan_cells(const Dev& d, const float4* __r
                 else { if (z1 < ncz) continue; a0 = 0; a1 = z1 - ncz; sz = bz; }
                 if (a0 > a1) continue;
                 const int s0 = start[row + a0], s1 = start[row + a1 + 1];
-                build_scan_run<RINT, IDX>(d, posq_s, orig_s, s0, s1, sx, sy, sz, rx, ry, rz, cand, ring, rows, lane,
-                                          pi, oi, wi, fari, anyfar, og, osp, cnt, flushed);
+                build_scan_run<RINT, IDX>(d, posq_s, orig_s, s0, s1, sx, sy, sz, rx, ry, rz, cand, mysub, cq, lane,
+                                          pi, oi, wi, fari, anyfar, og, osp, cnt, overflow);
             }
         }
     }
 }
 
+// dynamic shared memory per CTA (one warp): 36 float4 candidates + 32 sub-lists of (cq + BUILD_SLACK) entries
+__host__ __device__ inline int build_sub_stride(int cq, int idx_bytes) {
+    // entries per sub-list, rounded so that the stride in 32-bit words is odd (lanes appending at equal offsets then
+    // hit different banks)
+    const int words = ((cq + BUILD_SLACK) * idx_bytes + 3) / 4 | 1;
+    return words * 4 / idx_bytes;
+}
+__host__ __device__ inline size_t build_smem_bytes(int cq, int idx_bytes) {
+    return 36 * sizeof(float4) + (size_t)32 * build_sub_stride(cq, idx_bytes) * idx_bytes;
+}
+
 template <typename IDX>
-__global__ void __launch_bounds__(BUILD_WARPS * 32) k_build_list(Dev d) {
-    const int r = blockIdx.y;
-    Globals& g = d.g[r];
-    if (!g.do_rebuild) return;
-    __shared__ float4 s_cand[BUILD_WARPS][36];                   // 4 pieces of 8 candidates + 1 pad each
-    __shared__ __align__(256) unsigned int s_ring[BUILD_WARPS][32 * BUILD_RING];    // per lane: 64 entries = 256 B
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int i0 = (blockIdx.x * BUILD_WARPS + w) * BUILD_GROUP, i = i0 + (lane & (BUILD_GROUP - 1));
+__global__ void __launch_bounds__(32) k_build_list(Dev d, int cq) {
+    extern __shared__ float4 s_build[];
+    float4* cand = s_build;
+    const int stride = build_sub_stride(cq, (int)sizeof(IDX));
+    IDX* subs = reinterpret_cast<IDX*>(s_build + 36);
+    const int lane = threadIdx.x;
+    IDX* mysub = subs + (size_t)lane * stride;
     const int N = d.N, Npad = d.Npad;
-    if (i0 >= Npad) return;
-    int* counts = d.nlo_count + ((size_t)r * Npad + i0) * BUILD_SUB;        // [atom of the group][subset]
-    if (i0 >= N) { counts[(lane & (BUILD_GROUP - 1)) * BUILD_SUB + (lane >> 3)] = 0; return; }
+    const int a = lane & (BUILD_GROUP - 1);
+    // the CTAs are shared by all walkers of the context: each starts on walker blockIdx.x % R and moves on to the next
+    // walker whose list is being rebuilt when a queue runs dry
+    for (int wk = 0; wk < d.R; ++wk) {
+    const int r = (blockIdx.x + wk) % d.R;
+    Globals& g = d.g[r];
+    if (!g.do_rebuild) continue;
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
     const int* __restrict__ orig_s = d.orig_s + (size_t)r * Npad;
     const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
-    IDX* rows = reinterpret_cast<IDX*>(d.nlo_list) + ((size_t)r * Npad + i0) * BUILD_SUB * d.nlo_M;
-    float4* cand = s_cand[w];
-    unsigned int* ring = s_ring[w];
-    const bool valid = i < N;
-    const float4 pi = posq_s[i];                                 // padding rows hold NaN: never in range
-    const int o0 = __shfl_sync(0xffffffffu, valid ? orig_s[i] : 0, 0);      // lane 0 is always a real atom
-    const int oi = valid ? orig_s[i] : o0;
-    const ull wi = valid ? (d.excl_win[oi] | (1ull << 32)) : 0ull;
-    const bool fari = valid ? d.has_far[oi] : false;
-    const bool anyfar = __any_sync(0xffffffffu, fari);
-    // exclusion window of every atom of the group as [og, og + osp] in topology indices (waters: their own molecule)
-    int og[BUILD_GROUP];
-    unsigned int osp[BUILD_GROUP];
-    {
-        const int below = valid ? 32 - (__ffsll((long long)wi) - 1) : 0, above = valid ? 31 - __clzll((long long)wi) : 0;
+    const int* __restrict__ groups = d.group_first + (size_t)r * d.group_capacity;
+    const int n_groups = g.n_groups;
+    const int a = lane & (BUILD_GROUP - 1);
+    for (;;) {
+        int gi = 0;
+        if (lane == 0) gi = atomicAdd(&g.build_cursor, 1);
+        gi = __shfl_sync(0xffffffffu, gi, 0);
+        if (gi >= n_groups) break;
+        const int packed = groups[gi];
+        const int i0 = packed >> 4, na = packed & 15;
+        const bool valid = a < na;
+        const int i = valid ? i0 + a : i0;
+        const float qnan = __int_as_float(0x7fc00000);
+        const float4 pa = posq_s[i];
+        const float4 pi = valid ? pa : make_float4(qnan, qnan, qnan, 0.f);   // idle lanes: never in range
+        const int oi = orig_s[i];
+        const ull wi = valid ? (d.excl_win[oi] | (1ull << 32)) : 0ull;
+        const bool fari = valid ? d.has_far[oi] : false;
+        const bool anyfar = __any_sync(0xffffffffu, fari);
+        // exclusion window of every atom of the group as [og, og + osp] in topology indices (waters: their own molecule)
+        int og[BUILD_GROUP];
+        unsigned int osp[BUILD_GROUP];
+        {
+            const int below = valid ? 32 - (__ffsll((long long)wi) - 1) : 0, above = valid ? 31 - __clzll((long long)wi) : 0;
 #pragma unroll
-        for (int k = 0; k < BUILD_GROUP; ++k) {
-            og[k] = __shfl_sync(0xffffffffu, oi - below, k);
-            osp[k] = (unsigned int)__shfl_sync(0xffffffffu, below + above, k);
+            for (int k = 0; k < BUILD_GROUP; ++k) {
+                og[k] = __shfl_sync(0xffffffffu, oi - below, k);
+                osp[k] = (unsigned int)__shfl_sync(0xffffffffu, below + above, k);
+            }
         }
-    }
-    int cnt = 0, flushed = 0;
-    if (!d.periodic) {
-        build_scan_run<false, IDX>(d, posq_s, orig_s, 0, N, 0.f, 0.f, 0.f, false, false, false, cand, ring, rows, lane,
-                                   pi, oi, wi, fari, anyfar, og, osp, cnt, flushed);
-    } else {
-        const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
-        // bounding box of the group, in cells and in space (padding lanes copy lane 0)
-        const float l0x = __shfl_sync(0xffffffffu, pi.x, 0), l0y = __shfl_sync(0xffffffffu, pi.y, 0);
-        const float l0z = __shfl_sync(0xffffffffu, pi.z, 0);
-        const float4 p0 = valid ? pi : make_float4(l0x, l0y, l0z, 0.f);
-        int cx, cy, cz;
-        atom_cell_coords(d, p0, cx, cy, cz);
-        const int xa = __reduce_min_sync(0xffffffffu, cx), xb = __reduce_max_sync(0xffffffffu, cx);
-        const int ya = __reduce_min_sync(0xffffffffu, cy), yb = __reduce_max_sync(0xffffffffu, cy);
-        const int za = __reduce_min_sync(0xffffffffu, cz), zb = __reduce_max_sync(0xffffffffu, cz);
-        const float lox = warp_min(p0.x), hix = warp_max(p0.x), loy = warp_min(p0.y), hiy = warp_max(p0.y);
-        const float loz = warp_min(p0.z), hiz = warp_max(p0.z);
-        // a dimension whose scan range would cover a cell twice is scanned once, with the rint() minimum image
-        const bool rx = xb - xa + 5 > ncx, ry = yb - ya + 5 > ncy, rz = zb - za + 5 > ncz;
-        const int x0 = rx ? 0 : xa - 2, x1 = rx ? ncx - 1 : xb + 2;
-        const int y0 = ry ? 0 : ya - 2, y1 = ry ? ncy - 1 : yb + 2;
-        if (rx || ry || rz)
-            build_scan_cells<true, IDX>(d, posq_s, orig_s, start, rx, ry, rz, x0, x1, y0, y1, za, zb, lox, hix, loy, hiy,
-                                        loz, hiz, cand, ring, rows, lane, pi, oi, wi, fari, anyfar, og, osp, cnt, flushed);
-        else
-            build_scan_cells<false, IDX>(d, posq_s, orig_s, start, false, false, false, x0, x1, y0, y1, za, zb, lox, hix,
-                                         loy, hiy, loz, hiz, cand, ring, rows, lane, pi, oi, wi, fari, anyfar, og, osp, cnt, flushed);
-    }
-    // drain the rings: the warp writes each lane's remaining (< 32) entries
-    __syncwarp();
-    for (int L = 0; L < 32; ++L) {
-        const int cL = __shfl_sync(0xffffffffu, flushed, L), nL = __shfl_sync(0xffffffffu, cnt, L) - cL;
-        if (lane < nL && cL + lane < d.nlo_M)
-            rows[(size_t)((L & (BUILD_GROUP - 1)) * BUILD_SUB + (L >> 3)) * d.nlo_M + cL + lane] =
-                (IDX)ring[L * BUILD_RING + ((cL + lane + L) & (BUILD_RING - 1))];
-    }
-    if (cnt > d.nlo_M) { g.item_overflow = 1; cnt = d.nlo_M; }
-    counts[(lane & (BUILD_GROUP - 1)) * BUILD_SUB + (lane >> 3)] = cnt;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// k_prune_list: refresh the inner Verlet list (cutoff + inner skin) from the outer one (cutoff + outer skin) at the
-// current coordinates: one warp per atom streams the outer list (coalesced), keeps the entries inside the inner list
-// cutoff with ordered ballot compaction, and records the reference positions of the inner list.
-// Runs every few steps; the expensive cell search (k_sort_atoms + k_build_list) only every ~10-20 steps.
-// ---------------------------------------------------------------------------------------------------------
-template <typename IDX>
-__global__ void __launch_bounds__(128) k_prune_list(Dev d) {
-    const int r = blockIdx.y;
-    Globals& g = d.g[r];
-    if (!g.do_prune) return;
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int N = d.N, Npad = d.Npad;
-    if (i >= Npad) return;
-    const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
-    const IDX* __restrict__ outer_rows = reinterpret_cast<const IDX*>(d.nlo_list) + ((size_t)r * Npad + i) * BUILD_SUB * d.nlo_M;
-    IDX* inner = reinterpret_cast<IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M;
-    const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
-    const float cut2 = d.list_cutoff2;
-    const float4 pi = posq_s[i];
-    int cnt = 0;
-    for (int sub = 0; sub < BUILD_SUB; ++sub) {
-        const IDX* __restrict__ outer = outer_rows + (size_t)sub * d.nlo_M;
-        const int n_outer = i < N ? d.nlo_count[((size_t)r * Npad + i) * BUILD_SUB + sub] : 0;
-        // two chunks of 32 entries per iteration: twice the gathers in flight (the kernel is latency bound)
-        for (int base = 0; base < n_outer; base += 64) {
-            const int k0 = base + lane, k1 = k0 + 32;
-            bool ok0 = k0 < n_outer, ok1 = k1 < n_outer;
-            const int s0 = ok0 ? (int)outer[k0] : i, s1 = ok1 ? (int)outer[k1] : i;
-            const float4 pj0 = posq_s[s0], pj1 = posq_s[s1];
-            float dx0 = pi.x - pj0.x, dy0 = pi.y - pj0.y, dz0 = pi.z - pj0.z;
-            float dx1 = pi.x - pj1.x, dy1 = pi.y - pj1.y, dz1 = pi.z - pj1.z;
-            if (d.periodic) {
-                dx0 -= bx * rintf(dx0 * ibx); dy0 -= by * rintf(dy0 * iby); dz0 -= bz * rintf(dz0 * ibz);
-                dx1 -= bx * rintf(dx1 * ibx); dy1 -= by * rintf(dy1 * iby); dz1 -= bz * rintf(dz1 * ibz);
-            }
-            ok0 = ok0 && (dx0 * dx0 + dy0 * dy0 + dz0 * dz0) < cut2;
-            ok1 = ok1 && (dx1 * dx1 + dy1 * dy1 + dz1 * dz1) < cut2;
-            const unsigned int m0 = __ballot_sync(0xffffffffu, ok0), m1 = __ballot_sync(0xffffffffu, ok1);
-            const unsigned int below = (1u << lane) - 1u;
-            if (ok0) {
-                const int slot = cnt + __popc(m0 & below);
-                if (slot < d.nl_M) inner[slot] = (IDX)s0;
-            }
-            cnt += __popc(m0);
-            if (ok1) {
-                const int slot = cnt + __popc(m1 & below);
-                if (slot < d.nl_M) inner[slot] = (IDX)s1;
-            }
-            cnt += __popc(m1);
+        int cnt = 0;
+        bool overflow = false;
+        if (!d.periodic) {
+            build_scan_run<false, IDX>(d, posq_s, orig_s, 0, N, 0.f, 0.f, 0.f, false, false, false, cand, mysub, cq, lane,
+                                       pi, oi, wi, fari, anyfar, og, osp, cnt, overflow);
+        } else {
+            const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
+            // bounding box of the group, in cells and in space (idle lanes hold the first atom)
+            int cx, cy, cz;
+            atom_cell_coords(d, pa, cx, cy, cz);
+            const int xa = __reduce_min_sync(0xffffffffu, cx), xb = __reduce_max_sync(0xffffffffu, cx);
+            const int ya = __reduce_min_sync(0xffffffffu, cy), yb = __reduce_max_sync(0xffffffffu, cy);
+            const int za = __reduce_min_sync(0xffffffffu, cz), zb = __reduce_max_sync(0xffffffffu, cz);
+            const float lox = warp_min(pa.x), hix = warp_max(pa.x), loy = warp_min(pa.y), hiy = warp_max(pa.y);
+            const float loz = warp_min(pa.z), hiz = warp_max(pa.z);
+            // a dimension whose scan range would cover a cell twice is scanned once, with the rint() minimum image
+            const bool rx = xb - xa + 5 > ncx, ry = yb - ya + 5 > ncy, rz = zb - za + 5 > ncz;
+            const int x0 = rx ? 0 : xa - 2, x1 = rx ? ncx - 1 : xb + 2;
+            const int y0 = ry ? 0 : ya - 2, y1 = ry ? ncy - 1 : yb + 2;
+            if (rx || ry || rz)
+                build_scan_cells<true, IDX>(d, posq_s, orig_s, start, rx, ry, rz, x0, x1, y0, y1, za, zb, lox, hix, loy,
+                                            hiy, loz, hiz, cand, mysub, cq, lane, pi, oi, wi, fari, anyfar, og, osp, cnt,
+                                            overflow);
+            else
+                build_scan_cells<false, IDX>(d, posq_s, orig_s, start, false, false, false, x0, x1, y0, y1, za, zb, lox,
+                                             hix, loy, hiy, loz, hiz, cand, mysub, cq, lane, pi, oi, wi, fari, anyfar, og,
+                                             osp, cnt, overflow);
         }
+        // concatenate the four sub-lists of every atom into its row (coalesced), in subset order
+        __syncwarp();
+        int off = 0;
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            const int c = __shfl_up_sync(0xffffffffu, cnt, 8 * k);
+            if (lane >= 8 * k) off += c;
+        }
+        const int total = __shfl_sync(0xffffffffu, off + cnt, 24 + a);       // lane (a, 3) knows the atom's total
+        IDX* rows = reinterpret_cast<IDX*>(d.nl_list) + ((size_t)r * Npad + i0) * d.nl_M;
+        for (int L = 0; L < 32; ++L) {
+            const int nL = __shfl_sync(0xffffffffu, cnt, L), oL = __shfl_sync(0xffffffffu, off, L);
+            const IDX* src = subs + (size_t)L * stride;
+            IDX* dst = rows + (size_t)(L & (BUILD_GROUP - 1)) * d.nl_M + oL;
+            for (int k = lane; k < nL; k += 32)
+                if (oL + k < d.nl_M) dst[k] = src[k];
+        }
+        if (__any_sync(0xffffffffu, overflow || total > d.nl_M)) { if (lane == 0) g.item_overflow = 1; }
+        if (lane < na) d.nl_count[(size_t)r * Npad + i0 + lane] = min(total, d.nl_M);
+        __syncwarp();
     }
-    if (cnt > d.nl_M) { g.item_overflow = 1; cnt = d.nl_M; }
-    if (lane == 0) {
-        d.nl_count[(size_t)r * Npad + i] = cnt;
-        if (i < N) d.pos_ref[(size_t)r * N + d.orig_s[(size_t)r * Npad + i]] = pi;     // inner-list reference positions
     }
 }
 
