@@ -266,15 +266,24 @@ def main():
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     integ_bytes = 128 * topo['n_atoms'] * R          # 128 B/atom/launch (f64 x,v in+out; fixed-point forces in)
     integ_us = ktimes['integrate']['us_per_launch']
-    roofline = {'kernel': 'k_pair (direct-space LJ + Ewald erfc, 32x32 tiles)', 'bound': 'fp32',
+    # DRAM traffic per launch of the dominant kernels from the committed `ncu --set full` capture (1 walker)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+    except Exception:
+        pass
+    roofline = {'kernel': 'k_pair (direct-space LJ + Ewald erfc over the Verlet list, 8 lanes per atom)', 'bound': 'fp32',
                 'achieved': achieved_tflops, 'peak': FP32_PEAK_NOMINAL_TFLOPS, 'unit': 'TFLOP/s',
-                'frac': achieved_tflops / FP32_PEAK_NOMINAL_TFLOPS, 'traffic': None,
+                'frac': achieved_tflops / FP32_PEAK_NOMINAL_TFLOPS,
+                'traffic': traffic.get('k_pair', {}).get('dram_bytes_per_launch'),
+                'traffic_source': traffic.get('source'),
                 'peak_source': 'nominal 148 SM x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP32 figure; '
                                'tensor cores unused: the pair work is not a dense contraction)',
                 'algorithmic_flops_per_launch': FLOP_PER_PAIR * P_IN_PAIRS * R, 'us_per_launch': pair_us}
     roofline_hbm = {'kernel': 'k_integrate (V/R/O + SHAKE/RATTLE + work bookkeeping)', 'bound': 'hbm',
                     'achieved': integ_bytes / (integ_us * 1e-6) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': integ_bytes / (integ_us * 1e-6) / 1e9 / hbm_peak, 'traffic': None,
+                    'frac': integ_bytes / (integ_us * 1e-6) / 1e9 / hbm_peak,
+                    'traffic': traffic.get('k_integrate', {}).get('dram_bytes_per_launch'),
                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650',
                     'us_per_launch': integ_us}
 

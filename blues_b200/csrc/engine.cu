@@ -155,12 +155,14 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         cufftSetStream(h->plan_c2r, s2);
         cudaStreamWaitEvent(s2, h->ev_fork, 0);
         { LaunchTimer t(h, BL_K_PME_SPREAD, s2);
-          k_pme_spread<<<dim3(d.gx, SPREAD_YSPLIT, R), 256, (d.gy / SPREAD_YSPLIT + 1) * d.gz * sizeof(int), s2>>>(d); }
-        { LaunchTimer t(h, BL_K_FFT, s2); cufftExecR2C(h->plan_r2c, d.grid_r, reinterpret_cast<cufftComplex*>(d.grid_c)); }
-        { LaunchTimer t(h, BL_K_PME_CONVOLVE, s2);
-          if (energy) k_pme_convolve<true><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d);
-          else k_pme_convolve<false><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d); }
-        { LaunchTimer t(h, BL_K_FFT, s2); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
+          // few walkers: latency bound, many wide CTAs; many walkers: throughput bound, fewer duplicate B-splines
+          if (R <= 2) k_pme_spread<8, 512><<<dim3(d.gx, 8, R), 512, (d.gy / 8 + 1) * d.gz * sizeof(int), s2>>>(d);
+          else k_pme_spread<4, 256><<<dim3(d.gx, 4, R), 256, (d.gy / 4 + 1) * d.gz * sizeof(int), s2>>>(d); }
+            { LaunchTimer t(h, BL_K_FFT, s2); cufftExecR2C(h->plan_r2c, d.grid_r, reinterpret_cast<cufftComplex*>(d.grid_c)); }
+            { LaunchTimer t(h, BL_K_PME_CONVOLVE, s2);
+              if (energy) k_pme_convolve<true><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d);
+              else k_pme_convolve<false><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d); }
+            { LaunchTimer t(h, BL_K_FFT, s2); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
         { LaunchTimer t(h, BL_K_PME_GATHER, s2); k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
         cudaEventRecord(h->ev_join, s2);
     }
@@ -896,10 +898,13 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         d.gsize = d.gx * d.gy * d.gz;
         d.csize = d.gx * d.gy * (d.gz / 2 + 1);
         {
-            const size_t plane_bytes = (size_t)(d.gy / SPREAD_YSPLIT + 1) * d.gz * sizeof(int);
+            const size_t plane_bytes = (size_t)(d.gy / 4 + 1) * d.gz * sizeof(int);
             if (plane_bytes > 200 * 1024) return fail(BL_ERR_INVALID, "PME grid plane does not fit in shared memory");
             if (plane_bytes > 48 * 1024)
-                cudaFuncSetAttribute(k_pme_spread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes);
+            {
+                cudaFuncSetAttribute(k_pme_spread<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes);
+                cudaFuncSetAttribute(k_pme_spread<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes);
+            }
         }
         d.grid_r = dalloc<float>(h, (size_t)R * d.gsize);
         d.grid_c = dalloc<float2>(h, (size_t)R * d.csize);

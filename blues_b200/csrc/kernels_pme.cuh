@@ -52,26 +52,55 @@ __device__ __forceinline__ void pme_atom_setup(const Dev& d, float4 p, int* base
 // atomics (order independent → deterministic).  The finished plane is written once, as float: no global atomics,
 // no separate conversion pass.
 #define SPREAD_SCALE 8388608.0f            /* 2^23 */
-#define SPREAD_YSPLIT 4                    /* CTAs per x-plane: each owns a band of y-rows */
-__global__ void __launch_bounds__(256) k_pme_spread(Dev d) {
+#define SPREAD_MAX_RUNS 64
+// YSPLIT: CTAs per x-plane, each owning a band of y-rows.  More, smaller bands shorten the kernel when one walker
+// leaves the device mostly idle (latency bound); fewer bands recompute fewer B-splines when many walkers fill it.
+template <int SPREAD_YSPLIT, int SPREAD_THREADS>
+__global__ void __launch_bounds__(SPREAD_THREADS) k_pme_spread(Dev d) {
     extern __shared__ int s_plane[];            // [rows * gz]
+    __shared__ int s_run0[SPREAD_MAX_RUNS], s_runoff[SPREAD_MAX_RUNS + 1];
     const int r = blockIdx.z, plane = blockIdx.x, part = blockIdx.y;
     const int ya = part * d.gy / SPREAD_YSPLIT, yb = (part + 1) * d.gy / SPREAD_YSPLIT;   // rows [ya, yb)
     const int npts = (yb - ya) * d.gz;
     for (int k = threadIdx.x; k < npts; k += blockDim.x) s_plane[k] = 0;
-    __syncthreads();
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * d.Npad;
     const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
-    const int ncx = d.ncell[0], col = d.ncell[1] * d.ncell[2];
-    // atoms with base_x in [plane-4, plane]: fractional x in [(plane-4)/gx, (plane+1)/gx); one cell of margin each
-    // side because the sorted order is only refreshed with the outer neighbour list
+    const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
+    // atoms with base_x in [plane-4, plane] and base_y in [ya-4, yb-1]: the cell columns that cover those fractional
+    // ranges, plus one cell of margin each side because the sorted order is only refreshed with the neighbour list
     int cxa = (int)floorf((float)(plane - 4) / d.gx * ncx) - 1;
     int cxb = (int)floorf((float)(plane + 1) / d.gx * ncx) + 1;
     if (cxb - cxa + 1 >= ncx) { cxa = 0; cxb = ncx - 1; }
-    for (int cxr = cxa; cxr <= cxb; ++cxr) {
-        const int cx = ((cxr % ncx) + ncx) % ncx;
-        const int s0 = start[cx * col], s1 = start[(cx + 1) * col];
-        for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+    int cya = (int)floorf((float)(ya - 4) / d.gy * ncy) - 1;
+    int cyb = (int)floorf((float)yb / d.gy * ncy) + 1;
+    if (cyb - cya + 1 >= ncy) { cya = 0; cyb = ncy - 1; }
+    // for one cell-plane cx the columns cya..cyb are contiguous in the sorted order (two runs when the range wraps);
+    // the runs are tabulated first so that the atom loop below is one flat, latency-tolerant index space
+    const int nruns = min(2 * (cxb - cxa + 1), SPREAD_MAX_RUNS);
+    if (threadIdx.x < nruns) {
+        const int run = threadIdx.x;
+        const int cx = (((cxa + (run >> 1)) % ncx) + ncx) % ncx;
+        int c0 = 0, c1 = -1;                              // y-cell range [c0, c1] of this run, not wrapped
+        if ((run & 1) == 0) { c0 = max(cya, 0); c1 = min(cyb, ncy - 1); }
+        else if (cya < 0) { c0 = cya + ncy; c1 = ncy - 1; }
+        else if (cyb >= ncy) { c0 = 0; c1 = cyb - ncy; }
+        int s0 = 0, n = 0;
+        if (c0 <= c1) { s0 = start[(cx * ncy + c0) * ncz]; n = start[(cx * ncy + c1 + 1) * ncz] - s0; }
+        s_run0[run] = s0;
+        s_runoff[run + 1] = n;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_runoff[0] = 0;
+        for (int k = 0; k < nruns; ++k) s_runoff[k + 1] += s_runoff[k];
+    }
+    __syncthreads();
+    const int total = s_runoff[nruns];
+    {
+        int run = 0;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            while (idx >= s_runoff[run + 1]) ++run;
+            const int s = s_run0[run] + (idx - s_runoff[run]);
             const float4 p = posq_s[s];
             if (p.w == 0.f) continue;
             int base[3];

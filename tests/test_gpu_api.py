@@ -208,3 +208,45 @@ def test_run_from_yaml(structure, tmp_path):
 def test_no_cpu_fallback_message():
     from blues_b200 import _native
     assert 'no CPU fallback' in (_native.load_library.__doc__ + open(_native.__file__).read())
+
+
+def test_water_translation_move(structure):
+    """tests/test_watertranslation.py:54-112: the alchemical water is swapped with one inside the sphere, translated to a
+    point of the sphere at the midpoint, and a water left outside forces rejection (protocol_work = 999999)."""
+    from blues_b200.moves import WaterTranslationMove
+    np.random.seed(7)
+    move = WaterTranslationMove(structure, protein_selection='(index 0) or (index 1)', radius=0.9 * unit.nanometers)
+    engine = MoveEngine(move)
+    engine.selectMove()
+    systems = SystemFactory(structure, move.atom_indices, system_cfg())
+    cfg = sim_cfg()
+    cfg['nstepsNC'] = 100
+    simulations = SimulationFactory(systems, engine, cfg)
+    ncmc = simulations.ncmc
+    idx = move.atom_indices
+
+    def positions():
+        return ncmc.context.getState(getPositions=True).getPositions(asNumpy=True)
+
+    before = positions()[idx, :].value_in_unit(unit.nanometers)
+    ncmc.context = move.beforeMove(ncmc.context)
+    swapped = positions()[idx, :].value_in_unit(unit.nanometers)
+    assert move.go and np.not_equal(before, swapped).all()           # another water took the alchemical slot
+    ncmc.context = engine.runEngine(ncmc.context)
+    moved = positions().value_in_unit(unit.nanometers)
+    assert np.not_equal(swapped, moved[idx]).all()
+    # the translated water oxygen sits inside the sphere around the selection's centre of mass (periodic distance)
+    box = np.asarray(structure.box[:3]) * 0.1
+    d = moved[idx[0]] - move._com
+    d -= box * np.round(d / box)
+    assert np.linalg.norm(d) <= 0.9 + 1e-6
+    # rigid translation: the water geometry is unchanged
+    assert np.allclose(moved[idx[1]] - moved[idx[0]], swapped[1] - swapped[0], atol=1e-6)
+    # in bounds: the work is untouched; pushed out of the sphere: afterMove forces rejection
+    ncmc.context = move.afterMove(ncmc.context)
+    assert ncmc.context._integrator.getGlobalVariableByName('protocol_work') == 0
+    out = moved.copy()
+    out[idx] = out[idx] - out[idx[0]] + (move._com + np.array([1.0, 0.0, 0.0]))    # 1.0 nm from the centre (< box / 2)
+    ncmc.context.setPositions(out * unit.nanometers)
+    ncmc.context = move.afterMove(ncmc.context)
+    assert ncmc.context._integrator.getGlobalVariableByName('protocol_work') >= 999999
