@@ -163,7 +163,9 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
               if (energy) k_pme_convolve<true><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d);
               else k_pme_convolve<false><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d); }
             { LaunchTimer t(h, BL_K_FFT, s2); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
-        { LaunchTimer t(h, BL_K_PME_GATHER, s2); k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
+        { LaunchTimer t(h, BL_K_PME_GATHER, s2);
+          if (R <= 2) k_pme_gather5<<<dim3(cdiv(cdiv(N, 6) * 32, 128), R), 128, 0, s2>>>(d);
+          else k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
         cudaEventRecord(h->ev_join, s2);
     }
     if (nterms > 0 || prefetch_noise > 0) {

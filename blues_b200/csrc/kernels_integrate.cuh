@@ -176,6 +176,8 @@ __device__ __forceinline__ void solve_fixed(double (&A)[NC > 0 ? NC : 1][NC > 0 
     }
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int NA, int NC, int SHAPE>
 struct FixedCluster {
     static constexpr int NCC = NC > 0 ? NC : 1;
@@ -279,7 +281,29 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
     }
 #pragma unroll
     for (int a = 0; a < NC; ++a) s.d2[a] = c.d2[a];
+    // the forces of the first V step and the kicks of the first O step are needed a few hundred dependent instructions
+    // from now: start pulling their lines into L1 (no registers held)
+    for (int o = 0; o < args.nops; ++o) {
+        const Op op = args.ops[o];
+        if (op.kind == OP_V || op.kind == OP_MD) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    prefetch_l1(&fenv[q * N + atom[k]]);
+                    if (d.n_alch > 0) prefetch_l1(&d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + atom[k]]);
+                }
+            break;
+        }
+    }
+    for (int o = 0; o < args.nops; ++o)
+        if (args.ops[o].kind == OP_O || args.ops[o].kind == OP_MD) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k) prefetch_l1(d.noise + ((size_t)r * MAX_NOISE_SETS * N + atom[k]) * 3);
+            break;
+        }
     int n_o = 0, n_md = 0;
+    bool x_changed = false;
     double xref[NA][3], x1[NA][3];
     // every op = [update] -> optional SHAKE -> [velocity fix-up] -> optional RATTLE, so that the constraint solvers
     // are instantiated once per cluster shape (keeps the kernel small enough for the instruction cache)
@@ -321,6 +345,7 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                 }
             do_shake = do_rattle = true;
             post = 1;
+            x_changed = true;
         } else if (op.kind == OP_O) {
 #pragma unroll
             for (int k = 0; k < NA; ++k) {
@@ -359,7 +384,9 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
             ++n_md;
             do_shake = true;
             post = 2;
+            x_changed = true;
         } else if (op.kind == OP_CONSTRAIN) {
+            x_changed = true;
 #pragma unroll
             for (int k = 0; k < NA; ++k)
 #pragma unroll
@@ -391,6 +418,17 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
         }
     }
     const float lim = d.skin_half2;
+    if (!x_changed) {
+        // velocity-only launch (e.g. the trailing "V H" of a pass): positions, mirrors and the displacement test are
+        // untouched
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+            vel[atom[k]] = make_double4(s.v[k][0], s.v[k][1], s.v[k][2], 0.0);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) mom[q] += s.mass[k] * s.v[k][q];
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
         const int a = atom[k];

@@ -224,3 +224,64 @@ __global__ void __launch_bounds__(128) k_pme_gather(Dev d) {
     fx_addf(&fenv[d.N + a], -q * fy * d.gy * d.boxf[4], (float)FORCE_SCALE);
     fx_addf(&fenv[2 * d.N + a], -q * fz * d.gz * d.boxf[5], (float)FORCE_SCALE);
 }
+
+// Latency-oriented gather for contexts with one or two walkers: five lanes per atom, one stencil x-plane each (25 grid
+// loads per lane instead of 125), combined with shuffles.  Six atoms per warp (lanes 30, 31 idle).
+__global__ void __launch_bounds__(128) k_pme_gather5(Dev d) {
+    const int r = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int slot = lane / PME_ORDER, i = lane - slot * PME_ORDER;       // atom slot 0..5 (6 = idle), x-plane 0..4
+    const int a = warp * 6 + slot;
+    const bool active = slot < 6 && a < d.N;
+    float fx = 0.f, fy = 0.f, fz = 0.f, q = 0.f;
+    if (active) {
+        const float4 p = d.posq[(size_t)r * d.N + a];
+        q = p.w;
+        if (q != 0.f) {
+            int base[3];
+            float frac[3];
+            pme_atom_setup(d, p, base, frac);
+            float wx[PME_ORDER], wy[PME_ORDER], wz[PME_ORDER], dx[PME_ORDER], dy[PME_ORDER], dz[PME_ORDER];
+            bspline5(frac[0], wx, dx);
+            bspline5(frac[1], wy, dy);
+            bspline5(frac[2], wz, dz);
+            float wxi = 0.f, dxi = 0.f;
+#pragma unroll
+            for (int k = 0; k < PME_ORDER; ++k) { wxi = (k == i) ? wx[k] : wxi; dxi = (k == i) ? dx[k] : dxi; }
+            const float* grid = d.grid_r + (size_t)r * d.gsize;
+            int gx = base[0] + i; gx -= gx >= d.gx ? d.gx : 0;
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+            for (int j = 0; j < PME_ORDER; ++j) {
+                int gy = base[1] + j; gy -= gy >= d.gy ? d.gy : 0;
+                const float* row = grid + ((size_t)gx * d.gy + gy) * d.gz;
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < PME_ORDER; ++k) {
+                    int gz = base[2] + k; gz -= gz >= d.gz ? d.gz : 0;
+                    const float v = row[gz];
+                    s0 += v * wz[k];
+                    s1 += v * dz[k];
+                }
+                sx += wy[j] * s0;
+                sy += dy[j] * s0;
+                sz += wy[j] * s1;
+            }
+            fx = dxi * sx; fy = wxi * sy; fz = wxi * sz;
+        }
+    }
+    // sum the five planes of each atom: lanes 5 slot + 1..4 into lane 5 slot (fixed order -> deterministic)
+    float tx = fx, ty = fy, tz = fz;
+#pragma unroll
+    for (int k = 1; k < PME_ORDER; ++k) {
+        const int src = min(lane + k, 31);
+        const float ox = __shfl_sync(0xffffffffu, fx, src), oy = __shfl_sync(0xffffffffu, fy, src), oz = __shfl_sync(0xffffffffu, fz, src);
+        tx += ox; ty += oy; tz += oz;
+    }
+    if (active && i == 0 && q != 0.f) {
+        long long* fenv = d.f_env + (size_t)r * 3 * d.N;
+        fx_addf(&fenv[a], -q * tx * d.gx * d.boxf[3], (float)FORCE_SCALE);
+        fx_addf(&fenv[d.N + a], -q * ty * d.gy * d.boxf[4], (float)FORCE_SCALE);
+        fx_addf(&fenv[2 * d.N + a], -q * tz * d.gz * d.boxf[5], (float)FORCE_SCALE);
+    }
+}
