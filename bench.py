@@ -179,8 +179,17 @@ def main():
     with ClockSampler(local_rank) as clocks:
         integ.step(W)                                    # warm-up (the sampler needs ~200 ms per sample)
         t_load = time.time()
+        done = W
         while time.time() - t_load < 0.7:                # keep the GPU under the same load while clocks are sampled
-            integ.step(max(W, 100))
+            if done + 200 > NSTEPS_NC:                   # a protocol is nstepsNC steps long: start the next one
+                integ.reset()
+                done = 0
+            integ.step(100)
+            eng.synchronize()
+            done += 100
+        # the timed region is steps W .. W+K of a fresh protocol (K + W < nstepsNC)
+        integ.reset()
+        integ.step(W)
         eng.synchronize()
         barrier()
         l0 = eng.launch_count()
@@ -190,6 +199,8 @@ def main():
         barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - l0
+    if launches <= 0 or K + W >= NSTEPS_NC:
+        raise SystemExit('bench: the timed region launched no kernels (K + W must stay below nstepsNC = %d)' % NSTEPS_NC)
     t = torch.tensor([ms], device='cuda', dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
