@@ -180,6 +180,75 @@ def compare_neighbors_dynamic(name, steps=60, n_replicas=2, dt=0.004, minimize=0
     return out
 
 
+def tile_structure(s, reps):
+    """Replicate a periodic Structure reps = (nx, ny, nz) times along its box vectors (orthorhombic)."""
+    d = s.to_arrays()
+    n = len(d['atom_names'])
+    nres = len(d['residue_names'])
+    nx, ny, nz = reps
+    ncopy = nx * ny * nz
+    out = {}
+    for k in ('atomic_numbers', 'masses', 'charges', 'lj_sigma', 'lj_epsilon', 'atom_names', 'atom_types'):
+        out[k] = np.tile(d[k], ncopy)
+    out['residue_names'] = np.tile(d['residue_names'], ncopy)
+    rp = np.asarray(d['residue_pointers'])
+    if len(rp) == nres + 1:
+        out['residue_pointers'] = np.concatenate([rp[:-1] + c * n for c in range(ncopy)] + [[ncopy * n]])
+    else:
+        out['residue_pointers'] = np.concatenate([rp + c * n for c in range(ncopy)])
+    out['atom_residue'] = np.concatenate([np.asarray(d['atom_residue']) + c * nres for c in range(ncopy)])
+    for idx, extra in (('bonds', ('bond_k', 'bond_r0')), ('angles', ('angle_k', 'angle_t0')),
+                       ('dihedrals', ('dihedral_k', 'dihedral_per', 'dihedral_phase', 'dihedral_scee', 'dihedral_scnb',
+                                      'dihedral_ignore_end', 'dihedral_improper'))):
+        a = np.asarray(d[idx])
+        out[idx] = np.concatenate([a + c * n for c in range(ncopy)]) if len(a) else a
+        for e in extra:
+            out[e] = np.tile(d[e], ncopy)
+    box = np.asarray(d['box'], float)
+    shifts = [(i, j, k) for i in range(nx) for j in range(ny) for k in range(nz)]
+    out['coordinates'] = np.concatenate([d['coordinates'] + np.asarray(sh) * box[:3] for sh in shifts])
+    out['box'] = np.concatenate([box[:3] * np.asarray(reps), box[3:]])
+    from blues_b200.structure import Structure as _S
+    return _S.from_arrays(out)
+
+
+def compare_tiled(name='tol_parm', reps=(4, 4, 5), verbose=False, **overrides):
+    """Forces, energy and neighbour sets on a tiled copy of a fixture (> 65 535 atoms: 32-bit list indices, larger
+    PME grid, many cells) against the oracle's C twin (forces) and the numpy oracle (pairs)."""
+    from oracle.ncmc_oracle import ForceField
+    from oracle.c_oracle import COracle
+    s0 = Structure.load_npz(os.path.join(GOLDEN, name + '.npz'))
+    s = tile_structure(s0, reps)
+    kw = dict(CASES[name]['kw'])
+    kw.update(overrides)
+    topo = s.createSystem(**kw).flatten()
+    x = s.coordinates * 0.1
+    eng = _native.Engine(topo, n_replicas=1, seed=1)
+    eng.set_langevin_integrator(300.0, 1.0, 0.002)
+    eng.set_positions(x)
+    ep, ek = eng.get_energy()
+    F = eng.get_forces()
+    codes = eng.neighbor_pairs()
+    eng.close()
+    Eo, Fo = COracle(topo).energy_forces(x)[:2]
+    ref = ForceField(topo).neighbor_pairs(x, topo['box'])
+    only_e, only_o = np.setdiff1d(codes, ref), np.setdiff1d(ref, codes)
+    edge = 0.0
+    if len(only_e) + len(only_o):
+        c = np.concatenate([only_e, only_o])
+        n = topo['n_atoms']
+        dd = x[c // n] - x[c % n]
+        dd -= topo['box'] * np.round(dd / topo['box'])
+        edge = float(np.max(np.abs(np.linalg.norm(dd, axis=1) - topo['cutoff'])))
+    out = {'n_atoms': topo['n_atoms'], 'energy_rel': abs(ep[0] - Eo) / max(abs(Eo), 1.0), 'pairs': len(ref),
+           'only_engine': len(only_e), 'only_oracle': len(only_o), 'duplicates': len(codes) - len(np.unique(codes)),
+           'edge': edge, 'pme_grid': [int(v) for v in topo['pme_grid']]}
+    out['force_max_rel'], out['force_rms_rel'] = rel_force_error(F, Fo)
+    if verbose:
+        print('--- tiled', name, reps, out)
+    return out
+
+
 def make_ncmc_pair(name, nsteps=10, dt=0.002, splitting='H V R O R V H', nprop=1, prop_lambda=0.3, seed=7,
                    temperature=300.0, n_replicas=1, minimize=False, **overrides):
     """Engine and oracle initialised identically for step-for-step comparisons."""

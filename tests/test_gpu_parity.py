@@ -48,6 +48,17 @@ def test_neighbour_and_exclusion_sets_bit_exact(name):
     assert out['n_engine'] == out['n_oracle'] or out['edge'] < 5e-7
 
 
+def test_tiled_system_above_65535_atoms_uses_32bit_list_indices():
+    # watDivaline tiled 3 x 3 x 3 = 69 957 atoms: the neighbour rows switch from uint16 to int32 entries, the PME grid
+    # and the cell grid grow; forces / energy against the oracle's C twin, neighbour set against the numpy oracle
+    out = gc.compare_tiled('wat_divaline', (3, 3, 3))
+    assert out['n_atoms'] == 69957
+    assert out['duplicates'] == 0
+    # coordinates up to ~9 nm in float32: a pair may differ only within 5e-6 nm of the cutoff
+    assert out['only_engine'] + out['only_oracle'] == 0 or out['edge'] < 5e-6, out
+    assert out['energy_rel'] < ENERGY_TOL and out['force_max_rel'] < FORCE_TOL, out
+
+
 @pytest.mark.parametrize('name,kw', [('wat_divaline', dict(steps=80, dt=0.002)),
                                      ('t4l_surrogate', dict(steps=60, dt=0.004, minimize=60))])
 def test_neighbour_sets_stay_exact_through_prunes_and_rebuilds(name, kw):
