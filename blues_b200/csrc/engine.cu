@@ -29,7 +29,7 @@ struct bl_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // reciprocal-space branch, forked from / joined to `stream` inside every evaluation
     cudaStream_t stream3 = nullptr, stream4 = nullptr;   // bonded branch, alchemical branch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
     std::string error;
     std::vector<void*> allocs;
     // host copies needed after creation
@@ -134,21 +134,24 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     cudaStream_t st = h->stream;
     const int R = d.R, N = d.N;
     {
+        // latches the rebuild request, then (only if due) the cell sort
+        LaunchTimer t(h, BL_K_NEIGHBOR);
+        k_sort_atoms<<<dim3(SORT_CTAS, R), 1024, 0, st>>>(d);
+    }
+    // Fork 1: reciprocal space (stream2) depends only on the cell-sorted positions; its gather waits for fork 2.
+    cudaEventRecord(h->ev_fork, st);
+    {
         LaunchTimer t(h, -1);
         long long nf = (long long)R * 3 * N * (d.n_alch > 0 ? 1 + ALCH_SLOTS : 1);
         int blocks = std::max(1, std::min(cdiv(nf, 256 * 4), 148 * 8));
         k_begin_eval<<<blocks, 256, 0, st>>>(d, adv_noise, adv_md, cm_mode, h->cm_parity);
     }
-    {
-        LaunchTimer t(h, BL_K_NEIGHBOR);
-        k_sort_atoms<<<dim3(SORT_CTAS, R), 1024, 0, st>>>(d);
-    }
-    // Fork: everything below depends only on the (cell-sorted) positions, not on each other.  Branches: reciprocal
-    // space (stream2), bonded terms (stream3), alchemical lists + kernel (stream4); the main stream keeps the list
-    // build / prune and the pair kernel.  All branches accumulate into the same fixed-point buffers with atomics.
+    // Fork 2: force accumulators are zeroed and the noise counters advanced.  Branches: bonded terms + noise prefetch
+    // (stream3), alchemical lists + kernel (stream4); the main stream keeps the list build and the pair kernel.  All
+    // branches accumulate into the same fixed-point buffers with atomics.
+    cudaEventRecord(h->ev_fork2, st);
     const bool pme = d.pme && h->has_fft;
     const int nterms = d.n_bonds + d.n_angles + d.n_torsions + d.n_excl + d.n_restraints + d.n_alch_exc;
-    cudaEventRecord(h->ev_fork, st);
     if (pme) {
         cudaStream_t s2 = h->profiling ? st : h->stream2;
         cufftSetStream(h->plan_r2c, s2);
@@ -170,7 +173,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     }
     if (nterms > 0 || prefetch_noise > 0) {
         cudaStream_t s3 = h->profiling ? st : h->stream3;
-        cudaStreamWaitEvent(s3, h->ev_fork, 0);
+        cudaStreamWaitEvent(s3, h->ev_fork2, 0);
         if (nterms > 0) { LaunchTimer t(h, BL_K_BONDED, s3); k_bonded<<<dim3(cdiv(nterms, 128), R), 128, 0, s3>>>(d); }
         if (prefetch_noise > 0) {
             // thermostat kicks of the next INTEGRATE launch with O steps: k_begin_eval above has advanced the noise
@@ -182,7 +185,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     }
     if (d.n_alch > 0) {
         cudaStream_t s4 = h->profiling ? st : h->stream4;
-        cudaStreamWaitEvent(s4, h->ev_fork, 0);
+        cudaStreamWaitEvent(s4, h->ev_fork2, 0);
         { LaunchTimer t(h, BL_K_NEIGHBOR, s4); k_alch_reset<<<cdiv(R * d.n_alch, 128), 128, 0, s4>>>(d); }
         { LaunchTimer t(h, BL_K_NEIGHBOR, s4);
           k_alch_list<<<dim3(cdiv(N, 128), R), 128, d.n_alch * sizeof(float4), s4>>>(d); }
@@ -663,6 +666,7 @@ int bl_destroy(bl_handle* h) {
     if (h->ev_join3) cudaEventDestroy(h->ev_join3);
     if (h->ev_join4) cudaEventDestroy(h->ev_join4);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return BL_OK;
@@ -690,6 +694,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
         return fail(BL_ERR_CUDA, "stream creation failed");
     Dev& d = h->d;

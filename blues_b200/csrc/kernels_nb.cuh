@@ -4,7 +4,8 @@
 #include "engine.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
-// k_begin_eval: clear accumulators before a force evaluation and latch the rebuild request.
+// k_begin_eval: clear accumulators before a force evaluation, advance the noise counters (the rebuild request is
+// latched by k_sort_atoms, which runs first so that reciprocal space can start before the zeroing).
 //   cm_mode: 0 keep, 1 zero cm_acc[parity], 2 zero cm_acc[parity] and flip parity (single-kernel steps)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_begin_eval(Dev d, int advance_noise, int advance_md, int cm_mode, int* cm_parity) {
@@ -19,12 +20,6 @@ __global__ void k_begin_eval(Dev d, int advance_noise, int advance_md, int cm_mo
         for (int i = threadIdx.x; i < d.R * ALCH_SLOTS * 3; i += blockDim.x) d.alch_acc[i] = 0;
         for (int i = threadIdx.x; i < d.R; i += blockDim.x) {
             Globals& g = d.g[i];
-            // the Verlet list is rebuilt (cell sort + search) when some atom moved > skin / 2 since the last build,
-            // or on request (host wrote coordinates, box changed)
-            g.do_rebuild = g.rebuild_request == 2 || g.prune_request;
-            g.do_prune = g.do_rebuild;                        // the alchemical pair list follows the same schedule
-            g.rebuild_request = 0;
-            g.prune_request = 0;
             g.noise_counter += advance_noise;
             g.md_counter += advance_md;
         }
@@ -60,8 +55,17 @@ __global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort
     cg::cluster_group cluster = cg::this_cluster();
     const int r = blockIdx.y;
     Globals& g = d.g[r];
-    if (!g.do_rebuild) return;                 // uniform over the cluster
     const int cta = (int)cluster.block_rank();
+    if (cta == 0 && threadIdx.x == 0) {
+        // latch: the Verlet list is rebuilt (cell sort + search) when some atom moved > skin / 2 since the last build,
+        // or on request (host wrote coordinates, box changed); the alchemical pair list follows the same schedule
+        g.do_rebuild = g.rebuild_request == 2 || g.prune_request;
+        g.do_prune = g.do_rebuild;
+        g.rebuild_request = 0;
+        g.prune_request = 0;
+    }
+    cluster.sync();
+    if (!g.do_rebuild) return;                 // uniform over the cluster
     const int tid = cta * blockDim.x + threadIdx.x, nt = SORT_CTAS * blockDim.x;
     const int lane = threadIdx.x & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int N = d.N, Npad = d.Npad, ncells = d.ncells;
