@@ -234,37 +234,118 @@ __device__ __forceinline__ void sts_idx(unsigned int addr, int v) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+#define BUILD_MAX_RUNS 64       /* a group sees at most 5 x 5 cell columns, each one run plus one periodic wrap */
+
+// Phase 1 of a group: tabulate the runs of cell-sorted atoms that can hold neighbours — one (x, y) cell column per lane,
+// its z range cut to the reach of the group's bounding box, split where it wraps — so that all cell_start loads are in
+// flight together.  runs[k] = (shift x, y, z, first sorted index as bits), off[k] = candidates before run k.
+__device__ __forceinline__ int build_group_runs(const Dev& d, const int* __restrict__ start, int lane, bool rx, bool ry,
+                                                bool rz, int x0, int x1, int y0, int y1, int za, int zb, float lox, float hix,
+                                                float loy, float hiy, float loz, float hiz, float4* runs, int* off) {
+    const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2];
+    const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
+    const float ex = bx / ncx, ey = by / ncy, ez = bz / ncz;
+    const float cut2 = d.list_cutoff2;
+    const int nyc = y1 - y0 + 1, ncols = (x1 - x0 + 1) * nyc;       // <= 25 (checked by the caller)
+    int nseg = 0, s0v[2] = {0, 0}, lenv[2] = {0, 0};
+    float szv[2] = {0.f, 0.f}, sx = 0.f, sy = 0.f;
+    if (lane < ncols) {
+        const int rxc = x0 + lane / nyc, ryc = y0 + lane % nyc;
+        int ax = rxc, ay = ryc;
+        float dxc = 0.f, dyc = 0.f;
+        if (!rx) {
+            if (ax < 0) { ax += ncx; sx = -bx; } else if (ax >= ncx) { ax -= ncx; sx = bx; }
+            dxc = fmaxf(0.f, fmaxf(rxc * ex - hix, lox - (rxc + 1) * ex));   // gap between the group and the slab
+        }
+        if (!ry) {
+            if (ay < 0) { ay += ncy; sy = -by; } else if (ay >= ncy) { ay -= ncy; sy = by; }
+            dyc = fmaxf(0.f, fmaxf(ryc * ey - hiy, loy - (ryc + 1) * ey));
+        }
+        const float rem2 = cut2 - dxc * dxc - dyc * dyc;
+        if (rem2 > 0.f) {                                                     // else: column out of reach
+            int z0 = 0, z1 = ncz - 1;
+            if (!rz) {
+                const float zr = sqrtf(rem2);
+                z0 = max(za - 2, (int)floorf((loz - zr) / ez));
+                z1 = min(zb + 2, (int)floorf((hiz + zr) / ez));
+            }
+            const int row = (ax * ncy + ay) * ncz;
+            // at most two of the three segments exist (the z range is no longer than the column)
+#pragma unroll
+            for (int seg = 0; seg < 3; ++seg) {
+                int a0, a1;
+                float sz = 0.f;
+                if (seg == 0) { a0 = max(z0, 0); a1 = min(z1, ncz - 1); }
+                else if (seg == 1) { a0 = z0 + ncz; a1 = z0 < 0 ? ncz - 1 : -1; sz = -bz; }
+                else { a0 = 0; a1 = z1 >= ncz ? z1 - ncz : -1; sz = bz; }
+                if (a0 <= a1 && nseg < 2) {
+                    const int b0 = start[row + a0], b1 = start[row + a1 + 1];
+                    if (b1 > b0) { s0v[nseg] = b0; lenv[nseg] = b1 - b0; szv[nseg] = sz; ++nseg; }
+                }
+            }
+        }
+    }
+    // compact the runs in column order; exclusive prefix of their lengths
+    int pos = nseg, cum = lenv[0] + lenv[1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int p2 = __shfl_up_sync(0xffffffffu, pos, o), c2 = __shfl_up_sync(0xffffffffu, cum, o);
+        if (lane >= o) { pos += p2; cum += c2; }
+    }
+    const int nruns = __shfl_sync(0xffffffffu, pos, 31), total = __shfl_sync(0xffffffffu, cum, 31);
+    pos -= nseg;
+    cum -= lenv[0] + lenv[1];
+    for (int j = 0; j < nseg; ++j) {
+        runs[pos + j] = make_float4(sx, sy, szv[j], __int_as_float(s0v[j]));
+        off[pos + j] = cum;
+        cum += lenv[j];
+    }
+    if (lane == 0) off[nruns] = total;
+    __syncwarp();
+    return nruns;
+}
+
+// Phase 2: stream the candidates of all runs 32 at a time.
 template <bool RINT, typename IDX>
-__device__ __forceinline__ void build_scan_run(const Dev& d, const float4* __restrict__ posq_s, const int* __restrict__ orig_s,
-                                               int s0, int s1, float sx, float sy, float sz, bool rx, bool ry, bool rz,
-                                               float4* cand, IDX* mysub, int cq, int lane, float4 pi, int oi, ull wi,
-                                               bool fari, bool anyfar, const int (&og)[BUILD_GROUP],
-                                               const unsigned int (&osp)[BUILD_GROUP], int& cnt, bool& overflow) {
+__device__ __forceinline__ void build_stream(const Dev& d, const float4* __restrict__ posq_s, const int* __restrict__ orig_s,
+                                             const float4* runs, const int* off, int nruns, bool rx, bool ry, bool rz,
+                                             float4* cand, IDX* mysub, int cq, int lane, float4 pi, int oi, ull wi,
+                                             bool fari, bool anyfar, const int (&og)[BUILD_GROUP],
+                                             const unsigned int (&osp)[BUILD_GROUP], int& cnt, bool& overflow) {
     const float cut2 = d.list_cutoff2;
     const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
     const float qnan = __int_as_float(0x7fc00000);
     const int q = lane >> 3;
     const unsigned int sub_addr = (unsigned int)__cvta_generic_to_shared(mysub);
-    // software pipeline: the candidate of the next chunk is requested before the current chunk is processed
+    const int total = off[nruns];
+    int kp = 0;                                           // run of this lane's next candidate (monotonic)
+    // software pipeline: the candidates of the next chunk are requested before the current chunk is processed (deeper
+    // pipelines were measured slower: the extra registers and moves cost more than the residual latency)
     float4 cnext = make_float4(qnan, qnan, qnan, 0.f);
     int ojnext = 0;
-    if (s0 + lane < s1) { cnext = posq_s[s0 + lane]; ojnext = orig_s[s0 + lane]; }
-    for (int base = s0; base < s1; base += 32) {
+    auto fetch = [&](int c) {
+        cnext = make_float4(qnan, qnan, qnan, 0.f);
+        if (c < total) {
+            while (c >= off[kp + 1]) ++kp;
+            const float4 rn = runs[kp];
+            const int s = __float_as_int(rn.w) + (c - off[kp]);
+            const float4 p = posq_s[s];
+            ojnext = orig_s[s];
+            cnext = make_float4(p.x + rn.x, p.y + rn.y, p.z + rn.z, __int_as_float(s));   // shifted image; w = sorted index
+        }
+    };
+    fetch(lane);
+    for (int c0 = 0; c0 < total; c0 += 32) {
         bool near = false;
         {
-            float4 c = cnext;
+            const float4 c = cnext;
             const int oj = ojnext;
-            const bool have = base + lane < s1;
-            const int sn = base + 32 + lane;
-            if (sn < s1) { cnext = posq_s[sn]; ojnext = orig_s[sn]; }
+            const bool have = c0 + lane < total;
+            fetch(c0 + 32 + lane);
             if (have) {
-                c.x += sx; c.y += sy; c.z += sz;
-                c.w = __int_as_float(oj);
 #pragma unroll
                 for (int k = 0; k < BUILD_GROUP; ++k)               // inside the exclusion window of a group atom
                     near = near || (unsigned int)(oj - og[k]) <= osp[k];
-            } else {
-                c = make_float4(qnan, qnan, qnan, 0.f);
             }
             __syncwarp();
             cand[lane + (lane >> 3)] = c;                           // 8-candidate pieces, padded: conflict-free LDS
@@ -277,9 +358,10 @@ __device__ __forceinline__ void build_scan_run(const Dev& d, const float4* __res
             // candidates are loaded and measured before the first store, so the eight chains overlap; every store is
             // unconditional and only the write pointer advance is predicated.
             float r2v[8];
+            int sv[8];
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                const float4 c = cand[q * 9 + t];                  // candidate 8 q + t
+                const float4 c = cand[q * 9 + t];                  // candidate 8 q + t of the chunk
                 float dx = c.x - pi.x, dy = c.y - pi.y, dz = c.z - pi.z;
                 if (RINT) {
                     if (rx) dx -= bx * rintf(dx * ibx);
@@ -287,11 +369,11 @@ __device__ __forceinline__ void build_scan_run(const Dev& d, const float4* __res
                     if (rz) dz -= bz * rintf(dz * ibz);
                 }
                 r2v[t] = dx * dx + dy * dy + dz * dz;
+                sv[t] = __float_as_int(c.w);
             }
-            const int vq = base + 8 * q;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
-                sts_idx(wp, (IDX)(vq + t));
+                sts_idx(wp, (IDX)sv[t]);
                 wp += r2v[t] < cut2 ? (unsigned int)sizeof(IDX) : 0u;   // NaN (padding) compares false
             }
         } else {
@@ -305,12 +387,13 @@ __device__ __forceinline__ void build_scan_run(const Dev& d, const float4* __res
                     if (rz) dz -= bz * rintf(dz * ibz);
                 }
                 if (dx * dx + dy * dy + dz * dz < cut2) {
-                    const int oj = __float_as_int(c.w);
+                    const int sj = __float_as_int(c.w);
+                    const int oj = orig_s[sj];
                     const unsigned int dd = (unsigned int)(oj - oi + 32);
                     bool ok = true;
                     if (dd < 64u) ok = !((wi >> dd) & 1ull);           // includes the atom itself (bit 32)
                     else if (fari) ok = !pair_excluded(d, oi, wi, true, oj, d.has_far[oj]);   // rare
-                    if (ok) { sts_idx(wp, (IDX)(base + 8 * q + t)); wp += (unsigned int)sizeof(IDX); }
+                    if (ok) { sts_idx(wp, (IDX)sj); wp += (unsigned int)sizeof(IDX); }
                 }
             }
         }
@@ -319,66 +402,15 @@ __device__ __forceinline__ void build_scan_run(const Dev& d, const float4* __res
     }
 }
 
-template <bool RINT, typename IDX>
-__device__ __forceinline__ void build_scan_cells(const Dev& d, const float4* __restrict__ posq_s, const int* __restrict__ orig_s,
-                                              const int* __restrict__ start, bool rx, bool ry, bool rz, int x0, int x1,
-                                              int y0, int y1, int za, int zb, float lox, float hix, float loy, float hiy,
-                                              float loz, float hiz, float4* cand, IDX* mysub, int cq, int lane,
-                                              float4 pi, int oi, ull wi, bool fari, bool anyfar,
-                                              const int (&og)[BUILD_GROUP], const unsigned int (&osp)[BUILD_GROUP], int& cnt,
-                                              bool& overflow) {
-    const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2];
-    const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
-    const float ex = bx / ncx, ey = by / ncy, ez = bz / ncz;
-    const float cut2 = d.list_cutoff2;
-    for (int rxc = x0; rxc <= x1; ++rxc) {
-        int ax = rxc;
-        float sx = 0.f, dxc = 0.f;
-        if (!rx) {
-            if (ax < 0) { ax += ncx; sx = -bx; } else if (ax >= ncx) { ax -= ncx; sx = bx; }
-            dxc = fmaxf(0.f, fmaxf(rxc * ex - hix, lox - (rxc + 1) * ex));   // gap between the group and the slab
-        }
-        for (int ryc = y0; ryc <= y1; ++ryc) {
-            int ay = ryc;
-            float sy = 0.f, dyc = 0.f;
-            if (!ry) {
-                if (ay < 0) { ay += ncy; sy = -by; } else if (ay >= ncy) { ay -= ncy; sy = by; }
-                dyc = fmaxf(0.f, fmaxf(ryc * ey - hiy, loy - (ryc + 1) * ey));
-            }
-            const float rem2 = cut2 - dxc * dxc - dyc * dyc;
-            if (rem2 <= 0.f) continue;                                        // column out of reach
-            int z0 = 0, z1 = ncz - 1;
-            if (!rz) {
-                const float zr = sqrtf(rem2);
-                z0 = max(za - 2, (int)floorf((loz - zr) / ez));
-                z1 = min(zb + 2, (int)floorf((hiz + zr) / ez));
-            }
-            const int row = (ax * ncy + ay) * ncz;
-#pragma unroll 1
-            for (int seg = 0; seg < 3; ++seg) {
-                int a0, a1;
-                float sz = 0.f;
-                if (seg == 0) { a0 = max(z0, 0); a1 = min(z1, ncz - 1); }
-                else if (seg == 1) { if (z0 >= 0) continue; a0 = z0 + ncz; a1 = ncz - 1; sz = -bz; }
-                else { if (z1 < ncz) continue; a0 = 0; a1 = z1 - ncz; sz = bz; }
-                if (a0 > a1) continue;
-                const int s0 = start[row + a0], s1 = start[row + a1 + 1];
-                build_scan_run<RINT, IDX>(d, posq_s, orig_s, s0, s1, sx, sy, sz, rx, ry, rz, cand, mysub, cq, lane,
-                                          pi, oi, wi, fari, anyfar, og, osp, cnt, overflow);
-            }
-        }
-    }
-}
-
-// dynamic shared memory per CTA (one warp): 36 float4 candidates + 32 sub-lists of (cq + BUILD_SLACK) entries
 __host__ __device__ inline int build_sub_stride(int cq, int idx_bytes) {
     // entries per sub-list, rounded so that the stride in 32-bit words is odd (lanes appending at equal offsets then
     // hit different banks)
     const int words = ((cq + BUILD_SLACK) * idx_bytes + 3) / 4 | 1;
     return words * 4 / idx_bytes;
 }
+#define BUILD_HEAD_F4 (36 + BUILD_MAX_RUNS + (BUILD_MAX_RUNS + 4) / 4)    /* candidates, run table, run offsets */
 __host__ __device__ inline size_t build_smem_bytes(int cq, int idx_bytes) {
-    return 36 * sizeof(float4) + (size_t)32 * build_sub_stride(cq, idx_bytes) * idx_bytes;
+    return BUILD_HEAD_F4 * sizeof(float4) + (size_t)32 * build_sub_stride(cq, idx_bytes) * idx_bytes;
 }
 
 template <typename IDX>
@@ -386,7 +418,9 @@ __global__ void __launch_bounds__(32) k_build_list(Dev d, int cq) {
     extern __shared__ float4 s_build[];
     float4* cand = s_build;
     const int stride = build_sub_stride(cq, (int)sizeof(IDX));
-    IDX* subs = reinterpret_cast<IDX*>(s_build + 36);
+    float4* runs = s_build + 36;
+    int* off = reinterpret_cast<int*>(s_build + 36 + BUILD_MAX_RUNS);
+    IDX* subs = reinterpret_cast<IDX*>(s_build + BUILD_HEAD_F4);
     const int lane = threadIdx.x;
     IDX* mysub = subs + (size_t)lane * stride;
     const int N = d.N, Npad = d.Npad;
@@ -433,11 +467,14 @@ __global__ void __launch_bounds__(32) k_build_list(Dev d, int cq) {
         int cnt = 0;
         bool overflow = false;
         if (!d.periodic) {
-            build_scan_run<false, IDX>(d, posq_s, orig_s, 0, N, 0.f, 0.f, 0.f, false, false, false, cand, mysub, cq, lane,
-                                       pi, oi, wi, fari, anyfar, og, osp, cnt, overflow);
+            if (lane == 0) { runs[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(0)); off[0] = 0; off[1] = N; }
+            __syncwarp();
+            build_stream<false, IDX>(d, posq_s, orig_s, runs, off, 1, false, false, false, cand, mysub, cq, lane, pi, oi,
+                                     wi, fari, anyfar, og, osp, cnt, overflow);
         } else {
             const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
-            // bounding box of the group, in cells and in space (idle lanes hold the first atom)
+            // bounding box of the group, in cells and in space (idle lanes hold the first atom); a group never
+            // straddles a cell column, so xa == xb and ya == yb and the search covers at most 5 x 5 columns
             int cx, cy, cz;
             atom_cell_coords(d, pa, cx, cy, cz);
             const int xa = __reduce_min_sync(0xffffffffu, cx), xb = __reduce_max_sync(0xffffffffu, cx);
@@ -449,14 +486,14 @@ __global__ void __launch_bounds__(32) k_build_list(Dev d, int cq) {
             const bool rx = xb - xa + 5 > ncx, ry = yb - ya + 5 > ncy, rz = zb - za + 5 > ncz;
             const int x0 = rx ? 0 : xa - 2, x1 = rx ? ncx - 1 : xb + 2;
             const int y0 = ry ? 0 : ya - 2, y1 = ry ? ncy - 1 : yb + 2;
+            const int nruns = build_group_runs(d, start, lane, rx, ry, rz, x0, x1, y0, y1, za, zb, lox, hix, loy, hiy, loz,
+                                               hiz, runs, off);
             if (rx || ry || rz)
-                build_scan_cells<true, IDX>(d, posq_s, orig_s, start, rx, ry, rz, x0, x1, y0, y1, za, zb, lox, hix, loy,
-                                            hiy, loz, hiz, cand, mysub, cq, lane, pi, oi, wi, fari, anyfar, og, osp, cnt,
-                                            overflow);
+                build_stream<true, IDX>(d, posq_s, orig_s, runs, off, nruns, rx, ry, rz, cand, mysub, cq, lane, pi, oi, wi,
+                                        fari, anyfar, og, osp, cnt, overflow);
             else
-                build_scan_cells<false, IDX>(d, posq_s, orig_s, start, false, false, false, x0, x1, y0, y1, za, zb, lox,
-                                             hix, loy, hiy, loz, hiz, cand, mysub, cq, lane, pi, oi, wi, fari, anyfar, og,
-                                             osp, cnt, overflow);
+                build_stream<false, IDX>(d, posq_s, orig_s, runs, off, nruns, false, false, false, cand, mysub, cq, lane,
+                                         pi, oi, wi, fari, anyfar, og, osp, cnt, overflow);
         }
         // concatenate the four sub-lists of every atom into its row (coalesced), in subset order
         __syncwarp();
