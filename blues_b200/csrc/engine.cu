@@ -69,6 +69,7 @@ struct bl_handle {
     std::vector<double> host_tmp;
     double skin = 0.0; int cell_capacity = 0;
     int build_cq = 0, build_ctas = 0;
+    int graph_steps = 4;         // plain NCMC steps captured per CUDA graph
     double4* pinned = nullptr;     // pinned staging for state uploads / downloads ([N] double4)
 };
 
@@ -234,7 +235,8 @@ static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a, bool noise_p
         k_integrate_generic<<<dim3(cdiv(h->n_generic, 64), h->d.R), 64, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity, h->n_generic);
     }
     LaunchTimer t(h, BL_K_INTEGRATE);
-    k_integrate<<<dim3(cdiv(h->d.n_clusters, 64), h->d.R), 64, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity);
+    // + 1: the last CTA holds no clusters (n_clusters is passed to the bounds check) and does the scalar bookkeeping
+    k_integrate<<<dim3(cdiv(h->d.n_clusters, 64) + 1, h->d.R), 64, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity);
 }
 
 static void enqueue_momentum(bl_handle* h) {
@@ -683,6 +685,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (device < 0 || device >= ndev) { g_create_error = "invalid device index"; return BL_ERR_INVALID; }
     if (t->nb_method != 0 && t->nb_method != 2 && t->nb_method != 4) { g_create_error = "unsupported nonbonded method"; return BL_ERR_INVALID; }
     bl_handle* h = new bl_handle();
+    if (getenv("BLUES_B200_GRAPH_STEPS")) h->graph_steps = std::max(1, atoi(getenv("BLUES_B200_GRAPH_STEPS")));
     counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping
     auto fail = [&](int code, const std::string& msg) { g_create_error = msg; bl_destroy(h); return code; };
     h->device = device;
@@ -1375,18 +1378,31 @@ int bl_ncmc_run(bl_handle* h, int n_steps, const bl_move* move) {
         int n_extra = 0;
         if (h->ic.nprop > 1 && lam_after > h->prop_lambda_min && lam_after <= h->prop_lambda_max) n_extra = h->ic.nprop - 1;
         const bool energy_end = (i == n_steps - 1) || (h->step + 1 >= h->ic.nsteps) || (has_move && i + 1 == move->step);
+        // several plain steps (no move, no extra propagation, no energy needed at their end) go into one graph: fewer
+        // graph launches and no inter-graph gap between them
+        int batch = 1;
+        if (h->ic.nprop == 1 && !energy_end && h->graph_steps > 1) {
+            batch = h->graph_steps;
+            batch = std::min(batch, n_steps - 1 - i);                          // the last step of the call carries energies
+            batch = std::min(batch, h->ic.nsteps - 1 - h->step);              // so does the last step of the protocol
+            if (has_move && move->step > i) batch = std::min(batch, move->step - 1 - i);   // and the step before a move
+            if (batch < h->graph_steps) batch = 1;                             // only full batches: few distinct graphs
+        }
         std::vector<Launch> ls;
         int cursor = h->cursor;
-        compile_pass(h, ls, cursor, true, n_extra == 0, energy_end);
-        for (int p = 0; p < n_extra; ++p) compile_pass(h, ls, cursor, false, p == n_extra - 1, energy_end);
+        for (int b = 0; b < batch; ++b) {
+            compile_pass(h, ls, cursor, true, n_extra == 0, energy_end);
+            for (int p = 0; p < n_extra; ++p) compile_pass(h, ls, cursor, false, p == n_extra - 1, energy_end);
+        }
         char key[96];
-        snprintf(key, sizeof key, "ncmc|c%d|e%d|x%d", h->cursor, energy_end ? 1 : 0, n_extra);
+        snprintf(key, sizeof key, "ncmc|c%d|e%d|x%d|b%d", h->cursor, energy_end ? 1 : 0, n_extra, batch);
         int rc = run_launches(h, key, ls);
         if (rc != BL_OK) return rc;
         h->cursor = cursor;
-        h->step += 1;
-        h->lambda_step = ls_after;
+        h->step += batch;
+        h->lambda_step = h->lambda_step + batch * h->n_H;
         h->forces_valid = true;
+        i += batch - 1;
     }
     return check_flags(h);
 }
