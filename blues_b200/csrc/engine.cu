@@ -70,6 +70,8 @@ struct bl_handle {
     double skin = 0.0; int cell_capacity = 0;
     int build_cq = 0, build_ctas = 0;
     int graph_steps = 4;         // plain NCMC steps captured per CUDA graph
+    // diagnostic timeline (BLUES_B200_TIMELINE=1): events recorded inside the step graphs, read after every replay
+    bool timeline = false; cudaEvent_t tl_ev[24] = {}; double tl_sum[24] = {}; long tl_n[24] = {}; int tl_int = 0;
     double4* pinned = nullptr;     // pinned staging for state uploads / downloads ([N] double4)
 };
 
@@ -128,6 +130,37 @@ static void collect_timings(bl_handle* h) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+enum { TL_START = 0, TL_SORT, TL_ZERO, TL_BUILD, TL_PAIR, TL_SPREAD, TL_R2C, TL_CONV, TL_C2R, TL_GATHER, TL_BONDED, TL_ALCH,
+       TL_JOINED, TL_INT0, TL_INT1, TL_INT2, TL_COUNT };
+static const char* TL_NAMES[] = {"step start", "sort done", "zero done", "build done", "pair done", "pme spread done",
+                                 "pme r2c done", "pme convolve done", "pme c2r done", "pme gather done", "bonded+noise done",
+                                 "alch done", "eval joined", "integrate #1 done", "integrate #2 done", "integrate #3 done"};
+static void tl_mark(bl_handle* h, cudaStream_t st, int id) {
+    if (!h->timeline || id >= TL_COUNT) return;
+    if (!h->tl_ev[id]) cudaEventCreate(&h->tl_ev[id]);
+    if (h->capturing) cudaEventRecordWithFlags(h->tl_ev[id], st, cudaEventRecordExternal);
+    else cudaEventRecord(h->tl_ev[id], st);
+}
+static void tl_collect(bl_handle* h) {
+    if (!h->timeline || !h->tl_ev[TL_START]) return;
+    cudaStreamSynchronize(h->stream);
+    for (int id = 1; id < TL_COUNT; ++id) {
+        if (!h->tl_ev[id]) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->tl_ev[TL_START], h->tl_ev[id]) == cudaSuccess && ms >= 0.f) {
+            h->tl_sum[id] += ms * 1e3;
+            h->tl_n[id] = labs(h->tl_n[id]) + 1;
+        }
+    }
+    cudaGetLastError();
+}
+static void tl_report(bl_handle* h) {
+    if (!h->timeline) return;
+    fprintf(stderr, "[blues_b200 timeline] mean microseconds after step start (graph replays, one step per graph)\n");
+    for (int id = 1; id < TL_COUNT; ++id)
+        if (labs(h->tl_n[id]) > 0) fprintf(stderr, "    %-22s %8.1f   (n = %ld)\n", TL_NAMES[id], h->tl_sum[id] / labs(h->tl_n[id]), labs(h->tl_n[id]));
+}
+
 // ---- force / energy evaluation at the current positions ---------------------------------------------------
 // energy: also accumulate energies; cm_mode: forwarded to k_begin_eval
 static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, int cm_mode, int prefetch_noise = 0) {
@@ -139,6 +172,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         LaunchTimer t(h, BL_K_NEIGHBOR);
         k_sort_atoms<<<dim3(SORT_CTAS, R), 1024, 0, st>>>(d);
     }
+    tl_mark(h, st, TL_SORT);
     // Fork 1: reciprocal space (stream2) depends only on the cell-sorted positions; its gather waits for fork 2.
     cudaEventRecord(h->ev_fork, st);
     {
@@ -151,6 +185,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     // (stream3), alchemical lists + kernel (stream4); the main stream keeps the list build and the pair kernel.  All
     // branches accumulate into the same fixed-point buffers with atomics.
     cudaEventRecord(h->ev_fork2, st);
+    tl_mark(h, st, TL_ZERO);
     const bool pme = d.pme && h->has_fft;
     const int nterms = d.n_bonds + d.n_angles + d.n_torsions + d.n_excl + d.n_restraints + d.n_alch_exc;
     if (pme) {
@@ -162,14 +197,19 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
           // few walkers: latency bound, many wide CTAs; many walkers: throughput bound, fewer duplicate B-splines
           if (R <= 2) k_pme_spread<8, 512><<<dim3(d.gx, 8, R), 512, (d.gy / 8 + 1) * d.gz * sizeof(int), s2>>>(d);
           else k_pme_spread<4, 256><<<dim3(d.gx, 4, R), 256, (d.gy / 4 + 1) * d.gz * sizeof(int), s2>>>(d); }
+        tl_mark(h, s2, TL_SPREAD);
             { LaunchTimer t(h, BL_K_FFT, s2); cufftExecR2C(h->plan_r2c, d.grid_r, reinterpret_cast<cufftComplex*>(d.grid_c)); }
+        tl_mark(h, s2, TL_R2C);
             { LaunchTimer t(h, BL_K_PME_CONVOLVE, s2);
               if (energy) k_pme_convolve<true><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d);
               else k_pme_convolve<false><<<dim3(cdiv(d.csize, 256), R), 256, 0, s2>>>(d); }
-            { LaunchTimer t(h, BL_K_FFT, s2); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
+            tl_mark(h, s2, TL_CONV);
+        { LaunchTimer t(h, BL_K_FFT, s2); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
+        tl_mark(h, s2, TL_C2R);
         { LaunchTimer t(h, BL_K_PME_GATHER, s2);
           if (R <= 2) k_pme_gather5<<<dim3(cdiv(cdiv(N, 6) * 32, 128), R), 128, 0, s2>>>(d);
           else k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
+        tl_mark(h, s2, TL_GATHER);
         cudaEventRecord(h->ev_join, s2);
     }
     if (nterms > 0 || prefetch_noise > 0) {
@@ -182,6 +222,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
             LaunchTimer t(h, BL_K_INTEGRATE, s3);
             k_noise<<<dim3(cdiv((long long)N * prefetch_noise, 128), R), 128, 0, s3>>>(d, h->ic, STREAM_LANGEVIN, prefetch_noise, 0);
         }
+        tl_mark(h, s3, TL_BONDED);
         cudaEventRecord(h->ev_join3, s3);
     }
     if (d.n_alch > 0) {
@@ -191,6 +232,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         { LaunchTimer t(h, BL_K_NEIGHBOR, s4);
           k_alch_list<<<dim3(cdiv(N, 128), R), 128, d.n_alch * sizeof(float4), s4>>>(d); }
         { LaunchTimer t(h, BL_K_ALCH, s4); k_alch<<<dim3(cdiv(d.alch_cap, 128), d.n_alch, R), 128, 0, s4>>>(d); }
+        tl_mark(h, s4, TL_ALCH);
         cudaEventRecord(h->ev_join4, s4);
     }
     {
@@ -200,6 +242,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         if (d.nl_u16) k_build_list<unsigned short><<<grid, 32, smem, st>>>(d, h->build_cq);
         else k_build_list<int><<<grid, 32, smem, st>>>(d, h->build_cq);
     }
+    tl_mark(h, st, TL_BUILD);
     {
         LaunchTimer t(h, BL_K_PAIR);
         dim3 grid(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R);
@@ -213,9 +256,11 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
 #undef PAIR2
 #undef PAIR
     }
+    tl_mark(h, st, TL_PAIR);
     if (pme) cudaStreamWaitEvent(st, h->ev_join, 0);
     if (nterms > 0 || prefetch_noise > 0) cudaStreamWaitEvent(st, h->ev_join3, 0);
     if (d.n_alch > 0) cudaStreamWaitEvent(st, h->ev_join4, 0);
+    tl_mark(h, st, TL_JOINED);
 }
 
 static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a, bool noise_prefetched) {
@@ -237,6 +282,7 @@ static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a, bool noise_p
     LaunchTimer t(h, BL_K_INTEGRATE);
     // + 1: the last CTA holds no clusters (n_clusters is passed to the bounds check) and does the scalar bookkeeping
     k_integrate<<<dim3(cdiv(h->d.n_clusters, 64) + 1, h->d.R), 64, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity);
+    tl_mark(h, h->stream, TL_INT0 + std::min(h->tl_int++, 2));
 }
 
 static void enqueue_momentum(bl_handle* h) {
@@ -364,6 +410,7 @@ static int noise_lookahead(const std::vector<Launch>& ls, size_t k) {
 
 // Enqueue the launches (dry = false) or only replay their host-side bookkeeping (dry = true, after a graph launch).
 static void issue(bl_handle* h, const std::vector<Launch>& ls, HostCounters& hc, bool dry = false) {
+    if (!dry) { h->tl_int = 0; tl_mark(h, h->stream, TL_START); }
     for (size_t k = 0; k < ls.size(); ++k) {
         const Launch& l = ls[k];
         if (l.is_eval) {
@@ -421,6 +468,7 @@ static int run_launches(bl_handle* h, const std::string& key, const std::vector<
     CK(cudaGraphLaunch(it->second, h->stream));
     h->launches += (unsigned long long)(uintptr_t)h->graphs[k + "#n"];
     issue(h, ls, hc, true);      // advance the host mirror of the counters exactly as the captured launches did
+    tl_collect(h);
     return BL_OK;
 }
 
@@ -654,6 +702,8 @@ void* bl_stream(bl_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int bl_destroy(bl_handle* h) {
     if (!h) return BL_OK;
+    tl_report(h);
+    for (auto& e : h->tl_ev) if (e) cudaEventDestroy(e);
     counter_map().erase(h);
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -686,12 +736,18 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (t->nb_method != 0 && t->nb_method != 2 && t->nb_method != 4) { g_create_error = "unsupported nonbonded method"; return BL_ERR_INVALID; }
     bl_handle* h = new bl_handle();
     if (getenv("BLUES_B200_GRAPH_STEPS")) h->graph_steps = std::max(1, atoi(getenv("BLUES_B200_GRAPH_STEPS")));
+    if (getenv("BLUES_B200_TIMELINE")) { h->timeline = true; h->graph_steps = 1; }
     counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping
     auto fail = [&](int code, const std::string& msg) { g_create_error = msg; bl_destroy(h); return code; };
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess) return fail(BL_ERR_CUDA, "cudaSetDevice failed");
+    // the reciprocal-space chain (seven short dependent kernels) is the critical path of most steps and loses against
+    // the wide pair kernel when they compete for SMs: its stream gets the highest priority
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (getenv("BLUES_B200_NO_PRIORITY")) prio_hi = prio_lo;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
