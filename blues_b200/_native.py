@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libblues_b200.so')
 
 BL_INTEGRATOR_NCMC, BL_INTEGRATOR_LANGEVIN = 1, 2
 BL_MOVE_NONE, BL_MOVE_ROTATE = 0, 1
+BL_MOVE_WATER_SWAP, BL_MOVE_WATER_TRANSLATE, BL_MOVE_WATER_CHECK = 2, 3, 4
 ENERGY_TERMS = ['bond', 'angle', 'torsion', 'restraint', 'pair_direct', 'exceptions', 'pme_reciprocal', 'ewald_self',
                 'dispersion', 'alch_sterics', 'alch_electrostatics', 'alch_exceptions']
 KERNEL_IDS = {'pair': 0, 'integrate': 1, 'pme_spread': 2, 'pme_gather': 3, 'pme_convolve': 4, 'bonded': 5, 'alch': 6,
@@ -51,7 +52,9 @@ class BlIntegratorParams(C.Structure):
 
 
 class BlMove(C.Structure):
-    _fields_ = [('kind', C.c_int32), ('step', C.c_int32), ('n_atoms', C.c_int32), ('atoms', _ip), ('masses', _dp)]
+    _fields_ = [('kind', C.c_int32), ('step', C.c_int32), ('n_atoms', C.c_int32), ('atoms', _ip), ('masses', _dp),
+                ('n_waters', C.c_int32), ('water_atoms', _ip), ('n_center', C.c_int32), ('center_atoms', _ip),
+                ('center_masses', _dp), ('radius', C.c_double)]
 
 
 # every symbol include/blues_b200.h declares: name → (restype, argtypes)
@@ -293,28 +296,45 @@ class Engine(object):
         self._check(self.lib.bl_reset_ncmc(self.h))
 
     # -- hot path -----------------------------------------------------------------------------------------
-    def _move(self, kind, step, atoms, masses):
+    def _move(self, kind, step, atoms, masses=None, waters=None, center_atoms=None, center_masses=None, radius=0.0):
         m = BlMove()
         m.kind, m.step = int(kind), int(step)
         a = _arr(atoms, np.int32)
-        ms = _arr(masses, np.float64).reshape(-1)
+        keep = [a]
         m.n_atoms = len(a)
-        m.atoms, m.masses = _p(a, C.c_int32), _p(ms, C.c_double)
-        return m, (a, ms)
+        m.atoms = _p(a, C.c_int32)
+        if masses is not None:
+            ms = _arr(masses, np.float64).reshape(-1)
+            m.masses = _p(ms, C.c_double)
+            keep.append(ms)
+        if waters is not None:
+            w = _arr(waters, np.int32).reshape(-1, len(a))
+            m.n_waters, m.water_atoms = len(w), _p(w, C.c_int32)
+            keep.append(w)
+        if center_atoms is not None:
+            ca = _arr(center_atoms, np.int32).reshape(-1)
+            cm = _arr(center_masses, np.float64).reshape(-1)
+            if len(ca) != len(cm):
+                raise ValueError('center_atoms and center_masses differ in length')
+            m.n_center, m.center_atoms, m.center_masses = len(ca), _p(ca, C.c_int32), _p(cm, C.c_double)
+            keep += [ca, cm]
+        m.radius = float(radius)
+        return m, keep
 
     def ncmc_run(self, n_steps, move=None):
         """move: None or dict(kind=BL_MOVE_ROTATE, step=k, atoms=[...], masses=[...])"""
         if move is None:
             self._check(self.lib.bl_ncmc_run(self.h, int(n_steps), None))
         else:
-            m, keep = self._move(move['kind'], move['step'], move['atoms'], move['masses'])
+            m, keep = self._move(**move)
             self._check(self.lib.bl_ncmc_run(self.h, int(n_steps), C.byref(m)))
 
     def md_run(self, n_steps):
         self._check(self.lib.bl_md_run(self.h, int(n_steps)))
 
-    def apply_move(self, kind, atoms, masses):
-        m, keep = self._move(kind, 0, atoms, masses)
+    def apply_move(self, kind, atoms, masses=None, **water):
+        """Apply a move now.  ``water``: waters=, center_atoms=, center_masses=, radius= for the BL_MOVE_WATER_* kinds."""
+        m, keep = self._move(kind, 0, atoms, masses, **water)
         self._check(self.lib.bl_apply_move(self.h, C.byref(m)))
 
     def accept_reject(self, correction=None):

@@ -66,6 +66,10 @@ struct bl_handle {
     int* d_iscratch = nullptr;     // [R*2]
     double4* d_saved = nullptr;    // minimizer
     int* d_move_atoms = nullptr; float* d_move_masses = nullptr; int move_capacity = 0;
+    // WaterTranslationMove: candidate waters, protein selection, per-walker {sphere centre, go}
+    int* d_water_atoms = nullptr; size_t water_capacity = 0;
+    int* d_center_atoms = nullptr; float* d_center_masses = nullptr; int center_capacity = 0;
+    double* d_water_state = nullptr;
     std::vector<double> host_tmp;
     double skin = 0.0; int cell_capacity = 0;
     int build_cq = 0, build_ctas = 0;
@@ -1355,17 +1359,51 @@ int bl_reset_ncmc(bl_handle* h) {
 }
 
 // ---- moves -----------------------------------------------------------------------------------------------------
+static bool is_water_move(int kind) {
+    return kind == BL_MOVE_WATER_SWAP || kind == BL_MOVE_WATER_TRANSLATE || kind == BL_MOVE_WATER_CHECK;
+}
 static int stage_move(bl_handle* h, const bl_move* m) {
-    if (m->n_atoms <= 0 || !m->atoms || !m->masses) { h->error = "move needs atoms and masses"; return BL_ERR_INVALID; }
+    const bool water = is_water_move(m->kind);
+    if (m->n_atoms <= 0 || !m->atoms || (!water && !m->masses)) { h->error = "move needs atoms and masses"; return BL_ERR_INVALID; }
+    for (int k = 0; k < m->n_atoms; ++k)
+        if (m->atoms[k] < 0 || m->atoms[k] >= h->d.N) { h->error = "move atom index out of range"; return BL_ERR_INVALID; }
     if (m->n_atoms > h->move_capacity) {
         h->d_move_atoms = dalloc<int>(h, m->n_atoms);
         h->d_move_masses = dalloc<float>(h, m->n_atoms);
         h->move_capacity = m->n_atoms;
     }
-    std::vector<float> mf(m->n_atoms);
-    for (int k = 0; k < m->n_atoms; ++k) mf[k] = (float)m->masses[k];
+    std::vector<float> mf(m->n_atoms, 0.f);
+    if (m->masses) for (int k = 0; k < m->n_atoms; ++k) mf[k] = (float)m->masses[k];
     CK(cudaMemcpyAsync(h->d_move_atoms, m->atoms, sizeof(int) * m->n_atoms, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_move_masses, mf.data(), sizeof(float) * m->n_atoms, cudaMemcpyHostToDevice, h->stream));
+    std::vector<float> cf;
+    if (water) {
+        if (m->n_atoms > 32) { h->error = "water move: at most 32 atoms per water"; return BL_ERR_INVALID; }
+        if (m->n_center <= 0 || !m->center_atoms || !m->center_masses || !(m->radius > 0.0)) {
+            h->error = "water move needs the protein selection (center_atoms, center_masses) and a radius";
+            return BL_ERR_INVALID;
+        }
+        for (int k = 0; k < m->n_center; ++k)
+            if (m->center_atoms[k] < 0 || m->center_atoms[k] >= h->d.N) { h->error = "water move: centre atom index out of range"; return BL_ERR_INVALID; }
+        if (m->n_center > h->center_capacity) {
+            h->d_center_atoms = dalloc<int>(h, m->n_center);
+            h->d_center_masses = dalloc<float>(h, m->n_center);
+            h->center_capacity = m->n_center;
+        }
+        cf.resize(m->n_center);
+        for (int k = 0; k < m->n_center; ++k) cf[k] = (float)m->center_masses[k];
+        CK(cudaMemcpyAsync(h->d_center_atoms, m->center_atoms, sizeof(int) * m->n_center, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_center_masses, cf.data(), sizeof(float) * m->n_center, cudaMemcpyHostToDevice, h->stream));
+        if (!h->d_water_state) h->d_water_state = dalloc<double>(h, (size_t)h->d.R * 4);
+        if (m->kind == BL_MOVE_WATER_SWAP) {
+            if (m->n_waters <= 0 || !m->water_atoms) { h->error = "water swap needs the candidate waters"; return BL_ERR_INVALID; }
+            const size_t n = (size_t)m->n_waters * m->n_atoms;
+            for (size_t k = 0; k < n; ++k)
+                if (m->water_atoms[k] < 0 || m->water_atoms[k] >= h->d.N) { h->error = "water move: water atom index out of range"; return BL_ERR_INVALID; }
+            if (n > h->water_capacity) { h->d_water_atoms = dalloc<int>(h, n); h->water_capacity = n; }
+            CK(cudaMemcpyAsync(h->d_water_atoms, m->water_atoms, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+        }
+    }
     CK(cudaStreamSynchronize(h->stream));
     return BL_OK;
 }
@@ -1374,6 +1412,24 @@ static int enqueue_move(bl_handle* h, const bl_move* m) {
     if (m->kind == BL_MOVE_ROTATE) {
         { LaunchTimer t(h, -1); k_move_rotate<<<d.R, 32, 0, h->stream>>>(d, m->n_atoms, h->d_move_atoms, h->d_move_masses, h->ic.seed); }
         { LaunchTimer t(h, -1); k_bump_counter<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d, 1); }
+    } else if (is_water_move(m->kind)) {
+        WaterMove w;
+        w.n_atoms = m->n_atoms; w.alch = h->d_move_atoms;
+        w.n_waters = m->n_waters; w.waters = h->d_water_atoms;
+        w.n_center = m->n_center; w.center = h->d_center_atoms; w.cmass = h->d_center_masses;
+        w.radius = m->radius; w.state = h->d_water_state;
+        if (m->kind == BL_MOVE_WATER_SWAP) {
+            { LaunchTimer t(h, -1); k_water_swap<<<d.R, WATER_BLOCK, 0, h->stream>>>(d, w, h->ic.seed); }
+            { LaunchTimer t(h, -1); k_bump_counter<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d, 1); }
+            h->vel_dirty = true;
+        } else if (m->kind == BL_MOVE_WATER_TRANSLATE) {
+            { LaunchTimer t(h, -1); k_water_translate<<<d.R, 32, 0, h->stream>>>(d, w, h->ic.seed); }
+            { LaunchTimer t(h, -1); k_bump_counter<<<cdiv(d.R, 64), 64, 0, h->stream>>>(d, 1); }
+        } else {
+            LaunchTimer t(h, -1);
+            k_water_check<<<d.R, WATER_BLOCK, 0, h->stream>>>(d, w);
+            return BL_OK;                                   // coordinates untouched
+        }
     } else {
         h->error = "unknown move kind";
         return BL_ERR_INVALID;

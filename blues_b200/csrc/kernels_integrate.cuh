@@ -848,6 +848,133 @@ __global__ void k_move_rotate(Dev d, int n, const int* atoms, const float* masse
     }
 }
 
+// ---- WaterTranslationMove on the device (blues/moves.py:846-1083): one CTA per walker --------------------------
+struct WaterMove {
+    int n_atoms;  const int* alch;          // atoms of the alchemical water, first = oxygen
+    int n_waters; const int* waters;        // [n_waters][n_atoms]
+    int n_center; const int* center; const float* cmass;
+    double radius;
+    double* state;                          // [R][4]: sphere centre of beforeMove (x, y, z), go flag
+};
+#define WATER_BLOCK 256
+
+// centre of mass of the protein selection: float32 coordinates times float32 masses like the reference
+// (blues/moves.py:921-949), summed in double by the CTA, returned as float32
+__device__ float3 water_center(const Dev& d, const WaterMove& w, int r, double* red /* shared [3*WATER_BLOCK] */) {
+    const double4* pos = d.pos + (size_t)r * d.N;
+    double sx = 0.0, sy = 0.0, sz = 0.0, sm = 0.0;
+    for (int k = threadIdx.x; k < w.n_center; k += WATER_BLOCK) {
+        const double4 p = pos[w.center[k]];
+        const float m = w.cmass[k];
+        sx += (double)((float)p.x * m); sy += (double)((float)p.y * m); sz += (double)((float)p.z * m); sm += (double)m;
+    }
+    __shared__ double tot[4];
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sm = warp_sum(sm);
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[wid * 4] = sx; red[wid * 4 + 1] = sy; red[wid * 4 + 2] = sz; red[wid * 4 + 3] = sm; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0, c = 0.0, m = 0.0;
+        for (int k = 0; k < WATER_BLOCK / 32; ++k) { a += red[k * 4]; b += red[k * 4 + 1]; c += red[k * 4 + 2]; m += red[k * 4 + 3]; }
+        tot[0] = a / m; tot[1] = b / m; tot[2] = c / m;
+    }
+    __syncthreads();
+    return make_float3((float)tot[0], (float)tot[1], (float)tot[2]);
+}
+
+// periodic distance between an atom and a point in float32, as mdtraj.compute_distances(periodic=True) does
+__device__ __forceinline__ float water_distance(const Dev& d, const double4 p, const float3 c) {
+    float dx = (float)p.x - c.x, dy = (float)p.y - c.y, dz = (float)p.z - c.z;
+    if (d.periodic) {
+        const float bx = (float)d.boxd[0], by = (float)d.boxd[1], bz = (float)d.boxd[2];
+        dx -= bx * rintf(dx / bx); dy -= by * rintf(dy / by); dz -= bz * rintf(dz / bz);
+    }
+    return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+// beforeMove: uniform choice (Philox) among the waters inside the sphere, then swap with the alchemical water
+__global__ void __launch_bounds__(WATER_BLOCK) k_water_swap(Dev d, WaterMove w, uint64_t seed) {
+    __shared__ double red[4 * WATER_BLOCK / 32];
+    __shared__ int cnt[WATER_BLOCK];
+    __shared__ int chosen;
+    const int r = blockIdx.x, t = threadIdx.x;
+    double4* pos = d.pos + (size_t)r * d.N;
+    double4* vel = d.vel + (size_t)r * d.N;
+    const float3 c = water_center(d, w, r, red);
+    // contiguous chunk of waters per thread keeps the candidates in residue order
+    const int chunk = (w.n_waters + WATER_BLOCK - 1) / WATER_BLOCK;
+    const int k0 = min(t * chunk, w.n_waters), k1 = min(k0 + chunk, w.n_waters);
+    int mine = 0;
+    for (int k = k0; k < k1; ++k)
+        mine += ((double)water_distance(d, pos[w.waters[(size_t)k * w.n_atoms]], c) <= w.radius) ? 1 : 0;
+    cnt[t] = mine;
+    if (t == 0) chosen = -1;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int k = 0; k < WATER_BLOCK; ++k) { if (k < t) before += cnt[k]; total += cnt[k]; }
+    if (total > 0) {
+        const Philox4 u = philox4x32_10(1u, d.g[r].move_counter, (uint32_t)r, STREAM_MOVE, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const int pick = min((int)(u01(u.x) * (double)total), total - 1);
+        if (pick >= before && pick < before + mine) {
+            int seen = before;
+            for (int k = k0; k < k1; ++k)
+                if ((double)water_distance(d, pos[w.waters[(size_t)k * w.n_atoms]], c) <= w.radius) {
+                    if (seen == pick) { chosen = k; break; }
+                    ++seen;
+                }
+        }
+    }
+    __syncthreads();
+    const int ch = chosen;
+    if (ch >= 0 && t < w.n_atoms) {
+        const int a = w.alch[t], b = w.waters[(size_t)ch * w.n_atoms + t];
+        if (a != b) {
+            const double4 pa = pos[a], pb = pos[b], va = vel[a], vb = vel[b];
+            pos[a] = pb; pos[b] = pa; vel[a] = vb; vel[b] = va;
+        }
+    }
+    if (t == 0) {
+        double* st = w.state + (size_t)r * 4;
+        st[0] = (double)c.x; st[1] = (double)c.y; st[2] = (double)c.z; st[3] = ch >= 0 ? 1.0 : 0.0;
+    }
+}
+
+// move: the sphere centre is the one beforeMove cached (the reference reuses that frame, blues/moves.py:1021);
+// r = R u^(1/3), phi = 2 pi u, cos(theta) = 2u - 1 (blues/moves.py:899-919)
+__global__ void k_water_translate(Dev d, WaterMove w, uint64_t seed) {
+    const int r = blockIdx.x, t = threadIdx.x;
+    const double* st = w.state + (size_t)r * 4;
+    if (st[3] == 0.0) return;
+    double4* pos = d.pos + (size_t)r * d.N;
+    const double4 po = pos[w.alch[0]];
+    const float3 c = make_float3((float)st[0], (float)st[1], (float)st[2]);
+    if ((double)water_distance(d, po, c) >= w.radius) return;
+    const Philox4 u = philox4x32_10(2u, d.g[r].move_counter, (uint32_t)r, STREAM_MOVE, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double rr = w.radius * cbrt(u01(u.x));
+    double sp, cp;
+    sincospi(2.0 * u01(u.y), &sp, &cp);
+    const double ct = 2.0 * u01(u.z) - 1.0, sn = sqrt(fmax(0.0, 1.0 - ct * ct));
+    const double tx = st[0] + rr * sn * cp, ty = st[1] + rr * sn * sp, tz = st[2] + rr * ct;
+    const double sx = po.x - tx, sy = po.y - ty, sz = po.z - tz;
+    __syncwarp();                                                      // every lane has read the oxygen
+    if (t < w.n_atoms) {
+        const int a = w.alch[t];
+        const double4 p = pos[a];
+        pos[a] = make_double4(p.x - sx, p.y - sy, p.z - sz, 0.0);
+    }
+}
+
+// afterMove: fresh centre of mass; outside the sphere and the move was on -> protocol_work = 999999
+__global__ void __launch_bounds__(WATER_BLOCK) k_water_check(Dev d, WaterMove w) {
+    __shared__ double red[4 * WATER_BLOCK / 32];
+    const int r = blockIdx.x;
+    const float3 c = water_center(d, w, r, red);
+    if (threadIdx.x == 0) {
+        const double4 po = d.pos[(size_t)r * d.N + w.alch[0]];
+        if ((double)water_distance(d, po, c) > w.radius && w.state[(size_t)r * 4 + 3] != 0.0) d.g[r].protocol_work = 999999.0;
+    }
+}
+
 // external work after a coordinate change between steps (blues/integrators.py:184-191):
 // protocol_work += perturbed_pe - unperturbed_pe, using the energies of the evaluation that just finished
 __global__ void k_external_work(Dev d, int slot, int first_step_only) {

@@ -270,9 +270,16 @@ def select_atoms(structure, expression):
 class WaterTranslationMove(Move):
     """Swap a random water inside a sphere around the protein selection's centre of mass with the alchemical
     water, translate it to a uniform random point of the sphere at the protocol midpoint and force rejection
-    (``protocol_work = 999999``) if it ends outside (``blues/moves.py:846-1083``)."""
+    (``protocol_work = 999999``) if it ends outside (``blues/moves.py:846-1083``).
 
-    def __init__(self, structure, water_name=['WAT', 'HOH'], protein_selection='protein', radius=2.3 * unit.nanometers):
+    ``on_device=True`` (default) runs the three hooks as kernels behind ``bl_apply_move`` / ``bl_ncmc_run``
+    (``BL_MOVE_WATER_SWAP`` / ``_TRANSLATE`` / ``_CHECK``): no state round-trip, one independent choice per walker,
+    random numbers from the engine's Philox stream.  ``on_device=False`` is the host path with the reference's use
+    of the global numpy RNG (one full-state round-trip per hook)."""
+
+    def __init__(self, structure, water_name=['WAT', 'HOH'], protein_selection='protein', radius=2.3 * unit.nanometers,
+                 on_device=True):
+        self.on_device = on_device
         self.radius = radius
         self.water_name = water_name
         self.water_residues = []
@@ -322,7 +329,40 @@ class WaterTranslationMove(Move):
         com = self._getCenterOfMass(numpy.asarray(xyz, numpy.float32)[self.protein_atoms], self.protein_masses)
         return pos, vel, xyz, box, numpy.asarray(com, float)
 
+    # ---- device path ------------------------------------------------------------------------------------
+    def _device(self, context):
+        return (self.on_device and hasattr(context, '_engine')
+                and type(self).move is WaterTranslationMove.move
+                and type(self).beforeMove is WaterTranslationMove.beforeMove
+                and type(self).afterMove is WaterTranslationMove.afterMove)
+
+    def _descriptor(self, kind, with_waters=False):
+        d = dict(kind=kind, step=0, atoms=list(self.atom_indices),
+                 center_atoms=numpy.asarray(self.protein_atoms, numpy.int32),
+                 center_masses=numpy.asarray(self.protein_masses._value, float).reshape(-1),
+                 radius=self.radius.value_in_unit(unit.nanometers))
+        if with_waters:
+            n = len(self.atom_indices)
+            d['waters'] = numpy.asarray([w for w in self.water_residues if len(w) == n], numpy.int32)
+        return d
+
+    def device_move(self):
+        """Descriptor of the on-device translation for ``bl_ncmc_run`` (None on the host path)."""
+        if not self.on_device or type(self).move is not WaterTranslationMove.move:
+            return None
+        return self._descriptor(_native.BL_MOVE_WATER_TRANSLATE)
+
+    def _apply(self, context, kind, with_waters=False):
+        d = self._descriptor(kind, with_waters)
+        d.pop('step')
+        context._engine.apply_move(d.pop('kind'), d.pop('atoms'), None, **d)
+        return context
+
+    # ---- hooks ---------------------------------------------------------------------------------------------
     def beforeMove(self, context):
+        if self._device(context):
+            self.go = True                     # the per-walker flag lives on the device
+            return self._apply(context, _native.BL_MOVE_WATER_SWAP, with_waters=True)
         pos, vel, xyz, box, com = self._frame(context)
         self._com = com
         radius = self.radius.value_in_unit(unit.nanometers)
@@ -346,6 +386,8 @@ class WaterTranslationMove(Move):
         return context
 
     def move(self, context):
+        if self._device(context):
+            return self._apply(context, _native.BL_MOVE_WATER_TRANSLATE)
         if self.go is False:
             return context
         pos, vel, xyz, box, _ = self._frame(context)
@@ -364,6 +406,8 @@ class WaterTranslationMove(Move):
         return context
 
     def afterMove(self, context):
+        if self._device(context):
+            return self._apply(context, _native.BL_MOVE_WATER_CHECK)
         pos, vel, xyz, box, com = self._frame(context)
         if self._distance(xyz, box, self.atom_indices[0], com) > self.radius.value_in_unit(unit.nanometers) and self.go:
             context._integrator.setGlobalVariableByName("protocol_work", 999999)

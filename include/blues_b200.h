@@ -88,14 +88,29 @@ typedef struct bl_integrator_params {
 } bl_integrator_params;
 
 /* On-device moves (blues/moves.py) */
-#define BL_MOVE_NONE       0
-#define BL_MOVE_ROTATE     1   /* RandomLigandRotationMove.move, blues/moves.py:278-310 */
+#define BL_MOVE_NONE             0
+#define BL_MOVE_ROTATE           1   /* RandomLigandRotationMove.move, blues/moves.py:278-310              */
+#define BL_MOVE_WATER_SWAP       2   /* WaterTranslationMove.beforeMove, blues/moves.py:951-1007: a uniformly
+                                        chosen water whose first atom lies within `radius` (periodic, float32)
+                                        of the centre of mass of `center_atoms` trades positions and velocities
+                                        with the alchemical water `atoms`; none found -> the walker's move is off */
+#define BL_MOVE_WATER_TRANSLATE  3   /* WaterTranslationMove.move, blues/moves.py:1009-1053: alchemical water
+                                        translated so that its first atom sits on a uniform point of the sphere */
+#define BL_MOVE_WATER_CHECK      4   /* WaterTranslationMove.afterMove, blues/moves.py:1055-1083: first atom
+                                        outside the sphere -> protocol_work = 999999 (forced rejection)         */
 typedef struct bl_move {
     int32_t kind;
     int32_t step;               /* moveStep: applied before the integrator step with this index       */
-    int32_t n_atoms;
+    int32_t n_atoms;            /* ROTATE: ligand atoms; WATER_*: atoms of the alchemical water        */
     const int32_t* atoms;
-    const double* masses;       /* element masses used for the centre of mass (float32 arithmetic)    */
+    const double* masses;       /* ROTATE: element masses used for the centre of mass (float32 arithmetic); WATER_*: unused */
+    /* WATER_* only */
+    int32_t n_waters;           /* candidate water residues (WATER_SWAP)                               */
+    const int32_t* water_atoms; /* [n_waters][n_atoms] atom indices, first atom of a row = its oxygen   */
+    int32_t n_center;           /* atoms of the protein selection defining the sphere centre           */
+    const int32_t* center_atoms;
+    const double* center_masses;/* element masses (float32 arithmetic)                                 */
+    double radius;              /* nm                                                                  */
 } bl_move;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------- */

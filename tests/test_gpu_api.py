@@ -210,12 +210,21 @@ def test_no_cpu_fallback_message():
     assert 'no CPU fallback' in (_native.load_library.__doc__ + open(_native.__file__).read())
 
 
-def test_water_translation_move(structure):
+def _selection_com(move, xyz_nm):
+    from blues_b200.structure import geometry
+    return np.asarray(geometry.center_of_mass(np.asarray(xyz_nm, np.float32)[move.protein_atoms], move.protein_masses),
+                      float).reshape(3)
+
+
+@pytest.mark.parametrize('on_device', [False, True])
+def test_water_translation_move(structure, on_device):
     """tests/test_watertranslation.py:54-112: the alchemical water is swapped with one inside the sphere, translated to a
-    point of the sphere at the midpoint, and a water left outside forces rejection (protocol_work = 999999)."""
+    point of the sphere at the midpoint, and a water left outside forces rejection (protocol_work = 999999).
+    Host path (numpy RNG, state round-trips) and device path (bl_apply_move kernels) obey the same contract."""
     from blues_b200.moves import WaterTranslationMove
     np.random.seed(7)
-    move = WaterTranslationMove(structure, protein_selection='(index 0) or (index 1)', radius=0.9 * unit.nanometers)
+    move = WaterTranslationMove(structure, protein_selection='(index 0) or (index 1)', radius=0.9 * unit.nanometers,
+                                on_device=on_device)
     engine = MoveEngine(move)
     engine.selectMove()
     systems = SystemFactory(structure, move.atom_indices, system_cfg())
@@ -224,29 +233,130 @@ def test_water_translation_move(structure):
     simulations = SimulationFactory(systems, engine, cfg)
     ncmc = simulations.ncmc
     idx = move.atom_indices
+    box = np.asarray(structure.box[:3]) * 0.1
 
     def positions():
         return ncmc.context.getState(getPositions=True).getPositions(asNumpy=True)
 
-    before = positions()[idx, :].value_in_unit(unit.nanometers)
+    def pdist(a, b):
+        d = np.asarray(a, float) - np.asarray(b, float)
+        d -= box * np.round(d / box)
+        return np.linalg.norm(d)
+
+    start = positions().value_in_unit(unit.nanometers)
+    vel0 = ncmc.context.getState(getVelocities=True).getVelocities(asNumpy=True)._value
+    com = _selection_com(move, start)
+    before = start[idx, :]
     ncmc.context = move.beforeMove(ncmc.context)
-    swapped = positions()[idx, :].value_in_unit(unit.nanometers)
-    assert move.go and np.not_equal(before, swapped).all()           # another water took the alchemical slot
+    after_swap = positions().value_in_unit(unit.nanometers)
+    swapped = after_swap[idx, :]
+    assert move.go
+    # the swap is a permutation of two waters: the alchemical slot holds the coordinates (and velocities) of a water
+    # whose oxygen was inside the sphere, that water holds the alchemical water's
+    partner = [w for w in move.water_residues if np.array_equal(start[w], swapped)]
+    assert len(partner) == 1
+    partner = partner[0]
+    assert pdist(start[partner[0]], com) <= 0.9 + 1e-6
+    assert np.array_equal(after_swap[partner], before)
+    vel1 = ncmc.context.getState(getVelocities=True).getVelocities(asNumpy=True)._value
+    assert np.array_equal(vel1[idx], vel0[partner]) and np.array_equal(vel1[partner], vel0[idx])
+    others = np.setdiff1d(np.arange(len(start)), np.concatenate([idx, partner]))
+    assert np.array_equal(after_swap[others], start[others])
+    if partner != list(idx):
+        assert np.not_equal(before, swapped).all()                   # another water took the alchemical slot
     ncmc.context = engine.runEngine(ncmc.context)
     moved = positions().value_in_unit(unit.nanometers)
     assert np.not_equal(swapped, moved[idx]).all()
     # the translated water oxygen sits inside the sphere around the selection's centre of mass (periodic distance)
-    box = np.asarray(structure.box[:3]) * 0.1
-    d = moved[idx[0]] - move._com
-    d -= box * np.round(d / box)
-    assert np.linalg.norm(d) <= 0.9 + 1e-6
-    # rigid translation: the water geometry is unchanged
+    assert pdist(moved[idx[0]], com) <= 0.9 + 1e-6
+    # rigid translation: the water geometry is unchanged, nothing else moved
     assert np.allclose(moved[idx[1]] - moved[idx[0]], swapped[1] - swapped[0], atol=1e-6)
+    assert np.allclose(moved[idx[2]] - moved[idx[0]], swapped[2] - swapped[0], atol=1e-6)
+    rest = np.setdiff1d(np.arange(len(start)), idx)
+    assert np.array_equal(moved[rest], after_swap[rest])
     # in bounds: the work is untouched; pushed out of the sphere: afterMove forces rejection
     ncmc.context = move.afterMove(ncmc.context)
     assert ncmc.context._integrator.getGlobalVariableByName('protocol_work') == 0
     out = moved.copy()
-    out[idx] = out[idx] - out[idx[0]] + (move._com + np.array([1.0, 0.0, 0.0]))    # 1.0 nm from the centre (< box / 2)
+    out[idx] = out[idx] - out[idx[0]] + (com + np.array([1.0, 0.0, 0.0]))    # 1.0 nm from the centre (< box / 2)
     ncmc.context.setPositions(out * unit.nanometers)
     ncmc.context = move.afterMove(ncmc.context)
     assert ncmc.context._integrator.getGlobalVariableByName('protocol_work') >= 999999
+
+
+def test_water_translation_on_device_many_walkers(structure):
+    """Every walker draws its own water and its own point of the sphere; a walker with no water in range keeps its
+    coordinates through all three hooks (the reference's `go = False`, blues/moves.py:1003-1013)."""
+    from blues_b200 import _native
+    from blues_b200.moves import WaterTranslationMove
+    from tests import gpu_checks as gc
+    R = 6
+    move = WaterTranslationMove(structure, protein_selection='(index 0) or (index 1)', radius=0.9 * unit.nanometers)
+    _, _, topo, x0 = gc.load_case('tol_parm')
+    eng = _native.Engine(topo, n_replicas=R, seed=11)
+    lam_s, lam_e = gc.lambda_tables(10)
+    eng.set_ncmc_integrator(300.0, 1.0, 0.002, 'H V R O R V H', 10, 1, 2.0, -1.0, lam_s, lam_e)
+    x0 = np.asarray(x0, float)
+    box = np.asarray(topo['box'], float).reshape(-1)[:3]
+    idx = list(move.atom_indices)
+    com = _selection_com(move, x0)
+    for r in range(R):
+        eng.set_positions(x0, r)
+    desc = move._descriptor(_native.BL_MOVE_WATER_SWAP, with_waters=True)
+    kind = desc.pop('kind'); desc.pop('step'); atoms = desc.pop('atoms')
+    eng.apply_move(kind, atoms, None, **desc)
+    partners = []
+    for r in range(R):
+        x = eng.get_positions(r)
+        partner = [w for w in move.water_residues if np.array_equal(x0[w], x[idx])]
+        assert len(partner) == 1
+        partners.append(partner[0][0])
+        d = x0[partner[0][0]] - com
+        d -= box * np.round(d / box)
+        assert np.linalg.norm(d) <= 0.9 + 1e-6
+        assert np.array_equal(x[partner[0]], x0[idx])
+    assert len(set(partners)) > 1                                        # independent draws per walker
+    desc = move._descriptor(_native.BL_MOVE_WATER_TRANSLATE)
+    kind = desc.pop('kind'); desc.pop('step'); atoms = desc.pop('atoms')
+    xs = [eng.get_positions(r) for r in range(R)]
+    eng.apply_move(kind, atoms, None, **desc)
+    targets = []
+    for r in range(R):
+        x = eng.get_positions(r)
+        d = x[idx[0]] - com
+        assert np.linalg.norm(d) <= 0.9 + 1e-6                           # the target is centre + r * direction, unwrapped
+        assert np.allclose(x[idx[1]] - x[idx[0]], xs[r][idx[1]] - xs[r][idx[0]], atol=1e-12)
+        targets.append(tuple(np.round(x[idx[0]], 6)))
+    assert len(set(targets)) == R
+    # empty sphere: nothing is swapped, translated or flagged
+    tiny = dict(move._descriptor(_native.BL_MOVE_WATER_SWAP, with_waters=True), radius=1e-4)
+    kind = tiny.pop('kind'); tiny.pop('step'); atoms = tiny.pop('atoms')
+    xs = [eng.get_positions(r) for r in range(R)]
+    eng.apply_move(kind, atoms, None, **tiny)
+    for k in (_native.BL_MOVE_WATER_TRANSLATE, _native.BL_MOVE_WATER_CHECK):
+        dd = dict(move._descriptor(k), radius=1e-4)
+        dd.pop('kind'); dd.pop('step'); a = dd.pop('atoms')
+        eng.apply_move(k, a, None, **dd)
+    for r in range(R):
+        assert np.array_equal(eng.get_positions(r), xs[r])
+        assert eng.get_global('protocol_work', r) == 0
+
+
+def test_blues_run_with_water_translation_on_device(structure, tmp_path):
+    """example_water.py's loop: WaterTranslationMove inside BLUESSimulation.run, hooks and midpoint move on the device."""
+    from blues_b200.moves import WaterTranslationMove
+    move = WaterTranslationMove(structure, protein_selection='(index 0) or (index 1)', radius=0.9 * unit.nanometers)
+    engine = MoveEngine(move)
+    systems = SystemFactory(structure, move.atom_indices, system_cfg())
+    cfg = sim_cfg()
+    cfg.update(nIter=2, nstepsNC=20, nstepsMD=4)
+    simulations = SimulationFactory(systems, engine, cfg)
+    for sim in (simulations.md, simulations.alch, simulations.ncmc):
+        sim.minimizeEnergy(maxIterations=50)
+    blues = BLUESSimulation(simulations)
+    launches0 = simulations.ncmc.context._engine.launch_count()
+    blues.run()
+    assert blues.accept + blues.reject == 2
+    assert simulations.ncmc.context._engine.launch_count() > launches0
+    w = simulations.ncmc.context._integrator.getGlobalVariableByName('protocol_work')
+    assert np.isfinite(w)
