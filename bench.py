@@ -28,21 +28,74 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NSTEPS_NC = 5000
-DT_PS = 0.004
-WORKLOAD = ('T4L-toluene geometry (22340 atoms, surrogate force field: eqToluene.prmtop is missing upstream), explicit '
-            'TIP3P, PME rc 1.0 nm tol 5e-3 grid 24x25x28, HBonds + rigid water, HMR 3.024 Da, dt 4 fs, 300 K, '
-            'nstepsNC=5000, RandomLigandRotationMove at moveStep')
-P_IN_PAIRS = 4672867          # non-excluded pairs within 1.0 nm at the fixture coordinates (oracle count)
 FLOP_PER_PAIR = 60
 FP32_PEAK_NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+FUNCS = {'lambda_sterics': 'min(1, (1/0.3)*abs(lambda-0.5))',
+         'lambda_electrostatics': 'step(0.2-lambda) - 1/0.2*lambda*step(0.2-lambda) + 1/0.2*(lambda-0.8)*step(lambda-0.8)'}
+
+# SURVEY.md §8(d) measurement configurations.  `t4l` (M2 = BASELINE configs[1]) is the bench line the driver reads;
+# the others are the same engine on the other configurations, selected with --workload.
+WORKLOADS = {
+    't4l': dict(
+        case='t4l_surrogate', nsteps_nc=5000, dt=0.004, move='rotate', replicas=1,
+        p_in=4672867,         # non-excluded pairs within 1.0 nm at the fixture coordinates (oracle count)
+        text='T4L-toluene geometry (22340 atoms, surrogate force field: eqToluene.prmtop is missing upstream), explicit '
+             'TIP3P, PME rc 1.0 nm tol 5e-3 grid 24x25x28, HBonds + rigid water, HMR 3.024 Da, dt 4 fs, 300 K, '
+             'nstepsNC=5000, RandomLigandRotationMove at moveStep'),
+    'tolparm': dict(
+        case='tol_parm', nsteps_nc=100, dt=0.002, move='rotate', replicas=1, p_in=None,
+        text='M1 / BASELINE configs[0]: toluene in TIP3P (TOL-parm.prmtop, 975 atoms, cubic 2.1786 nm), PME rc 0.8 nm '
+             'tol 5e-4 grid 24^3, HBonds, dt 2 fs, 300 K, nstepsNC=100, RandomLigandRotationMove at moveStep'),
+    'water': dict(
+        case='t4l_surrogate', nsteps_nc=1000, dt=0.002, move='water', replicas=1, p_in=4672867,
+        alch=[2657, 2658, 2659], selection='(index 1656) or (index 1657)', radius_nm=0.9,
+        text='M4 / BASELINE configs[3]: WaterTranslationMove on the T4L geometry (22340 atoms, surrogate force field), '
+             'alchemical water = first HOH (atoms 2657-2659), sphere 0.9 nm around atoms 1656/1657, nstepsNC=1000, '
+             'dt 2 fs, swap / translate / check hooks on the device'),
+    'm5': dict(
+        case='tol_parm', tile=(6, 6, 7), nsteps_nc=5000, dt=0.002, move='rotate', replicas=8, p_in=None,
+        kw=dict(cutoff_angstrom=10.0, ewaldErrorTolerance=0.005),
+        text='M5 / BASELINE configs[4]: TOL-parm tiled 6x6x7 = 245700 atoms, box 13.07x13.07x15.25 nm, PME rc 1.0 nm '
+             'tol 5e-3, HBonds, dt 2 fs, 300 K, nstepsNC=5000, one alchemical toluene, 8 walkers per GPU'),
+}
 
 
-def load_workload():
-    from tests.gpu_checks import load_case, lambda_tables
-    s, system, topo, x = load_case('t4l_surrogate', True)
-    ls, le = lambda_tables(NSTEPS_NC)
-    return s, system, topo, x, ls, le
+def load_workload(name='t4l'):
+    """Structure, alchemical System, flat topology and start coordinates (nm) of a measurement configuration."""
+    from tests.gpu_checks import CASES, GOLDEN, tile_structure
+    from blues_b200 import unit as u
+    from blues_b200.structure import Structure
+    from blues_b200.alchemy import AbsoluteAlchemicalFactory, AlchemicalRegion
+    w = WORKLOADS[name]
+    base = Structure.load_npz(os.path.join(GOLDEN, w['case'] + '.npz'))
+    s = tile_structure(base, w['tile']) if w.get('tile') else base
+    kw = dict(CASES[w['case']]['kw'])
+    over = dict(w.get('kw', {}))
+    if 'cutoff_angstrom' in over:
+        kw['nonbondedCutoff'] = over.pop('cutoff_angstrom') * u.angstroms
+    kw.update(over)
+    system = s.createSystem(**kw)
+    alch = w.get('alch', CASES[w['case']]['alch'])
+    system = AbsoluteAlchemicalFactory().create_alchemical_system(system, AlchemicalRegion(alchemical_atoms=alch))
+    return dict(w, name=name, structure=s, base_structure=base, system=system, topo=system.flatten(),
+                x=s.coordinates * 0.1, alch=alch)
+
+
+def lambda_tables_for_cpu(nsteps_nc):
+    """lambda tables for the CPU leg (the native arm evaluates the same expressions inside the integrator object)"""
+    from tests.gpu_checks import lambda_tables
+    return lambda_tables(nsteps_nc)
+
+
+def make_move(wl):
+    """The move object of the workload and its on-device descriptor."""
+    from blues_b200 import unit
+    from blues_b200.moves import RandomLigandRotationMove, WaterTranslationMove
+    if wl['move'] == 'water':
+        mv = WaterTranslationMove(wl['structure'], protein_selection=wl['selection'], radius=wl['radius_nm'] * unit.nanometers)
+        mv.atom_indices = list(wl['alch'])
+        return mv
+    return RandomLigandRotationMove(wl['base_structure'], 'LIG')     # tiled boxes: the first copy's toluene
 
 
 class ClockSampler(object):
@@ -85,11 +138,46 @@ class ClockSampler(object):
                 'reasons': reasons, 'samples': len(self.rows)}
 
 
-def cpu_reference_run(topo, x, ls, le, steps, warmup, budget_s):
+def cpu_relax(topo, x, iters=60, max_disp=0.005):
+    """Capped steepest descent with the constraints re-imposed (CPU oracle): the TOL-parm start coordinates carry
+    the type-index quirk documented in DESIGN.md §8 and, like the reference's tests, need minimising before dynamics."""
+    from oracle.c_oracle import COracle
+    from oracle.ncmc_oracle import Constraints
+    c = COracle(topo)
+    cons = Constraints(topo)
+    mobile = (np.asarray(topo['mass']) > 0)[:, None]
+    x = cons.apply_positions(np.asarray(x, float), np.asarray(x, float), tol=1e-10)
+    e, f = c.energy_forces(x)[:2]
+    step = 1e-5
+    for _ in range(iters):
+        d = step * f * mobile
+        n = np.linalg.norm(d, axis=1, keepdims=True)
+        d *= np.minimum(1.0, max_disp / np.maximum(n, 1e-30))
+        xn = cons.apply_positions(x + d, x, tol=1e-10)
+        en, fn = c.energy_forces(xn)[:2]
+        if np.isfinite(en) and en < e:
+            x, e, f, step = xn, en, fn, step * 1.3
+        else:
+            step *= 0.4
+    return x
+
+
+def cpu_reference_run(wl, steps, warmup, budget_s, x=None):
     """The reference path on the host: oracle C twin, reference semantics (3 evaluations/step), all cores."""
     from oracle.c_oracle import COracle
-    c = COracle(topo, ls, le, 'H V R O R V H', 300.0, 1.0, DT_PS, NSTEPS_NC, 1, 0.2, 0.8, seed=20261017)
-    c.set_state(x)
+    ls, le = lambda_tables_for_cpu(wl['nsteps_nc'])
+    c = COracle(wl['topo'], ls, le, 'H V R O R V H', 300.0, 1.0, wl['dt'], wl['nsteps_nc'], 1, 0.2, 0.8, seed=20261017)
+    if x is None and wl['case'] == 'tol_parm':
+        # relax one periodic image on the CPU, then tile the relaxed coordinates
+        from tests.gpu_checks import CASES
+        base = wl['base_structure']
+        kw = dict(CASES['tol_parm']['kw'])
+        xb = cpu_relax(base.createSystem(**kw).flatten(), base.coordinates * 0.1)
+        reps = wl.get('tile') or (1, 1, 1)
+        box = np.asarray(base.box[:3], float) * 0.1
+        x = np.concatenate([xb + np.asarray((i, j, k)) * box for i in range(reps[0]) for j in range(reps[1])
+                            for k in range(reps[2])])
+    c.set_state(wl['x'] if x is None else x)
     c.velocities_to_temperature(300.0)
     c.step(max(1, warmup))
     t0 = time.time()
@@ -105,17 +193,17 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    s, system, topo, x, ls, le = load_workload()
-    rate, done, dt, cores = cpu_reference_run(topo, x, ls, le, args.steps, min(args.warmup, 3), 150.0)
+    wl = load_workload(args.workload)
+    rate, done, dt, cores = cpu_reference_run(wl, args.steps, min(args.warmup, 3), 150.0)
     line = {'metric': 'NCMC steps/s (aggregate)', 'value': rate, 'unit': 'steps/s', 'n_gpus': args.gpus, 'steps': done,
             'warmup': min(args.warmup, 3), 'ms_per_step': 1e3 * dt / done, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': WORKLOAD, 'replicas_per_gpu': 1},
+            'config': {'workload': wl['text'], 'replicas_per_gpu': 1},
             'cpu_baseline': {'value': rate, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
                              'sample': '%d NCMC steps of one walker (time-budgeted), CPU restatement of BLUES+OpenMM '
                                        'semantics: 3 full evaluations per step, float64, not OpenMM itself' % done},
             'e2e': {'value': rate, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'ns_per_day': rate * DT_PS * 86.4}
+            'ns_per_day': rate * wl['dt'] * 86.4}
     print(json.dumps(line))
 
 
@@ -124,7 +212,9 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=200)
-    ap.add_argument('--replicas', type=int, default=1, help='independent walkers per GPU')
+    ap.add_argument('--replicas', type=int, default=0, help='independent walkers per GPU (0 = the workload\'s own)')
+    ap.add_argument('--workload', default='t4l', choices=sorted(WORKLOADS),
+                    help='t4l = BASELINE configs[1] (default, the line the driver reads); tolparm = M1; water = M4; m5 = 250k atoms')
     ap.add_argument('--impl', default='native')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--batched', type=int, default=8, help='also report a batched run with this many walkers (0 = skip)')
@@ -144,12 +234,17 @@ def main():
 
     from blues_b200 import mm, unit, _native
     from blues_b200.integrators import AlchemicalExternalLangevinIntegrator
-    from blues_b200.moves import RandomLigandRotationMove
 
-    K, W, R = args.steps, max(args.warmup, 3), args.replicas
-    s, system, topo, x, ls, le = load_workload()
-    funcs = {'lambda_sterics': 'min(1, (1/0.3)*abs(lambda-0.5))',
-             'lambda_electrostatics': 'step(0.2-lambda) - 1/0.2*lambda*step(0.2-lambda) + 1/0.2*(lambda-0.8)*step(lambda-0.8)'}
+    wl = load_workload(args.workload)
+    system, topo, x = wl['system'], wl['topo'], wl['x']
+    NSTEPS_NC, DT_PS = wl['nsteps_nc'], wl['dt']
+    W = max(args.warmup, 3)
+    K = args.steps
+    if K + W >= NSTEPS_NC:                               # short protocols (M1): the timed region stays inside one of them
+        W = min(W, max(3, NSTEPS_NC // 5))
+        K = NSTEPS_NC - W - 2
+    R = args.replicas or wl['replicas']
+    funcs = FUNCS
 
     def make_context(n_rep, seed):
         integ = AlchemicalExternalLangevinIntegrator(funcs, splitting='H V R O R V H', temperature=300 * unit.kelvin,
@@ -165,8 +260,10 @@ def main():
 
     ctx, integ = make_context(R, 20261017 + 1000 * rank)
     eng = ctx._engine
-    move = RandomLigandRotationMove(s, 'LIG')
+    x_relaxed = eng.get_positions(0)                     # start of the CPU leg: same relaxed coordinates
+    move = make_move(wl)
     dmove = move.device_move()
+    chunk = max(1, min(100, NSTEPS_NC // 4))
 
     def barrier():
         if world > 1:
@@ -181,12 +278,12 @@ def main():
         t_load = time.time()
         done = W
         while time.time() - t_load < 0.7:                # keep the GPU under the same load while clocks are sampled
-            if done + 200 > NSTEPS_NC:                   # a protocol is nstepsNC steps long: start the next one
+            if done + 2 * chunk > NSTEPS_NC:             # a protocol is nstepsNC steps long: start the next one
                 integ.reset()
                 done = 0
-            integ.step(100)
+            integ.step(chunk)
             eng.synchronize()
-            done += 100
+            done += chunk
         # the timed region is steps W .. W+K of a fresh protocol (K + W < nstepsNC)
         integ.reset()
         integ.step(W)
@@ -223,9 +320,13 @@ def main():
     for r in range(R):
         ctx.setPositions(pos_h[r].numpy() * unit.nanometers, replica=r)
         ctx.setVelocities(vel_h[r].numpy() * (unit.nanometers / unit.picoseconds), replica=r)
+    if wl['move'] == 'water':
+        move.beforeMove(ctx)                             # swap with a water inside the sphere (device, every walker)
     integ._scheduled_move = dict(dmove, step=move_at) if move_at < K else None
     integ.step(K)
     integ._scheduled_move = None
+    if wl['move'] == 'water':
+        move.afterMove(ctx)                              # out of the sphere -> protocol_work = 999999 (device)
     out_pos = [ctx.getState(getPositions=True, replica=r).getPositions(asNumpy=True) for r in range(R)]
     works = [integ.get_protocol_work(dimensionless=True, replica=r) for r in range(R)]
     acc, logp, logu = eng.accept_reject()
@@ -268,6 +369,9 @@ def main():
         ktimes[name] = {'us_per_step': 1e3 * tot / n_prof, 'us_per_launch': 1e3 * tot / max(n, 1), 'launches': n}
     eng.set_profiling(False)
     pair_us = ktimes['pair']['us_per_launch']
+    P_IN_PAIRS = wl['p_in']
+    if P_IN_PAIRS is None:                               # pairs inside the cutoff, counted through the engine's list
+        P_IN_PAIRS = int(len(eng.neighbor_pairs(0)))     # (bit-exact against the oracle's O(N^2) set in tests/)
     achieved_tflops = FLOP_PER_PAIR * P_IN_PAIRS * R / (pair_us * 1e-6) / 1e12
     peaks = {}
     try:
@@ -300,7 +404,7 @@ def main():
 
     # ---- batched walkers on one GPU (BASELINE configs[2] per-GPU share) -----------------------------------------
     batched = None
-    if args.batched and args.batched != R and world == 1:
+    if args.batched and args.batched != R and world == 1 and args.workload == 't4l':
         ctx_b, integ_b = make_context(args.batched, 777)
         nb = max(50, K // 4)
         integ_b.step(max(W // 4, 3))
@@ -319,7 +423,7 @@ def main():
     # ---- CPU baseline (bounded sample) ---------------------------------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        rate, done, dt, cores = cpu_reference_run(topo, x, ls, le, 40, 2, 20.0)
+        rate, done, dt, cores = cpu_reference_run(wl, min(40, NSTEPS_NC - 4), 2, 20.0, x=x_relaxed)
         cpu = {'value': rate, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
                'sample': '%d NCMC steps of one walker in %.1f s; CPU restatement of the reference step program (3 full '
                          'evaluations/step, float64, OpenMP) — not OpenMM itself, which is not installable here' % (done, dt)}
@@ -327,7 +431,7 @@ def main():
     line = {'metric': 'NCMC steps/s (aggregate)', 'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': K,
             'warmup': W, 'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32 pair math / f64 integration / i64 fixed-point accumulation', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'replicas_per_gpu': R, 'global_walkers': world * R,
+            'config': {'workload': wl['text'], 'replicas_per_gpu': R, 'global_walkers': world * R,
                        'l2': 'not flushed between steps: the walker state (~2 MB per walker) is the step\'s own working '
                              'set and stays L2-resident in production exactly as here',
                        'timed_region': 'K consecutive device-resident NCMC steps (CUDA-graph replay), CUDA events on the '
@@ -335,7 +439,7 @@ def main():
             'ns_per_day': value * DT_PS * 86.4,
             'e2e': {'value': e2e_value, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'what': 'Context.setPositions/setVelocities from pinned host arrays, K steps (the slice of the protocol '
-                            'around lambda = 0.5) incl. the on-device rotation move, getState positions + protocol work '
+                            'around lambda = 0.5) incl. the on-device move, getState positions + protocol work '
                             '+ Metropolis test, wall clock'},
             'gpu_launches': int(launches), 'clocks': clocks.summary(), 'roofline': roofline, 'roofline_hbm': roofline_hbm,
             'kernels_us_per_step': {k: round(v['us_per_step'], 2) for k, v in ktimes.items()},
