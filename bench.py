@@ -270,6 +270,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    v_start = [eng.get_velocities(r) for r in range(R)]
+
+    def restart():
+        """A new protocol starts at lambda = 0 from the relaxed coordinates (as every BLUES iteration starts from an
+        equilibrated MD state): restarting from the end of a cut-short protocol would switch a half-decoupled ligand
+        back on inside the solvent."""
+        integ.reset()
+        ctx.setPositions(x_relaxed * unit.nanometers)
+        for r in range(R):
+            ctx.setVelocities(v_start[r] * (unit.nanometers / unit.picoseconds), replica=r)
+
     # ---- device-resident throughput (value) --------------------------------------------------------------------
     stream = torch.cuda.ExternalStream(eng.lib.bl_stream(eng.h))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -279,13 +290,13 @@ def main():
         done = W
         while time.time() - t_load < 0.7:                # keep the GPU under the same load while clocks are sampled
             if done + 2 * chunk > NSTEPS_NC:             # a protocol is nstepsNC steps long: start the next one
-                integ.reset()
+                restart()
                 done = 0
             integ.step(chunk)
             eng.synchronize()
             done += chunk
         # the timed region is steps W .. W+K of a fresh protocol (K + W < nstepsNC)
-        integ.reset()
+        restart()
         integ.step(W)
         eng.synchronize()
         barrier()
