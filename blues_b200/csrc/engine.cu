@@ -944,9 +944,12 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     d.nl_count = dalloc<int>(h, (size_t)R * d.Npad);
     d.nl_list = dalloc<unsigned char>(h, (size_t)R * d.Npad * d.nl_M * (d.nl_u16 ? 2 : 4));
     {
-        // k_build_list: per-lane sub-list capacity (a quarter of a row + margin), its shared memory and the number of
-        // persistent single-warp CTAs that fit on the device
-        h->build_cq = d.nl_M / 4 + 48;
+        // k_build_list: per-lane sub-lists in shared memory are write-combining buffers flushed to the rows whenever one
+        // of them passes build_cq entries (a chunk adds at most BUILD_SLACK): ~8 KB (u16) / ~10 KB (int32) per single-warp
+        // CTA, so that registers, not shared memory, bound the number of resident CTAs; then the number of persistent
+        // CTAs that fit on the device
+        h->build_cq = (d.nl_u16 && R <= 2) ? 88 : 56;      // measured: 8 walkers 657 us per step at 56 against 690 at 88
+        if (getenv("BLUES_B200_BUILD_CQ")) h->build_cq = std::max(8, std::min(d.nl_M / 4 + 48, atoi(getenv("BLUES_B200_BUILD_CQ"))));
         const size_t smem = build_smem_bytes(h->build_cq, d.nl_u16 ? 2 : 4);
         if (smem > 200 * 1024) return fail(BL_ERR_CAPACITY, "neighbour list rows do not fit the builder's shared memory");
         int per_sm = 0, n_sm = 148;

@@ -306,12 +306,40 @@ __device__ __forceinline__ int build_group_runs(const Dev& d, const int* __restr
 }
 
 // Phase 2: stream the candidates of all runs 32 at a time.
+// Move the 32 shared-memory sub-lists to the rows of the group's atoms (coalesced stores).  Lane (a, q) holds the
+// entries of atom a found among candidates 8q..8q+7 of every chunk since the last flush; a row is the sequence of
+// flushes, each holding the atom's four sub-lists in subset order.  Scan order is fixed, hence so is every row.
+// `done` = entries already in the row of this lane's atom (equal across the four lanes of an atom).
+// Not inlined: flushes are rare (every ~30 chunks) and the chunk loop must stay lean; returns the new `done`.
+template <typename IDX>
+__device__ __noinline__ int build_flush(const IDX* subs, int stride, IDX* rows, int nl_M, int lane, int cnt, int done) {
+    __syncwarp();
+    int off = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        const int c = __shfl_up_sync(0xffffffffu, cnt, 8 * k);
+        if (lane >= 8 * k) off += c;
+    }
+    const int total = __shfl_sync(0xffffffffu, off + cnt, 24 + (lane & (BUILD_GROUP - 1)));   // lane (a, 3) knows it
+    const int base = done + off;
+    for (int L = 0; L < 32; ++L) {
+        const int nL = __shfl_sync(0xffffffffu, cnt, L), oL = __shfl_sync(0xffffffffu, base, L);
+        const IDX* src = subs + (size_t)L * stride;
+        IDX* dst = rows + (size_t)(L & (BUILD_GROUP - 1)) * nl_M + oL;
+        for (int k = lane; k < nL; k += 32)
+            if (oL + k < nl_M) dst[k] = src[k];
+    }
+    __syncwarp();
+    return done + total;
+}
+
 template <bool RINT, typename IDX>
 __device__ __forceinline__ void build_stream(const Dev& d, const float4* __restrict__ posq_s, const int* __restrict__ orig_s,
                                              const float4* runs, const int* off, int nruns, bool rx, bool ry, bool rz,
                                              float4* cand, IDX* mysub, int cq, int lane, float4 pi, int oi, ull wi,
                                              bool fari, bool anyfar, const int (&og)[BUILD_GROUP],
-                                             const unsigned int (&osp)[BUILD_GROUP], int& cnt, bool& overflow) {
+                                             const unsigned int (&osp)[BUILD_GROUP], int& cnt, int& done,
+                                             const IDX* subs, int stride, IDX* rows) {
     const float cut2 = d.list_cutoff2;
     const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
     const float qnan = __int_as_float(0x7fc00000);
@@ -398,7 +426,8 @@ __device__ __forceinline__ void build_stream(const Dev& d, const float4* __restr
             }
         }
         cnt = (int)((wp - sub_addr) / (unsigned int)sizeof(IDX));
-        if (cnt > cq) { overflow = true; cnt = cq; }               // the sub-list has BUILD_SLACK spare slots
+        // a chunk appends at most 8 entries per lane: flush before any sub-list could run past its cq + BUILD_SLACK slots
+        if (__any_sync(0xffffffffu, cnt > cq)) { done = build_flush<IDX>(subs, stride, rows, d.nl_M, lane, cnt, done); cnt = 0; }
     }
 }
 
@@ -464,13 +493,13 @@ __global__ void __launch_bounds__(32) k_build_list(Dev d, int cq) {
                 osp[k] = (unsigned int)__shfl_sync(0xffffffffu, below + above, k);
             }
         }
-        int cnt = 0;
-        bool overflow = false;
+        int cnt = 0, done = 0;
+        IDX* rows = reinterpret_cast<IDX*>(d.nl_list) + ((size_t)r * Npad + i0) * d.nl_M;
         if (!d.periodic) {
             if (lane == 0) { runs[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(0)); off[0] = 0; off[1] = N; }
             __syncwarp();
             build_stream<false, IDX>(d, posq_s, orig_s, runs, off, 1, false, false, false, cand, mysub, cq, lane, pi, oi,
-                                     wi, fari, anyfar, og, osp, cnt, overflow);
+                                     wi, fari, anyfar, og, osp, cnt, done, subs, stride, rows);
         } else {
             const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
             // bounding box of the group, in cells and in space (idle lanes hold the first atom); a group never
@@ -490,29 +519,14 @@ __global__ void __launch_bounds__(32) k_build_list(Dev d, int cq) {
                                                hiz, runs, off);
             if (rx || ry || rz)
                 build_stream<true, IDX>(d, posq_s, orig_s, runs, off, nruns, rx, ry, rz, cand, mysub, cq, lane, pi, oi, wi,
-                                        fari, anyfar, og, osp, cnt, overflow);
+                                        fari, anyfar, og, osp, cnt, done, subs, stride, rows);
             else
                 build_stream<false, IDX>(d, posq_s, orig_s, runs, off, nruns, false, false, false, cand, mysub, cq, lane,
-                                         pi, oi, wi, fari, anyfar, og, osp, cnt, overflow);
+                                         pi, oi, wi, fari, anyfar, og, osp, cnt, done, subs, stride, rows);
         }
-        // concatenate the four sub-lists of every atom into its row (coalesced), in subset order
-        __syncwarp();
-        int off = 0;
-#pragma unroll
-        for (int k = 1; k < 4; ++k) {
-            const int c = __shfl_up_sync(0xffffffffu, cnt, 8 * k);
-            if (lane >= 8 * k) off += c;
-        }
-        const int total = __shfl_sync(0xffffffffu, off + cnt, 24 + a);       // lane (a, 3) knows the atom's total
-        IDX* rows = reinterpret_cast<IDX*>(d.nl_list) + ((size_t)r * Npad + i0) * d.nl_M;
-        for (int L = 0; L < 32; ++L) {
-            const int nL = __shfl_sync(0xffffffffu, cnt, L), oL = __shfl_sync(0xffffffffu, off, L);
-            const IDX* src = subs + (size_t)L * stride;
-            IDX* dst = rows + (size_t)(L & (BUILD_GROUP - 1)) * d.nl_M + oL;
-            for (int k = lane; k < nL; k += 32)
-                if (oL + k < d.nl_M) dst[k] = src[k];
-        }
-        if (__any_sync(0xffffffffu, overflow || total > d.nl_M)) { if (lane == 0) g.item_overflow = 1; }
+        // whatever is left in the sub-lists
+        const int total = build_flush<IDX>(subs, stride, rows, d.nl_M, lane, cnt, done);                                              // lanes 0..7: atoms 0..7 of the group
+        if (__any_sync(0xffffffffu, total > d.nl_M)) { if (lane == 0) g.item_overflow = 1; }
         if (lane < na) d.nl_count[(size_t)r * Npad + i0 + lane] = min(total, d.nl_M);
         __syncwarp();
     }
