@@ -549,6 +549,10 @@ __device__ __forceinline__ float erfc_times(float ar, float expar) {
     return (0.254829592f + (-0.284496736f + (1.421413741f + (-1.453152027f + 1.061405429f * t) * t) * t) * t) * t * expar;
 }
 
+// rintf for |x| < 2^22 on the FMA pipe (two adds with the 1.5 * 2^23 constant, round-half-even like rintf, bitwise the
+// same result): the XU pipe, which also serves rsqrt / rcp / ex2, is the busiest execution unit of the pair loop
+__device__ __forceinline__ float rint_fma(float x) { return __fadd_rn(__fadd_rn(x, 12582912.0f), -12582912.0f); }
+
 template <int METHOD, bool ENERGY, typename IDX>
 __global__ void __launch_bounds__(NL_BLOCK) k_pair(Dev d) {
     const int r = blockIdx.y;
@@ -576,9 +580,9 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair(Dev d) {
         const float2 se_j = sigeps_s[s];
         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         if (METHOD != NB_NOCUT) {
-            dx -= bx * rintf(dx * ibx);
-            dy -= by * rintf(dy * iby);
-            dz -= bz * rintf(dz * ibz);
+            dx -= bx * rint_fma(dx * ibx);
+            dy -= by * rint_fma(dy * iby);
+            dz -= bz * rint_fma(dz * ibz);
         }
         const float r2 = dx * dx + dy * dy + dz * dz;
         // branch-free: entries in the skin shell are computed and masked, so the loads of the unrolled iterations
