@@ -806,6 +806,55 @@ def random_sphere_point(radius, origin, u_r, u_phi, u_cos):
     return np.array([math.sin(th) * math.cos(phi), math.sin(th) * math.sin(phi), math.cos(th)]) * r + origin
 
 
+# ---- WaterTranslationMove (blues/moves.py:846-1083) ------------------------------------------------------------
+def center_of_mass_f32(x, atoms, masses):
+    """blues/moves.py:921-949: float32 coordinates and masses, mass-weighted mean."""
+    c32 = np.asarray(x, np.float32)[np.asarray(atoms)]
+    m32 = np.asarray(masses, np.float32).reshape(-1)
+    return ((c32 * m32[:, None]).sum(axis=0) / m32.sum()).astype(np.float64)
+
+
+def periodic_distance_f32(p, c, box):
+    """mdtraj.compute_distances(periodic=True) on an orthorhombic cell: float32 minimum-image distance."""
+    d = np.asarray(p, np.float32) - np.asarray(c, np.float32)
+    if box is not None:
+        b = np.asarray(box, np.float32)
+        d = d - b * np.round(d / b)
+    return float(np.sqrt(np.sum(d * d)))
+
+
+def waters_in_sphere(x, box, waters, center, radius):
+    """Candidate waters of beforeMove (blues/moves.py:981-991): first atom within `radius` of the centre, residue order."""
+    return [list(w) for w in waters if periodic_distance_f32(x[w[0]], center, box) <= radius]
+
+
+def water_swap(x, v, alch, chosen):
+    """blues/moves.py:993-999: the chosen water and the alchemical water trade positions and velocities."""
+    x, v = x.copy(), v.copy()
+    a, b = list(alch), list(chosen)
+    x[a], x[b] = x[b].copy(), x[a].copy()
+    v[a], v[b] = v[b].copy(), v[a].copy()
+    return x, v
+
+
+def water_translate(x, box, alch, center, radius, u_r, u_phi, u_cos):
+    """blues/moves.py:1009-1053: nothing happens if the alchemical water's first atom is at or beyond the radius;
+    otherwise the molecule is translated so that this atom sits on the random point of the sphere."""
+    if periodic_distance_f32(x[alch[0]], center, box) >= radius:
+        return x.copy()
+    target = random_sphere_point(radius, np.asarray(center, float), u_r, u_phi, u_cos)
+    out = x.copy()
+    out[list(alch)] = x[list(alch)] - (x[alch[0]] - target)
+    return out
+
+
+def water_after_move(x, box, alch, center, radius, go, protocol_work):
+    """blues/moves.py:1055-1083: outside the sphere after the protocol and the move was on -> work = 999999."""
+    if periodic_distance_f32(x[alch[0]], center, box) > radius and go:
+        return 999999.0
+    return protocol_work
+
+
 def alchemical_correction(e_ncmc0, e_md0, e_alch1, e_ncmc1, kT):
     """blues/simulation.py:1100-1119"""
     return (e_ncmc0 - e_md0 + e_alch1 - e_ncmc1) * (-1.0 / kT)

@@ -307,13 +307,7 @@ def test_water_translation_on_device_many_walkers(structure):
     eng.apply_move(kind, atoms, None, **desc)
     from oracle import ncmc_oracle as orc
     # oracle: the candidates in residue order, choice = floor(u * n_inside) with the walker's first STREAM_MOVE draw
-    inside = []
-    for w in move.water_residues:
-        d = (x0[w[0]].astype(np.float32) - com.astype(np.float32)).astype(np.float32)
-        b32 = box.astype(np.float32)
-        d = d - b32 * np.round(d / b32)
-        if float(np.sqrt(np.sum(d * d))) <= 0.9:
-            inside.append(w)
+    inside = orc.waters_in_sphere(x0, box, move.water_residues, com, 0.9)
     partners = []
     for r in range(R):
         x = eng.get_positions(r)
@@ -338,8 +332,8 @@ def test_water_translation_on_device_many_walkers(structure):
         assert np.linalg.norm(d) <= 0.9 + 1e-6                           # the target is centre + r * direction, unwrapped
         assert np.allclose(x[idx[1]] - x[idx[0]], xs[r][idx[1]] - xs[r][idx[0]], atol=1e-12)
         u = orc.philox_uniform4(11, orc.STREAM_MOVE, r, 1, [2])
-        want = orc.random_sphere_point(0.9, com.astype(np.float32).astype(float), u[0][0], u[1][0], u[2][0])
-        assert np.allclose(x[idx[0]], want, atol=1e-6)        # float32 centre: 1 ulp
+        want = orc.water_translate(xs[r], box, idx, com.astype(np.float32).astype(float), 0.9, u[0][0], u[1][0], u[2][0])
+        assert np.allclose(x, want, atol=1e-6)                # float32 centre: 1 ulp
         targets.append(tuple(np.round(x[idx[0]], 6)))
     assert len(set(targets)) == R
     # empty sphere: nothing is swapped, translated or flagged

@@ -160,3 +160,38 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, name)
     assert b'sm_100a' in lib.bl_version()
     assert ctypes.sizeof(_native.BlTopology) > 0
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """include/blues_b200.h is the contract: the ctypes mirrors in blues_b200/_native.py must have the same size and
+    the same offset for every field (compiled with gcc from the header itself, no GPU needed)."""
+    import ctypes
+    import re
+    import subprocess
+    from blues_b200 import _native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = [('bl_topology', _native.BlTopology), ('bl_integrator_params', _native.BlIntegratorParams),
+             ('bl_move', _native.BlMove)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "blues_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.check_call(['gcc', '-std=c99', '-I', os.path.join(root, 'include'), str(src), '-o', str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    want = {}
+    for line in out.splitlines():
+        a, b, c = line.split()
+        want[(a, b)] = int(c)
+    for cname, cls in pairs:
+        assert ctypes.sizeof(cls) == want[(cname, 'sizeof')], cname
+        for fname, _ in cls._fields_:
+            assert getattr(cls, fname).offset == want[(cname, fname)], (cname, fname)
+    # every move kind the header defines is known to the binding
+    hdr = open(os.path.join(root, 'include', 'blues_b200.h')).read()
+    for name, value in re.findall(r'#define (BL_MOVE_\w+)\s+(\d+)', hdr):
+        assert getattr(_native, name) == int(value), name

@@ -136,3 +136,39 @@ def test_moves_and_acceptance_rules():
     assert orc.metropolis_accept(-1.0, 0.0, -2.0) is True
     assert orc.metropolis_accept(-999999 / 2.49, 0.0, -2.0) is False        # the 999999 sentinel forces rejection
     assert orc.alchemical_correction(1.0, 2.0, 3.0, 4.0, 2.0) == pytest.approx(1.0)
+
+
+def test_water_translation_contract():
+    """blues/tests/test_watertranslation.py:54-112 on the oracle's restatement of the three hooks: the alchemical water
+    trades places with a water inside the sphere, lands on a point of the sphere, protocol_work stays 0 in bounds and
+    becomes 999999 out of bounds (and only when the swap happened)."""
+    s, topo, x = _case('tol_parm', nonbondedMethod='PME', nonbondedCutoff=8.0 * u.angstroms, constraints='HBonds')
+    box = np.asarray(topo['box'], float).reshape(-1)[:3]
+    waters = [[a.index for a in r.atoms()] for r in s.topology.residues() if r.name in ('WAT', 'HOH')]
+    alch = waters[0]
+    masses = np.array([12.011, 12.011])
+    com = orc.center_of_mass_f32(x, [0, 1], masses)
+    assert np.allclose(com, 0.5 * (x[0] + x[1]), atol=1e-6)
+    inside = orc.waters_in_sphere(x, box, waters, com, 0.9)
+    assert 0 < len(inside) < len(waters)
+    for w in inside:
+        d = x[w[0]] - com
+        d -= box * np.round(d / box)
+        assert np.linalg.norm(d) <= 0.9 + 1e-6
+    v = np.random.RandomState(1).normal(size=x.shape)
+    chosen = inside[len(inside) // 2]
+    xs, vs = orc.water_swap(x, v, alch, chosen)
+    assert np.array_equal(xs[alch], x[chosen]) and np.array_equal(xs[chosen], x[alch])
+    assert np.array_equal(vs[alch], v[chosen]) and np.array_equal(vs[chosen], v[alch])
+    xt = orc.water_translate(xs, box, alch, com, 0.9, 0.3, 0.6, 0.8)
+    assert orc.periodic_distance_f32(xt[alch[0]], com, box) <= 0.9
+    assert np.allclose(xt[alch[1]] - xt[alch[0]], xs[alch[1]] - xs[alch[0]], atol=1e-12)      # rigid translation
+    rest = np.setdiff1d(np.arange(len(x)), alch)
+    assert np.array_equal(xt[rest], xs[rest])
+    assert orc.water_after_move(xt, box, alch, com, 0.9, True, 0.0) == 0.0
+    out = xt.copy()
+    out[alch] = out[alch] - out[alch[0]] + (com + np.array([1.0, 0.0, 0.0]))
+    assert orc.water_after_move(out, box, alch, com, 0.9, True, 0.0) >= 999999
+    assert orc.water_after_move(out, box, alch, com, 0.9, False, 0.0) == 0.0
+    # a water at or beyond the radius is not translated (blues/moves.py:1037-1040)
+    assert np.array_equal(orc.water_translate(out, box, alch, com, 0.9, 0.3, 0.6, 0.8), out)
