@@ -359,9 +359,8 @@ static void compile_pass(bl_handle* h, std::vector<Launch>& out, int& cursor, bo
     // re-evaluation invalidated it — alchemical slot energies are always present, e_env only with `energy`
     bool last_eval_energy = false;
     int first_int = -1, last_int = -1;
-    bool eval_between = false;
     for (size_t k = 0; k < pass.size(); ++k) {
-        if (pass[k].is_eval) { last_eval_energy = pass[k].energy; if (first_int >= 0) eval_between = true; }
+        if (pass[k].is_eval) last_eval_energy = pass[k].energy;
         else { if (first_int < 0) first_int = (int)k; last_int = (int)k; }
     }
     pass[last_int].args.energy_valid = last_eval_energy ? 1 : 0;
@@ -377,7 +376,6 @@ static void compile_pass(bl_handle* h, std::vector<Launch>& out, int& cursor, bo
             pass[last_int].flip_after = true;
         }
     }
-    (void)eval_between;
     for (auto& l : pass) out.push_back(l);
 }
 
@@ -1190,8 +1188,6 @@ int bl_get_velocities(bl_handle* h, int replica, double* v) {
     cudaSetDevice(h->device);
     return download_vec3(h, h->d.vel, replica, v);
 }
-
-static bool g_env_energy_valid(bl_handle* h);
 
 int bl_get_forces(bl_handle* h, int replica, double* f) {
     if (!h || !f || replica < 0 || replica >= h->d.R) return BL_ERR_INVALID;

@@ -190,7 +190,7 @@ struct FixedCluster {
     }
 
     __device__ __forceinline__ void rattle() {
-        if (NC == 0) return;
+        if constexpr (NC > 0) {
         double sv[NCC][3], A[NCC][NCC], rhs[NCC];
 #pragma unroll
         for (int a = 0; a < NC; ++a) {
@@ -216,10 +216,11 @@ struct FixedCluster {
                 v[j][k] -= cc * im[j];
             }
         }
+        }
     }
 
     __device__ __forceinline__ void shake(const double (&xref)[NA][3], double tol) {
-        if (NC == 0) return;
+        if constexpr (NC > 0) {
         double rr[NCC][3];
 #pragma unroll
         for (int a = 0; a < NC; ++a)
@@ -260,6 +261,7 @@ struct FixedCluster {
                 }
             }
             if (nearly < 0.0) break;
+        }
         }
     }
 };

@@ -453,7 +453,6 @@ __global__ void __launch_bounds__(32) k_build_list(Dev d, int cq) {
     const int lane = threadIdx.x;
     IDX* mysub = subs + (size_t)lane * stride;
     const int N = d.N, Npad = d.Npad;
-    const int a = lane & (BUILD_GROUP - 1);
     // the CTAs are shared by all walkers of the context: each starts on walker blockIdx.x % R and moves on to the next
     // walker whose list is being rebuilt when a queue runs dry
     for (int wk = 0; wk < d.R; ++wk) {
