@@ -14,7 +14,7 @@ import numpy as np
 
 from . import unit as u
 from . import _native
-from .system import System
+from .system import System, MonteCarloBarostat
 
 logger = logging.getLogger(__name__)
 OpenMMException = _native.EngineError
@@ -119,8 +119,22 @@ class LangevinIntegrator(object):
         context._engine.set_langevin_integrator(self._temperature, self._friction, self._dt, self._tol)
 
     def step(self, n):
-        self._context._engine.md_run(int(n))
-        self._context._time += n * self._dt
+        ctx = self._context
+        baro = ctx._barostat
+        n = int(n)
+        if baro is None:
+            ctx._engine.md_run(n)
+        else:
+            # MonteCarloBarostat: a volume move whenever the step count reaches a multiple of its frequency
+            done = 0
+            while done < n:
+                chunk = min(n - done, baro.frequency - ctx._md_steps % baro.frequency)
+                ctx._engine.md_run(chunk)
+                done += chunk
+                ctx._md_steps += chunk
+                if ctx._md_steps % baro.frequency == 0:
+                    baro.attempt(ctx._engine)
+        ctx._time += n * self._dt
 
 
 class State(object):
@@ -185,6 +199,14 @@ class Context(object):
         self._engine = _native.Engine(self._topo, device=dev, n_replicas=self._n_replicas, seed=seed)
         self._time = 0.0
         self._molecules = None
+        self._barostat = None
+        self._md_steps = 0
+        if isinstance(integrator, LangevinIntegrator):
+            for f in system.getForces():
+                if isinstance(f, MonteCarloBarostat) and self._topo['nb_method'] != 0:
+                    from .barostat import MonteCarloBarostatDriver
+                    self._barostat = MonteCarloBarostatDriver(self._topo, f.pressure, f.temperature, f.frequency,
+                                                              seed=(seed or None))
         integrator._bind(self)
 
     # -- accessors ---------------------------------------------------------------------------------

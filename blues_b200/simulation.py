@@ -156,8 +156,9 @@ class SimulationFactory(object):
 
     @classmethod
     def addBarostat(cls, system, temperature=300 * unit.kelvin, pressure=1 * unit.atmospheres, frequency=25, **kwargs):
-        """Attach a ``MonteCarloBarostat`` record (``blues/simulation.py:602-626``).  The native MD leg is NVT:
-        the barostat is carried on the System but volume moves are not performed (out of scope)."""
+        """Attach a ``MonteCarloBarostat`` (``blues/simulation.py:602-626``).  A ``Context`` built from this system
+        with a ``LangevinIntegrator`` (the MD leg) attempts a volume move every ``frequency`` steps
+        (``blues_b200/barostat.py``); the NCMC context never does, as upstream."""
         logger.info('Adding MonteCarloBarostat with {}. MD simulation will be {} NPT.'.format(pressure, temperature))
         system.addForce(MonteCarloBarostat(pressure, temperature, frequency))
         return system

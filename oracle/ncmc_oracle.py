@@ -855,6 +855,32 @@ def water_after_move(x, box, alch, center, radius, go, protocol_work):
     return protocol_work
 
 
+# ---- MonteCarloBarostat of the MD leg (blues/simulation.py:602-626 attaches it; algorithm: OpenMM
+# MonteCarloBarostatImpl::updateContextState + ReferenceMonteCarloBarostat::applyBarostat) ---------------------------
+def mc_barostat_trial(x, box, molecules, energy_fn, pressure_bar, temperature, volume_scale, u_vol, u_acc):
+    """One isotropic volume move.  molecules: list of atom-index lists; energy_fn(x, box) -> kJ/mol.
+    Returns (accepted, x, box, w)."""
+    box = np.asarray(box, float)
+    volume = box[0] * box[1] * box[2]
+    d_volume = volume_scale * 2.0 * (u_vol - 0.5)
+    new_volume = volume + d_volume
+    scale = (new_volume / volume) ** (1.0 / 3.0)
+    e0 = energy_fn(x, box)
+    xn = x.copy()
+    for atoms in molecules:
+        centre = x[atoms].sum(axis=0) / len(atoms)
+        wrapped = centre - np.floor(centre / box) * box           # into the first periodic box
+        xn[atoms] = x[atoms] + (wrapped * scale - centre)
+    new_box = box * scale
+    e1 = energy_fn(xn, new_box)
+    kT = 0.0083144626181532 * temperature
+    pressure = pressure_bar * 6.02214076e23 * 1e-25                # bar -> kJ/mol/nm^3
+    w = e1 - e0 + pressure * d_volume - len(molecules) * kT * math.log(new_volume / volume)
+    if w > 0.0 and u_acc > math.exp(-w / kT):
+        return False, x, box, w
+    return True, xn, new_box, w
+
+
 def alchemical_correction(e_ncmc0, e_md0, e_alch1, e_ncmc1, kT):
     """blues/simulation.py:1100-1119"""
     return (e_ncmc0 - e_md0 + e_alch1 - e_ncmc1) * (-1.0 / kT)

@@ -368,3 +368,42 @@ def test_blues_run_with_water_translation_on_device(structure, tmp_path):
     assert simulations.ncmc.context._engine.launch_count() > launches0
     w = simulations.ncmc.context._integrator.getGlobalVariableByName('protocol_work')
     assert np.isfinite(w)
+
+
+def test_md_leg_with_monte_carlo_barostat(structure):
+    """`pressure` in the simulation config attaches a MonteCarloBarostat to the MD system only
+    (blues/simulation.py:602-626, 781-785); the MD leg then attempts a volume move every `frequency` steps."""
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, system_cfg())
+    cfg = sim_cfg()
+    cfg['pressure'] = 1 * unit.atmospheres
+    simulations = SimulationFactory(systems, MoveEngine(RandomLigandRotationMove(structure, 'LIG')), cfg)
+    md, ncmc = simulations.md, simulations.ncmc
+    assert type(md.system.getForces()[-1]).__name__ == 'MonteCarloBarostat'        # tests/test_simulation.py:241-250
+    baro = md.context._barostat
+    assert baro is not None and ncmc.context._barostat is None
+    assert baro.frequency == 25 and baro.n_molecules == 321                        # toluene + 320 waters
+    md.minimizeEnergy(maxIterations=100)
+    md.context.setVelocitiesToTemperature(300 * unit.kelvin)
+    box0 = np.diag(md.context.getState().getPeriodicBoxVectors(asNumpy=True).value_in_unit(unit.nanometers))
+    e0 = md.context.getState(getEnergy=True).getPotentialEnergy()._value
+    md.step(110)
+    assert baro.total_attempted == 4                                               # steps 25, 50, 75, 100
+    state = md.context.getState(getPositions=True, getEnergy=True)
+    box1 = np.diag(state.getPeriodicBoxVectors(asNumpy=True).value_in_unit(unit.nanometers))
+    assert np.isfinite(state.getPotentialEnergy()._value) and np.isfinite(e0)
+    assert np.all(np.isfinite(state.getPositions(asNumpy=True)._value))
+    if baro.total_accepted:
+        assert not np.allclose(box0, box1, rtol=0, atol=1e-9)
+    else:
+        assert np.allclose(box0, box1, rtol=0, atol=1e-12)
+    assert abs(np.prod(box1) / np.prod(box0) - 1.0) < 0.05                         # <= 4 moves of <= 1 % each
+    assert np.allclose(box1 / box0, (box1 / box0)[0])                              # isotropic scaling
+    # a rejected trial leaves positions and box exactly as they were
+    x_before = md.context._engine.get_positions(0)
+    b_before = md.context._engine.get_box()
+    baro.volume_scale = 0.29 * np.prod(b_before)                                   # an absurd compression: rejected
+    ok = baro.attempt(md.context._engine, uniforms=(0.0, 0.999999))
+    assert ok is False
+    assert np.array_equal(md.context._engine.get_box(), b_before)
+    assert np.allclose(md.context._engine.get_positions(0), x_before, rtol=0, atol=0)

@@ -172,3 +172,72 @@ def test_water_translation_contract():
     assert orc.water_after_move(out, box, alch, com, 0.9, False, 0.0) == 0.0
     # a water at or beyond the radius is not translated (blues/moves.py:1037-1040)
     assert np.array_equal(orc.water_translate(out, box, alch, com, 0.9, 0.3, 0.6, 0.8), out)
+
+
+class _OracleEngine(object):
+    """Duck type of blues_b200._native.Engine for host-logic tests on the CPU: state in numpy, energies from the oracle."""
+
+    def __init__(self, topo, x):
+        from oracle.c_oracle import COracle
+        self.topo = dict(topo)
+        self.n_replicas = 1
+        self.x = np.asarray(x, float).copy()
+        self.box = np.asarray(topo['box'], float).reshape(-1)[:3].copy()
+        self._mk = lambda t: COracle(t)
+
+    def get_box(self):
+        return self.box.copy()
+
+    def set_box(self, box):
+        self.box = np.asarray(box, float).copy()
+
+    def get_positions(self, replica=0):
+        return self.x.copy()
+
+    def set_positions(self, x, replica=-1):
+        self.x = np.asarray(x, float).copy()
+
+    def energy_at(self, x, box):
+        t = dict(self.topo)
+        t['box'] = np.asarray(box, float)
+        return self._mk(t).energy_forces(x)[0]
+
+    def get_energy(self, potential=True, kinetic=True):
+        return np.array([self.energy_at(self.x, self.box)]), np.zeros(1)
+
+
+def test_monte_carlo_barostat_host_logic_matches_oracle_restatement():
+    """blues_b200.barostat (the MD leg's MonteCarloBarostat, blues/simulation.py:602-626) against the oracle's
+    independent restatement of OpenMM's volume move: same trial coordinates, box, work and decision for the same
+    uniforms; a rejected move restores the state; the step size adapts after 10 attempts."""
+    from blues_b200.barostat import MonteCarloBarostatDriver, molecule_ids
+    s, topo, x = _case('wat_divaline', nonbondedMethod='CutoffPeriodic', nonbondedCutoff=9.0 * u.angstroms,
+                       constraints='HBonds')
+    eng = _OracleEngine(topo, x)
+    drv = MonteCarloBarostatDriver(topo, 1.01325, 300.0, 25, seed=5)
+    mol = molecule_ids(topo)
+    molecules = [np.nonzero(mol == m)[0].tolist() for m in range(mol.max() + 1)]
+    assert drv.n_molecules == len(molecules) and len(molecules) > 100
+    assert sorted(len(m) for m in molecules)[len(molecules) // 2] == 3          # mostly waters
+    rs = np.random.RandomState(3)
+    n_acc = 0
+    for k in range(12):
+        u_vol, u_acc = rs.random_sample(2)
+        x0, box0 = eng.get_positions(), eng.get_box()
+        scale = drv.volume_scale if drv.volume_scale is not None else 0.01 * np.prod(box0)
+        ok_ref, x_ref, box_ref, w = orc.mc_barostat_trial(x0, box0, molecules, eng.energy_at, 1.01325, 300.0, scale, u_vol, u_acc)
+        ok = drv.attempt(eng, (u_vol, u_acc))
+        assert ok == ok_ref, (k, w)
+        assert np.allclose(eng.get_box(), box_ref, rtol=0, atol=1e-12)
+        assert np.allclose(eng.get_positions(), x_ref, rtol=0, atol=1e-10)
+        if not ok:
+            assert np.array_equal(eng.get_positions(), x0) and np.array_equal(eng.get_box(), box0)
+        n_acc += int(ok)
+        # rigid translation of whole molecules: intramolecular geometry untouched
+        m = molecules[7]
+        assert np.allclose(eng.get_positions()[m] - eng.get_positions()[m][0], x[m] - x[m][0], atol=1e-9)
+    assert drv.total_attempted == 12 and drv.total_accepted == n_acc
+    # OpenMM resets its window only when it retunes the step (< 25 % or > 75 % accepted after >= 10 attempts)
+    assert drv.attempted in (12, 2) and drv.volume_scale > 0
+    if drv.attempted == 2:
+        assert drv.volume_scale != pytest.approx(0.01 * np.prod(np.asarray(topo['box'], float).reshape(-1)[:3]))
