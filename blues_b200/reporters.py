@@ -95,7 +95,7 @@ class ReporterConfig(object):
             self.trajectory_interval = self._cfg['traj_netcdf'].get('reportInterval', 0)
             out.append(NetCDF4Reporter(self._name('traj_netcdf') + '.nc', **self._args('traj_netcdf')))
         if 'restart' in self._cfg:
-            out.append(RestartReporter(self._name('restart') + '.rst7', **self._args('restart')))
+            out.append(RestartReporter(self._name('restart') + '.rst7', **dict({'netcdf': True}, **self._args('restart'))))
         if 'progress' in self._cfg:
             args = self._args('progress')
             args.setdefault('progress', True)
@@ -279,28 +279,36 @@ class StateDataReporter(BLUESStateDataReporter):
 
 
 class RestartReporter(_Periodic):
-    """AMBER ASCII restart (positions, velocities, box) every ``reportInterval`` steps; resume with the YAML key
-    ``structure: restart:`` (``blues/settings.py:76-85``)."""
+    """AMBER restart (positions, velocities, box) every ``reportInterval`` steps — NetCDF (``AMBERRESTART``) when
+    ``netcdf=True`` as the reference's ``ReporterConfig`` asks (``blues/reporters.py:224``), ASCII otherwise; resume
+    with the YAML key ``structure: restart:`` (``blues/settings.py:76-85``), either format."""
 
     def __init__(self, file, reportInterval=1, write_multiple=False, netcdf=False, write_velocities=True, **kwargs):
         self._init_schedule(reportInterval, [])
         self.fname = file
         self.write_multiple = write_multiple
+        self.netcdf = netcdf
         self.write_velocities = write_velocities
 
     def describeNextReport(self, simulation):
         return (self._next(simulation), True, self.write_velocities, False, False)
 
     def report(self, simulation, state):
-        from .structure import Structure, write_inpcrd
+        from .structure import Structure, write_inpcrd, write_netcdf_restart
+        xyz = state.getPositions(asNumpy=True).value_in_unit(unit.angstroms)
+        vel = state.getVelocities(asNumpy=True).value_in_unit(VELUNIT) if self.write_velocities else None
+        bv = state.getPeriodicBoxVectors(asNumpy=True).value_in_unit(unit.angstroms)
+        box = [bv[0][0], bv[1][1], bv[2][2], 90.0, 90.0, 90.0]
+        fname = self.fname + ('.%d' % simulation.currentStep if self.write_multiple else '')
+        if self.netcdf:
+            write_netcdf_restart(fname, xyz, vel, box, time=state.getTime().value_in_unit(unit.picoseconds))
+            return
         s = Structure()
         s.n_atoms = simulation.system.getNumParticles()
-        s.coordinates = state.getPositions(asNumpy=True).value_in_unit(unit.angstroms)
-        if self.write_velocities:
-            s._velocities = state.getVelocities(asNumpy=True).value_in_unit(VELUNIT)
-        box = state.getPeriodicBoxVectors(asNumpy=True).value_in_unit(unit.angstroms)
-        s.box = [box[0][0], box[1][1], box[2][2], 90.0, 90.0, 90.0]
-        fname = self.fname + ('.%d' % simulation.currentStep if self.write_multiple else '')
+        s.coordinates = xyz
+        if vel is not None:
+            s._velocities = vel
+        s.box = box
         with open(fname, 'w') as f:
             write_inpcrd(s, f)
 

@@ -525,11 +525,93 @@ def write_inpcrd(s, f):
         f.write(''.join('%12.7f' % x for x in s.box) + '\n')
 
 
+AMBER_VEL_SCALE = 20.455         # AMBER internal velocity unit -> Angstrom / ps (scale_factor of the NetCDF conventions)
+
+
+def is_netcdf(path):
+    with open(path, 'rb') as fh:
+        return fh.read(3) == b'CDF'
+
+
+def write_netcdf_restart(path, coordinates, velocities=None, box=None, time=0.0, title=''):
+    """AMBER NetCDF restart (Conventions ``AMBERRESTART`` 1.0) — what the reference writes through parmed's
+    ``RestartReporter(netcdf=True)`` (``blues/reporters.py:224``).  Coordinates / box in Angstrom, velocities in
+    Angstrom/ps (stored in AMBER units with ``scale_factor`` 20.455), time in ps.  NetCDF-3 64-bit offset file."""
+    from scipy.io import netcdf_file
+    xyz = np.asarray(coordinates, float).reshape(-1, 3)
+    nc = netcdf_file(path, 'w', version=2)
+    try:
+        nc.Conventions = 'AMBERRESTART'
+        nc.ConventionVersion = '1.0'
+        nc.program = 'blues_b200'
+        nc.programVersion = '0.1.0'
+        nc.title = title or 'restart created by blues_b200'
+        nc.createDimension('spatial', 3)
+        nc.createDimension('atom', len(xyz))
+        v = nc.createVariable('spatial', 'c', ('spatial',))
+        v[:] = np.frombuffer(b'xyz', dtype='S1')
+        v = nc.createVariable('time', 'd', ())
+        v.units = 'picosecond'
+        v.data[...] = float(time)                  # (scipy's assignValue indexes a 0-d array with [:])
+        v = nc.createVariable('coordinates', 'd', ('atom', 'spatial'))
+        v.units = 'angstrom'
+        v[:] = xyz
+        if velocities is not None:
+            v = nc.createVariable('velocities', 'd', ('atom', 'spatial'))
+            v.units = 'angstrom/picosecond'
+            v.scale_factor = np.float64(AMBER_VEL_SCALE)
+            v[:] = np.asarray(velocities, float).reshape(-1, 3) / AMBER_VEL_SCALE
+        if box is not None:
+            nc.createDimension('cell_spatial', 3)
+            nc.createDimension('cell_angular', 3)
+            nc.createDimension('label', 5)
+            v = nc.createVariable('cell_spatial', 'c', ('cell_spatial',))
+            v[:] = np.frombuffer(b'abc', dtype='S1')
+            v = nc.createVariable('cell_angular', 'c', ('cell_angular', 'label'))
+            v[:] = np.frombuffer(b'alphabeta gamma', dtype='S1').reshape(3, 5)
+            v = nc.createVariable('cell_lengths', 'd', ('cell_spatial',))
+            v.units = 'angstrom'
+            v[:] = np.asarray(box[:3], float)
+            v = nc.createVariable('cell_angles', 'd', ('cell_angular',))
+            v.units = 'degree'
+            v[:] = np.asarray(list(box[3:6]) if len(box) >= 6 else [90.0, 90.0, 90.0], float)
+    finally:
+        nc.close()
+
+
+def read_netcdf_restart(path):
+    """(coords Angstrom, velocities Angstrom/ps or None, box or None, time ps) of an AMBER NetCDF restart."""
+    from scipy.io import netcdf_file
+    nc = netcdf_file(path, 'r', mmap=False)
+    try:
+        conv = getattr(nc, 'Conventions', b'')
+        conv = conv.decode() if isinstance(conv, bytes) else str(conv)
+        if 'AMBERRESTART' not in conv:
+            raise ValueError('%s is a NetCDF file but not an AMBER restart (Conventions = %r)' % (path, conv))
+        coords = np.array(nc.variables['coordinates'][:], float).reshape(-1, 3)
+        vel = None
+        if 'velocities' in nc.variables:
+            var = nc.variables['velocities']
+            vel = np.array(var[:], float).reshape(-1, 3) * float(getattr(var, 'scale_factor', 1.0))
+        box = None
+        if 'cell_lengths' in nc.variables:
+            ang = np.array(nc.variables['cell_angles'][:], float) if 'cell_angles' in nc.variables else [90.0] * 3
+            box = [float(x) for x in nc.variables['cell_lengths'][:]] + [float(x) for x in ang]
+        time = float(nc.variables['time'].getValue()) if 'time' in nc.variables else 0.0
+    finally:
+        nc.close()
+    return coords, vel, box, time
+
+
 class Rst7(object):
-    """Restart-file reader (``parmed.amber.Rst7`` surface used at ``blues/settings.py:79-85``)."""
+    """Restart-file reader, ASCII or NetCDF by content like ``parmed.amber.Rst7`` (``blues/settings.py:79-85``)."""
 
     def __init__(self, filename):
-        c, v, b = read_inpcrd(filename)
+        self.time = 0.0
+        if is_netcdf(filename):
+            c, v, b, self.time = read_netcdf_restart(filename)
+        else:
+            c, v, b = read_inpcrd(filename)
         self.coordinates = c
         self.vels = v
         self.box = b

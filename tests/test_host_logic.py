@@ -195,3 +195,64 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     hdr = open(os.path.join(root, 'include', 'blues_b200.h')).read()
     for name, value in re.findall(r'#define (BL_MOVE_\w+)\s+(\d+)', hdr):
         assert getattr(_native, name) == int(value), name
+
+
+def test_restart_files_round_trip_ascii_and_netcdf(tmp_path):
+    """RestartReporter (blues/reporters.py:224 asks parmed for NetCDF restarts) and the Rst7 reader behind the YAML
+    `structure: restart:` key (blues/settings.py:76-85): both AMBER formats, detected by content."""
+    from scipy.io import netcdf_file
+    from blues_b200.reporters import RestartReporter, ReporterConfig
+    from blues_b200.structure import Rst7, is_netcdf
+    rs = np.random.RandomState(2)
+    n = 37
+    xyz = rs.uniform(0, 30, size=(n, 3))
+    vel = rs.normal(size=(n, 3))
+    box = np.diag([31.0, 32.5, 29.75])
+
+    class FakeState(object):
+        def getPositions(self, asNumpy=False):
+            return u.Quantity(xyz.copy(), u.angstroms)
+
+        def getVelocities(self, asNumpy=False):
+            return u.Quantity(vel.copy(), u.angstroms / u.picoseconds)
+
+        def getPeriodicBoxVectors(self, asNumpy=False):
+            return u.Quantity(box.copy(), u.angstroms)
+
+        def getTime(self):
+            return u.Quantity(12.5, u.picoseconds)
+
+    class FakeSystem(object):
+        def getNumParticles(self):
+            return n
+
+    class FakeSim(object):
+        system = FakeSystem()
+        currentStep = 40
+
+    for netcdf in (False, True):
+        fname = str(tmp_path / ('r_%s.rst7' % netcdf))
+        rep = RestartReporter(fname, reportInterval=10, netcdf=netcdf)
+        assert rep.describeNextReport(FakeSim())[0] == 10 and rep.describeNextReport(FakeSim())[1:3] == (True, True)
+        rep.report(FakeSim(), FakeState())
+        assert is_netcdf(fname) == netcdf
+        r = Rst7(fname)
+        tol = 1e-12 if netcdf else 1e-6                       # the ASCII format keeps 7 decimals
+        assert np.allclose(r.positions.value_in_unit(u.angstroms), xyz, atol=tol)
+        assert np.allclose(r.velocities.value_in_unit(u.angstroms / u.picoseconds), vel, atol=30 * tol)
+        assert np.allclose(r.box[:3], np.diag(box), atol=tol) and r.box[3:] == [90.0, 90.0, 90.0]
+        assert r.hasvels and r.hasbox
+    # AMBER NetCDF restart conventions (what parmed / cpptraj / sander expect to find)
+    nc = netcdf_file(str(tmp_path / 'r_True.rst7'), 'r', mmap=False)
+    assert nc.Conventions == b'AMBERRESTART' and nc.ConventionVersion == b'1.0'
+    assert nc.variables['coordinates'].shape == (n, 3) and nc.variables['coordinates'].units == b'angstrom'
+    assert nc.variables['velocities'].units == b'angstrom/picosecond'
+    assert float(nc.variables['velocities'].scale_factor) == pytest.approx(20.455)
+    assert np.allclose(nc.variables['velocities'][:] * 20.455, vel)
+    assert nc.variables['time'].getValue() == pytest.approx(12.5)
+    assert bytes(nc.variables['cell_angular'][:].tobytes()) == b'alphabeta gamma'
+    assert np.allclose(nc.variables['cell_lengths'][:], np.diag(box))
+    nc.close()
+    # ReporterConfig follows the reference: restarts are NetCDF unless the YAML says otherwise
+    reps = ReporterConfig(str(tmp_path / 'out'), {'restart': {'reportInterval': 5}}).makeReporters()
+    assert isinstance(reps[0], RestartReporter) and reps[0].netcdf is True
