@@ -155,6 +155,8 @@ def test_run_from_yaml(structure, tmp_path):
           nstepsNC: 4
           platform: CUDA
         md_reporters:
+          restart:
+            reportInterval: 4
           stream:
             title: md
             reportInterval: 1
@@ -193,6 +195,15 @@ def test_run_from_yaml(structure, tmp_path):
     after = blues._md_sim.context.getState(getPositions=True).getPositions(asNumpy=True)._value
     assert np.not_equal(before, after).all()
     assert blues.accept + blues.reject == 2
+    # the MD leg's restart file (NetCDF, as the reference's ReporterConfig asks) holds the final MD state
+    from blues_b200.structure import Rst7, is_netcdf
+    rst = os.path.join(str(tmp_path), 'tol-test.rst7')
+    assert is_netcdf(rst)
+    r = Rst7(rst)
+    box = np.asarray(r.box[:3]) * 0.1
+    d = r.positions.value_in_unit(unit.nanometers) - after
+    d -= box * np.round(d / box)                                     # the reporter wraps molecules into the box
+    assert np.max(np.abs(d)) < 1e-9 and r.hasvels
     log = open(os.path.join(str(tmp_path), 'tol-test.log')).read()
     assert 'ncmc:' in log and 'md:' in log and 'Acceptance Ratio' in log
     for rep in cfg['ncmc_reporters']:
