@@ -7,8 +7,8 @@ working (they cost one host round-trip at ``moveStep``).  A move may additionall
 ``device_move()`` returning a descriptor executed inside ``bl_ncmc_run`` with no host round-trip;
 ``RandomLigandRotationMove`` does whenever the caller has not pinned a numpy random state.
 
-Not provided: ``SideChainMove`` / ``SmartDartMove`` / ``CombinationMove`` (OpenEye-licensed, marked untested
-upstream ``blues/moves.py:413-415``; outside the NCMC hot path — DESIGN.md).
+``CombinationMove`` chains moves.  Not provided: ``SideChainMove`` / ``SmartDartMove`` (OpenEye / chemcoord
+dependent, marked untested upstream ``blues/moves.py:413-415``; outside the NCMC hot path — DESIGN.md).
 """
 import copy
 import re
@@ -172,6 +172,51 @@ class MoveEngine(object):
             traceback.print_tb(sys.exc_info()[2])
             print(e)
             raise SystemExit
+
+
+class CombinationMove(Move):
+    """Several moves applied as one, in listed or in reverse order with equal probability (detailed balance) —
+    ``blues/moves.py:1517-1560``.  The upstream class is marked untested and cannot run as written (it reads
+    ``self.move_list`` and calls an undefined ``reverse``, and returns nothing); this one keeps its constructor and
+    intent.  ``atom_indices`` is the union of the members' (``SimulationFactory`` builds the alchemical region from
+    the first move's ``atom_indices``); the ``beforeMove`` / ``afterMove`` / ``_error`` hooks fan out in the same order.
+    """
+
+    def __init__(self, moves):
+        self.moves = list(moves)
+        self.move_list = self.moves
+        seen = []
+        for m in self.moves:
+            for a in getattr(m, 'atom_indices', []):
+                if a not in seen:
+                    seen.append(a)
+        self.atom_indices = seen
+
+    def initializeSystem(self, system, integrator):
+        for m in self.moves:
+            system, integrator = m.initializeSystem(system, integrator)
+        return system, integrator
+
+    def beforeMove(self, context):
+        for m in self.moves:
+            context = m.beforeMove(context)
+        return context
+
+    def afterMove(self, context):
+        for m in self.moves:
+            context = m.afterMove(context)
+        return context
+
+    def _error(self, context):
+        for m in self.moves:
+            context = m._error(context)
+        return context
+
+    def move(self, context):
+        order = self.moves if numpy.random.random() > 0.5 else list(reversed(self.moves))
+        for single_move in order:
+            context = single_move.move(context)
+        return context
 
 
 # ---------------------------------------------------------------------------------------------------------

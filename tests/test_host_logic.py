@@ -256,3 +256,41 @@ def test_restart_files_round_trip_ascii_and_netcdf(tmp_path):
     # ReporterConfig follows the reference: restarts are NetCDF unless the YAML says otherwise
     reps = ReporterConfig(str(tmp_path / 'out'), {'restart': {'reportInterval': 5}}).makeReporters()
     assert isinstance(reps[0], RestartReporter) and reps[0].netcdf is True
+
+
+def test_combination_move_orders_and_hooks():
+    """blues/moves.py:1517-1560 (unrunnable upstream): members run in listed or reverse order, hooks fan out."""
+    from blues_b200.moves import CombinationMove
+    log = []
+
+    class Rec(Move):
+        def __init__(self, name, atoms):
+            self.name, self.atom_indices = name, atoms
+
+        def beforeMove(self, context):
+            log.append(('before', self.name))
+            return context
+
+        def move(self, context):
+            log.append(('move', self.name))
+            return context + [self.name]
+
+        def afterMove(self, context):
+            log.append(('after', self.name))
+            return context
+
+    combo = CombinationMove([Rec('a', [1, 2]), Rec('b', [2, 3]), Rec('c', [7])])
+    assert combo.atom_indices == [1, 2, 3, 7]
+    np.random.seed(0)
+    orders = set()
+    for _ in range(40):
+        out = combo.move([])
+        assert out in (['a', 'b', 'c'], ['c', 'b', 'a'])
+        orders.add(tuple(out))
+    assert len(orders) == 2
+    log.clear()
+    assert combo.beforeMove('ctx') == 'ctx' and combo.afterMove('ctx') == 'ctx'
+    assert log == [('before', 'a'), ('before', 'b'), ('before', 'c'), ('after', 'a'), ('after', 'b'), ('after', 'c')]
+    eng = MoveEngine(combo)
+    eng.selectMove()
+    assert eng.move_name == 'CombinationMove' and eng.runEngine([]) in (['a', 'b', 'c'], ['c', 'b', 'a'])
