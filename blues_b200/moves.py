@@ -7,8 +7,9 @@ working (they cost one host round-trip at ``moveStep``).  A move may additionall
 ``device_move()`` returning a descriptor executed inside ``bl_ncmc_run`` with no host round-trip;
 ``RandomLigandRotationMove`` does whenever the caller has not pinned a numpy random state.
 
-``CombinationMove`` chains moves.  Not provided: ``SideChainMove`` / ``SmartDartMove`` (OpenEye / chemcoord
-dependent, marked untested upstream ``blues/moves.py:413-415``; outside the NCMC hot path — DESIGN.md).
+``SmartDartMove`` (centre-of-mass darting) and ``CombinationMove`` are host-path moves.  Not provided:
+``SideChainMove`` (OpenEye-licensed, marked untested upstream ``blues/moves.py:413-415``; outside the NCMC hot
+path — DESIGN.md).
 """
 import copy
 import re
@@ -172,6 +173,134 @@ class MoveEngine(object):
             traceback.print_tb(sys.exc_info()[2])
             print(e)
             raise SystemExit
+
+
+class SmartDartMove(RandomLigandRotationMove):
+    """Centre-of-mass smart darting between pre-defined ligand positions (``blues/moves.py:1086-1514``; Andricioaei,
+    Straub and Voter, J. Chem. Phys. 114, 6994 (2001)).
+
+    Every file of ``coord_files`` (with ``topology`` when the files carry coordinates only) contributes one dart:
+    the ligand's centre of mass expressed in the local frame of three ``basis_particles`` (origin p1, axes p2 − p1,
+    p3 − p1 and their cross product), so that darts follow the protein.  ``move`` rebuilds the darts from the
+    current basis particles; if the ligand's centre of mass lies within ``dart_radius`` of exactly one dart, the
+    ligand is translated to another dart chosen uniformly (the same one allowed with ``self_dart``), keeping its
+    offset from the dart centre.  Overlapping darts raise, as upstream.  Marked untested upstream; host path only
+    (one state round-trip at ``moveStep``).
+    """
+
+    def __init__(self, structure, basis_particles, coord_files, topology=None, dart_radius=0.2 * unit.nanometers,
+                 self_dart=False, resname='LIG'):
+        super(SmartDartMove, self).__init__(structure, resname=resname)
+        if len(coord_files) < 2:
+            raise ValueError('You should include at least two files in coord_files ' +
+                             'in order to benefit from smart darting')
+        self.dartboard = []
+        self.n_dartboard = []
+        self.particle_pairs = []
+        self.particle_weights = []
+        self.basis_particles = list(basis_particles)
+        self.dart_radius = dart_radius
+        self.self_dart = self_dart
+        self.dartsFromParmEd(coord_files, topology)
+
+    def device_move(self):
+        return None
+
+    # ---- frame algebra (plain arrays in nanometers) ---------------------------------------------------------
+    @staticmethod
+    def _nm(v):
+        return numpy.asarray(v.value_in_unit(unit.nanometers) if unit.is_quantity(v) else v, float)
+
+    def _normalize(self, vector):
+        v = numpy.asarray(vector, float)
+        return v / numpy.sqrt(numpy.sum(v * v))
+
+    def _localCoord(self, particle1, particle2, particle3):
+        p1, p2, p3 = self._nm(particle1), self._nm(particle2), self._nm(particle3)
+        v1, v2 = p2 - p1, p3 - p1
+        return v1, v2, numpy.cross(v1, v2)
+
+    def _changeBasis(self, a, b):
+        """Coordinates of the vector ``b`` in the basis whose vectors are the rows of ``a``."""
+        return numpy.linalg.solve(numpy.asarray(a, float).T, numpy.asarray(b, float))
+
+    def _undoBasis(self, a, b):
+        """Cartesian vector with coordinates ``b`` in the basis whose vectors are the rows of ``a``."""
+        return numpy.dot(numpy.asarray(a, float).T, numpy.asarray(b, float))
+
+    def _findNewCoord(self, particle1, particle2, particle3, center):
+        basis = numpy.array(self._localCoord(particle1, particle2, particle3))
+        return self._changeBasis(basis, self._nm(center) - self._nm(particle1)) * unit.nanometers
+
+    def _findOldCoord(self, particle1, particle2, particle3, center):
+        basis = numpy.array(self._localCoord(particle1, particle2, particle3))
+        return (self._undoBasis(basis, self._nm(center)) + self._nm(particle1)) * unit.nanometers
+
+    # ---- darts -------------------------------------------------------------------------------------------------
+    def dartsFromParmEd(self, coord_files, topology=None):
+        from .structure import load_file
+        n_dartboard, dartboard = [], []
+        for coord_file in coord_files:
+            if not isinstance(coord_file, str):
+                temp = coord_file                                 # an already loaded Structure
+            elif topology is None:
+                temp = load_file(coord_file)
+            else:
+                temp = load_file(topology, xyz=coord_file)
+            pos = self._nm(temp.positions)
+            lig = pos[self.atom_indices] * unit.nanometers
+            p = pos[self.basis_particles]
+            com = self.getCenterOfMass(lig, self.masses)
+            new_coord = self._findNewCoord(p[0], p[1], p[2], com)
+            old_coord = self._findOldCoord(p[0], p[1], p[2], new_coord)
+            numpy.testing.assert_almost_equal(self._nm(old_coord), self._nm(com).reshape(3), decimal=1)
+            n_dartboard.append(new_coord)
+            dartboard.append(old_coord)
+        self.n_dartboard = n_dartboard
+        self.dartboard = dartboard
+
+    def _findDart(self, context):
+        pos = self._nm(context.getState(getPositions=True).getPositions(asNumpy=True))
+        p = pos[self.basis_particles]
+        self.dartboard = [self._findOldCoord(p[0], p[1], p[2], dart) for dart in self.n_dartboard]
+        return self.dartboard[:]
+
+    def _calc_from_center(self, com):
+        c = self._nm(com).reshape(3)
+        radius = self._nm(self.dart_radius)
+        diffs = [c - self._nm(dart).reshape(3) for dart in self.dartboard]
+        inside = [k for k, d in enumerate(diffs) if numpy.sqrt(numpy.sum(d * d)) <= radius]
+        if len(inside) == 1:
+            return inside[0], diffs[inside[0]] * unit.nanometers
+        if len(inside) == 0:
+            return None, diffs[-1] * unit.nanometers
+        raise ValueError(' The spheres defining two darting regions have overlapped, ' +
+                         'which results in potential problems with detailed balance. ' +
+                         'We are terminating the simulation. Please check the size and ' +
+                         'identity of your darting regions defined by dart_radius.')
+
+    def _reDart(self, selected_dart, changevec):
+        dartindex = list(range(len(self.dartboard)))
+        if self.self_dart is False:
+            dartindex.pop(selected_dart)
+        choice = numpy.random.choice(dartindex)
+        return (self._nm(self.dartboard[choice]).reshape(3) + self._nm(changevec).reshape(3)) * unit.nanometers
+
+    def move(self, context):
+        if len(self.n_dartboard) == 0:
+            raise ValueError('No darts are specified. Make sure you use ' +
+                             'SmartDartMove.dartsFromParmed() before using the move() function')
+        positions = context.getState(getPositions=True).getPositions(asNumpy=True)
+        xyz = self._nm(positions)
+        self._findDart(context)
+        center = self.getCenterOfMass(xyz[self.atom_indices] * unit.nanometers, self.masses)
+        selected_dart, changevec = self._calc_from_center(com=center)
+        if selected_dart is not None:
+            shift = self._nm(self._reDart(selected_dart, changevec)) - self._nm(center).reshape(3)
+            new = xyz.copy()
+            new[self.atom_indices] = new[self.atom_indices] + shift
+            context.setPositions(new * unit.nanometers)
+        return context                     # (upstream returns None when no dart is hit; the Move contract wants the context)
 
 
 class CombinationMove(Move):

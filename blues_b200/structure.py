@@ -722,11 +722,11 @@ def load_file(filename, xyz=None, **kwargs):
         s = load_prmtop(filename)
     if xyz is not None:
         if isinstance(xyz, str):
-            c, v, b = read_inpcrd(xyz)
-            s.coordinates = c
-            s._velocities = v
-            if b is not None:
-                s.box = b
+            r = Rst7(xyz)                                   # ASCII or NetCDF, by content
+            s.coordinates = r.coordinates
+            s._velocities = r.vels
+            if r.box is not None:
+                s.box = r.box
         else:
             s.positions = xyz
     return s

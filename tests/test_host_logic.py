@@ -294,3 +294,80 @@ def test_combination_move_orders_and_hooks():
     eng = MoveEngine(combo)
     eng.selectMove()
     assert eng.move_name == 'CombinationMove' and eng.runEngine([]) in (['a', 'b', 'c'], ['c', 'b', 'a'])
+
+
+class _FakeContext(object):
+    """Positions in, positions out: what a host-path Move needs from a Context."""
+
+    def __init__(self, xyz_nm):
+        self.xyz = np.asarray(xyz_nm, float).copy()
+
+    def getState(self, getPositions=False, **kw):
+        ctx = self
+
+        class S(object):
+            def getPositions(self, asNumpy=False):
+                return u.Quantity(ctx.xyz.copy(), u.nanometers)
+        return S()
+
+    def setPositions(self, pos):
+        self.xyz = np.asarray(pos.value_in_unit(u.nanometers), float).copy()
+
+
+def test_smart_dart_move(tol, tmp_path):
+    """blues/moves.py:1086-1514: darts are ligand centres of mass stored in the frame of three basis particles; a
+    ligand inside one dart jumps to another keeping its offset, follows the basis particles, and is left alone
+    outside every dart; overlapping darts are an error."""
+    from blues_b200.moves import SmartDartMove
+    lig = [a.index for a in tol.topology.atoms() if a.residue.name == 'LIG']
+    basis = [15, 18, 21]                                    # three water oxygens: not collinear
+    shift = np.array([6.0, 0.0, 0.0])                       # Angstrom
+    import copy
+    other = copy.deepcopy(tol)
+    c = np.array(tol.coordinates, float)
+    c[lig] += shift
+    other.coordinates = c
+    # darts from Structure objects and from files give the same dartboard
+    f1, f2 = str(tmp_path / 'a.pdb'), str(tmp_path / 'b.pdb')
+    tol.save(f1, format='pdb')
+    other.save(f2, format='pdb')
+    mv = SmartDartMove(tol, basis, [tol, other], dart_radius=0.2 * u.nanometers)
+    mv_files = SmartDartMove(tol, basis, [f1, f2], dart_radius=0.2 * u.nanometers)
+    for a, b in zip(mv.n_dartboard, mv_files.n_dartboard):
+        assert np.allclose(a.value_in_unit(u.nanometers), b.value_in_unit(u.nanometers), atol=2e-3)   # PDB: 3 decimals
+    assert np.allclose(mv.dartboard[1].value_in_unit(u.nanometers) - mv.dartboard[0].value_in_unit(u.nanometers),
+                       shift * 0.1, atol=1e-5)
+    # frame algebra round trip
+    p = np.array(tol.coordinates, float)[basis] * 0.1
+    x = np.array([0.3, -0.2, 0.7])
+    assert np.allclose(mv._findOldCoord(p[0], p[1], p[2], mv._findNewCoord(p[0], p[1], p[2], x)).value_in_unit(u.nanometers), x)
+    # inside dart 0 (slightly off-centre): the ligand lands at dart 1 with the same offset, nothing else moves
+    x0 = np.array(tol.coordinates, float) * 0.1
+    off = np.array([0.05, -0.03, 0.02])
+    x0[lig] += off
+    ctx = _FakeContext(x0)
+    assert mv.move(ctx) is ctx
+    moved = ctx.xyz
+    assert np.allclose(moved[lig] - x0[lig], shift * 0.1, atol=1e-5)
+    rest = np.setdiff1d(np.arange(len(x0)), lig)
+    assert np.array_equal(moved[rest], x0[rest])
+    # and back again (two darts, self_dart False: the move is its own inverse)
+    mv.move(ctx)
+    assert np.allclose(ctx.xyz, x0, atol=1e-5)
+    # the darts follow the basis particles: translate the whole system, the jump is unchanged
+    ctx2 = _FakeContext(x0 + np.array([0.4, 0.1, -0.2]))
+    mv.move(ctx2)
+    assert np.allclose(ctx2.xyz[lig] - (x0[lig] + np.array([0.4, 0.1, -0.2])), shift * 0.1, atol=1e-5)
+    # outside every dart: untouched
+    far = x0.copy()
+    far[lig] += np.array([0.0, 0.3, 0.0])
+    ctx3 = _FakeContext(far)
+    assert mv.move(ctx3) is ctx3 and np.array_equal(ctx3.xyz, far)
+    # overlapping darts
+    with pytest.raises(ValueError):
+        mid = np.array(tol.coordinates, float) * 0.1
+        mid[lig] += 0.5 * shift * 0.1                        # 0.3 nm from both dart centres
+        SmartDartMove(tol, basis, [tol, other], dart_radius=0.4 * u.nanometers).move(_FakeContext(mid))
+    with pytest.raises(ValueError):
+        SmartDartMove(tol, basis, [tol])
+    assert mv.device_move() is None
