@@ -303,6 +303,16 @@ class SmartDartMove(RandomLigandRotationMove):
         return context                     # (upstream returns None when no dart is hit; the Move contract wants the context)
 
 
+class SideChainMove(Move):
+    """Placeholder for ``blues/moves.py:413-843``: upstream needs the OpenEye toolkits (a licensed dependency) for its
+    rotor perception and prints "SideChainMove class will be unavailable" without them; here the class exists so that
+    ``from blues.moves import SideChainMove`` resolves, and constructing it says why it cannot run."""
+
+    def __init__(self, *args, **kwargs):
+        raise ImportError('SideChainMove needs the OpenEye toolkits (openeye.oechem), which are not available; '
+                          'it is outside the NCMC hot path this package covers (DESIGN.md)')
+
+
 class CombinationMove(Move):
     """Several moves applied as one, in listed or in reverse order with equal probability (detailed balance) —
     ``blues/moves.py:1517-1560``.  The upstream class is marked untested and cannot run as written (it reads

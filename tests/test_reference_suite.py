@@ -1,0 +1,56 @@
+"""The reference's own test file, unmodified, against this package through ``blues_b200.compat``.
+
+Runs only where the reference checkout is mounted (this container: ``/root/reference``; it does not exist on the GPU
+box, and nothing is copied into the repository — the test file is copied to a temporary directory at run time because
+pytest would otherwise import it as ``blues.tests.…`` from the read-only checkout).  Without a GPU the host-side tests
+of ``blues/tests/test_simulation.py`` must pass as they are; every other test of that file must get as far as creating
+a ``Context`` and stop there with the engine's "no CUDA device … no CPU fallback" error — i.e. nothing is blocked by a
+missing name or a different signature.
+"""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+REFERENCE = os.environ.get('BLUES_REFERENCE', '/root/reference')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+RUNNER = r'''
+import sys
+sys.dont_write_bytecode = True
+sys.path.insert(0, %(root)r)
+import blues_b200.compat as compat
+compat.install(data_root=%(ref)r)
+import pytest
+sys.exit(pytest.main(['-p', 'no:cacheprovider', '-q', '-rA', '--tb=line', '--rootdir', %(tmp)r, '-c', '/dev/null', %(tmp)r]))
+'''
+
+HOST_ONLY = {
+    'TestSystemFactory::test_atom_selections', 'TestSystemFactory::test_atomidx_to_atomlist',
+    'TestSystemFactory::test_generateSystem', 'TestSystemFactory::test_generateAlchSystem',
+    'TestSystemFactory::test_restrain_postions', 'TestSystemFactory::test_freeze_atoms',
+    'TestSystemFactory::test_freeze_radius', 'TestSimulationFactory::test_addBarostat',
+    'TestSimulationFactory::test_generateIntegrator', 'TestSimulationFactory::test_generateNCMCIntegrator',
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, 'blues', 'tests')),
+                    reason='reference checkout not mounted (it is absent on the GPU box)')
+def test_reference_test_simulation_runs_unmodified(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('with a GPU the remaining tests of the file run too; this check is about the CPU container')
+    shutil.copy(os.path.join(REFERENCE, 'blues', 'tests', 'test_simulation.py'), str(tmp_path))
+    code = RUNNER % {'root': ROOT, 'ref': REFERENCE, 'tmp': str(tmp_path)}
+    env = dict(os.environ, COLUMNS='400', PYTHONDONTWRITEBYTECODE='1')
+    out = subprocess.run([sys.executable, '-c', code], cwd=str(tmp_path), env=env, capture_output=True, text=True,
+                         timeout=600).stdout
+    passed = set(re.findall(r'^PASSED \S*test_simulation\.py::(\S+)', out, re.M))
+    blocked = re.findall(r'^(?:FAILED|ERROR) \S*test_simulation\.py::(\S+) - (.*)$', out, re.M)
+    assert HOST_ONLY <= passed, (sorted(HOST_ONLY - passed), out[-3000:])
+    assert len(passed) + len(blocked) == 25, out[-3000:]             # the file has 25 tests
+    for name, why in blocked:
+        assert 'no CUDA device available' in why and 'no CPU fallback' in why, (name, why)
