@@ -48,7 +48,7 @@ def install(data_root=None, force=False):
                                                                                             'MonteCarloBarostat')}
     for k in ('Context', 'State', 'Platform', 'LangevinIntegrator', 'Vec3', 'OpenMMException'):
         openmm_attrs[k] = getattr(mm, k)
-    app = _module('simtk.openmm.app', Simulation=mm.Simulation,
+    app = _module('simtk.openmm.app', Simulation=mm.Simulation, StateDataReporter=reporters.StateDataReporter,
                   NoCutoff=system.NoCutoff, CutoffNonPeriodic=system.CutoffNonPeriodic,
                   CutoffPeriodic=system.CutoffPeriodic, Ewald=system.Ewald, PME=system.PME,
                   HBonds=system.HBonds, AllBonds=system.AllBonds, HAngles=system.HAngles)
@@ -88,6 +88,13 @@ def install(data_root=None, force=False):
     blues.__path__ = []
     mods.update({'blues': blues, 'blues.utils': blues_utils, 'blues.simulation': simulation, 'blues.moves': moves,
                  'blues.integrators': integrators, 'blues.reporters': reporters, 'blues.settings': settings})
+
+    # code written for BLUES configures logging by the reference's module names ("blues.simulation", …)
+    import logging
+    for short, mod in (('simulation', simulation), ('moves', moves), ('reporters', reporters), ('settings', settings),
+                       ('utils', utils), ('integrators', integrators)):
+        if isinstance(getattr(mod, 'logger', None), logging.Logger):
+            mod.logger = logging.getLogger('blues.' + short)
 
     done = []
     for name, m in mods.items():

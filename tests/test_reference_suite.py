@@ -54,3 +54,39 @@ def test_reference_test_simulation_runs_unmodified(tmp_path):
     assert len(passed) + len(blocked) == 25, out[-3000:]             # the file has 25 tests
     for name, why in blocked:
         assert 'no CUDA device available' in why and 'no CPU fallback' in why, (name, why)
+
+
+ORACLE_RUNNER = r'''
+import sys
+sys.dont_write_bytecode = True
+sys.path.insert(0, %(root)r)
+import blues_b200.compat as compat
+compat.install(data_root=%(ref)r)
+import blues_b200._native as native
+from tests.oracle_engine import OracleEngine
+native.Engine = OracleEngine            # test infrastructure: the C ABI's Python face answered by the CPU oracle
+import pytest
+sys.exit(pytest.main(['-p', 'no:cacheprovider', '-q', '-rA', '--tb=short', '--rootdir', %(tmp)r, '-c', '/dev/null', %(tmp)r]))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, 'blues', 'tests')),
+                    reason='reference checkout not mounted (it is absent on the GPU box)')
+def test_reference_tests_pass_on_the_host_layer_over_the_oracle_engine(tmp_path):
+    """All 25 tests of ``test_simulation.py`` and ``test_randomrotation.py``, unmodified, against this package's host
+    layer (SystemFactory … BLUESSimulation.run, YAML settings, reporters, the rotation move, state sync, accept/reject)
+    with ``tests/oracle_engine.OracleEngine`` standing in for the CUDA engine below the C ABI.  Together with the
+    ``-m gpu`` tests (CUDA engine == oracle on the same inputs) this is the reference's own acceptance test for the
+    drop-in.  Not run: ``test_watertranslation.py`` (its ``eqToluene.prmtop`` is missing upstream), ``test_ethylene.py``
+    (generic ``Custom*Force`` system; its populations are reproduced by ``tests/test_oracle_ethylene.py``),
+    ``test_sidechain.py`` (OpenEye)."""
+    for name in ('test_simulation.py', 'test_randomrotation.py'):
+        shutil.copy(os.path.join(REFERENCE, 'blues', 'tests', name), str(tmp_path))
+    code = ORACLE_RUNNER % {'root': ROOT, 'ref': REFERENCE, 'tmp': str(tmp_path)}
+    env = dict(os.environ, COLUMNS='400', PYTHONDONTWRITEBYTECODE='1')
+    run = subprocess.run([sys.executable, '-c', code], cwd=str(tmp_path), env=env, capture_output=True, text=True,
+                         timeout=1500)
+    out = run.stdout
+    passed = set(re.findall(r'^PASSED (\S+)', out, re.M))
+    assert run.returncode == 0 and len(passed) == 26, out[-4000:]
+    assert any('test_randomrotation.py' in p for p in passed)
