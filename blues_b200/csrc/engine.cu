@@ -74,6 +74,7 @@ struct bl_handle {
     double skin = 0.0; int cell_capacity = 0;
     int build_cq = 0, build_ctas = 0;
     int graph_steps = 4;         // plain NCMC steps captured per CUDA graph
+    bool pdl = true;             // programmatic dependent launch on the B -> flip -> A -> sort edges (BLUES_B200_PDL=0: off)
     // diagnostic timeline (BLUES_B200_TIMELINE=1): events recorded inside the step graphs, read after every replay
     bool timeline = false; cudaEvent_t tl_ev[24] = {}; double tl_sum[24] = {}; long tl_n[24] = {}; int tl_int = 0;
     double4* pinned = nullptr;     // pinned staging for state uploads / downloads ([N] double4)
@@ -165,6 +166,21 @@ static void tl_report(bl_handle* h) {
         if (labs(h->tl_n[id]) > 0) fprintf(stderr, "    %-22s %8.1f   (n = %ld)\n", TL_NAMES[id], h->tl_sum[id] / labs(h->tl_n[id]), labs(h->tl_n[id]));
 }
 
+// Launch with the programmatic-stream-serialization attribute: the kernel may be scheduled while its stream
+// predecessor is still running and blocks in cudaGridDependencySynchronize() until that one has completed, which takes
+// the launch latency off the dependent chain.  Only used on edges whose consumer waits at its very first instruction.
+template <typename... KArgs, typename... Args>
+static void launch_pdl(bl_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ---- force / energy evaluation at the current positions ---------------------------------------------------
 // energy: also accumulate energies; cm_mode: forwarded to k_begin_eval
 static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, int cm_mode, int prefetch_noise = 0) {
@@ -174,7 +190,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     {
         // latches the rebuild request, then (only if due) the cell sort
         LaunchTimer t(h, BL_K_NEIGHBOR);
-        k_sort_atoms<<<dim3(SORT_CTAS, R), 1024, 0, st>>>(d);
+        launch_pdl(h, k_sort_atoms, dim3(SORT_CTAS, R), dim3(1024), st, d);
     }
     tl_mark(h, st, TL_SORT);
     // Fork 1: reciprocal space (stream2) depends only on the cell-sorted positions; its gather waits for fork 2.
@@ -285,7 +301,8 @@ static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a, bool noise_p
     }
     LaunchTimer t(h, BL_K_INTEGRATE);
     // + 1: the last CTA holds no clusters (n_clusters is passed to the bounds check) and does the scalar bookkeeping
-    k_integrate<<<dim3(cdiv(h->d.n_clusters, 64) + 1, h->d.R), 64, 0, h->stream>>>(h->d, h->ic, a, h->cm_parity);
+    launch_pdl(h, k_integrate, dim3(cdiv(h->d.n_clusters, 64) + 1, h->d.R), dim3(64), h->stream, h->d, h->ic, a,
+               (const int*)h->cm_parity);
     tl_mark(h, h->stream, TL_INT0 + std::min(h->tl_int++, 2));
 }
 
@@ -434,7 +451,7 @@ static void issue(bl_handle* h, const std::vector<Launch>& ls, HostCounters& hc,
             hc.pending_md += n_md;
             if (l.flip_after && !dry) {
                 LaunchTimer t(h, -1);
-                k_cm_flip<<<1, 64, 0, h->stream>>>(h->d, h->cm_parity);
+                launch_pdl(h, k_cm_flip, dim3(1), dim3(64), h->stream, h->d, h->cm_parity);
             }
         }
     }
@@ -737,6 +754,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (device < 0 || device >= ndev) { g_create_error = "invalid device index"; return BL_ERR_INVALID; }
     if (t->nb_method != 0 && t->nb_method != 2 && t->nb_method != 4) { g_create_error = "unsupported nonbonded method"; return BL_ERR_INVALID; }
     bl_handle* h = new bl_handle();
+    if (getenv("BLUES_B200_PDL")) h->pdl = atoi(getenv("BLUES_B200_PDL")) != 0;
     if (getenv("BLUES_B200_GRAPH_STEPS")) h->graph_steps = std::max(1, atoi(getenv("BLUES_B200_GRAPH_STEPS")));
     if (getenv("BLUES_B200_TIMELINE")) { h->timeline = true; h->graph_steps = 1; }
     counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping

@@ -595,6 +595,7 @@ __device__ __forceinline__ void run_cluster_generic(const Dev& d, const Integrat
 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) k_integrate(Dev d, IntegratorConsts ic, IntegrateArgs args, const int* cm_parity) {
+    cudaGridDependencySynchronize();       // (see k_cm_flip)
     const int r = blockIdx.y;
     const int cid = blockIdx.x * blockDim.x + threadIdx.x;
     Globals& g = d.g[r];
@@ -741,6 +742,7 @@ __global__ void k_momentum(Dev d, const int* cm_parity) {
 
 // zero the consumed centre-of-mass accumulator and flip the parity (single-INTEGRATE passes)
 __global__ void k_cm_flip(Dev d, int* cm_parity) {
+    cudaGridDependencySynchronize();       // programmatic dependent launch: no-op when launched without the attribute
     const int p = *cm_parity;
     for (int i = threadIdx.x; i < d.R * 3; i += blockDim.x) d.cm_acc[(size_t)p * d.R * 3 + i] = 0;
     __syncthreads();

@@ -52,6 +52,7 @@ __device__ __forceinline__ void atom_cell_coords(const Dev& d, float4 p, int& cx
 __global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort_atoms(Dev d) {
     // one thread-block cluster (8 CTAs, hardware cluster barrier) per walker
     namespace cg = cooperative_groups;
+    cudaGridDependencySynchronize();       // programmatic dependent launch: no-op when launched without the attribute
     cg::cluster_group cluster = cg::this_cluster();
     const int r = blockIdx.y;
     Globals& g = d.g[r];
