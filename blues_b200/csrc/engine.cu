@@ -251,6 +251,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         { LaunchTimer t(h, BL_K_NEIGHBOR, s4); k_alch_reset<<<cdiv(R * d.n_alch, 128), 128, 0, s4>>>(d); }
         { LaunchTimer t(h, BL_K_NEIGHBOR, s4);
           k_alch_list<<<dim3(cdiv(N, 128), R), 128, d.n_alch * sizeof(float4), s4>>>(d); }
+        { LaunchTimer t(h, BL_K_NEIGHBOR, s4); k_alch_sort<<<dim3(d.n_alch, R), 512, 0, s4>>>(d); }
         { LaunchTimer t(h, BL_K_ALCH, s4); k_alch<<<dim3(cdiv(d.alch_cap, 128), d.n_alch, R), 128, 0, s4>>>(d); }
         tl_mark(h, s4, TL_ALCH);
         cudaEventRecord(h->ev_join4, s4);

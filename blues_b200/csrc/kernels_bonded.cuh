@@ -256,6 +256,37 @@ __global__ void __launch_bounds__(128) k_alch_list(Dev d) {
     }
 }
 
+// Order every alchemical atom's pair list by atom index (bitonic sort in shared memory; alch_cap <= 2048).  The atomic
+// append of k_alch_list leaves an arbitrary order, and the assignment of entries to the threads of k_alch decides how
+// their double partial sums round when they enter the fixed-point accumulators: sorted lists make the alchemical
+// energies and forces bitwise reproducible from run to run.  Rebuild steps only, off the critical path (stream 4).
+#define ALCH_SORT_MAX 2048
+__global__ void __launch_bounds__(512) k_alch_sort(Dev d) {
+    __shared__ int s_key[ALCH_SORT_MAX];
+    const int k = blockIdx.x, r = blockIdx.y, na = d.n_alch;
+    if (!d.g[r].do_prune) return;
+    const int n = min(d.alch_count[r * na + k], min(d.alch_cap, ALCH_SORT_MAX));
+    if (n <= 1) return;
+    int* list = d.alch_list + ((size_t)r * na + k) * d.alch_cap;
+    int m = 2;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s_key[i] = i < n ? list[i] : 0x7fffffff;
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const int a = s_key[i], b = s_key[j];
+                    const bool ascending = (i & size) == 0;
+                    if ((a > b) == ascending) { s_key[i] = b; s_key[j] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) list[i] = s_key[i];
+}
+
 __global__ void k_alch_reset(Dev d) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= d.R * d.n_alch) return;

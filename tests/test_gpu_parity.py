@@ -223,3 +223,27 @@ def test_full_size_properties_t4l():
     F = eng.get_forces(0)
     assert np.all(np.isfinite(F))
     eng.close()
+
+
+def test_alchemical_run_is_bitwise_reproducible():
+    """Fixed-point accumulation makes every sum independent of the order in which threads arrive; the one list that is
+    filled through an atomic cursor (the alchemical pair list) is sorted before use.  Two walkers with the same start
+    relax to bitwise equal energies, and two engines with the same seed produce bitwise equal trajectories and work."""
+    from blues_b200 import _native
+    s, system, topo, x = gc.load_case('t4l_surrogate', True)
+    ls, le = gc.lambda_tables(5000)
+    outs = []
+    for rep in range(2):
+        eng = _native.Engine(topo, n_replicas=2, seed=5)
+        eng.set_ncmc_integrator(300.0, 1.0, 0.004, 'H V R O R V H', 5000, 1, 0.2, 0.8, ls, le)
+        eng.set_positions(x)
+        eng.minimize(20, 10.0)
+        ep, _ = eng.get_energy()
+        assert ep[0] == ep[1]
+        eng.velocities_to_temperature(300.0)
+        eng.ncmc_run(40)
+        outs.append((eng.get_positions(0), eng.get_positions(1), eng.get_global('protocol_work', 0),
+                     eng.get_global('protocol_work', 1)))
+        eng.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3]
