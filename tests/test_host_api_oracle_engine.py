@@ -1,0 +1,63 @@
+"""The package's own API tests (tests/test_gpu_api.py) on a machine without a GPU: the same test functions, with
+``tests/oracle_engine.OracleEngine`` (the CPU oracle behind the engine interface — test infrastructure) standing in for
+the CUDA engine.  Covers the host layer end to end here — BLUESSimulation flows, YAML settings and reporters, both
+paths of the water move, the barostat driver — so that host-side regressions show up before GPU time is spent.  The
+``-m gpu`` run executes the very same functions against the CUDA engine."""
+import pytest
+
+from blues_b200 import _native
+from blues_b200.structure import Structure
+from tests.oracle_engine import OracleEngine
+import tests.test_gpu_api as api
+
+
+@pytest.fixture(autouse=True)
+def oracle_engine(monkeypatch):
+    monkeypatch.setattr(_native, 'Engine', OracleEngine)
+
+
+@pytest.fixture(scope='module')
+def structure():
+    import os
+    return Structure.load_npz(os.path.join(api.GOLDEN, 'tol_parm.npz'))
+
+
+@pytest.fixture()
+def blues_sim(structure):
+    from blues_b200 import utils
+    from blues_b200.simulation import SystemFactory, SimulationFactory, BLUESSimulation
+    from blues_b200.moves import MoveEngine
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, api.system_cfg())
+    simulations = SimulationFactory(systems, MoveEngine(api.NoRandomLigandRotation(structure, 'LIG')), api.sim_cfg())
+    b = BLUESSimulation(simulations)
+    for sim in (b._md_sim, b._alch_sim, b._ncmc_sim):
+        sim.minimizeEnergy()
+    return b
+
+
+def test_simulation_set_state_sync_and_iteration(blues_sim, structure):
+    api.test_simulation_set(blues_sim, structure)
+    api.test_state_and_sync(blues_sim)
+    api.test_step_ncmc_accept_reject_md(blues_sim)
+
+
+def test_random_rotation_move(structure):
+    api.test_random_rotation_move(structure)
+
+
+def test_run_from_yaml(structure, tmp_path):
+    api.test_run_from_yaml(structure, tmp_path)
+
+
+@pytest.mark.parametrize('on_device', [False, True])
+def test_water_translation_move(structure, on_device):
+    api.test_water_translation_move(structure, on_device)
+
+
+def test_blues_run_with_water_translation(structure, tmp_path):
+    api.test_blues_run_with_water_translation_on_device(structure, tmp_path)
+
+
+def test_md_leg_with_monte_carlo_barostat(structure):
+    api.test_md_leg_with_monte_carlo_barostat(structure)
