@@ -26,22 +26,24 @@ class Settings(object):
 
     @staticmethod
     def load_yaml(yaml_config):
+        """A dict as is, the path of a YAML file, or YAML text (``blues/settings.py:33-58``)."""
         if isinstance(yaml_config, dict):
             return yaml_config
+        is_file = os.path.isfile(str(yaml_config))
         try:
-            if os.path.isfile(str(yaml_config)):
-                with open(yaml_config, 'r') as stream:
-                    return yaml.safe_load(stream)
-            return yaml.safe_load(yaml_config)
-        except IOError as e:
+            if not is_file:
+                return yaml.safe_load(yaml_config)
+            with open(yaml_config, 'r') as stream:
+                return yaml.safe_load(stream)
+        except IOError:
             print("Unable to open file:", yaml_config)
-            raise e
-        except yaml.YAMLError as e:
-            if hasattr(e, 'problem_mark'):
-                mark = e.problem_mark
+            raise
+        except yaml.YAMLError as err:
+            mark = getattr(err, 'problem_mark', None)
+            if mark is not None:
                 print('YAML parsing error in file: {}\nError on Line:{} Column:{}'.format(yaml_config, mark.line + 1,
                                                                                         mark.column + 1))
-            raise e
+            raise
 
     @staticmethod
     def set_Structure(config):
@@ -165,20 +167,18 @@ class Settings(object):
 
     @staticmethod
     def set_Parameters(config):
+        """Every section in the reference's order (``blues/settings.py:228-255``); errors are logged and re-raised."""
+        steps = [Settings.set_Output, Settings.set_Logger]
+        if 'structure' in config:
+            steps += [Settings.set_Structure, lambda c: (Settings.check_SystemModifications(c), c)[1]]
+        steps += [Settings.set_Units, Settings.set_Apps, Settings.set_ncmcSteps, Settings.set_Reporters]
         try:
-            config = Settings.set_Output(config)
-            config = Settings.set_Logger(config)
-            if 'structure' in config:
-                config = Settings.set_Structure(config)
-                Settings.check_SystemModifications(config)
-            config = Settings.set_Units(config)
-            config = Settings.set_Apps(config)
-            config = Settings.set_ncmcSteps(config)
-            config = Settings.set_Reporters(config)
-        except Exception as e:
+            for step in steps:
+                config = step(config)
+        except Exception as err:
             if 'Logger' in config:
-                config['Logger'].exception(e)
-            raise e
+                config['Logger'].exception(err)
+            raise
         return config
 
     def asDict(self):

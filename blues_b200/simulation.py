@@ -135,24 +135,20 @@ class SimulationFactory(object):
     """Builds the three Simulations (md / alch / ncmc) BLUES needs (``blues/simulation.py:483-600``)."""
 
     def __init__(self, systems, move_engine, config=None, md_reporters=None, ncmc_reporters=None):
-        self._structure = systems.structure
-        self._system = systems.md
-        self._alch_system = systems.alch
-        self._atom_indices = move_engine.moves[0].atom_indices
+        self._structure, self._system, self._alch_system = systems.structure, systems.md, systems.alch
         self._move_engine = move_engine
+        self._atom_indices = move_engine.moves[0].atom_indices
         self.config = config
-        if self.config:
+        if config:
             try:
                 self.generateSimulationSet()
-            except Exception as e:
-                logger.exception(e)
-                raise e
-        if md_reporters:
-            self._md_reporters = md_reporters
-            self.md = SimulationFactory.attachReporters(self.md, self._md_reporters)
-        if ncmc_reporters:
-            self._ncmc_reporters = ncmc_reporters
-            self.ncmc = SimulationFactory.attachReporters(self.ncmc, self._ncmc_reporters)
+            except Exception as err:
+                logger.exception(err)
+                raise
+        for which, reporters in (('md', md_reporters), ('ncmc', ncmc_reporters)):
+            if reporters:
+                setattr(self, '_%s_reporters' % which, reporters)
+                setattr(self, which, self.attachReporters(getattr(self, which), reporters))
 
     @classmethod
     def addBarostat(cls, system, temperature=300 * unit.kelvin, pressure=1 * unit.atmospheres, frequency=25, **kwargs):
@@ -205,26 +201,24 @@ class SimulationFactory(object):
 
     def generateSimulationSet(self, config=None):
         """md, alch (MD system, energy only) and ncmc Simulations (``blues/simulation.py:768-809``)."""
-        if not config:
-            config = self.config
-        self.integrator = self.generateIntegrator(**config)
-        if 'pressure' in config.keys():
-            self._system = self.addBarostat(self._system, **config)
+        cfg = config or self.config
+        if 'pressure' in cfg:
+            self._system = self.addBarostat(self._system, **cfg)
             logger.warning('NCMC simulation will NOT have pressure control. NCMC will use pressure from last MD state.')
         else:
-            logger.info('MD simulation will be {} NVT.'.format(config['temperature']))
-        self.md = self.generateSimFromStruct(self._structure, self._system, self.integrator, **config)
-        alch_integrator = self.generateIntegrator(**config)
-        self.alch = self.generateSimFromStruct(self._structure, self._system, alch_integrator, **config)
-        if 'moveStep' not in config.keys():
+            logger.info('MD simulation will be {} NVT.'.format(cfg['temperature']))
+        # the MD leg and the energy-only copy used by the alchemical correction share the MD system
+        self.integrator = self.generateIntegrator(**cfg)
+        self.md, self.alch = (self.generateSimFromStruct(self._structure, self._system, integ, **cfg)
+                              for integ in (self.integrator, self.generateIntegrator(**cfg)))
+        if 'moveStep' not in cfg:
             logger.warning('Did not find `moveStep` in configuration. Checking NCMC paramters')
-            for k, v in utils.calculateNCMCSteps(**config).items():
-                config[k] = v
-            self.config = config
-        self.ncmc_integrator = self.generateNCMCIntegrator(**config)
-        for move in self._move_engine.moves:
+            cfg.update(utils.calculateNCMCSteps(**cfg))
+            self.config = cfg
+        self.ncmc_integrator = self.generateNCMCIntegrator(**cfg)
+        for move in self._move_engine.moves:          # a move may edit the alchemical system / integrator once
             self._alch_system, self.ncmc_integrator = move.initializeSystem(self._alch_system, self.ncmc_integrator)
-        self.ncmc = self.generateSimFromStruct(self._structure, self._alch_system, self.ncmc_integrator, **config)
+        self.ncmc = self.generateSimFromStruct(self._structure, self._alch_system, self.ncmc_integrator, **cfg)
         utils.print_host_info(self.ncmc)
 
 
@@ -237,25 +231,17 @@ class BLUESSimulation(object):
 
     def __init__(self, simulations, config=None):
         self._move_engine = simulations._move_engine
-        self._md_sim = simulations.md
-        self._alch_sim = simulations.alch
-        self._ncmc_sim = simulations.ncmc
-        self._config = None
-        if not config:
-            if hasattr(simulations, 'config'):
-                self._config = simulations.config
-        else:
-            self._config = config
+        self._md_sim, self._alch_sim, self._ncmc_sim = simulations.md, simulations.alch, simulations.ncmc
+        self._config = config or getattr(simulations, 'config', None)
         if self._config:
             self._printSimulationTiming()
-        self.accept = 0
-        self.reject = 0
+        self.accept = self.reject = 0
         self.acceptRatio = 0
         self.currentIter = 0
-        self.stateTable = {'md': {'state0': {}, 'state1': {}}, 'ncmc': {'state0': {}, 'state1': {}}}
+        self.stateTable = {sim: {'state0': {}, 'state1': {}} for sim in ('md', 'ncmc')}
         self._integrator_keys_ = ['lambda', 'shadow_work', 'protocol_work', 'Eold', 'Enew']
-        self._state_keys = {'getPositions': True, 'getVelocities': True, 'getForces': False, 'getEnergy': True,
-                            'getParameters': True, 'enforcePeriodicBox': True}
+        self._state_keys = dict(getPositions=True, getVelocities=True, getForces=False, getEnergy=True,
+                                getParameters=True, enforcePeriodicBox=True)
 
     # -- state plumbing -----------------------------------------------------------------------------------
     @classmethod
@@ -396,29 +382,32 @@ class BLUESSimulation(object):
         return (ncmc_state0_PE - md_state0_PE + alch_PE - ncmc_state1_PE) * (-1.0 / self._ncmc_sim.context._integrator.kT)
 
     def _acceptRejectMove(self, write_move=False):
-        """Metropolis test on the protocol work plus the alchemical correction (``blues/simulation.py:1121-1166``)."""
-        work_ncmc = self._ncmc_sim.context._integrator.getLogAcceptanceProbability(self._ncmc_sim.context)
-        randnum = math.log(np.random.random())
-        if not np.isnan(work_ncmc):
-            correction_factor = self._computeAlchemicalCorrection()
-            logger.debug('NCMCLogAcceptanceProbability = %.6f + Alchemical Correction = %.6f' % (work_ncmc, correction_factor))
-            work_ncmc = work_ncmc + correction_factor
-        if work_ncmc > randnum:
+        """Metropolis test on the protocol work plus the alchemical correction (``blues/simulation.py:1121-1166``).
+        NaN work skips the correction and can never pass the test; on acceptance the MD context takes the NCMC end
+        positions (not the velocities); on rejection the MD potential energy must still equal its value before NCMC."""
+        ncmc_context = self._ncmc_sim.context
+        log_p = ncmc_context._integrator.getLogAcceptanceProbability(ncmc_context)
+        log_u = math.log(np.random.random())
+        if not np.isnan(log_p):
+            correction = self._computeAlchemicalCorrection()
+            logger.debug('NCMCLogAcceptanceProbability = %.6f + Alchemical Correction = %.6f' % (log_p, correction))
+            log_p += correction
+        if log_p > log_u:
             self.accept += 1
-            logger.info('NCMC MOVE ACCEPTED: work_ncmc {} > randnum {}'.format(work_ncmc, randnum))
-            ncmc_state1 = self.stateTable['ncmc']['state1']
-            self._md_sim.context = self.setContextFromState(self._md_sim.context, ncmc_state1, velocities=False)
+            logger.info('NCMC MOVE ACCEPTED: work_ncmc {} > randnum {}'.format(log_p, log_u))
+            self._md_sim.context = self.setContextFromState(self._md_sim.context, self.stateTable['ncmc']['state1'],
+                                                            velocities=False)
             if write_move:
                 utils.saveSimulationFrame(self._md_sim, '{}acc-it{}.pdb'.format(self._config['outfname'], self.currentIter))
-        else:
-            self.reject += 1
-            logger.info('NCMC MOVE REJECTED: work_ncmc {} < {}'.format(work_ncmc, randnum))
-            md_state0 = self.stateTable['md']['state0']
-            md_PE = self._md_sim.context.getState(getEnergy=True).getPotentialEnergy()
-            if not math.isclose(md_state0['potential_energy']._value, md_PE._value, rel_tol=float('1e-%s' % rtol)):
-                logger.error('Last MD potential energy %s != Current MD potential energy %s. Potential energy should '
-                             'match the prior state.' % (md_state0['potential_energy'], md_PE))
-                sys.exit(1)
+            return
+        self.reject += 1
+        logger.info('NCMC MOVE REJECTED: work_ncmc {} < {}'.format(log_p, log_u))
+        before = self.stateTable['md']['state0']['potential_energy']
+        now = self._md_sim.context.getState(getEnergy=True).getPotentialEnergy()
+        if not math.isclose(before._value, now._value, rel_tol=10.0 ** -rtol):
+            logger.error('Last MD potential energy %s != Current MD potential energy %s. Potential energy should '
+                         'match the prior state.' % (before, now))
+            sys.exit(1)
 
     def _resetSimulations(self, temperature=None):
         """Reset the NCMC integrator, redraw MD velocities (``blues/simulation.py:1168-1187``)."""
@@ -431,34 +420,31 @@ class BLUESSimulation(object):
     def _stepMD(self, nstepsMD):
         """Advance the MD simulation (``blues/simulation.py:1189-1213``); failure writes a PDB and exits."""
         logger.info('Advancing %i MD steps...' % (nstepsMD))
-        self._md_sim.currentIter = self.currentIter
-        md_state0 = self.stateTable['md']['state0']
+        sim = self._md_sim
+        sim.currentIter = self.currentIter
         try:
-            self._md_sim.step(int(nstepsMD))
-        except Exception as e:
-            logger.error(e, exc_info=True)
-            logger.error('potential energy before NCMC: %s' % md_state0['potential_energy'])
-            logger.error('kinetic energy before NCMC: %s' % md_state0['kinetic_energy'])
+            sim.step(int(nstepsMD))
+        except Exception as err:
+            start = self.stateTable['md']['state0']
+            logger.error(err, exc_info=True)
+            for key, label in (('potential_energy', 'potential'), ('kinetic_energy', 'kinetic')):
+                logger.error('%s energy before NCMC: %s' % (label, start[key]))
             try:
-                utils.saveSimulationFrame(self._md_sim, 'MD-fail-it%s-md%i.pdb' % (self.currentIter, self._md_sim.currentStep))
+                utils.saveSimulationFrame(sim, 'MD-fail-it%s-md%i.pdb' % (self.currentIter, sim.currentStep))
             except Exception:
                 pass
             sys.exit(1)
 
     def run(self, nIter=0, nstepsNC=0, moveStep=0, nstepsMD=0, temperature=300, write_move=False, **config):
-        """NCMC → accept/reject → MD, ``nIter`` times (``blues/simulation.py:1215-1257``)."""
-        if not nIter:
-            nIter = self._config['nIter']
-        if not nstepsNC:
-            nstepsNC = self._config['nstepsNC']
-        if not nstepsMD:
-            nstepsMD = self._config['nstepsMD']
-        if not moveStep:
-            moveStep = self._config['moveStep']
+        """NCMC → accept/reject → MD, ``nIter`` times (``blues/simulation.py:1215-1257``); arguments left at 0 come
+        from the configuration."""
+        cfg = self._config or {}
+        nIter, nstepsNC, nstepsMD, moveStep = (given or cfg[key] for given, key in (
+            (nIter, 'nIter'), (nstepsNC, 'nstepsNC'), (nstepsMD, 'nstepsMD'), (moveStep, 'moveStep')))
         logger.info('Running %i BLUES iterations...' % (nIter))
-        for N in range(int(nIter)):
-            self.currentIter = N
-            logger.info('BLUES Iteration: %s' % N)
+        for it in range(int(nIter)):
+            self.currentIter = it
+            logger.info('BLUES Iteration: %s' % it)
             self._syncStatesMDtoNCMC()
             self._stepNCMC(nstepsNC, moveStep)
             self._acceptRejectMove(write_move)
@@ -476,39 +462,37 @@ class MonteCarloSimulation(BLUESSimulation):
         super(MonteCarloSimulation, self).__init__(simulations, config)
 
     def _stepMC_(self):
+        """Apply the selected move to the MD context and record the trial state."""
         self._move_engine.selectMove()
-        new_context = self._move_engine.runEngine(self._md_sim.context)
-        md_state1 = self.getStateFromContext(new_context, self._state_keys)
-        self._setStateTable('md', 'state1', md_state1)
+        trial = self._move_engine.runEngine(self._md_sim.context)
+        self._setStateTable('md', 'state1', self.getStateFromContext(trial, self._state_keys))
 
     def _acceptRejectMove(self, temperature=None):
-        md_state0 = self.stateTable['md']['state0']
-        md_state1 = self.stateTable['md']['state1']
-        work_mc = (md_state1['potential_energy'] - md_state0['potential_energy']) * (
-            -1.0 / self._ncmc_sim.context._integrator.kT)
-        randnum = math.log(np.random.random())
-        if work_mc > randnum:
+        """exp(−ΔE/kT) Metropolis test between the recorded MD states, then fresh velocities."""
+        old, trial = self.stateTable['md']['state0'], self.stateTable['md']['state1']
+        kT = self._ncmc_sim.context._integrator.kT
+        log_p = -1.0 * (trial['potential_energy'] - old['potential_energy']) / kT
+        log_u = math.log(np.random.random())
+        accepted = log_p > log_u
+        if accepted:
             self.accept += 1
-            logger.info('MC MOVE ACCEPTED: work_mc {} > randnum {}'.format(work_mc, randnum))
-            self._md_sim.context.setPositions(md_state1['positions'])
+            logger.info('MC MOVE ACCEPTED: work_mc {} > randnum {}'.format(log_p, log_u))
         else:
             self.reject += 1
-            logger.info('MC MOVE REJECTED: work_mc {} < {}'.format(work_mc, randnum))
-            self._md_sim.context.setPositions(md_state0['positions'])
+            logger.info('MC MOVE REJECTED: work_mc {} < {}'.format(log_p, log_u))
+        self._md_sim.context.setPositions((trial if accepted else old)['positions'])
         self._md_sim.context.setVelocitiesToTemperature(temperature)
 
     def run(self, nIter=0, mc_per_iter=0, nstepsMD=0, temperature=300, write_move=False):
-        if not nIter:
-            nIter = self._config['nIter']
-        if not nstepsMD:
-            nstepsMD = self._config['nstepsMD']
-        if not mc_per_iter:
-            mc_per_iter = self._config['mc_per_iter']
+        cfg = self._config or {}
+        nIter = nIter or cfg['nIter']
+        nstepsMD = nstepsMD or cfg['nstepsMD']
+        mc_per_iter = mc_per_iter or cfg['mc_per_iter']
         self._syncStatesMDtoNCMC()
-        for N in range(nIter):
-            self.currentIter = N
-            logger.info('MonteCarlo Iteration: %s' % N)
-            for i in range(mc_per_iter):
+        for it in range(nIter):
+            self.currentIter = it
+            logger.info('MonteCarlo Iteration: %s' % it)
+            for _ in range(mc_per_iter):
                 self._syncStatesMDtoNCMC()
                 self._stepMC_()
                 self._acceptRejectMove(temperature)
