@@ -247,3 +247,22 @@ def test_alchemical_run_is_bitwise_reproducible():
         eng.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3]
+
+
+def test_madelung_constant_of_rock_salt_on_the_engine():
+    """Literature anchor (tests/test_oracle.py has the same check for the oracle): lattice energy per ion pair of NaCl
+    = -1.747565 e^2 / (4 pi eps0 r0), from the engine's erfc pair sum + smooth PME + self term; no net force on an ion."""
+    from blues_b200 import _native
+    from tests.test_oracle import _rock_salt
+    a0, cells = 0.564, 4
+    r0 = 0.5 * a0
+    expect = -1.747565 * 138.935456 / r0
+    topo, x = _rock_salt(cells, a0, 5e-4, cutoff=0.9)
+    eng = _native.Engine(topo, n_replicas=1, seed=1)
+    eng.set_langevin_integrator(300.0, 1.0, 0.002)
+    eng.set_positions(x)
+    ep, _ = eng.get_energy()
+    f = eng.get_forces()
+    eng.close()
+    assert ep[0] / (topo['n_atoms'] // 2) == pytest.approx(expect, rel=2e-3)
+    assert np.max(np.abs(f)) < 2e-3 * abs(expect) / r0

@@ -241,3 +241,52 @@ def test_monte_carlo_barostat_host_logic_matches_oracle_restatement():
     assert drv.attempted in (12, 2) and drv.volume_scale > 0
     if drv.attempted == 2:
         assert drv.volume_scale != pytest.approx(0.01 * np.prod(np.asarray(topo['box'], float).reshape(-1)[:3]))
+
+
+def _rock_salt(cells, a0, method_tol=5e-4, cutoff=None):
+    """NaCl lattice, cells^3 conventional cells of edge a0 (nm): flat topology for the oracles."""
+    from blues_b200.system import System, NonbondedForce, PME
+    basis_na = [(0, 0, 0), (.5, .5, 0), (.5, 0, .5), (0, .5, .5)]
+    basis_cl = [(.5, 0, 0), (0, .5, 0), (0, 0, .5), (.5, .5, .5)]
+    xyz, q = [], []
+    for i in range(cells):
+        for j in range(cells):
+            for k in range(cells):
+                for b, charge in ((basis_na, 1.0), (basis_cl, -1.0)):
+                    for f in b:
+                        xyz.append(((i + f[0]) * a0, (j + f[1]) * a0, (k + f[2]) * a0))
+                        q.append(charge)
+    n = len(q)
+    system = System(n)
+    system.masses[:] = 22.99
+    nb = NonbondedForce(n)
+    nb.charge[:] = q
+    nb.sigma[:] = 0.3
+    nb.epsilon[:] = 0.0                                     # Coulomb only
+    nb.method = PME
+    nb.cutoff = cutoff or 0.45 * cells * a0
+    nb.ewald_tol = method_tol
+    nb.use_dispersion_correction = False
+    system.addForce(nb)
+    system.box = np.array([cells * a0] * 3)
+    return system.flatten(), np.asarray(xyz, float)
+
+
+def test_madelung_constant_of_rock_salt():
+    """Literature anchor for the Ewald / smooth-PME arithmetic (direct erfc sum + reciprocal space + self term): the
+    lattice energy per ion pair of NaCl is -M e^2 / (4 pi eps0 r0) with the Madelung constant M = 1.747565.  Both
+    oracle implementations (numpy, C) reproduce it at two Ewald tolerances, within the accuracy each tolerance buys."""
+    from oracle.c_oracle import COracle
+    a0, cells = 0.564, 4                                    # 512 ions, box 2.256 nm
+    r0 = 0.5 * a0
+    expect = -1.747565 * orc.ONE_4PI_EPS0 / r0 if hasattr(orc, 'ONE_4PI_EPS0') else -1.747565 * 138.935456 / r0
+    for tol, rel in ((5e-4, 2e-3), (1e-5, 1e-4)):
+        topo, x = _rock_salt(cells, a0, tol)
+        pairs = topo['n_atoms'] // 2
+        e_np = orc.ForceField(topo).energy(x, np.asarray(topo['box'], float))
+        e_c = COracle(topo).energy_forces(x)[0]
+        assert e_np / pairs == pytest.approx(expect, rel=rel), (tol, e_np / pairs, expect)
+        assert e_c == pytest.approx(e_np, rel=1e-10)
+        # a perfect lattice: no net force on any ion
+        f = COracle(topo).energy_forces(x)[1]
+        assert np.max(np.abs(f)) < 1e-3 * abs(expect) / r0
