@@ -371,3 +371,29 @@ def test_smart_dart_move(tol, tmp_path):
     with pytest.raises(ValueError):
         SmartDartMove(tol, basis, [tol])
     assert mv.device_move() is None
+
+
+def test_committed_bench_line_keeps_the_contract():
+    """profiles/r01_bench_1gpu.json is a line bench.py printed on a B200: every key of the bench contract is present
+    and self-consistent (value = walkers x steps / time, roofline fraction = achieved / peak, e2e carries its bytes)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.load(open(os.path.join(root, 'profiles', 'r01_bench_1gpu.json')))
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
+        assert key in line, key
+    assert line['n_gpus'] == 1 and line['warmup'] >= 3 and line['higher_is_better'] is True and line['scaling'] == 'weak'
+    assert line['data'] == 'synthetic' and 'workload' in line['config'] and 'model' not in line['config']
+    walkers = line['config']['global_walkers']
+    assert line['value'] == pytest.approx(walkers * 1e3 / line['ms_per_step'], rel=1e-6)
+    assert line['gpu_launches'] > line['steps']                      # several kernels per NCMC step
+    e2e = line['e2e']
+    assert e2e['unit'] == line['unit'] and e2e['h2d_bytes_per_step'] > 0 and e2e['d2h_bytes_per_step'] > 0
+    assert 0 < e2e['value'] <= 1.02 * line['value']                  # host copies cannot make it faster
+    roof = line['roofline']
+    for key in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+        assert key in roof, key
+    assert roof['frac'] == pytest.approx(roof['achieved'] / roof['peak'], rel=1e-9) and 0 < roof['frac'] < 1
+    cpu = line['cpu_baseline']
+    assert cpu['kind'] in ('port', 'reference') and cpu['cores'] >= 1 and cpu['value'] > 0 and cpu['sample']
+    assert not {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'} & set(line['clocks']['reasons'])
+    assert line['clocks']['sm_mhz'] >= 0.9 * line['clocks']['sm_max_mhz']
