@@ -61,3 +61,31 @@ def test_blues_run_with_water_translation(structure, tmp_path):
 
 def test_md_leg_with_monte_carlo_barostat(structure):
     api.test_md_leg_with_monte_carlo_barostat(structure)
+
+
+def _run_example(name, func, tmp_path, monkeypatch):
+    """The scripts under examples/ with a short protocol, in a scratch directory (they write reporter files)."""
+    import importlib.util
+    import os
+    import shutil
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ex = tmp_path / 'examples'
+    shutil.copytree(os.path.join(root, 'examples'), str(ex))
+    os.makedirs(str(tmp_path / 'tests' / 'golden'))
+    shutil.copy(os.path.join(api.GOLDEN, 'tol_parm.npz'), str(tmp_path / 'tests' / 'golden'))
+    monkeypatch.chdir(str(ex))
+    spec = importlib.util.spec_from_file_location(name, str(ex / (name + '.py')))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    blues = getattr(mod, func)('rotmove_b200.yml', nIter=2, nstepsNC=6, nstepsMD=4)
+    assert blues.accept + blues.reject == 2
+    assert os.path.exists(str(ex / 'toluene-b200.log')) and os.path.exists(str(ex / 'toluene-b200-ncmc.nc'))
+    return blues
+
+
+def test_example_rotmove(tmp_path, monkeypatch):
+    _run_example('example_rotmove', 'rotmove', tmp_path, monkeypatch)
+
+
+def test_example_water(tmp_path, monkeypatch):
+    _run_example('example_water', 'watermove', tmp_path, monkeypatch)
