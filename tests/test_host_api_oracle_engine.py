@@ -89,3 +89,23 @@ def test_example_rotmove(tmp_path, monkeypatch):
 
 def test_example_water(tmp_path, monkeypatch):
     _run_example('example_water', 'watermove', tmp_path, monkeypatch)
+
+
+def test_monte_carlo_simulation_driver(structure):
+    """MonteCarloSimulation (blues/simulation.py:1260-1335): plain Metropolis moves on the MD context, no NCMC."""
+    import numpy as np
+    from blues_b200 import utils
+    from blues_b200.simulation import SystemFactory, SimulationFactory, MonteCarloSimulation
+    from blues_b200.moves import MoveEngine, RandomLigandRotationMove
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, api.system_cfg())
+    cfg = api.sim_cfg()
+    cfg.update(nIter=2, mc_per_iter=3, nstepsMD=2)
+    simulations = SimulationFactory(systems, MoveEngine(RandomLigandRotationMove(structure, 'LIG', 11)), cfg)
+    simulations.md.minimizeEnergy(maxIterations=100)
+    mc = MonteCarloSimulation(simulations, cfg)
+    before = simulations.md.context.getState(getPositions=True).getPositions(asNumpy=True)._value
+    mc.run()
+    assert mc.accept + mc.reject == 6
+    after = simulations.md.context.getState(getPositions=True).getPositions(asNumpy=True)._value
+    assert np.all(np.isfinite(after)) and not np.array_equal(before, after)
