@@ -95,6 +95,7 @@ SYMBOLS = {
     'bl_stream': (C.c_void_p, [_H]),
     'bl_synchronize': (C.c_int, [_H]),
     'bl_version': (C.c_char_p, []),
+    'bl_measure_fp32_peak': (C.c_int, [C.c_int, _dp]),
 }
 
 _lib = None
@@ -174,6 +175,15 @@ def build_topology(topo):
     t.annihilate_sterics = int(topo['annihilate_sterics'])
     t.annihilate_electrostatics = int(topo['annihilate_electrostatics'])
     return t, keep
+
+
+def measure_fp32_peak(device=0):
+    """Measured FP32 FMA throughput of the device in TFLOP/s (register-only microbenchmark inside the library)."""
+    v = C.c_double()
+    rc = load_library().bl_measure_fp32_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise EngineError('bl_measure_fp32_peak failed (%d)' % rc)
+    return v.value
 
 
 class Engine(object):

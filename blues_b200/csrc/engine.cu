@@ -43,6 +43,7 @@ struct bl_handle {
     int step = 0, lambda_step = 0, first_step = 0;
     int cursor = 0;               // alchemical slot holding the energy/forces of the current lambda_step
     bool forces_valid = false;    // f_env / slots match the current positions
+    bool work_pending = false;    // coordinates changed outside the integrator since the last external-work evaluation
     bool vel_dirty = true;        // cm_acc must be recomputed
     int* cm_parity = nullptr;     // device int
     int n_cons_total = 0;
@@ -99,6 +100,12 @@ static T* dalloc(bl_handle* h, size_t n) {
     cudaMemset(p, 0, n * sizeof(T));
     h->allocs.push_back(p);
     return static_cast<T*>(p);
+}
+static void dfree(bl_handle* h, void* p) {
+    if (!p) return;
+    auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
+    if (it != h->allocs.end()) h->allocs.erase(it);
+    cudaFree(p);
 }
 template <typename T>
 static T* dupload(bl_handle* h, const std::vector<T>& v) {
@@ -498,7 +505,9 @@ static void invalidate_graphs(bl_handle* h) {
     h->graphs.clear();
 }
 
-static int check_flags(bl_handle* h) {
+// nan_is_error: the stepping entry points report a walker whose coordinates went non-finite (OpenMM raises "Particle
+// coordinate is nan" from step()); state queries do not, so that the caller can still read the state and reject the move
+static int check_flags(bl_handle* h, bool nan_is_error = true) {
     Dev& d = h->d;
     std::vector<Globals> g(d.R);
     CK(cudaMemcpyAsync(g.data(), d.g, sizeof(Globals) * d.R, cudaMemcpyDeviceToHost, h->stream));
@@ -509,7 +518,7 @@ static int check_flags(bl_handle* h) {
             h->error = "neighbour work-item list overflow";
             return BL_ERR_CAPACITY;
         }
-        if (g[r].nan_flag) {
+        if (g[r].nan_flag && nan_is_error) {
             char b[96];
             snprintf(b, sizeof b, "Particle coordinate is nan (walker %d)", r);
             h->error = b;
@@ -1154,11 +1163,14 @@ static int download_vec3(bl_handle* h, const double4* src, int replica, double* 
     return BL_OK;
 }
 
-static void positions_changed(bl_handle* h) {
+// replica: the walker whose coordinates were written by the host (-1: all) — its NaN / overflow latches are cleared,
+// fresh coordinates make the walker usable again (a NaN in one NCMC leg must not poison the next iteration)
+static void positions_changed(bl_handle* h, int replica = -2) {
     Dev& d = h->d;
     LaunchTimer t(h, -1);
-    k_refresh_mirrors<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, 1);
+    k_refresh_mirrors<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, 1, replica);
     h->forces_valid = false;
+    h->work_pending = true;      // consumed by k_external_work only (blues/integrators.py:184-191)
 }
 
 int bl_set_positions(bl_handle* h, int replica, const double* xyz) {
@@ -1166,7 +1178,7 @@ int bl_set_positions(bl_handle* h, int replica, const double* xyz) {
     cudaSetDevice(h->device);
     int rc = upload_vec3(h, h->d.pos, replica, xyz);
     if (rc != BL_OK) return rc;
-    positions_changed(h);
+    positions_changed(h, replica);
     return BL_OK;
 }
 int bl_set_velocities(bl_handle* h, int replica, const double* v) {
@@ -1215,7 +1227,7 @@ int bl_get_forces(bl_handle* h, int replica, double* f) {
     if (!h->forces_valid) eval_now(h, true);
     { LaunchTimer t(h, -1); k_export_forces<<<cdiv(d.N, 128), 128, 0, h->stream>>>(d, replica, h->cursor, h->d_scratch); }
     CK(cudaMemcpyAsync(f, h->d_scratch, sizeof(double) * 3 * d.N, cudaMemcpyDeviceToHost, h->stream));
-    return check_flags(h);
+    return check_flags(h, false);
 }
 
 int bl_get_energy(bl_handle* h, double* epot, double* ekin) {
@@ -1233,7 +1245,7 @@ int bl_get_energy(bl_handle* h, double* epot, double* ekin) {
         { LaunchTimer t(h, -1); k_kinetic_energy<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, h->d_scratch); }
         CK(cudaMemcpyAsync(ekin, h->d_scratch, sizeof(double) * d.R, cudaMemcpyDeviceToHost, h->stream));
     }
-    return check_flags(h);
+    return check_flags(h, false);
 }
 
 int bl_get_energy_terms(bl_handle* h, int replica, double terms[BL_NUM_ENERGY_TERMS]) {
@@ -1246,7 +1258,7 @@ int bl_get_energy_terms(bl_handle* h, int replica, double terms[BL_NUM_ENERGY_TE
     CK(cudaMemcpyAsync(e, d.eacc + (size_t)replica * N_ETERMS, sizeof e, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(a, d.alch_acc + (size_t)replica * ALCH_SLOTS * 3, sizeof a, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(box, d.boxd, sizeof box, cudaMemcpyDeviceToHost, h->stream));
-    int rc = check_flags(h);
+    int rc = check_flags(h, false);
     if (rc != BL_OK) return rc;
     for (int k = 0; k < N_ETERMS; ++k) terms[k] = (double)e[k] / ENERGY_SCALE;
     const double V = d.periodic ? box[0] * box[1] * box[2] : 1.0;
@@ -1275,7 +1287,7 @@ int bl_copy_state(bl_handle* dst, const bl_handle* src, int flags) {
     }
     if (flags & 1) CK(cudaMemcpyAsync(dst->d.pos, src->d.pos, n, cudaMemcpyDeviceToDevice, h->stream));
     if (flags & 2) { CK(cudaMemcpyAsync(dst->d.vel, src->d.vel, n, cudaMemcpyDeviceToDevice, h->stream)); h->vel_dirty = true; }
-    if (flags & 5) positions_changed(h);
+    if (flags & 5) positions_changed(h, (flags & 1) ? -1 : -2);
     return BL_OK;
 }
 
@@ -1305,7 +1317,7 @@ int bl_get_global(bl_handle* h, int replica, const char* name, double* value) {
     if (n == "lambda") *value = g.lambda;
     else if (n == "lambda_step") *value = g.lambda_step;
     else if (n == "step") *value = g.step;
-    else if (n == "protocol_work") *value = g.protocol_work;
+    else if (n == "protocol_work") *value = g.nan_flag ? NAN : g.protocol_work;     // a blown-up walker can never be accepted
     else if (n == "shadow_work") *value = g.shadow_work;
     else if (n == "heat") *value = g.heat + (double)heat / ENERGY_SCALE;
     else if (n == "first_step") *value = g.first_step;
@@ -1369,6 +1381,7 @@ int bl_reset_ncmc(bl_handle* h) {
     for (auto& x : g) {
         x.step = 0; x.lambda = 0.0; x.protocol_work = 0.0; x.shadow_work = 0.0; x.first_step = 0;
         x.perturbed_pe = 0.0; x.unperturbed_pe = 0.0; x.prop = 1; x.lambda_step = 0; x.e_valid = 0;
+        x.nan_flag = 0; x.item_overflow = 0;
     }
     CK(cudaMemcpy(h->d.g, g.data(), sizeof(Globals) * h->d.R, cudaMemcpyHostToDevice));
     h->step = 0; h->lambda_step = 0; h->first_step = 0;
@@ -1386,6 +1399,8 @@ static int stage_move(bl_handle* h, const bl_move* m) {
     for (int k = 0; k < m->n_atoms; ++k)
         if (m->atoms[k] < 0 || m->atoms[k] >= h->d.N) { h->error = "move atom index out of range"; return BL_ERR_INVALID; }
     if (m->n_atoms > h->move_capacity) {
+        CK(cudaStreamSynchronize(h->stream));
+        dfree(h, h->d_move_atoms); dfree(h, h->d_move_masses);
         h->d_move_atoms = dalloc<int>(h, m->n_atoms);
         h->d_move_masses = dalloc<float>(h, m->n_atoms);
         h->move_capacity = m->n_atoms;
@@ -1404,6 +1419,8 @@ static int stage_move(bl_handle* h, const bl_move* m) {
         for (int k = 0; k < m->n_center; ++k)
             if (m->center_atoms[k] < 0 || m->center_atoms[k] >= h->d.N) { h->error = "water move: centre atom index out of range"; return BL_ERR_INVALID; }
         if (m->n_center > h->center_capacity) {
+            CK(cudaStreamSynchronize(h->stream));
+            dfree(h, h->d_center_atoms); dfree(h, h->d_center_masses);
             h->d_center_atoms = dalloc<int>(h, m->n_center);
             h->d_center_masses = dalloc<float>(h, m->n_center);
             h->center_capacity = m->n_center;
@@ -1418,7 +1435,11 @@ static int stage_move(bl_handle* h, const bl_move* m) {
             const size_t n = (size_t)m->n_waters * m->n_atoms;
             for (size_t k = 0; k < n; ++k)
                 if (m->water_atoms[k] < 0 || m->water_atoms[k] >= h->d.N) { h->error = "water move: water atom index out of range"; return BL_ERR_INVALID; }
-            if (n > h->water_capacity) { h->d_water_atoms = dalloc<int>(h, n); h->water_capacity = n; }
+            if (n > h->water_capacity) {
+                CK(cudaStreamSynchronize(h->stream));
+                dfree(h, h->d_water_atoms);
+                h->d_water_atoms = dalloc<int>(h, n); h->water_capacity = n;
+            }
             CK(cudaMemcpyAsync(h->d_water_atoms, m->water_atoms, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
         }
     }
@@ -1470,6 +1491,7 @@ static void external_work_eval(bl_handle* h, bool first_only) {
     LaunchTimer t(h, -1);
     k_external_work<<<cdiv(h->d.R, 64), 64, 0, h->stream>>>(h->d, 0, first_only ? 1 : 0);
     h->first_step = 1;
+    h->work_pending = false;
 }
 
 int bl_ncmc_run(bl_handle* h, int n_steps, const bl_move* move) {
@@ -1494,14 +1516,13 @@ int bl_ncmc_run(bl_handle* h, int n_steps, const bl_move* move) {
             h->vel_dirty = true;
         }
         if (has_move && i == move->step) {
-            if (!h->forces_valid && h->first_step >= 1) {
-                // unperturbed energy unknown at the pre-move coordinates: evaluate it first
-            }
             int rc = enqueue_move(h, move);
             if (rc != BL_OK) return rc;
         }
         if (h->vel_dirty) { enqueue_momentum(h); h->vel_dirty = false; }
-        if (!h->forces_valid) external_work_eval(h, false);
+        // forces_valid alone is not enough: an energy query between a host-side coordinate change and this step made the
+        // forces current without booking perturbed_pe - unperturbed_pe
+        if (!h->forces_valid || h->work_pending) external_work_eval(h, false);
         // one integrator step = main pass + optional extra propagation passes
         const int ls_after = h->lambda_step + h->n_H;
         const double lam_after = (double)ls_after / (double)h->ic.n_lambda_steps;
@@ -1648,6 +1669,56 @@ int bl_minimize(bl_handle* h, int max_iterations, double tolerance) {
 }
 
 // ---- introspection ----------------------------------------------------------------------------------------------
+}  // extern "C"
+
+// FP32 FMA throughput microbenchmark: the roofline denominator of the pair kernel (MEASURED_PEAKS.json carries HBM and
+// bf16 tensor figures only).  16 independent FMA chains per thread, 8 warps x 8 CTAs per SM, no memory traffic.
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+    float x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = fmaf(x[k], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += x[k];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;      // never true: keeps the chains alive
+}
+
+extern "C" {
+
+int bl_measure_fp32_peak(int device, double* tflops) {
+    if (!tflops) return BL_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return BL_ERR_NO_DEVICE; }
+    cudaSetDevice(device);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    float* out = nullptr;
+    const int blocks = n_sm * 8, threads = 256, iters = 4096;
+    if (cudaMalloc(&out, sizeof(float) * blocks * threads) != cudaSuccess) return BL_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 12; ++rep) {                 // first repeats warm the clocks up; best of the rest
+        cudaEventRecord(e0, 0);
+        k_fma_peak<<<blocks, threads>>>(out, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+        if (rep >= 2 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return BL_ERR_CUDA;
+    *tflops = best;
+    return BL_OK;
+}
+
 int bl_neighbor_pairs(bl_handle* h, int replica, int64_t* codes, size_t capacity, size_t* n_pairs) {
     if (!h || !n_pairs || replica < 0 || replica >= h->d.R) return BL_ERR_INVALID;
     cudaSetDevice(h->device);
@@ -1655,7 +1726,7 @@ int bl_neighbor_pairs(bl_handle* h, int replica, int64_t* codes, size_t capacity
     // coordinates changed by the host since the last evaluation: build a fresh list.  Otherwise report the list the
     // last evaluation used (tests use this to check the skin / prune / rebuild logic after dynamics).
     if (!h->forces_valid) {
-        { LaunchTimer t(h, -1); k_refresh_mirrors<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, 1); }
+        { LaunchTimer t(h, -1); k_refresh_mirrors<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, 1, -2); }
         eval_now(h, false);
     }
     long long* dcodes = nullptr;
@@ -1676,7 +1747,7 @@ int bl_neighbor_pairs(bl_handle* h, int replica, int64_t* codes, size_t capacity
     }
     cudaFree(dcodes);
     cudaFree(dn);
-    return check_flags(h);
+    return check_flags(h, false);
 }
 
 int bl_neighbor_stats(bl_handle* h, int replica, int64_t* n_tiles, int64_t* n_rebuilds) {

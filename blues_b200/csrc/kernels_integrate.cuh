@@ -656,6 +656,7 @@ __global__ void __launch_bounds__(64) k_integrate(Dev d, IntegratorConsts ic, In
                 }
                 g.step += 1;
                 g.prop = 1;
+                if (g.nan_flag) g.protocol_work = __longlong_as_double(0x7ff8000000000000LL);   // rejected by the Metropolis test
             }
         }
     }
@@ -713,9 +714,11 @@ __global__ void __launch_bounds__(128) k_noise(Dev d, IntegratorConsts ic, unsig
 // small state kernels
 // ---------------------------------------------------------------------------------------------------------
 // refresh the float mirrors from the double positions (after host writes / moves); request a rebuild
-__global__ void k_refresh_mirrors(Dev d, int request_rebuild) {
+// clear_replica: walker whose NaN / list-overflow latches are cleared (-1 all, -2 none)
+__global__ void k_refresh_mirrors(Dev d, int request_rebuild, int clear_replica) {
     const int r = blockIdx.y;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == 0 && (clear_replica == -1 || clear_replica == r)) { d.g[r].nan_flag = 0; d.g[r].item_overflow = 0; }
     if (a >= d.N) return;
     const double4 p = d.pos[(size_t)r * d.N + a];
     const float4 pf = wrapped_mirror(d, p.x, p.y, p.z, d.charge[a]);
@@ -1016,6 +1019,7 @@ __global__ void k_accept(Dev d, double kT, const double* correction, int* accept
     if (r >= d.R) return;
     Globals& g = d.g[r];
     double w = -(g.protocol_work + g.shadow_work) / kT;
+    if (g.nan_flag) w = __longlong_as_double(0x7ff8000000000000LL);
     Philox4 u = philox4x32_10(0u, g.accept_counter, (uint32_t)r, STREAM_ACCEPT, (uint32_t)seed, (uint32_t)(seed >> 32));
     const double lu = log(u01(u.x));
     if (!isnan(w) && correction) w += correction[r];

@@ -9,6 +9,7 @@ OpenMM does; ``setPositions``/``setVelocities`` copy in.  Each ``Context`` owns 
 address walker 0 unless ``replica=`` is given.
 """
 import logging
+import os
 import time as _time
 import numpy as np
 
@@ -195,7 +196,13 @@ class Context(object):
             n_replicas = int(self._properties.get('Replicas', 1))
         self._n_replicas = int(n_replicas)
         self._topo = system.flatten()
-        seed = getattr(integrator, '_seed', 0) or 0
+        # OpenMM semantics: seed 0 asks for a fresh random seed per Context (independent runs, and the md / alch / ncmc
+        # contexts of one job, must not share their thermostat noise); the seed in use is reported by
+        # integrator.getRandomNumberSeed()
+        seed = int(getattr(integrator, '_seed', 0) or 0)
+        if seed == 0:
+            seed = (int.from_bytes(os.urandom(8), 'little') >> 1) or 1
+            integrator._seed = seed
         self._engine = _native.Engine(self._topo, device=dev, n_replicas=self._n_replicas, seed=seed)
         self._time = 0.0
         self._molecules = None
@@ -206,7 +213,7 @@ class Context(object):
                 if isinstance(f, MonteCarloBarostat) and self._topo['nb_method'] != 0:
                     from .barostat import MonteCarloBarostatDriver
                     self._barostat = MonteCarloBarostatDriver(self._topo, f.pressure, f.temperature, f.frequency,
-                                                              seed=(seed or None))
+                                                              seed=seed % (2 ** 32))
         integrator._bind(self)
 
     # -- accessors ---------------------------------------------------------------------------------
@@ -308,6 +315,20 @@ class Context(object):
         return State(pos, vel, frc, pe, ke, box, self._time, params)
 
 
+def chunk_limit(reporters, simulation):
+    """Steps until the next listed frame index of any ``frame_indices`` reporter that is not reporting right now
+    (None: no such reporter).  Keeps device-resident chunks from jumping over an explicitly requested frame."""
+    best = None
+    for rep in reporters:
+        fn = getattr(rep, 'stepsToNextFrameIndex', None)
+        if fn is None:
+            continue
+        n = fn(simulation)
+        if n is not None and n > 0 and (best is None or n < best):
+            best = n
+    return best
+
+
 class Simulation(object):
     """``simtk.openmm.app.Simulation`` stand-in: steps the context in chunks bounded by the reporters'
     ``describeNextReport`` so no host round-trip happens between report steps."""
@@ -341,6 +362,11 @@ class Simulation(object):
                 if 0 < r[0] <= nextSteps:
                     nextSteps = r[0]
                     anyReport = True
+            # reporters with explicit frame_indices answer -1 until currentStep is a listed index (reference semantics,
+            # blues/reporters.py:362-367, written for a one-step-at-a-time loop): stop the chunk there
+            limit = chunk_limit(self.reporters, self)
+            if limit is not None and limit < nextSteps:
+                nextSteps, anyReport = limit, False
             self.integrator.step(nextSteps)
             self.currentStep += nextSteps
             if anyReport:

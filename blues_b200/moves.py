@@ -514,11 +514,14 @@ class WaterTranslationMove(Move):
         return pos, vel, xyz, box, numpy.asarray(com, float)
 
     # ---- device path ------------------------------------------------------------------------------------
-    def _device(self, context):
-        return (self.on_device and hasattr(context, '_engine')
-                and type(self).move is WaterTranslationMove.move
+    def _hooks_on_device(self):
+        # the three hooks share per-walker device state (sphere centre, go flag): all of them run there or none does
+        return (self.on_device and type(self).move is WaterTranslationMove.move
                 and type(self).beforeMove is WaterTranslationMove.beforeMove
                 and type(self).afterMove is WaterTranslationMove.afterMove)
+
+    def _device(self, context):
+        return self._hooks_on_device() and hasattr(context, '_engine')
 
     def _descriptor(self, kind, with_waters=False):
         d = dict(kind=kind, step=0, atoms=list(self.atom_indices),
@@ -532,7 +535,7 @@ class WaterTranslationMove(Move):
 
     def device_move(self):
         """Descriptor of the on-device translation for ``bl_ncmc_run`` (None on the host path)."""
-        if not self.on_device or type(self).move is not WaterTranslationMove.move:
+        if not self._hooks_on_device():
             return None
         return self._descriptor(_native.BL_MOVE_WATER_TRANSLATE)
 

@@ -120,6 +120,15 @@ class _Periodic(object):
             return 1 if simulation.currentStep in self.frame_indices else -1
         return self._reportInterval - simulation.currentStep % self._reportInterval
 
+    def stepsToNextFrameIndex(self, simulation):
+        """Distance from ``currentStep`` to the next listed frame index (0: reporting now; None: no index ahead or
+        interval schedule).  ``describeNextReport`` keeps the reference's 1 / -1 answer; the chunked steppers
+        (``mm.Simulation._simulate``, ``BLUESSimulation._run_with_device_move``) use this to stop at listed frames."""
+        if not self.frame_indices:
+            return None
+        ahead = [i - simulation.currentStep for i in self.frame_indices if i >= simulation.currentStep]
+        return min(ahead) if ahead else None
+
 
 def _remaining(total, initial, elapsed_s, elapsed_steps):
     if elapsed_steps == 0:

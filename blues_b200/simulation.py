@@ -160,21 +160,29 @@ class SimulationFactory(object):
         return system
 
     @classmethod
-    def generateIntegrator(cls, temperature=300 * unit.kelvin, dt=0.002 * unit.picoseconds, friction=1, **kwargs):
-        """Langevin integrator of the MD / alch Simulations (``blues/simulation.py:628-648``)."""
-        return openmm.LangevinIntegrator(temperature, friction, dt)
+    def generateIntegrator(cls, temperature=300 * unit.kelvin, dt=0.002 * unit.picoseconds, friction=1, seed=None,
+                           **kwargs):
+        """Langevin integrator of the MD / alch Simulations (``blues/simulation.py:628-648``).  ``seed`` (an addition:
+        YAML ``simulation: seed:``) fixes the Philox key; without it every Context draws its own, like OpenMM."""
+        integrator = openmm.LangevinIntegrator(temperature, friction, dt)
+        if seed:
+            integrator.setRandomNumberSeed(int(seed))
+        return integrator
 
     @classmethod
     def generateNCMCIntegrator(cls, nstepsNC=None, alchemical_functions={
             'lambda_sterics': 'min(1, (1/0.3)*abs(lambda-0.5))',
             'lambda_electrostatics': 'step(0.2-lambda) - 1/0.2*lambda*step(0.2-lambda) + 1/0.2*(lambda-0.8)*step(lambda-0.8)'},
             splitting="H V R O R V H", temperature=300 * unit.kelvin, dt=0.002 * unit.picoseconds, nprop=1,
-            propLambda=0.3, **kwargs):
+            propLambda=0.3, seed=None, **kwargs):
         """NCMC integrator with the reference's defaults (``blues/simulation.py:650-705``); note that, as in the
         reference, ``friction`` is not forwarded (collision rate stays 1/ps)."""
-        return AlchemicalExternalLangevinIntegrator(alchemical_functions=alchemical_functions, splitting=splitting,
-                                                    temperature=temperature, nsteps_neq=nstepsNC, timestep=dt,
-                                                    nprop=nprop, prop_lambda=propLambda)
+        integrator = AlchemicalExternalLangevinIntegrator(alchemical_functions=alchemical_functions, splitting=splitting,
+                                                          temperature=temperature, nsteps_neq=nstepsNC, timestep=dt,
+                                                          nprop=nprop, prop_lambda=propLambda)
+        if seed:
+            integrator.setRandomNumberSeed(int(seed) + 2)      # md, alch and ncmc contexts use distinct keys
+        return integrator
 
     @classmethod
     def generateSimFromStruct(cls, structure, system, integrator, platform=None, properties={}, **kwargs):
@@ -209,8 +217,11 @@ class SimulationFactory(object):
             logger.info('MD simulation will be {} NVT.'.format(cfg['temperature']))
         # the MD leg and the energy-only copy used by the alchemical correction share the MD system
         self.integrator = self.generateIntegrator(**cfg)
+        alch_integrator = self.generateIntegrator(**cfg)
+        if cfg.get('seed'):
+            alch_integrator.setRandomNumberSeed(int(cfg['seed']) + 1)
         self.md, self.alch = (self.generateSimFromStruct(self._structure, self._system, integ, **cfg)
-                              for integ in (self.integrator, self.generateIntegrator(**cfg)))
+                              for integ in (self.integrator, alch_integrator))
         if 'moveStep' not in cfg:
             logger.warning('Did not find `moveStep` in configuration. Checking NCMC paramters')
             cfg.update(utils.calculateNCMCSteps(**cfg))
@@ -361,6 +372,9 @@ class BLUESSimulation(object):
                 r = rep.describeNextReport(sim)
                 if 0 < r[0] < chunk:
                     chunk = r[0]
+            limit = openmm.chunk_limit(sim.reporters, sim)
+            if limit is not None and limit < chunk:
+                chunk = limit
             if done <= moveStep < done + chunk:
                 m = dict(device_move)
                 m['step'] = moveStep - done

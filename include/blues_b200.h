@@ -192,6 +192,9 @@ int bl_use_graphs(bl_handle* h, int on);           /* CUDA-graph replay of the s
 void* bl_stream(bl_handle* h);                     /* cudaStream_t the handle launches on                */
 int bl_synchronize(bl_handle* h);
 const char* bl_version(void);
+/* FP32 FMA throughput of the device measured by a register-only microbenchmark (TFLOP/s, best of 10 launches):
+ * the roofline denominator bench.py reports the pair kernel against. */
+int bl_measure_fp32_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -29,8 +29,16 @@ def load():
         lib.orc_get.argtypes = [C.c_void_p, C.c_char_p]
         lib.orc_set_lambda.argtypes = [C.c_void_p, C.c_double, C.c_double]
         lib.orc_num_threads.restype = C.c_int
+        lib.orc_set_num_threads.argtypes = [C.c_int]
+        lib.orc_set_fast.argtypes = [C.c_void_p, C.c_int]
         _lib = lib
     return _lib
+
+
+def set_threads(n):
+    """OpenMP threads used by oracles created from now on (torchrun exports OMP_NUM_THREADS=1)."""
+    load().orc_set_num_threads(int(n))
+    return load().orc_num_threads()
 
 
 def _p(a):
@@ -87,6 +95,11 @@ class COracle(object):
 
     def reset(self):
         self.lib.orc_reset(self.h)
+
+    def set_fast(self, on=True):
+        """One full evaluation per coordinate set, alchemical pairs re-evaluated on lambda changes (bench context row:
+        the lambda-separable evaluation the engine uses; same trajectory and work as the 3-evaluation program)."""
+        self.lib.orc_set_fast(self.h, 1 if on else 0)
 
     def get(self, name):
         return self.lib.orc_get(self.h, name.encode())

@@ -59,6 +59,10 @@ typedef struct orc_handle {
     int nthreads;
     double* Fthr;               /* per-thread force buffers */
     int cache_valid; double cache_E; double* cache_F;   /* evaluation at the current (x, lambda) */
+    /* "optimised CPU" mode (bench context row, not the reference's semantics): one full evaluation per coordinate set,
+     * lambda changes re-evaluate only the pairs that involve alchemical atoms (the lambda-separable form the engine uses) */
+    int fast, xcache_valid; double env_E; double* env_F; double* alch_F;
+    int* apairs; long n_apairs, apairs_cap;
 } orc_handle;
 
 /* ------------------------------------------------------------------------------------------------ philox */
@@ -288,6 +292,16 @@ static void build_list(orc_handle* h, const double* x) {
     free(cnt); free(head); free(cell); free(order);
     memcpy(h->x_ref, x, sizeof(double) * 3 * N);
     h->nl_valid = 1;
+    if (h->fast) {
+        h->n_apairs = 0;
+        for (int i = 0; i < N; ++i)
+            for (int k = h->nl_ptr[i]; k < h->nl_ptr[i + 1]; ++k) {
+                int j = h->nl_idx[k];
+                if (!h->is_alch[i] && !h->is_alch[j]) continue;
+                if (h->n_apairs + 1 > h->apairs_cap) { h->apairs_cap = h->apairs_cap * 2 + 1024; h->apairs = (int*)realloc(h->apairs, sizeof(int) * 2 * h->apairs_cap); }
+                h->apairs[2 * h->n_apairs] = i; h->apairs[2 * h->n_apairs + 1] = j; h->n_apairs++;
+            }
+    }
 }
 static void ensure_list(orc_handle* h, const double* x) {
     if (h->nl_valid && h->periodic) {
@@ -502,8 +516,69 @@ static void update_alch(orc_handle* h) {
 }
 /* OpenMM computes energy and forces together and keeps them while positions and parameters are unchanged
  * (CustomIntegrator force/energy validity): the reference costs 3 evaluations per step, so does this. */
+/* alchemical terms only (softcore sterics, lambda-scaled direct-space electrostatics, alchemical exceptions): the same
+ * formulas as the pair loop of orc_energy_forces, over the pairs of the current Verlet list that involve an alchemical atom */
+static double alch_only(orc_handle* h, const double* x, double lam_s, double lam_e, double* F) {
+    const bl_topology* t = &h->t;
+    const double rc2 = h->periodic ? t->cutoff * t->cutoff : 1e300, alpha = t->ewald_alpha;
+    const double krf = (t->nb_method == 2) ? (1.0 / (t->cutoff * t->cutoff * t->cutoff)) * (78.3 - 1) / (2 * 78.3 + 1) : 0;
+    const double crf = (t->nb_method == 2) ? (1.0 / t->cutoff) * 3 * 78.3 / (2 * 78.3 + 1) : 0;
+    memset(F, 0, sizeof(double) * 3 * h->N);
+    double e = 0;
+    for (long p = 0; p < h->n_apairs; ++p) {
+        const int i = h->apairs[2 * p], j = h->apairs[2 * p + 1];
+        double d[3] = {x[3 * i] - x[3 * j], x[3 * i + 1] - x[3 * j + 1], x[3 * i + 2] - x[3 * j + 2]};
+        minimg(h, d);
+        const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        if (r2 >= rc2) continue;
+        const double r = sqrt(r2);
+        double fr = 0;
+        int both = h->is_alch[i] && h->is_alch[j];
+        double sa = 0.5 * ((h->is_alch[i] ? h->asig[i] : t->sigma[i]) + (h->is_alch[j] ? h->asig[j] : t->sigma[j]));
+        double ea = sqrt((h->is_alch[i] ? h->aeps[i] : t->epsilon[i]) * (h->is_alch[j] ? h->aeps[j] : t->epsilon[j]));
+        double qa = (h->is_alch[i] ? h->aq[i] : t->charge[i]) * (h->is_alch[j] ? h->aq[j] : t->charge[j]);
+        double ls = (both && !t->annihilate_sterics) ? 1.0 : lam_s, le = (both && !t->annihilate_electrostatics) ? 1.0 : lam_e;
+        if (ea > 0) { double f2; e += softcore(r, sa, ea, ls, t->softcore_alpha, t->softcore_a, t->softcore_b, t->softcore_c, &f2); fr += f2; }
+        double kq = KE_COUL * qa * le;
+        if (kq != 0) {
+            if (h->pme) { double ar = alpha * r, erc = erfc(ar); e += kq * erc / r; fr += kq * (erc / r + TWO_OVER_SQRT_PI * alpha * exp(-ar * ar)) / r2; }
+            else if (t->nb_method == 2) { e += kq * (1 / r + krf * r2 - crf); fr += kq * (1 / (r * r2) - 2 * krf); }
+            else { e += kq / r; fr += kq / (r * r2); }
+        }
+        for (int q = 0; q < 3; ++q) { F[3 * i + q] += fr * d[q]; F[3 * j + q] -= fr * d[q]; }
+    }
+    for (int k = 0; k < t->n_alch_exc; ++k) {
+        int i = t->alch_exc_pairs[2 * k], j = t->alch_exc_pairs[2 * k + 1];
+        int both = h->is_alch[i] && h->is_alch[j];
+        double ls = (both && !t->annihilate_sterics) ? 1.0 : lam_s, le = (both && !t->annihilate_electrostatics) ? 1.0 : lam_e;
+        double d[3] = {x[3 * i] - x[3 * j], x[3 * i + 1] - x[3 * j + 1], x[3 * i + 2] - x[3 * j + 2]};
+        minimg(h, d);
+        double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2], r = sqrt(r2), fr = 0;
+        if (t->alch_exc_eps[k] != 0) e += softcore(r, t->alch_exc_sigma[k], t->alch_exc_eps[k], ls, t->softcore_alpha, t->softcore_a, t->softcore_b, t->softcore_c, &fr);
+        double kq = KE_COUL * t->alch_exc_qq[k] * le;
+        e += kq / r; fr += kq / (r * r2);
+        for (int q = 0; q < 3; ++q) { F[3 * i + q] += fr * d[q]; F[3 * j + q] -= fr * d[q]; }
+    }
+    return e;
+}
 static void evaluate(orc_handle* h, const double* x) {
     if (h->cache_valid) return;
+    if (h->fast) {
+        if (!h->xcache_valid) {
+            const double full = orc_energy_forces(h, x, h->lam_s, h->lam_e, h->cache_F, NULL);
+            const double ea = alch_only(h, x, h->lam_s, h->lam_e, h->alch_F);
+            h->env_E = full - ea;
+            for (int a = 0; a < 3 * h->N; ++a) h->env_F[a] = h->cache_F[a] - h->alch_F[a];
+            h->cache_E = full;
+            h->xcache_valid = 1;
+        } else {
+            const double ea = alch_only(h, x, h->lam_s, h->lam_e, h->alch_F);
+            h->cache_E = h->env_E + ea;
+            for (int a = 0; a < 3 * h->N; ++a) h->cache_F[a] = h->env_F[a] + h->alch_F[a];
+        }
+        h->cache_valid = 1;
+        return;
+    }
     h->cache_E = orc_energy_forces(h, x, h->lam_s, h->lam_e, h->cache_F, NULL);
     h->cache_valid = 1;
 }
@@ -534,7 +609,7 @@ static void one_pass(orc_handle* h, double* x, double* v) {
             memcpy(x0, x, sizeof(double) * 3 * N);
             for (int a = 0; a < N; ++a) if (h->invm[a] > 0) for (int q = 0; q < 3; ++q) x[3 * a + q] += hh * v[3 * a + q];
             memcpy(x1, x, sizeof(double) * 3 * N);
-            h->cache_valid = 0;
+            h->cache_valid = 0; h->xcache_valid = 0;
             shake(h, x, x0);
             for (int a = 0; a < 3 * N; ++a) v[a] += (x[a] - x1[a]) / hh;
             rattle(h, x, v);
@@ -565,14 +640,14 @@ static void one_pass(orc_handle* h, double* x, double* v) {
 }
 
 void orc_step(orc_handle* h, double* x, double* v, int n) {
-    h->cache_valid = 0;      /* the caller may have changed x between calls */
+    h->cache_valid = 0; h->xcache_valid = 0;      /* the caller may have changed x between calls */
     for (int i = 0; i < n; ++i) {
         if (h->step == 0) {
             h->perturbed_pe = h->unperturbed_pe = energy(h, x);
             double* x0 = (double*)dup_mem(x, sizeof(double) * 3 * h->N);
             shake(h, x, x0); free(x0);
             rattle(h, x, v);
-            h->cache_valid = 0;
+            h->cache_valid = 0; h->xcache_valid = 0;
             h->protocol_work = 0; h->lambda = 0; h->lambda_step = 0; update_alch(h);
         }
         if (h->step < h->nsteps) {
@@ -618,6 +693,24 @@ int orc_num_threads(void) {
     return omp_get_max_threads();
 #else
     return 1;
+#endif
+}
+/* launchers such as torchrun export OMP_NUM_THREADS=1: the caller states the thread count explicitly (before orc_create,
+   which sizes the per-thread force buffers) */
+/* bench context row: one force evaluation per step (lambda-separable); call before the first step */
+void orc_set_fast(orc_handle* h, int on) {
+    h->fast = on != 0;
+    h->nl_valid = 0; h->cache_valid = 0; h->xcache_valid = 0;
+    if (h->fast && !h->env_F) {
+        h->env_F = (double*)malloc(sizeof(double) * 3 * h->N);
+        h->alch_F = (double*)malloc(sizeof(double) * 3 * h->N);
+    }
+}
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
 #endif
 }
 

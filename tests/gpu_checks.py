@@ -18,27 +18,38 @@ from blues_b200.structure import Structure  # noqa: E402
 from blues_b200.alchemy import AbsoluteAlchemicalFactory, AlchemicalRegion  # noqa: E402
 from blues_b200 import _native  # noqa: E402
 
-DEFAULT_FUNCS = {
-    'lambda_sterics': 'min(1, (1/0.3)*abs(lambda-0.5))',
-    'lambda_electrostatics': 'step(0.2-lambda) - 1/0.2*lambda*step(0.2-lambda) + 1/0.2*(lambda-0.8)*step(lambda-0.8)'}
-
-CASES = {
-    'tol_parm': dict(kw=dict(nonbondedMethod='PME', nonbondedCutoff=8.0 * u.angstroms, constraints='HBonds'),
-                     alch=list(range(15))),
-    'wat_divaline': dict(kw=dict(nonbondedMethod='PME', nonbondedCutoff=10.0 * u.angstroms, constraints='HBonds',
-                                 ewaldErrorTolerance=0.005), alch=list(range(16, 35))),
-    'vac_divaline': dict(kw=dict(nonbondedMethod='NoCutoff', constraints='HBonds'), alch=list(range(16, 35))),
-    't4l_surrogate': dict(kw=dict(nonbondedMethod='PME', nonbondedCutoff=10.0 * u.angstroms, constraints='HBonds',
-                                  hydrogenMass=3.024 * u.dalton, ewaldErrorTolerance=0.005),
-                          alch=list(range(2634, 2649))),
-}
+from blues_b200.workloads import CASES, DEFAULT_FUNCS, tile_structure  # noqa: E402,F401
 
 
-def load_case(name, alchemical=False, **overrides):
+def far_residue_atoms(s, center_atoms, distance_nm):
+    """Atoms of every residue that has no atom within ``distance_nm`` of the centre atoms (periodic): the complement of
+    the reference's ``:LIG<:d`` residue selection (blues/simulation.py:395-480), usable on fixtures without a protein."""
+    x = np.asarray(s.coordinates, float) * 0.1
+    box = np.asarray(s.box[:3], float) * 0.1
+    res = np.asarray(s.to_arrays()['atom_residue'])
+    near = np.zeros(len(x), bool)
+    for c in center_atoms:
+        d = x - x[c]
+        d -= box * np.round(d / box)
+        near |= (np.sum(d * d, axis=1) <= distance_nm ** 2)
+    keep = np.zeros(res.max() + 1, bool)
+    keep[res[near]] = True
+    return np.nonzero(~keep[res])[0]
+
+
+def load_case(name, alchemical=False, freeze_beyond_nm=None, restrain=None, **overrides):
+    """freeze_beyond_nm: zero the masses (utils.zero_masses, as freeze_radius does) of all residues farther than that from
+    the alchemical atoms; restrain: Amber mask for SystemFactory.restrain_positions."""
     s = Structure.load_npz(os.path.join(GOLDEN, name + '.npz'))
     kw = dict(CASES[name]['kw'])
     kw.update(overrides)
     system = s.createSystem(**kw)
+    if restrain:
+        from blues_b200.simulation import SystemFactory
+        system = SystemFactory.restrain_positions(s, system, selection=restrain, weight=5.0)
+    if freeze_beyond_nm is not None:
+        from blues_b200 import utils
+        system = utils.zero_masses(system, far_residue_atoms(s, CASES[name]['alch'], freeze_beyond_nm))
     if alchemical:
         system = AbsoluteAlchemicalFactory().create_alchemical_system(
             system, AlchemicalRegion(alchemical_atoms=CASES[name]['alch']))
@@ -180,38 +191,6 @@ def compare_neighbors_dynamic(name, steps=60, n_replicas=2, dt=0.004, minimize=0
     return out
 
 
-def tile_structure(s, reps):
-    """Replicate a periodic Structure reps = (nx, ny, nz) times along its box vectors (orthorhombic)."""
-    d = s.to_arrays()
-    n = len(d['atom_names'])
-    nres = len(d['residue_names'])
-    nx, ny, nz = reps
-    ncopy = nx * ny * nz
-    out = {}
-    for k in ('atomic_numbers', 'masses', 'charges', 'lj_sigma', 'lj_epsilon', 'atom_names', 'atom_types'):
-        out[k] = np.tile(d[k], ncopy)
-    out['residue_names'] = np.tile(d['residue_names'], ncopy)
-    rp = np.asarray(d['residue_pointers'])
-    if len(rp) == nres + 1:
-        out['residue_pointers'] = np.concatenate([rp[:-1] + c * n for c in range(ncopy)] + [[ncopy * n]])
-    else:
-        out['residue_pointers'] = np.concatenate([rp + c * n for c in range(ncopy)])
-    out['atom_residue'] = np.concatenate([np.asarray(d['atom_residue']) + c * nres for c in range(ncopy)])
-    for idx, extra in (('bonds', ('bond_k', 'bond_r0')), ('angles', ('angle_k', 'angle_t0')),
-                       ('dihedrals', ('dihedral_k', 'dihedral_per', 'dihedral_phase', 'dihedral_scee', 'dihedral_scnb',
-                                      'dihedral_ignore_end', 'dihedral_improper'))):
-        a = np.asarray(d[idx])
-        out[idx] = np.concatenate([a + c * n for c in range(ncopy)]) if len(a) else a
-        for e in extra:
-            out[e] = np.tile(d[e], ncopy)
-    box = np.asarray(d['box'], float)
-    shifts = [(i, j, k) for i in range(nx) for j in range(ny) for k in range(nz)]
-    out['coordinates'] = np.concatenate([d['coordinates'] + np.asarray(sh) * box[:3] for sh in shifts])
-    out['box'] = np.concatenate([box[:3] * np.asarray(reps), box[3:]])
-    from blues_b200.structure import Structure as _S
-    return _S.from_arrays(out)
-
-
 def compare_tiled(name='tol_parm', reps=(4, 4, 5), verbose=False, **overrides):
     """Forces, energy and neighbour sets on a tiled copy of a fixture (> 65 535 atoms: 32-bit list indices, larger
     PME grid, many cells) against the oracle's C twin (forces) and the numpy oracle (pairs)."""
@@ -269,6 +248,51 @@ def make_ncmc_pair(name, nsteps=10, dt=0.002, splitting='H V R O R V H', nprop=1
     orc.x = x.copy()
     orc.set_velocities_to_temperature(temperature, 0)
     return eng, orc, topo
+
+
+def make_ncmc_pair_c(name, nsteps=10, dt=0.002, splitting='H V R O R V H', seed=7, temperature=300.0, n_replicas=1,
+                     minimize=0, **overrides):
+    """Engine and the oracle's C twin (fast enough for long protocols on solvated systems) initialised identically."""
+    from oracle.c_oracle import COracle
+    s, system, topo, x = load_case(name, True, **overrides)
+    n_H = splitting.split().count('H')
+    ls_tab, le_tab = lambda_tables(nsteps, n_H)
+    eng = _native.Engine(topo, n_replicas=n_replicas, seed=seed)
+    eng.set_ncmc_integrator(temperature, 1.0, dt, splitting, nsteps, 1, 0.2, 0.8, ls_tab, le_tab)
+    eng.set_positions(x)
+    if minimize:
+        eng.minimize(minimize, 10.0)
+        x = eng.get_positions(0)
+        eng.set_positions(x)
+    eng.velocities_to_temperature(temperature)
+    orcs = []
+    for r in range(n_replicas):
+        c = COracle(topo, ls_tab, le_tab, splitting, temperature, 1.0, dt, nsteps, 1, 0.2, 0.8, seed=seed, replica=r)
+        c.set_state(x)
+        c.velocities_to_temperature(temperature)
+        orcs.append(c)
+    return eng, orcs, topo, x
+
+
+def compare_trajectory_c(name, nsteps=50, stride=10, verbose=False, **kw):
+    """Noisy trajectory of the engine against the C oracle, compared every ``stride`` steps."""
+    eng, orcs, topo, x0 = make_ncmc_pair_c(name, nsteps=nsteps, **kw)
+    orc = orcs[0]
+    dv0 = float(np.max(np.abs(eng.get_velocities(0) - orc.v)))
+    rows = []
+    for k in range(0, nsteps, stride):
+        eng.ncmc_run(stride)
+        orc.step(stride)
+        xe, ve = eng.get_positions(0), eng.get_velocities(0)
+        rows.append(dict(step=k + stride, dx=float(np.max(np.abs(xe - orc.x))), dv=float(np.max(np.abs(ve - orc.v))),
+                         work_engine=eng.get_global('protocol_work'), work_oracle=orc.get('protocol_work')))
+        if verbose:
+            print('   step %3d  max|dx| %.2e  max|dv| %.2e  work engine %.6f oracle %.6f' %
+                  (rows[-1]['step'], rows[-1]['dx'], rows[-1]['dv'], rows[-1]['work_engine'], rows[-1]['work_oracle']))
+    mass = np.asarray(topo['mass'], float)
+    out = dict(dv0=dv0, rows=rows, x0=x0, x_engine=eng.get_positions(0), frozen=np.nonzero(mass == 0)[0], topo=topo)
+    eng.close()
+    return out
 
 
 def compare_trajectory(name, nsteps=6, verbose=False, **kw):

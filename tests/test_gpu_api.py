@@ -418,3 +418,77 @@ def test_md_leg_with_monte_carlo_barostat(structure):
     assert ok is False
     assert np.array_equal(md.context._engine.get_box(), b_before)
     assert np.allclose(md.context._engine.get_positions(0), x_before, rtol=0, atol=0)
+
+
+def test_frame_indices_reporter_without_an_interval_reporter(structure, tmp_path):
+    """a reporter scheduled by explicit frame_indices (blues/reporters.py:362-367) must see every listed frame
+    even when no interval-1 reporter forces single steps — the chunked stepper stops at the listed indices."""
+    from blues_b200.reporters import NetCDF4Reporter
+    from scipy.io import netcdf_file
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, system_cfg())
+    cfg = sim_cfg()
+    cfg.update(nstepsNC=6, nstepsMD=2)
+    fname = os.path.join(str(tmp_path), 'frames.nc')
+    rep = NetCDF4Reporter(fname, frame_indices=[1, 3, 6], protocolWork=True, alchemicalLambda=True)
+    simulations = SimulationFactory(systems, MoveEngine(RandomLigandRotationMove(structure, 'LIG')), cfg,
+                                    ncmc_reporters=[rep])
+    b = BLUESSimulation(simulations)
+    b._md_sim.minimizeEnergy(maxIterations=50)
+    b._syncStatesMDtoNCMC()
+    b._stepNCMC(6, 3)
+    assert b._ncmc_sim.currentStep == 6
+    rep.close() if hasattr(rep, 'close') else None
+    nc = netcdf_file(fname, 'r', mmap=False)
+    lam = np.array(nc.variables['alchemicalLambda'][:], float)
+    nc.close()
+    assert len(lam) == 3                                            # frames after steps 1, 3 and 6
+    assert np.allclose(lam, [1 / 6.0, 3 / 6.0, 1.0], atol=1e-6)
+
+
+class _NaNMove(RandomLigandRotationMove):
+    """A host-path move that breaks one coordinate: the reference's flow then rejects the move and carries on."""
+
+    def move(self, context):
+        x = context.getState(getPositions=True).getPositions(asNumpy=True)
+        if getattr(self, 'poison', False):
+            x._value[self.atom_indices[0], 0] = np.nan
+        context.setPositions(x)
+        return context
+
+
+def test_blues_iteration_survives_a_nan_move(structure):
+    """after a NaN inside one NCMC leg `run()` must reject that move and keep iterating, as the
+    reference does (blues/simulation.py:1082-1094, 1130-1140), instead of failing every later state query."""
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, system_cfg())
+    cfg = sim_cfg()
+    cfg.update(nIter=1, nstepsNC=6, nstepsMD=2)
+    move = _NaNMove(structure, 'LIG', 3)
+    simulations = SimulationFactory(systems, MoveEngine(move), cfg)
+    b = BLUESSimulation(simulations)
+    b._md_sim.minimizeEnergy(maxIterations=50)
+    move.poison = True
+    b.run()
+    assert (b.accept, b.reject) == (0, 1)
+    x = b._md_sim.context.getState(getPositions=True).getPositions(asNumpy=True)._value
+    assert np.all(np.isfinite(x))
+    move.poison = False
+    b.run()
+    assert b.accept + b.reject == 2
+    assert np.isfinite(b._ncmc_sim.integrator.getGlobalVariableByName('protocol_work'))
+
+
+def test_contexts_draw_distinct_seeds_unless_one_is_configured(structure):
+    """seed 0 means a fresh seed per Context (OpenMM semantics); `seed` in the simulation config pins it."""
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, system_cfg())
+    sims = SimulationFactory(systems, MoveEngine(RandomLigandRotationMove(structure, 'LIG')), sim_cfg())
+    seeds = [s.integrator.getRandomNumberSeed() for s in (sims.md, sims.alch, sims.ncmc)]
+    assert all(seeds) and len(set(seeds)) == 3
+    cfg = sim_cfg()
+    cfg['seed'] = 1234
+    sims2 = SimulationFactory(systems, MoveEngine(RandomLigandRotationMove(structure, 'LIG')), cfg)
+    assert [s.integrator.getRandomNumberSeed() for s in (sims2.md, sims2.alch, sims2.ncmc)] == [1234, 1235, 1236]
+    v = [s.context.getState(getVelocities=True).getVelocities(asNumpy=True)._value for s in (sims2.md, sims2.alch)]
+    assert not np.array_equal(v[0], v[1])

@@ -266,3 +266,245 @@ def test_madelung_constant_of_rock_salt_on_the_engine():
     eng.close()
     assert ep[0] / (topo['n_atoms'] // 2) == pytest.approx(expect, rel=2e-3)
     assert np.max(np.abs(f)) < 2e-3 * abs(expect) / r0
+
+
+# ---- round 2: dynamic parity on solvated PME systems, frozen / restrained systems, full M1 protocol ensemble ----------
+
+def test_long_noisy_trajectory_on_solvated_pme_system():
+    """50 noisy NCMC steps of the solvated dipeptide (PME, SETTLE waters, 2591 atoms) against the oracle's C twin: the
+    float32 pair / PME arithmetic must not pull the trajectory or the accumulated work away from the float64 reference."""
+    out = gc.compare_trajectory_c('wat_divaline', nsteps=50, stride=10, dt=0.002, seed=17, minimize=100)
+    assert out['dv0'] < 1e-9
+    for r in out['rows']:
+        assert r['dx'] < 2e-4 and r['dv'] < 2e-2, r
+        assert abs(r['work_engine'] - r['work_oracle']) < 2e-3 * max(1.0, abs(r['work_oracle'])) + 2e-3, r
+
+
+@pytest.mark.parametrize('name,kw', [('tol_parm', dict(freeze_beyond_nm=0.6, minimize=100)),
+                                     ('wat_divaline', dict(freeze_beyond_nm=0.5, minimize=100)),
+                                     ('wat_divaline', dict(restrain='(@CA,C,N)', minimize=100))])
+def test_frozen_and_restrained_systems_match_oracle(name, kw):
+    """freeze_radius / freeze_atoms zero the masses (blues/simulation.py:364-480), restrain_positions adds the harmonic
+    CustomExternalForce (:319-362): forces, a 20-step noisy trajectory and the work against the oracle; frozen atoms keep
+    their coordinates bit for bit and carry zero velocity."""
+    from oracle.ncmc_oracle import ForceField
+    s, system, topo, x = gc.load_case(name, True, **{k: v for k, v in kw.items() if k != 'minimize'})
+    mass = np.asarray(topo['mass'], float)
+    if 'freeze_beyond_nm' in kw:
+        assert 0 < np.count_nonzero(mass == 0) < len(mass) - len(gc.CASES[name]['alch'])
+    else:
+        assert len(topo['restraint_atoms']) > 0
+    cmp_ = gc.compare_forces(name, alchemical=True, lam_index=3, nsteps=10, **{k: v for k, v in kw.items() if k != 'minimize'})
+    assert cmp_['energy_rel'] < ENERGY_TOL and cmp_['force_max_rel'] < FORCE_TOL
+    a, b = cmp_['terms']['restraint']
+    assert abs(a - b) <= 1e-6 * max(abs(b), 1.0) + 1e-6
+    out = gc.compare_trajectory_c(name, nsteps=20, stride=5, dt=0.002, seed=23, **kw)
+    for r in out['rows']:
+        assert r['dx'] < 5e-5 and r['dv'] < 5e-3, r
+        assert abs(r['work_engine'] - r['work_oracle']) < 1e-3 * max(1.0, abs(r['work_oracle'])) + 1e-3, r
+    fz = out['frozen']
+    if len(fz):
+        assert np.array_equal(out['x_engine'][fz], out['x0'][fz])
+
+
+def test_t4l_freeze_radius_variant_runs_with_frozen_atoms_untouched():
+    """The example's default variant (examples/rotmove_cuda.yml:42-45, docs/BLUES_tutorial.ipynb:718): freeze_radius 5 A
+    leaves 275 mobile atoms of 22 340; the engine integrates those, keeps the other 22 065 bit for bit and their
+    constraints satisfied, and its forces still match the oracle's on every atom."""
+    from blues_b200 import _native, unit
+    from blues_b200.simulation import SystemFactory
+    from oracle.c_oracle import COracle
+    s, system, topo, x = gc.load_case('t4l_surrogate', False)
+    system = SystemFactory.freeze_radius(s, system, freeze_distance=5.0 * unit.angstroms, freeze_center=':LIG',
+                                         freeze_solvent=':HOH,NA,CL,Cl-')
+    from blues_b200.alchemy import AbsoluteAlchemicalFactory, AlchemicalRegion
+    system = AbsoluteAlchemicalFactory().create_alchemical_system(
+        system, AlchemicalRegion(alchemical_atoms=gc.CASES['t4l_surrogate']['alch']))
+    topo = system.flatten()
+    mass = np.asarray(topo['mass'], float)
+    assert np.count_nonzero(mass == 0) == 22065
+    ls, le = gc.lambda_tables(5000)
+    eng = _native.Engine(topo, n_replicas=2, seed=3)
+    eng.set_ncmc_integrator(300.0, 1.0, 0.004, 'H V R O R V H', 5000, 1, 0.2, 0.8, ls, le)
+    eng.set_positions(x)
+    eng.minimize(30, 10.0)
+    x0 = eng.get_positions(0)
+    F = eng.get_forces(0)
+    Eo, Fo = COracle(topo, ls, le, nsteps_neq=5000).energy_forces(x0, ls[0], le[0])[:2]
+    fmax, frms = gc.rel_force_error(F, Fo)
+    assert fmax < FORCE_TOL
+    eng.velocities_to_temperature(300.0)
+    v = eng.get_velocities(0)
+    assert np.all(v[mass == 0] == 0.0) and np.any(v[mass > 0] != 0.0)
+    eng.ncmc_run(40)
+    for r in range(2):
+        xr = eng.get_positions(r)
+        assert np.array_equal(xr[mass == 0], x0[mass == 0])
+        assert not np.array_equal(xr[mass > 0], x0[mass > 0])
+        c = topo['constraints']
+        if len(c):
+            d = np.linalg.norm(xr[c[:, 0]] - xr[c[:, 1]], axis=1)
+            assert np.max(np.abs(d - topo['constraint_d']) / topo['constraint_d']) < 1e-6
+        assert np.isfinite(eng.get_global('protocol_work', r))
+    eng.close()
+
+
+def test_m1_full_protocol_ensemble_work_and_acceptance():
+    """North-star criterion 3 on M1 = BASELINE configs[0]: 64 walkers of toluene in TIP3P (TOL-parm, PME, HBonds),
+    the full nstepsNC = 100 protocol with the rotation at moveStep = 50, the alchemical correction and the Metropolis
+    test (blues/simulation.py:1039-1166).  Engine walkers and oracle walkers share seeds, noise streams and rotations:
+    per-walker work agrees while trajectories coincide, the work distributions are KS-indistinguishable and the
+    acceptance counts are consistent (binomial test)."""
+    from scipy.stats import ks_2samp, binomtest
+    from oracle import ncmc_oracle as orc
+    from oracle.c_oracle import COracle
+    from blues_b200 import _native
+    R, nsteps, move_step, seed, dt, T = 64, 100, 50, 4242, 0.002, 300.0
+    s, system_md, topo_md, x = gc.load_case('tol_parm', False)
+    _, _, topo, _ = gc.load_case('tol_parm', True)
+    ls, le = gc.lambda_tables(nsteps)
+    atoms = np.arange(15)
+    masses = np.asarray(topo_md['mass'], float)[atoms]
+    kT = orc.KB * T
+    eng = _native.Engine(topo, n_replicas=R, seed=seed)
+    eng.set_ncmc_integrator(T, 1.0, dt, 'H V R O R V H', nsteps, 1, 0.2, 0.8, ls, le)
+    eng.set_positions(x)
+    eng.minimize(200, 10.0)
+    x0 = eng.get_positions(0)
+    eng.set_positions(x0)                                    # every walker starts from the same relaxed frame
+    eng.velocities_to_temperature(T)
+    md = _native.Engine(topo_md, n_replicas=R, seed=seed + 1)
+    md.set_langevin_integrator(T, 1.0, dt)
+    md.set_positions(x0)
+    e_md0 = md.get_energy(True, False)[0]
+    e_nc0 = eng.get_energy(True, False)[0]
+    eng.ncmc_run(nsteps, dict(kind=_native.BL_MOVE_ROTATE, step=move_step, atoms=atoms, masses=masses))
+    w_gpu = np.array([eng.get_global('protocol_work', r) for r in range(R)])
+    e_nc1 = eng.get_energy(True, False)[0]
+    x1 = [eng.get_positions(r) for r in range(R)]
+    for r in range(R):
+        md.set_positions(x1[r], r)
+    e_md1 = md.get_energy(True, False)[0]
+    corr_gpu = -(e_nc0 - e_md0 + e_md1 - e_nc1) / kT
+    acc_gpu, logp_gpu, logu = eng.accept_reject(corr_gpu)
+    # oracle walkers
+    o_md = COracle(topo_md)
+    w_cpu, corr_cpu, acc_cpu, dx = [], [], [], []
+    for r in range(R):
+        c = COracle(topo, ls, le, 'H V R O R V H', T, 1.0, dt, nsteps, 1, 0.2, 0.8, seed=seed, replica=r)
+        c.set_state(x0)
+        c.velocities_to_temperature(T)
+        e0n = c.energy_forces(x0, ls[0], le[0])[0]
+        e0m = o_md.energy_forces(x0)[0]
+        c.step(move_step)
+        u0, u1, u2, _ = orc.philox_uniform4(seed, orc.STREAM_MOVE, r, 0, [0])
+        Rm = orc.rotation_matrix_from_quaternion(orc.quaternion_from_uniforms(u0[0], u1[0], u2[0]))
+        c.x = np.ascontiguousarray(orc.rotate_ligand(c.x, atoms, masses, Rm))
+        c.step(nsteps - move_step)
+        w_cpu.append(c.get('protocol_work'))
+        e1n = c.energy_forces(c.x, ls[-1], le[-1])[0]
+        e1m = o_md.energy_forces(c.x)[0]
+        corr_cpu.append(orc.alchemical_correction(e0n, e0m, e1m, e1n, kT))
+        lu = np.log(orc.philox_uniform4(seed, orc.STREAM_ACCEPT, r, 0, [0])[0][0])
+        assert logu[r] == pytest.approx(lu, rel=1e-12)
+        acc_cpu.append(orc.metropolis_accept(-w_cpu[-1] / kT, corr_cpu[-1], lu))
+        dx.append(float(np.max(np.abs(c.x - x1[r]))))
+    w_cpu, corr_cpu, acc_cpu = np.array(w_cpu), np.array(corr_cpu), np.array(acc_cpu, bool)
+    assert np.std(w_gpu) > 0
+    # (i) walker by walker: the float32 engine stays on the float64 oracle's trajectory through the whole protocol
+    assert np.median(dx) < 1e-3, (np.median(dx), np.max(dx))
+    assert np.median(np.abs(w_gpu - w_cpu)) < 0.05 * kT, np.abs(w_gpu - w_cpu)
+    # (ii) the alchemical correction (difference of four ~1e4 kJ/mol totals) to 1e-3 kT per walker where they coincide
+    same = np.asarray(dx) < 1e-4
+    assert same.sum() >= R // 2
+    assert np.max(np.abs(corr_gpu - corr_cpu)[same]) < 0.05, np.abs(corr_gpu - corr_cpu)[same]
+    # (iii) distributions and acceptance
+    assert ks_2samp(w_gpu, w_cpu).pvalue > 0.05
+    k_gpu, k_cpu = int(np.sum(acc_gpu)), int(np.sum(acc_cpu))
+    p_ref = min(max(k_cpu / R, 0.5 / R), 1 - 0.5 / R)
+    assert binomtest(k_gpu, R, p_ref).pvalue > 0.01, (k_gpu, k_cpu)
+    decided = np.abs((-w_cpu / kT + corr_cpu) - logu) > 0.1          # walkers whose decision is not on the edge
+    assert np.array_equal(acc_gpu.astype(bool)[decided], acc_cpu[decided])
+    eng.close()
+    md.close()
+
+
+def test_alchemical_correction_value_matches_oracle():
+    """`_computeAlchemicalCorrection` (blues/simulation.py:1100-1119) through the public API on TOL-parm: the value —
+    a difference of four totals of order 1e4 kJ/mol — against oracle.alchemical_correction on the same coordinates."""
+    import os
+    from oracle import ncmc_oracle as orc
+    from oracle.c_oracle import COracle
+    from blues_b200 import unit, utils
+    from blues_b200.structure import Structure
+    from blues_b200.simulation import SystemFactory, SimulationFactory, BLUESSimulation
+    from blues_b200.moves import RandomLigandRotationMove, MoveEngine
+    import tests.test_gpu_api as api
+    structure = Structure.load_npz(os.path.join(gc.GOLDEN, 'tol_parm.npz'))
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, api.system_cfg())
+    cfg = api.sim_cfg()
+    cfg.update(nstepsNC=20, seed=99)
+    simulations = SimulationFactory(systems, MoveEngine(RandomLigandRotationMove(structure, 'LIG')), cfg)
+    b = BLUESSimulation(simulations)
+    b._md_sim.minimizeEnergy(maxIterations=200)
+    b._syncStatesMDtoNCMC()
+    b._stepNCMC(20, 10)
+    corr = b._computeAlchemicalCorrection()
+    st = b.stateTable
+    x0 = st['md']['state0']['positions'].value_in_unit(unit.nanometers)
+    x1 = st['ncmc']['state1']['positions'].value_in_unit(unit.nanometers)
+    topo_md, topo_nc = systems.md.flatten(), systems.alch.flatten()
+    o_md, o_nc = COracle(topo_md), COracle(topo_nc)
+    e_md0, e_md1 = o_md.energy_forces(x0)[0], o_md.energy_forces(x1)[0]
+    e_nc0, e_nc1 = o_nc.energy_forces(x0, 1.0, 1.0)[0], o_nc.energy_forces(x1, 1.0, 1.0)[0]
+    kT = orc.KB * 300.0
+    want = orc.alchemical_correction(e_nc0, e_md0, e_md1, e_nc1, kT)
+    assert np.isfinite(corr)
+    assert corr == pytest.approx(want, abs=1e-3)                     # 1e-3 kT
+    # each of the four totals to 1e-6 relative
+    for got, ref in ((st['md']['state0']['potential_energy']._value, e_md0),
+                     (st['ncmc']['state0']['potential_energy']._value, e_nc0),
+                     (st['ncmc']['state1']['potential_energy']._value, e_nc1)):
+        assert got == pytest.approx(ref, rel=2e-6)
+
+
+def test_nan_in_one_ncmc_leg_is_rejected_and_the_next_iteration_recovers():
+    """a non-finite coordinate raises from the stepping call (OpenMM: 'Particle coordinate is nan'), the state
+    stays readable, the work reads NaN so the move can only be rejected, and fresh coordinates clear the latch."""
+    from blues_b200 import _native
+    eng, o, topo = gc.make_ncmc_pair('vac_divaline', nsteps=10, seed=9)
+    good = eng.get_positions(0)
+    bad = good.copy()
+    bad[3, 0] = np.nan
+    eng.set_positions(bad)
+    with pytest.raises(_native.EngineError, match='nan'):
+        eng.ncmc_run(2)
+    assert np.isnan(eng.get_global('protocol_work'))
+    eng.get_energy()                                          # state queries do not raise on the flagged walker
+    acc, logp, logu = eng.accept_reject()
+    assert acc[0] == 0
+    eng.reset_ncmc()
+    eng.set_positions(good)
+    eng.velocities_to_temperature(300.0)
+    eng.ncmc_run(4)
+    assert np.isfinite(eng.get_global('protocol_work')) and eng.get_global('step') == 4
+    eng.close()
+
+
+def test_energy_query_between_host_move_and_step_keeps_the_external_work():
+    """setPositions followed by getState(getEnergy=True) must not swallow perturbed_pe - unperturbed_pe."""
+    from oracle import ncmc_oracle as orc
+    eng, o, topo = gc.make_ncmc_pair('vac_divaline', nsteps=10, seed=9)
+    eng.ncmc_run(3)
+    o.step(3)
+    x = eng.get_positions(0)
+    x[20] += np.array([0.01, -0.02, 0.015])
+    eng.set_positions(x)
+    eng.get_energy()                                          # the query a user Move subclass might make
+    eng.get_forces(0)
+    o.x = x.copy()
+    eng.ncmc_run(2)
+    o.step(2)
+    assert eng.get_global('protocol_work') == pytest.approx(o.g['protocol_work'], rel=1e-4, abs=1e-4)
+    eng.close()

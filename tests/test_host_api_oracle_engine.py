@@ -109,3 +109,25 @@ def test_monte_carlo_simulation_driver(structure):
     assert mc.accept + mc.reject == 6
     after = simulations.md.context.getState(getPositions=True).getPositions(asNumpy=True)._value
     assert np.all(np.isfinite(after)) and not np.array_equal(before, after)
+
+
+def test_frame_indices_reporter(structure, tmp_path):
+    api.test_frame_indices_reporter_without_an_interval_reporter(structure, tmp_path)
+
+
+def test_distinct_seeds(structure):
+    api.test_contexts_draw_distinct_seeds_unless_one_is_configured(structure)
+
+
+def test_water_move_device_predicate_follows_all_three_hooks(structure):
+    """a subclass overriding one hook takes all three hooks (and the midpoint move) to the host path."""
+    from blues_b200 import unit
+    from blues_b200.moves import WaterTranslationMove
+
+    class Custom(WaterTranslationMove):
+        def beforeMove(self, context):
+            return context
+
+    kw = dict(protein_selection='(index 0) or (index 1)', radius=0.9 * unit.nanometers)
+    assert WaterTranslationMove(structure, **kw).device_move() is not None
+    assert Custom(structure, **kw).device_move() is None

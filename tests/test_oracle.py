@@ -290,3 +290,25 @@ def test_madelung_constant_of_rock_salt():
         # a perfect lattice: no net force on any ion
         f = COracle(topo).energy_forces(x)[1]
         assert np.max(np.abs(f)) < 1e-3 * abs(expect) / r0
+
+
+def test_c_oracle_one_evaluation_mode_is_the_same_trajectory():
+    """The bench's "optimised CPU" row (oracle/c_oracle.py: set_fast): one full evaluation per coordinate set plus the
+    alchemical pairs on lambda changes gives the trajectory and work of the reference's 3-evaluation program."""
+    from oracle.c_oracle import COracle
+    from blues_b200.workloads import lambda_tables
+    from tests import gpu_checks as gc
+    s, system, topo, x = gc.load_case('wat_divaline', True)
+    ls, le = lambda_tables(10)
+    out = []
+    for fast in (False, True):
+        c = COracle(topo, ls, le, 'H V R O R V H', 300.0, 1.0, 0.001, 10, 1, 0.2, 0.8, seed=5)
+        if fast:
+            c.set_fast(True)
+        c.set_state(x)
+        c.velocities_to_temperature(300.0)
+        c.step(6)
+        out.append((c.x.copy(), c.get('protocol_work'), c.get('n_evals')))
+    assert np.max(np.abs(out[0][0] - out[1][0])) < 1e-10
+    assert out[0][1] == pytest.approx(out[1][1], abs=1e-7)
+    assert out[1][2] < 0.5 * out[0][2]
