@@ -74,6 +74,7 @@ struct bl_handle {
     std::vector<double> host_tmp;
     double skin = 0.0; int cell_capacity = 0;
     int build_cq = 0, build_ctas = 0;
+    int pair_variant = 0;        // BLUES_B200_PAIR: 0 = k_pair, else k_pair2 <ewald, lanes, U> (see enqueue_eval)
     int graph_steps = 4;         // plain NCMC steps captured per CUDA graph
     bool pdl = true;             // programmatic dependent launch on the B -> flip -> A -> sort edges (BLUES_B200_PDL=0: off)
     // diagnostic timeline (BLUES_B200_TIMELINE=1): events recorded inside the step graphs, read after every replay
@@ -271,7 +272,47 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         else k_build_list<int><<<grid, 32, smem, st>>>(d, h->build_cq);
     }
     tl_mark(h, st, TL_BUILD);
-    {
+    if (h->pair_variant >= 1000) {
+        LaunchTimer t(h, BL_K_PAIR);
+        // 1000 + 100 * ewald + 10 * log2(lanes): cp.async ring (k_pair3)
+        const int ew = ((h->pair_variant / 100) % 10) && d.ewk_ok && d.nb_method == 4 ? 1 : 0;
+        const int lanes = 1 << ((h->pair_variant / 10) % 10);
+        dim3 grid(cdiv((long long)d.Npad * lanes, NL_BLOCK), R);
+#define P3C(M, E, T, L, W) k_pair3<M, E, T, L, W><<<grid, NL_BLOCK, 0, st>>>(d)
+#define P3B(M, E, T, L) if (ew) P3C(M, E, T, L, 1); else P3C(M, E, T, L, 0)
+#define P3A(M, E, T) if (lanes == 4) { P3B(M, E, T, 4); } else if (lanes == 16) { P3B(M, E, T, 16); } else { P3B(M, E, T, 8); }
+#define P30(M, E) if (d.nl_u16) { P3A(M, E, unsigned short) } else { P3A(M, E, int) }
+#define P3E(M) if (energy) { P30(M, true) } else { P30(M, false) }
+        if (d.nb_method == 4) { P3E(NB_PME) }
+        else if (d.nb_method == 2) { P3E(NB_RF) }
+        else { P3E(NB_NOCUT) }
+#undef P3C
+#undef P3B
+#undef P3A
+#undef P30
+#undef P3E
+    } else if (h->pair_variant > 0) {
+        LaunchTimer t(h, BL_K_PAIR);
+        // variant = 100 * ewald + 10 * log2(lanes) + U  (BLUES_B200_PAIR; 0 = the round-1 kernel)
+        const int ew = (h->pair_variant / 100) && d.ewk_ok && d.nb_method == 4 ? 1 : 0;
+        const int lanes = 1 << ((h->pair_variant / 10) % 10), U = h->pair_variant % 10;
+        dim3 grid(cdiv((long long)d.Npad * lanes, NL_BLOCK), R);
+#define PV3(M, E, T, L, UU, W) k_pair2<M, E, T, L, UU, W><<<grid, NL_BLOCK, 0, st>>>(d)
+#define PV2(M, E, T, L, UU) if (ew) PV3(M, E, T, L, UU, 1); else PV3(M, E, T, L, UU, 0)
+#define PV1(M, E, T) if (lanes == 8 && U == 2) { PV2(M, E, T, 8, 2); } else if (lanes == 8 && U == 4) { PV2(M, E, T, 8, 4); } \
+                     else if (lanes == 16 && U == 2) { PV2(M, E, T, 16, 2); } else if (lanes == 4 && U == 4) { PV2(M, E, T, 4, 4); } \
+                     else { PV2(M, E, T, 16, 4); }
+#define PV0(M, E) if (d.nl_u16) { PV1(M, E, unsigned short) } else { PV1(M, E, int) }
+#define PVE(M) if (energy) { PV0(M, true) } else { PV0(M, false) }
+        if (d.nb_method == 4) { PVE(NB_PME) }
+        else if (d.nb_method == 2) { PVE(NB_RF) }
+        else { PVE(NB_NOCUT) }
+#undef PV3
+#undef PV2
+#undef PV1
+#undef PV0
+#undef PVE
+    } else {
         LaunchTimer t(h, BL_K_PAIR);
         dim3 grid(cdiv((long long)d.Npad * NL_LANES, NL_BLOCK), R);
 #define PAIR2(M, E)                                                           \
@@ -648,6 +689,39 @@ static void bspline_moduli_host(int K, std::vector<float>& out) {
     for (int m = 0; m < K; ++m) out[m] = (float)mod[m];
 }
 
+// k(z) = (erf(sqrt z) / sqrt z - 2 / sqrt(pi) exp(-z)) / z: the smooth part of the Ewald real-space force,
+// F(r) = qq (1 / r^3 - alpha^3 k(alpha^2 r^2)) r_vec
+static double ewald_k(double z) {
+    if (z < 1e-3) return 4.0 / (3.0 * sqrt(M_PI)) * (1.0 - 3.0 * z / 5.0 + 3.0 * z * z / 14.0 - z * z * z / 18.0);
+    const double s = sqrt(z);
+    return (erf(s) / s - 2.0 / sqrt(M_PI) * exp(-z)) / z;
+}
+// Chebyshev interpolant of k on [0, zmax] of degree EWK_DEG, returned as monomial coefficients in t = 2 z / zmax - 1
+// (sum of |c| ~ 0.75: a Horner evaluation in float is accurate to ~2e-7 absolute; interpolation error 1e-8 at zmax 11.5)
+static void fit_ewald_k(double zmax, float out[16]) {
+    const int n = EWK_DEG + 1;
+    double f[n], c[n];
+    for (int j = 0; j < n; ++j) f[j] = ewald_k(0.5 * zmax * (cos(M_PI * (j + 0.5) / n) + 1.0));
+    for (int m = 0; m < n; ++m) {
+        double acc = 0;
+        for (int j = 0; j < n; ++j) acc += f[j] * cos(M_PI * m * (j + 0.5) / n);
+        c[m] = acc * 2.0 / n;
+    }
+    c[0] *= 0.5;
+    double mono[n] = {0}, tm1[n] = {0}, tm[n] = {0};     // T_{m-1}, T_m as monomial coefficient arrays
+    tm1[0] = 1.0;                                         // T_0
+    tm[1] = 1.0;                                          // T_1
+    mono[0] += c[0];
+    mono[1] += c[1];
+    for (int m = 2; m < n; ++m) {
+        double tn[n] = {0};
+        for (int k = 0; k + 1 < n; ++k) tn[k + 1] += 2.0 * tm[k];
+        for (int k = 0; k < n; ++k) tn[k] -= tm1[k];
+        for (int k = 0; k < n; ++k) { mono[k] += c[m] * tn[k]; tm1[k] = tm[k]; tm[k] = tn[k]; }
+    }
+    for (int k = 0; k < 16; ++k) out[k] = k < n ? (float)mono[k] : 0.f;
+}
+
 static uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
     auto part = [](uint32_t v) {
         uint64_t r = v & 0x1fffff;
@@ -767,6 +841,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_PDL")) h->pdl = atoi(getenv("BLUES_B200_PDL")) != 0;
     if (getenv("BLUES_B200_GRAPH_STEPS")) h->graph_steps = std::max(1, atoi(getenv("BLUES_B200_GRAPH_STEPS")));
     if (getenv("BLUES_B200_TIMELINE")) { h->timeline = true; h->graph_steps = 1; }
+    if (getenv("BLUES_B200_PAIR")) h->pair_variant = atoi(getenv("BLUES_B200_PAIR"));
     counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping
     auto fail = [&](int code, const std::string& msg) { g_create_error = msg; bl_destroy(h); return code; };
     h->device = device;
@@ -807,6 +882,13 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     d.list_cutoff2 = d.periodic ? (float)((t->cutoff + skin) * (t->cutoff + skin)) : 3.0e38f;
     d.skin_half2 = d.periodic ? (float)(0.25 * skin * skin) : 3.0e38f;
     d.alpha = (float)t->ewald_alpha;
+    if (t->nb_method == 4) {
+        const double zmax = 1.02 * t->ewald_alpha * t->ewald_alpha * t->cutoff * t->cutoff;
+        d.ewk_ok = zmax <= 11.5;          // beyond that (ewaldErrorTolerance < 5e-6) the erfc form is used
+        fit_ewald_k(std::min(zmax, 11.5), d.ewk);
+        d.ewk_scale = (float)(2.0 * t->ewald_alpha * t->ewald_alpha / std::min(zmax, 11.5));
+        d.alpha3 = (float)(t->ewald_alpha * t->ewald_alpha * t->ewald_alpha);
+    }
     if (t->nb_method == 2) {
         const double eps_rf = 78.3, rc = t->cutoff;
         d.krf = (float)((1.0 / (rc * rc * rc)) * (eps_rf - 1.0) / (2.0 * eps_rf + 1.0));
@@ -956,6 +1038,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     d.atom_cell = dalloc<int>(h, RN); d.rank = dalloc<int>(h, RN);
     d.posq_s = dalloc<float4>(h, (size_t)R * d.Npad);
     d.sigeps_s = dalloc<float2>(h, (size_t)R * d.Npad);
+    d.rec_s = dalloc<float4>(h, (size_t)R * d.Npad * 2);
     d.orig_s = dalloc<int>(h, (size_t)R * d.Npad);
     {
         // row capacity per atom: 1.5 x the mean number of atoms inside the list-cutoff sphere (+ margin)
@@ -968,7 +1051,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     }
     d.nl_u16 = d.Npad < 65536 ? 1 : 0;
     d.nl_count = dalloc<int>(h, (size_t)R * d.Npad);
-    d.nl_list = dalloc<unsigned char>(h, (size_t)R * d.Npad * d.nl_M * (d.nl_u16 ? 2 : 4));
+    d.nl_list = dalloc<unsigned char>(h, ((size_t)R * d.Npad * d.nl_M + PAIR_SLACK_ENTRIES) * (d.nl_u16 ? 2 : 4));
     {
         // k_build_list: per-lane sub-lists in shared memory are write-combining buffers flushed to the rows whenever one
         // of them passes build_cq entries (a chunk adds at most BUILD_SLACK): ~8 KB (u16) / ~10 KB (int32) per single-warp

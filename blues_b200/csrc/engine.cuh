@@ -8,6 +8,7 @@
 #define MAX_OPS 16
 #define ALCH_SLOTS 3
 #define MAX_NOISE_SETS 4              /* thermostat ops (O / MD) per INTEGRATE launch */
+#define EWK_DEG 14
 #define MAX_ALCH_SMEM 512             /* alchemical atoms staged in shared memory by k_alch                 */
 
 enum EnergyTerm { E_BOND = 0, E_ANGLE, E_TORSION, E_RESTRAINT, E_PAIR, E_EXCEPT, E_PME, E_SELF, E_DISP,
@@ -64,6 +65,9 @@ struct Dev {
     double* boxd;
     float* boxf;
     float cutoff, cutoff2, list_cutoff2, skin_half2, alpha, krf, crf;
+    // Ewald real-space force without exp / erfc: F = qq (1/r^3 - alpha^3 k(alpha^2 r^2)), k(z) = (erf(sqrt z)/sqrt z -
+    // 2/sqrt(pi) exp(-z)) / z as a degree-EWK_DEG polynomial in t = ewk_scale r^2 - 1 on [0, (alpha rc)^2] (fitted at bl_create)
+    float ewk[16]; float ewk_scale, alpha3; int ewk_ok;
     double cutoffd, alphad;
     // static per-atom data (original order)
     double* mass; double* invmass;
@@ -92,6 +96,7 @@ struct Dev {
     int* group_first; int group_capacity;   // [R][group_capacity] (first sorted index << 4 | atoms) of every build group
     int* rank;                              // [R*N] position of atom a in the sorted order
     float4* posq_s; float2* sigeps_s; int* orig_s;   // [R*Npad] sorted copies (pads: NaN position, orig -1)
+    float4* rec_s;                          // [R*Npad][2] packed sorted records for k_pair3's gathers: (x, y, z, q), (sigma/2, 2 sqrt eps, -, -)
     int nl_M;                               // capacity of one row of the Verlet list
     int* nl_count;                          // [R*Npad]
     void* nl_list;                          // [R*Npad][nl_M] sorted indices of the neighbours within cutoff + skin

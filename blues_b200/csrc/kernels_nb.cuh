@@ -1,6 +1,7 @@
 // Neighbour-list construction (K1) and the tiled direct-space pair kernel (K2).
 #pragma once
 #include <cooperative_groups.h>
+#include <type_traits>
 #include "engine.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
@@ -147,14 +148,19 @@ __global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort
         const int a = orig_s[s];
         rank[a] = s;
         const float4 p = posq[a];
+        const float2 se = d.sigeps[a];
         posq_s[s] = p;
-        sigeps_s[s] = d.sigeps[a];
+        sigeps_s[s] = se;
+        d.rec_s[2 * ((size_t)r * Npad + s)] = p;
+        d.rec_s[2 * ((size_t)r * Npad + s) + 1] = make_float4(se.x, se.y, 0.f, 0.f);
         pos_ref[a] = p;
     }
     const float qnan = __int_as_float(0x7fc00000);
     for (int s = N + tid; s < Npad; s += nt) {
         posq_s[s] = make_float4(qnan, qnan, qnan, 0.f);
         sigeps_s[s] = make_float2(0.f, 0.f);
+        d.rec_s[2 * ((size_t)r * Npad + s)] = make_float4(qnan, qnan, qnan, 0.f);
+        d.rec_s[2 * ((size_t)r * Npad + s) + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         orig_s[s] = -1;
     }
     if (tid == 0) {
@@ -628,6 +634,282 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair(Dev d) {
     }
     if (ENERGY) {
         // every pair appears in both atoms' lists
+        const float e = warp_sum(etot);
+        if (lane == 0 && e != 0.f) fx_add(&d.eacc[r * N_ETERMS + E_PAIR], 0.5 * (double)e, ENERGY_SCALE);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_pair2: the same sum as k_pair, software pipelined.  ncu on k_pair (profiles/r01_final2_ncu_summary.md, source page):
+// 67 % of the stall samples are long-scoreboard waits at the two consumers of a dependent load chain — the list index,
+// then the gather it addresses.  Here a lane owns the entries part, part + LANES, ... of its atom's row and works in
+// trips of U entries: while trip t is computed the gathers of trip t + 1 and the index loads of trip t + 2 are in flight.
+// Reads may run up to two trips past the end of a row: rows are contiguous (the next row holds valid indices) and the
+// array carries that much slack after the last row; such entries are masked by their position in the row.
+// EWALD 1: real-space Ewald force from the polynomial of Dev::ewk (no MUFU.EX2 / MUFU.RCP: the XU pipe is the busiest
+// unit of k_pair); energies, on the steps that need them, still come from erfc.
+// ---------------------------------------------------------------------------------------------------------
+#define PAIR_SLACK_ENTRIES 512
+// volatile so that the loads of the NEXT trips keep their place at the top of the loop body (the compiler otherwise
+// sinks them to the bottom, next to their consumers in the following iteration, and the latency is exposed again)
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_nc_f2(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_nc_idx(const unsigned short* p) {
+    unsigned short v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return (int)v;
+}
+__device__ __forceinline__ int ldg_nc_idx(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// one trip: U entries of this lane, data already in registers
+template <int METHOD, bool ENERGY, int U, int EWALD>
+__device__ __forceinline__ void pair_trip(const Dev& d, const float4 (&pc)[U], const float2 (&ec)[U], int first, int nm,
+                                          const float4 pi, const float2 se_i, float qi, float cut2, float& fx, float& fy,
+                                          float& fz, float& etot) {
+    const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2];
+    const float ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float4 pj = pc[u];
+        const float2 se_j = ec[u];
+        float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+        if (METHOD != NB_NOCUT) {
+            dx -= bx * rint_fma(dx * ibx);
+            dy -= by * rint_fma(dy * iby);
+            dz -= bz * rint_fma(dz * ibz);
+        }
+        const float r2 = dx * dx + dy * dy + dz * dz;
+        const bool inr = (first + u < nm) && (r2 < cut2);
+        const float invr = rsqrtf(r2);
+        const float invr2 = invr * invr;
+        const float sig = se_i.x + se_j.x;
+        const float s2 = sig * sig * invr2;
+        const float s6 = s2 * s2 * s2;
+        const float eps4 = se_i.y * se_j.y;
+        float de = eps4 * (12.0f * s6 * s6 - 6.0f * s6) * invr2;
+        const float qq = qi * pj.w;
+        float e = 0.f;
+        if (METHOD == NB_PME) {
+            if (EWALD == 1) {
+                const float tt = fmaf(r2, d.ewk_scale, -1.0f);
+                float k = d.ewk[EWK_DEG];
+#pragma unroll
+                for (int c = EWK_DEG - 1; c >= 0; --c) k = fmaf(k, tt, d.ewk[c]);
+                de += qq * fmaf(-d.alpha3, k, invr * invr2);
+                if (ENERGY) {
+                    const float ar = d.alpha * r2 * invr;
+                    e = eps4 * (s6 * s6 - s6) + qq * invr * erfc_times(ar, __expf(-ar * ar));
+                }
+            } else {
+                const float ar = d.alpha * r2 * invr;
+                const float ex = __expf(-ar * ar);
+                const float ec2 = erfc_times(ar, ex);
+                de += qq * invr * (ec2 + (float)TWO_OVER_SQRT_PI * ar * ex) * invr2;
+                if (ENERGY) e = eps4 * (s6 * s6 - s6) + qq * invr * ec2;
+            }
+        } else if (METHOD == NB_RF) {
+            de += qq * (invr - 2.0f * d.krf * r2) * invr2;
+            if (ENERGY) e = eps4 * (s6 * s6 - s6) + qq * (invr + d.krf * r2 - d.crf);
+        } else {
+            de += qq * invr * invr2;
+            if (ENERGY) e = eps4 * (s6 * s6 - s6) + qq * invr;
+        }
+        // select, not a mask multiply: entries past the end of the row or in the skin shell may be anything
+        de = inr ? de : 0.f;
+        fx += dx * de; fy += dy * de; fz += dz * de;
+        if (ENERGY) etot += inr ? e : 0.f;
+    }
+}
+
+template <int METHOD, bool ENERGY, typename IDX, int LANES, int U, int EWALD>
+__global__ void __launch_bounds__(NL_BLOCK) k_pair2(Dev d) {
+    const int r = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int part = lane & (LANES - 1);
+    const int i = (blockIdx.x * NL_BLOCK + threadIdx.x) / LANES;
+    const int N = d.N, Npad = d.Npad;
+    if (i >= Npad) return;
+    const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
+    const float2* __restrict__ sigeps_s = d.sigeps_s + (size_t)r * Npad;
+    const IDX* __restrict__ lp = reinterpret_cast<const IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M + part;
+    const int cnt = d.nl_count[(size_t)r * Npad + i];
+    const int nm = cnt > part ? (cnt - part + LANES - 1) / LANES : 0;        // entries owned by this lane
+    const int ntrip = (nm + U - 1) / U;
+    const float cut2 = METHOD == NB_NOCUT ? 3.0e38f : d.cutoff2;
+    const float4 pi = posq_s[i];
+    const float2 se_i = sigeps_s[i];
+    const float qi = pi.w * (float)ONE_4PI_EPS0;
+    float fx = 0.f, fy = 0.f, fz = 0.f, etot = 0.f;
+    // two buffers of gathered data (trips t, t + 1 in flight or in use) and two of indices (trips t + 2, t + 3)
+    int iA[U], iB[U];
+    float4 pA[U], pB[U];
+    float2 eA[U], eB[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { iA[u] = ldg_nc_idx(lp + LANES * u); iB[u] = ldg_nc_idx(lp + LANES * (U + u)); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { pA[u] = ldg_nc_f4(posq_s + iA[u]); eA[u] = ldg_nc_f2(sigeps_s + iA[u]); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { pB[u] = ldg_nc_f4(posq_s + iB[u]); eB[u] = ldg_nc_f2(sigeps_s + iB[u]); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { iA[u] = ldg_nc_idx(lp + LANES * (2 * U + u)); iB[u] = ldg_nc_idx(lp + LANES * (3 * U + u)); }
+    for (int t = 0; t < ntrip; t += 2) {
+        pair_trip<METHOD, ENERGY, U, EWALD>(d, pA, eA, t * U, nm, pi, se_i, qi, cut2, fx, fy, fz, etot);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { pA[u] = ldg_nc_f4(posq_s + iA[u]); eA[u] = ldg_nc_f2(sigeps_s + iA[u]); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) iA[u] = ldg_nc_idx(lp + LANES * ((t + 4) * U + u));
+        pair_trip<METHOD, ENERGY, U, EWALD>(d, pB, eB, (t + 1) * U, nm, pi, se_i, qi, cut2, fx, fy, fz, etot);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { pB[u] = ldg_nc_f4(posq_s + iB[u]); eB[u] = ldg_nc_f2(sigeps_s + iB[u]); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) iB[u] = ldg_nc_idx(lp + LANES * ((t + 5) * U + u));
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    if (part == 0 && i < N) {
+        const int oi = d.orig_s[(size_t)r * Npad + i];
+        long long* fenv = d.f_env + (size_t)r * 3 * N;
+        fx_addf(&fenv[oi], fx, (float)FORCE_SCALE);
+        fx_addf(&fenv[N + oi], fy, (float)FORCE_SCALE);
+        fx_addf(&fenv[2 * N + oi], fz, (float)FORCE_SCALE);
+    }
+    if (ENERGY) {
+        const float e = warp_sum(etot);
+        if (lane == 0 && e != 0.f) fx_add(&d.eacc[r * N_ETERMS + E_PAIR], 0.5 * (double)e, ENERGY_SCALE);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_pair3: the pair sum with asynchronous gathers (cp.async → shared memory ring).  ptxas schedules plain loads next to
+// their consumers whatever the source order (k_pair2's software pipeline ends up with every load at the bottom of the loop
+// body), so the prefetch is made explicit: a lane owns the entry PAIRS (2 part, 2 part + 1) + 2 LANES m of its atom's row.
+// In iteration t it waits for the copy group of trip t, reads the two indices of trip t + 2 from its index slot, issues
+// the gathers of trip t + 2 (posq 16 B, sigeps 8 B per entry) and the index copy of trip t + 4 as one group, then computes
+// trip t from shared memory while two groups are in flight.  Every thread touches only its own slots: no barrier.
+// ---------------------------------------------------------------------------------------------------------
+#define P3_STAGES 3
+__device__ __forceinline__ void cp_async16(unsigned int dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned int dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned int dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename IDX> __device__ __forceinline__ void p3_copy_idx(unsigned int dst, const IDX* src);
+template <> __device__ __forceinline__ void p3_copy_idx<unsigned short>(unsigned int dst, const unsigned short* src) { cp_async4(dst, src); }
+template <> __device__ __forceinline__ void p3_copy_idx<int>(unsigned int dst, const int* src) { cp_async8(dst, src); }
+
+template <int METHOD, bool ENERGY, typename IDX, int LANES, int EWALD>
+__global__ void __launch_bounds__(NL_BLOCK) k_pair3(Dev d) {
+    // per thread and stage: 2 records of 2 x float4 and 2 indices; arrays are [stage][slot][thread] (conflict-free LDS.128)
+    __shared__ float4 s_rec[P3_STAGES * 4 * NL_BLOCK];
+    __shared__ IDX s_idx[P3_STAGES * 2 * NL_BLOCK];           // [stage][thread][2]
+    const int r = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int part = lane & (LANES - 1);
+    const int i = (blockIdx.x * NL_BLOCK + tid) / LANES;
+    const int N = d.N, Npad = d.Npad;
+    if (i >= Npad) return;
+    const float4* __restrict__ rec = d.rec_s + 2 * (size_t)r * Npad;
+    const IDX* __restrict__ lp = reinterpret_cast<const IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M + 2 * part;
+    const int cnt = d.nl_count[(size_t)r * Npad + i];
+    const int ntrip = (cnt + 2 * LANES - 1) / (2 * LANES);       // the same for the LANES lanes of an atom
+    const float cut2 = METHOD == NB_NOCUT ? 3.0e38f : d.cutoff2;
+    const float4 pi = rec[2 * i];
+    const float4 ri = rec[2 * i + 1];
+    const float2 se_i = make_float2(ri.x, ri.y);
+    const float qi = pi.w * (float)ONE_4PI_EPS0;
+    float fx = 0.f, fy = 0.f, fz = 0.f, etot = 0.f;
+    const unsigned int a_rec = (unsigned int)__cvta_generic_to_shared(s_rec) + tid * 16u;
+    const unsigned int a_idx = (unsigned int)__cvta_generic_to_shared(s_idx) + tid * 2u * (unsigned int)sizeof(IDX);
+    constexpr unsigned int REC_STAGE = 4 * NL_BLOCK * 16, REC_SLOT = NL_BLOCK * 16, IDX_STAGE = 2 * NL_BLOCK * sizeof(IDX);
+    constexpr int TRIP = 2 * LANES;                              // entries of a row consumed per trip
+    auto gather = [&](int stage, int s0, int s1) {
+        const float4* g0 = rec + 2 * s0;
+        const float4* g1 = rec + 2 * s1;
+        cp_async16(a_rec + stage * REC_STAGE, g0);
+        cp_async16(a_rec + stage * REC_STAGE + REC_SLOT, g0 + 1);
+        cp_async16(a_rec + stage * REC_STAGE + 2 * REC_SLOT, g1);
+        cp_async16(a_rec + stage * REC_STAGE + 3 * REC_SLOT, g1 + 1);
+    };
+    // one iteration with compile-time stage numbers: trip t lives in stage ST, trip t + 2 goes to ST2, the indices of
+    // trip t + 4 to the slot trip t + 1 used
+    auto step = [&](int t, auto st_c, auto st2_c, auto st4_c) {
+        constexpr int ST = decltype(st_c)::value, ST2 = decltype(st2_c)::value, ST4 = decltype(st4_c)::value;
+        cp_async_wait<1>();                  // gathers of trip t and the indices of trip t + 2 have landed
+        {
+            const IDX* si = s_idx + ST2 * 2 * NL_BLOCK + tid * 2;
+            int s0, s1;
+            if (sizeof(IDX) == 2) {
+                const unsigned int v = *reinterpret_cast<const unsigned int*>(si);
+                s0 = (int)(v & 0xffffu); s1 = (int)(v >> 16);
+            } else {
+                const int2 v = *reinterpret_cast<const int2*>(si);
+                s0 = v.x; s1 = v.y;
+            }
+            gather(ST2, s0, s1);
+            p3_copy_idx<IDX>(a_idx + ST4 * IDX_STAGE, lp + (t + 4) * TRIP);
+            cp_async_commit();
+        }
+        float4 pc[2];
+        float2 ec[2];
+        const float4 q0 = s_rec[(ST * 4 + 1) * NL_BLOCK + tid], q1 = s_rec[(ST * 4 + 3) * NL_BLOCK + tid];
+        pc[0] = s_rec[(ST * 4 + 0) * NL_BLOCK + tid]; pc[1] = s_rec[(ST * 4 + 2) * NL_BLOCK + tid];
+        ec[0] = make_float2(q0.x, q0.y); ec[1] = make_float2(q1.x, q1.y);
+        pair_trip<METHOD, ENERGY, 2, EWALD>(d, pc, ec, 2 * part + TRIP * t, cnt, pi, se_i, qi, cut2, fx, fy, fz, etot);
+    };
+    // prologue: trips 0 and 1 need their indices in registers; the index copies of trips 2 and 3 ride in the same groups
+    {
+        const int s00 = (int)lp[0], s01 = (int)lp[1], s10 = (int)lp[TRIP], s11 = (int)lp[TRIP + 1];
+        gather(0, s00, s01);
+        p3_copy_idx<IDX>(a_idx + 2 * IDX_STAGE, lp + 2 * TRIP);
+        cp_async_commit();
+        gather(1, s10, s11);
+        p3_copy_idx<IDX>(a_idx + 0 * IDX_STAGE, lp + 3 * TRIP);
+        cp_async_commit();
+    }
+    using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+    for (int t = 0; t < ntrip; t += 3) {
+        step(t, I0(), I2(), I1());
+        if (t + 1 < ntrip) step(t + 1, I1(), I0(), I2());
+        if (t + 2 < ntrip) step(t + 2, I2(), I1(), I0());
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    if (part == 0 && i < N) {
+        const int oi = d.orig_s[(size_t)r * Npad + i];
+        long long* fenv = d.f_env + (size_t)r * 3 * N;
+        fx_addf(&fenv[oi], fx, (float)FORCE_SCALE);
+        fx_addf(&fenv[N + oi], fy, (float)FORCE_SCALE);
+        fx_addf(&fenv[2 * N + oi], fz, (float)FORCE_SCALE);
+    }
+    if (ENERGY) {
         const float e = warp_sum(etot);
         if (lane == 0 && e != 0.f) fx_add(&d.eacc[r * N_ETERMS + E_PAIR], 0.5 * (double)e, ENERGY_SCALE);
     }
