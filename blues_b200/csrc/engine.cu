@@ -74,7 +74,8 @@ struct bl_handle {
     std::vector<double> host_tmp;
     double skin = 0.0; int cell_capacity = 0;
     int build_cq = 0, build_ctas = 0;
-    int pair_variant = 0;        // BLUES_B200_PAIR: 0 = k_pair, else k_pair2 <ewald, lanes, U> (see enqueue_eval)
+    bool own_dft = false;        // reciprocal space by the fused direct-DFT kernels (small grids) instead of cuFFT
+    int pair_variant = 132;      // BLUES_B200_PAIR: 0 = k_pair (round 1), else k_pair2 <ewald, lanes, U> (see enqueue_eval); measured: gpurun_out/pair_sweep.log
     int graph_steps = 4;         // plain NCMC steps captured per CUDA graph
     bool pdl = true;             // programmatic dependent launch on the B -> flip -> A -> sort edges (BLUES_B200_PDL=0: off)
     // diagnostic timeline (BLUES_B200_TIMELINE=1): events recorded inside the step graphs, read after every replay
@@ -189,6 +190,18 @@ static void launch_pdl(bl_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 b
     cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+template <typename... KArgs, typename... Args>
+static void launch_pdl_smem(bl_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ---- force / energy evaluation at the current positions ---------------------------------------------------
 // energy: also accumulate energies; cm_mode: forwarded to k_begin_eval
 static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, int cm_mode, int prefetch_noise = 0) {
@@ -226,6 +239,22 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
           if (R <= 2) k_pme_spread<8, 512><<<dim3(d.gx, 8, R), 512, (d.gy / 8 + 1) * d.gz * sizeof(int), s2>>>(d);
           else k_pme_spread<4, 256><<<dim3(d.gx, 4, R), 256, (d.gy / 4 + 1) * d.gz * sizeof(int), s2>>>(d); }
         tl_mark(h, s2, TL_SPREAD);
+        if (h->own_dft) {
+            const int Zc = d.gz / 2 + 1;
+            const size_t sm1 = sizeof(float) * ((d.gy * d.gz + 1) & ~1) + sizeof(float2) * (d.gy * Zc + d.gz + d.gy);
+            const size_t sm3 = sizeof(float2) * (2 * d.gy * Zc + d.gz + d.gy);
+            { LaunchTimer t(h, BL_K_FFT, s2);
+              launch_pdl_smem(h, k_pme_dft_zy, dim3(d.gx, R), dim3(PME_DFT_THREADS), sm1, s2, d); }
+            tl_mark(h, s2, TL_R2C);
+            { LaunchTimer t(h, BL_K_PME_CONVOLVE, s2);
+              const dim3 gridx(cdiv(d.gy * Zc, PME_X_LINES), R);
+              if (energy) launch_pdl_smem(h, k_pme_dft_x<true>, gridx, dim3(PME_X_LINES * 32), 0, s2, d);
+              else launch_pdl_smem(h, k_pme_dft_x<false>, gridx, dim3(PME_X_LINES * 32), 0, s2, d); }
+            tl_mark(h, s2, TL_CONV);
+            { LaunchTimer t(h, BL_K_FFT, s2);
+              launch_pdl_smem(h, k_pme_idft_yz, dim3(d.gx, R), dim3(PME_DFT_THREADS), sm3, s2, d); }
+            tl_mark(h, s2, TL_C2R);
+        } else {
             { LaunchTimer t(h, BL_K_FFT, s2); cufftExecR2C(h->plan_r2c, d.grid_r, reinterpret_cast<cufftComplex*>(d.grid_c)); }
         tl_mark(h, s2, TL_R2C);
             { LaunchTimer t(h, BL_K_PME_CONVOLVE, s2);
@@ -234,6 +263,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
             tl_mark(h, s2, TL_CONV);
         { LaunchTimer t(h, BL_K_FFT, s2); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
         tl_mark(h, s2, TL_C2R);
+        }
         { LaunchTimer t(h, BL_K_PME_GATHER, s2);
           if (R <= 2) k_pme_gather5<<<dim3(cdiv(cdiv(N, 6) * 32, 128), R), 128, 0, s2>>>(d);
           else k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
@@ -1097,6 +1127,23 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         std::vector<float> mx, my, mz;
         bspline_moduli_host(d.gx, mx); bspline_moduli_host(d.gy, my); bspline_moduli_host(d.gz, mz);
         d.bmod_x = dupload(h, mx); d.bmod_y = dupload(h, my); d.bmod_z = dupload(h, mz);
+        {
+            auto twiddles = [&](int L) {
+                std::vector<float2> tw(L);
+                for (int m = 0; m < L; ++m) tw[m] = make_float2((float)cos(2.0 * M_PI * m / L), (float)sin(2.0 * M_PI * m / L));
+                return dupload(h, tw);
+            };
+            d.tw_x = twiddles(d.gx); d.tw_y = twiddles(d.gy); d.tw_z = twiddles(d.gz);
+            h->own_dft = d.gx <= PME_DFT_MAX && d.gy <= PME_DFT_MAX && d.gz <= PME_DFT_MAX;
+            if (getenv("BLUES_B200_DFT")) h->own_dft = h->own_dft && atoi(getenv("BLUES_B200_DFT")) != 0;
+            const int Zc = d.gz / 2 + 1;
+            const size_t sm = std::max(sizeof(float) * ((d.gy * d.gz + 1) & ~1) + sizeof(float2) * (d.gy * Zc + d.gz + d.gy),
+                                       sizeof(float2) * (2 * d.gy * Zc + d.gz + d.gy));
+            if (h->own_dft && sm > 48 * 1024) {
+                cudaFuncSetAttribute(k_pme_dft_zy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                cudaFuncSetAttribute(k_pme_idft_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            }
+        }
         int n[3] = {d.gx, d.gy, d.gz};
         if (cufftPlanMany(&h->plan_r2c, 3, n, nullptr, 1, d.gsize, nullptr, 1, d.csize, CUFFT_R2C, R) != CUFFT_SUCCESS ||
             cufftPlanMany(&h->plan_c2r, 3, n, nullptr, 1, d.csize, nullptr, 1, d.gsize, CUFFT_C2R, R) != CUFFT_SUCCESS)
@@ -1777,6 +1824,7 @@ int bl_measure_fp32_peak(int device, double* tflops) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return BL_ERR_NO_DEVICE; }
     cudaSetDevice(device);
+    cudaGetLastError();                                   // a stale error of an unrelated earlier call is not ours
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
     float* out = nullptr;
@@ -1795,9 +1843,10 @@ int bl_measure_fp32_peak(int device, double* tflops) {
         const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
         if (rep >= 2 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
+    const cudaError_t err = cudaDeviceSynchronize();
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(out);
-    if (cudaGetLastError() != cudaSuccess) return BL_ERR_CUDA;
+    if (err != cudaSuccess || best <= 0.0) { cudaGetLastError(); return BL_ERR_CUDA; }
     *tflops = best;
     return BL_OK;
 }

@@ -122,6 +122,7 @@ struct Dev {
     float* grid_r;                          // [R][gsize]
     float2* grid_c;                         // [R][csize]
     float* bmod_x; float* bmod_y; float* bmod_z;
+    float2* tw_x; float2* tw_y; float2* tw_z;       // (cos, sin)(2 pi m / L) of the direct-DFT reciprocal-space kernels
     double self_energy_coeff;               // -k_e alpha/sqrt(pi) sum q^2  (constant)
     double sumq;
     double dispersion_coeff;

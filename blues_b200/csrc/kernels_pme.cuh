@@ -182,6 +182,160 @@ __global__ void __launch_bounds__(256) k_pme_convolve(Dev d) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Reciprocal space without cuFFT for small grids (every dimension <= PME_DFT_MAX): three kernels instead of seven.
+// The grids of the measured systems (24 x 25 x 28, 24^3) are so small that a library FFT is pure launch latency — six
+// kernels of ~6 us each around the convolution, 3-4 x longer while the pair kernel shares the SMs
+// (profiles/r01_step_timeline.md).  A direct DFT per dimension with exact twiddle tables costs 4.5 MFMA for
+// 24 x 25 x 28, nothing for the device, and lets the passes fuse:
+//   k_pme_dft_zy   one CTA per x-plane: real z-transform (half spectrum), y-transform        -> grid_c
+//   k_pme_dft_x    CTAs of lines along x: x-transform, influence function (+ energy), inverse x-transform (in place)
+//   k_pme_idft_yz  one CTA per x-plane: inverse y-transform, Hermitian inverse z-transform   -> grid_r
+// Conventions are cuFFT's (unnormalised, forward sign -), so spread / gather and the energy are unchanged.
+// ---------------------------------------------------------------------------------------------------------
+#define PME_DFT_MAX 64
+#define PME_DFT_THREADS 256
+
+// out = sum_n in[n * stride] * w^(sign k n), w = exp(-2 pi i / L), twiddles tw[m] = (cos, sin)(2 pi m / L)
+__device__ __forceinline__ float2 dft_line_c(const float2* in, int stride, int L, int k, const float2* tw, float sign) {
+    float re = 0.f, im = 0.f;
+    int m = 0;
+    for (int n = 0; n < L; ++n) {
+        const float2 v = in[n * stride];
+        const float2 w = tw[m];
+        const float ws = sign * w.y;                 // forward: e^{-i theta} = (cos, -sin)
+        re = fmaf(v.x, w.x, re); re = fmaf(-v.y, ws, re);
+        im = fmaf(v.x, ws, im); im = fmaf(v.y, w.x, im);
+        m += k; m -= m >= L ? L : 0;
+    }
+    return make_float2(re, im);
+}
+
+__global__ void __launch_bounds__(PME_DFT_THREADS) k_pme_dft_zy(Dev d) {
+    extern __shared__ float s_dft[];                 // plane [Y][Z] floats, then tmp [Y][Zc] float2, then twiddles
+    cudaGridDependencySynchronize();
+    const int r = blockIdx.y, x = blockIdx.x;
+    const int Y = d.gy, Z = d.gz, Zc = Z / 2 + 1;
+    float* plane = s_dft;
+    float2* tmp = reinterpret_cast<float2*>(s_dft + ((Y * Z + 1) & ~1));
+    float2* twz = tmp + Y * Zc;
+    float2* twy = twz + Z;
+    const float* src = d.grid_r + (size_t)r * d.gsize + (size_t)x * Y * Z;
+    for (int k = threadIdx.x; k < Y * Z; k += blockDim.x) plane[k] = src[k];
+    for (int k = threadIdx.x; k < Z; k += blockDim.x) twz[k] = d.tw_z[k];
+    for (int k = threadIdx.x; k < Y; k += blockDim.x) twy[k] = d.tw_y[k];
+    __syncthreads();
+    for (int o = threadIdx.x; o < Y * Zc; o += blockDim.x) {
+        const int y = o / Zc, kz = o - y * Zc;
+        const float* in = plane + y * Z;
+        float re = 0.f, im = 0.f;
+        int m = 0;
+        for (int z = 0; z < Z; ++z) {
+            const float v = in[z];
+            const float2 w = twz[m];
+            re = fmaf(v, w.x, re); im = fmaf(-v, w.y, im);
+            m += kz; m -= m >= Z ? Z : 0;
+        }
+        tmp[o] = make_float2(re, im);
+    }
+    __syncthreads();
+    float2* dst = d.grid_c + (size_t)r * d.csize + (size_t)x * Y * Zc;
+    for (int o = threadIdx.x; o < Y * Zc; o += blockDim.x) {
+        const int ky = o / Zc, kz = o - ky * Zc;
+        dst[o] = dft_line_c(tmp + kz, Zc, Y, ky, twy, -1.f);
+    }
+}
+
+// lines along x: PME_X_LINES consecutive (ky, kz) lines per CTA, one thread per (line, kx)
+#define PME_X_LINES 8
+template <bool ENERGY>
+__global__ void __launch_bounds__(PME_X_LINES * 32) k_pme_dft_x(Dev d) {
+    __shared__ float2 s_line[PME_X_LINES][PME_DFT_MAX + 1];
+    __shared__ float2 s_out[PME_X_LINES][PME_DFT_MAX + 1];
+    __shared__ float2 s_tw[PME_DFT_MAX];
+    cudaGridDependencySynchronize();
+    const int r = blockIdx.y;
+    const int X = d.gx, Y = d.gy, Zc = d.gz / 2 + 1, plane = Y * Zc;
+    const int li = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int line = blockIdx.x * PME_X_LINES + li;              // = ky * Zc + kz
+    const bool live = line < plane;
+    float2* grid = d.grid_c + (size_t)r * d.csize;
+    for (int k = threadIdx.x; k < X; k += blockDim.x) s_tw[k] = d.tw_x[k];
+    if (live)
+        for (int x = lane; x < X; x += 32) s_line[li][x] = grid[(size_t)x * plane + line];
+    __syncthreads();
+    double e = 0.0;
+    if (live) {
+        const int ky = line / Zc, kz = line - ky * Zc;
+        const int my = ky <= Y / 2 ? ky : ky - Y;
+        const float fy = my * d.boxf[4], fz = kz * d.boxf[5];
+        const float V = d.boxf[0] * d.boxf[1] * d.boxf[2];
+        const float pi2_over_a2 = 9.8696044010893586f / (d.alpha * d.alpha);
+        for (int kx = lane; kx < X; kx += 32) {
+            float2 c = dft_line_c(&s_line[li][0], 1, X, kx, s_tw, -1.f);
+            float eterm = 0.f;
+            if (kx != 0 || line != 0) {
+                const int mx = kx <= X / 2 ? kx : kx - X;
+                const float fx = mx * d.boxf[3];
+                const float m2 = fx * fx + fy * fy + fz * fz;
+                const float denom = m2 * d.bmod_x[kx] * d.bmod_y[ky] * d.bmod_z[kz] * 3.14159265358979f * V;
+                eterm = (float)ONE_4PI_EPS0 * expf(-pi2_over_a2 * m2) / denom;
+            }
+            if (ENERGY) {
+                const double w = (kz == 0 || (2 * kz == d.gz)) ? 1.0 : 2.0;
+                e += 0.5 * w * (double)eterm * ((double)c.x * c.x + (double)c.y * c.y);
+            }
+            s_out[li][kx] = make_float2(c.x * eterm, c.y * eterm);
+        }
+    }
+    __syncthreads();
+    if (live)
+        for (int x = lane; x < X; x += 32) grid[(size_t)x * plane + line] = dft_line_c(&s_out[li][0], 1, X, x, s_tw, 1.f);
+    if (ENERGY) {
+        e = warp_sum(e);
+        if (lane == 0 && e != 0.0) fx_add(&d.eacc[r * N_ETERMS + E_PME], e, ENERGY_SCALE);
+    }
+}
+
+__global__ void __launch_bounds__(PME_DFT_THREADS) k_pme_idft_yz(Dev d) {
+    extern __shared__ float s_dft[];                 // in [Y][Zc] float2, tmp [Y][Zc] float2, twiddles
+    cudaGridDependencySynchronize();
+    const int r = blockIdx.y, x = blockIdx.x;
+    const int Y = d.gy, Z = d.gz, Zc = Z / 2 + 1;
+    float2* in = reinterpret_cast<float2*>(s_dft);
+    float2* tmp = in + Y * Zc;
+    float2* twz = tmp + Y * Zc;
+    float2* twy = twz + Z;
+    const float2* src = d.grid_c + (size_t)r * d.csize + (size_t)x * Y * Zc;
+    for (int k = threadIdx.x; k < Y * Zc; k += blockDim.x) in[k] = src[k];
+    for (int k = threadIdx.x; k < Z; k += blockDim.x) twz[k] = d.tw_z[k];
+    for (int k = threadIdx.x; k < Y; k += blockDim.x) twy[k] = d.tw_y[k];
+    __syncthreads();
+    for (int o = threadIdx.x; o < Y * Zc; o += blockDim.x) {
+        const int y = o / Zc, kz = o - y * Zc;
+        tmp[o] = dft_line_c(in + kz, Zc, Y, y, twy, 1.f);
+    }
+    __syncthreads();
+    float* dst = d.grid_r + (size_t)r * d.gsize + (size_t)x * Y * Z;
+    const bool even = (Z & 1) == 0;
+    for (int o = threadIdx.x; o < Y * Z; o += blockDim.x) {
+        const int y = o / Z, z = o - y * Z;
+        const float2* c = tmp + y * Zc;
+        // Hermitian half spectrum: kz = 0 (and Z / 2 for even Z) count once with their real part, the others twice
+        float acc = c[0].x;
+        int m = z;                                    // (kz z) mod Z for kz = 1
+        const int last = even ? Zc - 1 : Zc;
+        for (int kz = 1; kz < last; ++kz) {
+            const float2 w = twz[m];
+            acc = fmaf(2.f * c[kz].x, w.x, acc);
+            acc = fmaf(-2.f * c[kz].y, w.y, acc);
+            m += z; m -= m >= Z ? Z : 0;
+        }
+        if (even) acc += (z & 1) ? -c[Zc - 1].x : c[Zc - 1].x;
+        dst[o] = acc;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_pme_gather(Dev d) {
     const int r = blockIdx.y;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
