@@ -74,6 +74,7 @@ struct bl_handle {
     std::vector<double> host_tmp;
     double skin = 0.0; int cell_capacity = 0;
     int build_cq = 0, build_ctas = 0;
+    bool builder2 = true; int build2_ctas = 0;   // ballot-compaction list builder (BLUES_B200_BUILDER=1: the round-1 builder)
     bool own_dft = false;        // reciprocal space by the fused direct-DFT kernels (small grids) instead of cuFFT
     int pair_variant = 132;      // BLUES_B200_PAIR: 0 = k_pair (round 1), else k_pair2 <ewald, lanes, U> (see enqueue_eval); measured: gpurun_out/pair_sweep.log
     int graph_steps = 4;         // plain NCMC steps captured per CUDA graph
@@ -298,7 +299,11 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         LaunchTimer t(h, BL_K_NEIGHBOR);
         dim3 grid(h->build_ctas);                          // persistent single-warp CTAs shared by all walkers
         const size_t smem = build_smem_bytes(h->build_cq, d.nl_u16 ? 2 : 4);
-        if (d.nl_u16) k_build_list<unsigned short><<<grid, 32, smem, st>>>(d, h->build_cq);
+        if (h->builder2) {
+            dim3 grid2(h->build2_ctas);
+            if (d.nl_u16) k_build_list2<unsigned short><<<grid2, 32, 0, st>>>(d);
+            else k_build_list2<int><<<grid2, 32, 0, st>>>(d);
+        } else if (d.nl_u16) k_build_list<unsigned short><<<grid, 32, smem, st>>>(d, h->build_cq);
         else k_build_list<int><<<grid, 32, smem, st>>>(d, h->build_cq);
     }
     tl_mark(h, st, TL_BUILD);
@@ -1106,6 +1111,13 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         if (R > 2 && per_sm > 2) per_sm -= 1;
         if (getenv("BLUES_B200_BUILD_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("BLUES_B200_BUILD_PER_SM"))));
         h->build_ctas = std::max(32, std::min(R * (cdiv(d.Npad, BUILD_GROUP) + 64), per_sm * n_sm));
+        if (getenv("BLUES_B200_BUILDER")) h->builder2 = atoi(getenv("BLUES_B200_BUILDER")) != 1;
+        int per_sm2 = 0;
+        if (d.nl_u16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_build_list2<unsigned short>, 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_build_list2<int>, 32, 0);
+        per_sm2 = std::max(1, per_sm2);
+        if (R > 2 && per_sm2 > 4) per_sm2 -= 2;          // leave room for the other streams' kernels
+        h->build2_ctas = std::max(32, std::min(R * (cdiv(d.Npad, BUILD_GROUP) + 64), per_sm2 * n_sm));
     }
     // PME
     if (d.pme) {

@@ -540,6 +540,188 @@ __global__ void __launch_bounds__(32) k_build_list(Dev d, int cq) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// k_build_list2: the same Verlet rows by warp-ballot compaction (round 2).  One warp per group of <= 8 cell-sorted atoms
+// as before, but lane = CANDIDATE: the 32 candidates of a chunk sit one per lane in registers, the (<= 8) group atoms
+// are broadcast from shared memory, so a chunk costs 8 x (1 LDS + ~9 ALU) warp-instructions for 256 distance tests
+// instead of 8 per-lane tests against staged candidates; chunks whose candidates all lie farther than the list cutoff
+// from the group's bounding box are skipped after one point-to-box test; survivors of atom a are ranked with
+// __ballot_sync / __popc and stored straight into its row (consecutive lanes -> consecutive entries).  No shared-memory
+// sub-lists, no flush pass; scan order and therefore row order are fixed (reproducible sums downstream).
+// ---------------------------------------------------------------------------------------------------------
+struct BuildGroupSmem {
+    float4 runs[BUILD_MAX_RUNS];
+    int off[BUILD_MAX_RUNS + 4];
+    float4 gat[BUILD_GROUP];            // group atoms: x, y, z, topology index (bits); NaN position for idle slots
+    ull gwin[BUILD_GROUP];
+    int2 gspan[BUILD_GROUP];            // exclusion window of every group atom as [first topology index, width]
+    unsigned char gfar[BUILD_GROUP];
+};
+
+template <bool RINT, typename IDX>
+__device__ __forceinline__ void build_stream2(const Dev& d, const float4* __restrict__ posq_s, const int* __restrict__ orig_s,
+                                              BuildGroupSmem& sm, int nruns, bool rx, bool ry, bool rz, int lane, bool anyfar,
+                                              float lox, float hix, float loy, float hiy, float loz, float hiz,
+                                              int (&cnt)[BUILD_GROUP], IDX* rows) {
+    const float cut2 = d.list_cutoff2;
+    const float bx = d.boxf[0], by = d.boxf[1], bz = d.boxf[2], ibx = d.boxf[3], iby = d.boxf[4], ibz = d.boxf[5];
+    const float qnan = __int_as_float(0x7fc00000);
+    const int nl_M = d.nl_M;
+    const int total = sm.off[nruns];
+    const unsigned int lt = (1u << lane) - 1u;
+    // centre and half extent of the group's bounding box (point-to-box distance of a candidate)
+    const float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+    const float ex = 0.5f * (hix - lox), ey = 0.5f * (hiy - loy), ez = 0.5f * (hiz - loz);
+    int kp = 0;
+    float4 cnext = make_float4(qnan, qnan, qnan, 0.f);
+    int ojnext = 0;
+    auto fetch = [&](int c) {
+        cnext = make_float4(qnan, qnan, qnan, 0.f);
+        if (c < total) {
+            while (c >= sm.off[kp + 1]) ++kp;
+            const float4 rn = sm.runs[kp];
+            const int s = __float_as_int(rn.w) + (c - sm.off[kp]);
+            const float4 p = posq_s[s];
+            ojnext = orig_s[s];
+            cnext = make_float4(p.x + rn.x, p.y + rn.y, p.z + rn.z, __int_as_float(s));   // shifted image; w = sorted index
+        }
+    };
+    fetch(lane);
+    for (int c0 = 0; c0 < total; c0 += 32) {
+        const float4 c = cnext;
+        const int oj = ojnext;
+        fetch(c0 + 32 + lane);
+        // distance from the candidate to the group's bounding box: a lower bound of its distance to every group atom
+        {
+            float qx = c.x - cx, qy = c.y - cy, qz = c.z - cz;
+            if (RINT) {
+                if (rx) qx -= bx * rintf(qx * ibx);
+                if (ry) qy -= by * rintf(qy * iby);
+                if (rz) qz -= bz * rintf(qz * ibz);
+            }
+            qx = fmaxf(fabsf(qx) - ex, 0.f); qy = fmaxf(fabsf(qy) - ey, 0.f); qz = fmaxf(fabsf(qz) - ez, 0.f);
+            if (!__any_sync(0xffffffffu, qx * qx + qy * qy + qz * qz < cut2)) continue;      // NaN (padding) compares false
+        }
+        bool near = false;
+#pragma unroll
+        for (int k = 0; k < BUILD_GROUP; ++k) { const int2 sp = sm.gspan[k]; near = near || (unsigned int)(oj - sp.x) <= (unsigned int)sp.y; }
+        const bool check = anyfar || __any_sync(0xffffffffu, near);
+        unsigned int bits = 0;
+#pragma unroll
+        for (int a = 0; a < BUILD_GROUP; ++a) {
+            const float4 g = sm.gat[a];
+            float dx = c.x - g.x, dy = c.y - g.y, dz = c.z - g.z;
+            if (RINT) {
+                if (rx) dx -= bx * rintf(dx * ibx);
+                if (ry) dy -= by * rintf(dy * iby);
+                if (rz) dz -= bz * rintf(dz * ibz);
+            }
+            bits |= (dx * dx + dy * dy + dz * dz < cut2) ? (1u << a) : 0u;
+        }
+        if (check && bits) {
+            // rare: this chunk holds a candidate inside the exclusion window of a group atom (or far exclusions exist)
+            for (int a = 0; a < BUILD_GROUP; ++a) {
+                if (!((bits >> a) & 1u)) continue;
+                const int oi = __float_as_int(sm.gat[a].w);
+                const unsigned int dd = (unsigned int)(oj - oi + 32);
+                bool ok = true;
+                if (dd < 64u) ok = !((sm.gwin[a] >> dd) & 1ull);                 // includes the atom itself (bit 32)
+                else if (sm.gfar[a]) ok = !pair_excluded(d, oi, sm.gwin[a], true, oj, d.has_far[oj]);
+                if (!ok) bits &= ~(1u << a);
+            }
+        }
+        const int sj = __float_as_int(c.w);
+#pragma unroll
+        for (int a = 0; a < BUILD_GROUP; ++a) {
+            const bool mine = (bits >> a) & 1u;
+            const unsigned int m = __ballot_sync(0xffffffffu, mine);
+            if (m) {
+                const int pos = cnt[a] + __popc(m & lt);
+                if (mine && pos < nl_M) rows[(size_t)a * nl_M + pos] = (IDX)sj;
+                cnt[a] += __popc(m);
+            }
+        }
+    }
+}
+
+template <typename IDX>
+__global__ void __launch_bounds__(32, 24) k_build_list2(Dev d) {
+    __shared__ BuildGroupSmem sm;
+    const int lane = threadIdx.x;
+    const int N = d.N, Npad = d.Npad;
+    for (int wk = 0; wk < d.R; ++wk) {
+    const int r = (blockIdx.x + wk) % d.R;
+    Globals& g = d.g[r];
+    if (!g.do_rebuild) continue;
+    const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
+    const int* __restrict__ orig_s = d.orig_s + (size_t)r * Npad;
+    const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
+    const int* __restrict__ groups = d.group_first + (size_t)r * d.group_capacity;
+    const int n_groups = g.n_groups;
+    const int a = lane & (BUILD_GROUP - 1);
+    for (;;) {
+        int gi = 0;
+        if (lane == 0) gi = atomicAdd(&g.build_cursor, 1);
+        gi = __shfl_sync(0xffffffffu, gi, 0);
+        if (gi >= n_groups) break;
+        const int packed = groups[gi];
+        const int i0 = packed >> 4, na = packed & 15;
+        const bool valid = a < na;
+        const int i = valid ? i0 + a : i0;
+        const float qnan = __int_as_float(0x7fc00000);
+        const float4 pa = posq_s[i];
+        const int oi = orig_s[i];
+        const ull wi = valid ? (d.excl_win[oi] | (1ull << 32)) : 0ull;
+        const bool fari = valid ? d.has_far[oi] : false;
+        const bool anyfar = __any_sync(0xffffffffu, fari);
+        __syncwarp();                                   // the previous group's readers are done with the shared tables
+        if (lane < BUILD_GROUP) {
+            sm.gat[lane] = valid ? make_float4(pa.x, pa.y, pa.z, __int_as_float(oi)) : make_float4(qnan, qnan, qnan, __int_as_float(-1));
+            sm.gwin[lane] = wi;
+            sm.gfar[lane] = fari ? 1 : 0;
+            // idle slots: an empty window ([1, 0] never contains a candidate)
+            const int below = valid ? 32 - (__ffsll((long long)wi) - 1) : 0, above = valid ? 31 - __clzll((long long)wi) : 0;
+            sm.gspan[lane] = valid ? make_int2(oi - below, below + above) : make_int2(0x7fffffff, 0);
+        }
+        int cnt[BUILD_GROUP];
+#pragma unroll
+        for (int k = 0; k < BUILD_GROUP; ++k) cnt[k] = 0;
+        IDX* rows = reinterpret_cast<IDX*>(d.nl_list) + ((size_t)r * Npad + i0) * d.nl_M;
+        if (!d.periodic) {
+            if (lane == 0) { sm.runs[0] = make_float4(0.f, 0.f, 0.f, __int_as_float(0)); sm.off[0] = 0; sm.off[1] = N; }
+            __syncwarp();
+            build_stream2<false, IDX>(d, posq_s, orig_s, sm, 1, false, false, false, lane, anyfar, -3.0e38f, 3.0e38f,
+                                      -3.0e38f, 3.0e38f, -3.0e38f, 3.0e38f, cnt, rows);
+        } else {
+            const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
+            int cx, cy, cz;
+            atom_cell_coords(d, pa, cx, cy, cz);
+            const int xa = __reduce_min_sync(0xffffffffu, cx), xb = __reduce_max_sync(0xffffffffu, cx);
+            const int ya = __reduce_min_sync(0xffffffffu, cy), yb = __reduce_max_sync(0xffffffffu, cy);
+            const int za = __reduce_min_sync(0xffffffffu, cz), zb = __reduce_max_sync(0xffffffffu, cz);
+            const float lox = warp_min(pa.x), hix = warp_max(pa.x), loy = warp_min(pa.y), hiy = warp_max(pa.y);
+            const float loz = warp_min(pa.z), hiz = warp_max(pa.z);
+            const bool rx = xb - xa + 5 > ncx, ry = yb - ya + 5 > ncy, rz = zb - za + 5 > ncz;
+            const int x0 = rx ? 0 : xa - 2, x1 = rx ? ncx - 1 : xb + 2;
+            const int y0 = ry ? 0 : ya - 2, y1 = ry ? ncy - 1 : yb + 2;
+            const int nruns = build_group_runs(d, start, lane, rx, ry, rz, x0, x1, y0, y1, za, zb, lox, hix, loy, hiy, loz,
+                                               hiz, sm.runs, sm.off);
+            if (rx || ry || rz)
+                build_stream2<true, IDX>(d, posq_s, orig_s, sm, nruns, rx, ry, rz, lane, anyfar, lox, hix, loy, hiy,
+                                         loz, hiz, cnt, rows);
+            else
+                build_stream2<false, IDX>(d, posq_s, orig_s, sm, nruns, false, false, false, lane, anyfar, lox, hix,
+                                          loy, hiy, loz, hiz, cnt, rows);
+        }
+        int mycnt = 0;
+#pragma unroll
+        for (int k = 0; k < BUILD_GROUP; ++k) mycnt = (lane == k) ? cnt[k] : mycnt;
+        if (__any_sync(0xffffffffu, lane < na && mycnt > d.nl_M)) { if (lane == 0) g.item_overflow = 1; }
+        if (lane < na) d.nl_count[(size_t)r * Npad + i0 + lane] = min(mycnt, d.nl_M);
+    }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // k_pair: direct-space Lennard-Jones + Coulomb (Ewald erfc / reaction field / plain) over the Verlet list.
 // NL_LANES lanes share one i-atom (register resident) and stride over its neighbour list with coalesced index
 // loads; j data are gathered from the spatially sorted float4 mirror (L1/L2 resident); the partial forces are
