@@ -77,6 +77,7 @@ SYMBOLS = {
     'bl_get_energy': (C.c_int, [_H, _dp, _dp]),
     'bl_get_energy_terms': (C.c_int, [_H, C.c_int, _dp]),
     'bl_copy_state': (C.c_int, [_H, _H, C.c_int]),
+    'bl_copy_state_masked': (C.c_int, [_H, _H, C.c_int, _ip]),
     'bl_velocities_to_temperature': (C.c_int, [_H, C.c_double]),
     'bl_get_global': (C.c_int, [_H, C.c_int, C.c_char_p, _dp]),
     'bl_set_global': (C.c_int, [_H, C.c_int, C.c_char_p, C.c_double]),
@@ -286,9 +287,15 @@ class Engine(object):
         self._check(self.lib.bl_get_energy_terms(self.h, replica, _p(out, C.c_double)))
         return dict(zip(ENERGY_TERMS, out.tolist()))
 
-    def copy_state_from(self, other, positions=True, velocities=True, box=True):
+    def copy_state_from(self, other, positions=True, velocities=True, box=True, mask=None):
+        """Device-to-device copy of the walkers' state from another engine on the same GPU (all walkers, or those with
+        mask[r] != 0; the box is shared by the walkers and only copied by the unmasked form)."""
         flags = (1 if positions else 0) | (2 if velocities else 0) | (4 if box else 0)
-        self._check(self.lib.bl_copy_state(self.h, other.h, flags))
+        if mask is None:
+            self._check(self.lib.bl_copy_state(self.h, other.h, flags))
+        else:
+            m = _arr(mask, np.int32).reshape(self.n_replicas)
+            self._check(self.lib.bl_copy_state_masked(self.h, other.h, flags & 3, _p(m, C.c_int32)))
 
     def velocities_to_temperature(self, temperature):
         self._check(self.lib.bl_velocities_to_temperature(self.h, float(temperature)))

@@ -74,8 +74,11 @@ struct bl_handle {
     std::vector<double> host_tmp;
     double skin = 0.0; int cell_capacity = 0;
     int build_cq = 0, build_ctas = 0;
-    bool builder2 = true; int build2_ctas = 0;   // ballot-compaction list builder (BLUES_B200_BUILDER=1: the round-1 builder)
-    bool own_dft = false;        // reciprocal space by the fused direct-DFT kernels (small grids) instead of cuFFT
+    bool builder2 = false; int build2_ctas = 0;  // BLUES_B200_BUILDER=2: ballot-compaction list builder (measured 10 % slower than
+                                                 // the shared-memory sub-list builder, gpurun_out/r2_builder.log: kept for reference)
+    bool fold_zero = true;       // step programs: force zeroing + rebuild latch inside the INTEGRATE launch before an evaluation
+    int own_dft = 0;             // reciprocal space: 0 cuFFT, 1 three fused direct-DFT kernels, 2 one cluster kernel (small grids)
+    size_t dft_smem = 0;
     int pair_variant = 132;      // BLUES_B200_PAIR: 0 = k_pair (round 1), else k_pair2 <ewald, lanes, U> (see enqueue_eval); measured: gpurun_out/pair_sweep.log
     int graph_steps = 4;         // plain NCMC steps captured per CUDA graph
     bool pdl = true;             // programmatic dependent launch on the B -> flip -> A -> sort edges (BLUES_B200_PDL=0: off)
@@ -205,19 +208,22 @@ static void launch_pdl_smem(bl_handle* h, void (*kernel)(KArgs...), dim3 grid, d
 
 // ---- force / energy evaluation at the current positions ---------------------------------------------------
 // energy: also accumulate energies; cm_mode: forwarded to k_begin_eval
-static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, int cm_mode, int prefetch_noise = 0) {
+// pre_zeroed: the preceding INTEGRATE launch ran with IntegrateArgs::pre_eval (forces cleared, rebuild latched, counters
+// advanced): no k_begin_eval
+static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, int cm_mode, int prefetch_noise = 0,
+                         bool pre_zeroed = false) {
     Dev& d = h->d;
     cudaStream_t st = h->stream;
     const int R = d.R, N = d.N;
     {
-        // latches the rebuild request, then (only if due) the cell sort
+        // latches the rebuild request (unless the integrator did), then (only if due) the cell sort
         LaunchTimer t(h, BL_K_NEIGHBOR);
-        launch_pdl(h, k_sort_atoms, dim3(SORT_CTAS, R), dim3(1024), st, d);
+        launch_pdl(h, k_sort_atoms, dim3(SORT_CTAS, R), dim3(1024), st, d, pre_zeroed ? 1 : 0, cm_mode, h->cm_parity);
     }
     tl_mark(h, st, TL_SORT);
     // Fork 1: reciprocal space (stream2) depends only on the cell-sorted positions; its gather waits for fork 2.
     cudaEventRecord(h->ev_fork, st);
-    {
+    if (!pre_zeroed) {
         LaunchTimer t(h, -1);
         long long nf = (long long)R * 3 * N * (d.n_alch > 0 ? 1 + ALCH_SLOTS : 1);
         int blocks = std::max(1, std::min(cdiv(nf, 256 * 4), 148 * 8));
@@ -240,7 +246,14 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
           if (R <= 2) k_pme_spread<8, 512><<<dim3(d.gx, 8, R), 512, (d.gy / 8 + 1) * d.gz * sizeof(int), s2>>>(d);
           else k_pme_spread<4, 256><<<dim3(d.gx, 4, R), 256, (d.gy / 4 + 1) * d.gz * sizeof(int), s2>>>(d); }
         tl_mark(h, s2, TL_SPREAD);
-        if (h->own_dft) {
+        if (h->own_dft == 2) {
+            // one cluster kernel for the whole transform chain
+            LaunchTimer t(h, BL_K_FFT, s2);
+            const int P = cdiv(d.gx, PME_CL);
+            if (energy) launch_pdl_smem(h, k_pme_dft_cluster<true>, dim3(PME_CL, R), dim3(PME_CL_THREADS), h->dft_smem, s2, d, P);
+            else launch_pdl_smem(h, k_pme_dft_cluster<false>, dim3(PME_CL, R), dim3(PME_CL_THREADS), h->dft_smem, s2, d, P);
+            tl_mark(h, s2, TL_C2R);
+        } else if (h->own_dft) {
             const int Zc = d.gz / 2 + 1;
             const size_t sm1 = sizeof(float) * ((d.gy * d.gz + 1) & ~1) + sizeof(float2) * (d.gy * Zc + d.gz + d.gy);
             const size_t sm3 = sizeof(float2) * (2 * d.gy * Zc + d.gz + d.gy);
@@ -265,6 +278,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         { LaunchTimer t(h, BL_K_FFT, s2); cufftExecC2R(h->plan_c2r, reinterpret_cast<cufftComplex*>(d.grid_c), d.grid_r); }
         tl_mark(h, s2, TL_C2R);
         }
+        if (!h->profiling) cudaStreamWaitEvent(s2, h->ev_fork2, 0);      // the gather adds to the cleared force accumulators
         { LaunchTimer t(h, BL_K_PME_GATHER, s2);
           if (R <= 2) k_pme_gather5<<<dim3(cdiv(cdiv(N, 6) * 32, 128), R), 128, 0, s2>>>(d);
           else k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
@@ -519,7 +533,8 @@ static void issue(bl_handle* h, const std::vector<Launch>& ls, HostCounters& hc,
         if (l.is_eval) {
             if (hc.pending_noise != 0 || hc.pending_md != 0) hc.noise_ready = 0;    // counters move: stale
             const int prefetch = hc.noise_ready > 0 ? 0 : noise_lookahead(ls, k);
-            if (!dry) enqueue_eval(h, l.energy, hc.pending_noise, hc.pending_md, l.cm_mode, prefetch);
+            const bool pre_zeroed = h->fold_zero && k > 0 && !ls[k - 1].is_eval;
+            if (!dry) enqueue_eval(h, l.energy, hc.pending_noise, hc.pending_md, l.cm_mode, prefetch, pre_zeroed);
             if (prefetch > 0) hc.noise_ready = prefetch;
             hc.pending_noise = 0;
             hc.pending_md = 0;
@@ -528,6 +543,12 @@ static void issue(bl_handle* h, const std::vector<Launch>& ls, HostCounters& hc,
             a.noise_offset = hc.pending_noise;
             a.md_offset = hc.pending_md;
             const int n_o = count_ops(a, OP_O), n_md = count_ops(a, OP_MD);
+            if (h->fold_zero && k + 1 < ls.size() && ls[k + 1].is_eval) {
+                a.pre_eval = 1;
+                a.pre_cm_mode = ls[k + 1].cm_mode;
+                a.pre_adv_noise = hc.pending_noise + n_o;
+                a.pre_adv_md = hc.pending_md + n_md;
+            }
             const bool prefetched = n_o > 0 && n_md == 0 && hc.pending_noise == 0 && hc.noise_ready >= n_o;
             if (!dry) enqueue_integrate(h, a, prefetched);
             if (n_o > 0 || n_md > 0) hc.noise_ready = 0;        // consumed, or overwritten by the inline kernels
@@ -877,6 +898,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_GRAPH_STEPS")) h->graph_steps = std::max(1, atoi(getenv("BLUES_B200_GRAPH_STEPS")));
     if (getenv("BLUES_B200_TIMELINE")) { h->timeline = true; h->graph_steps = 1; }
     if (getenv("BLUES_B200_PAIR")) h->pair_variant = atoi(getenv("BLUES_B200_PAIR"));
+    if (getenv("BLUES_B200_FOLD_ZERO")) h->fold_zero = atoi(getenv("BLUES_B200_FOLD_ZERO")) != 0;
     counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping
     auto fail = [&](int code, const std::string& msg) { g_create_error = msg; bl_destroy(h); return code; };
     h->device = device;
@@ -1060,6 +1082,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     d.cm_acc = dalloc<long long>(h, (size_t)2 * R * 3);
     d.heat_acc = dalloc<long long>(h, R);
     d.g = dalloc<Globals>(h, R);
+    d.cta_done = dalloc<int>(h, R);
     d.noise = dalloc<double>(h, (size_t)R * MAX_NOISE_SETS * N * 3);
     h->cm_parity = dalloc<int>(h, 1);
     h->d_scratch = dalloc<double>(h, std::max((size_t)R * 4, (size_t)N * 3));
@@ -1111,7 +1134,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         if (R > 2 && per_sm > 2) per_sm -= 1;
         if (getenv("BLUES_B200_BUILD_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("BLUES_B200_BUILD_PER_SM"))));
         h->build_ctas = std::max(32, std::min(R * (cdiv(d.Npad, BUILD_GROUP) + 64), per_sm * n_sm));
-        if (getenv("BLUES_B200_BUILDER")) h->builder2 = atoi(getenv("BLUES_B200_BUILDER")) != 1;
+        if (getenv("BLUES_B200_BUILDER")) h->builder2 = atoi(getenv("BLUES_B200_BUILDER")) == 2;
         int per_sm2 = 0;
         if (d.nl_u16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_build_list2<unsigned short>, 32, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_build_list2<int>, 32, 0);
@@ -1146,8 +1169,17 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
                 return dupload(h, tw);
             };
             d.tw_x = twiddles(d.gx); d.tw_y = twiddles(d.gy); d.tw_z = twiddles(d.gz);
-            h->own_dft = d.gx <= PME_DFT_MAX && d.gy <= PME_DFT_MAX && d.gz <= PME_DFT_MAX;
-            if (getenv("BLUES_B200_DFT")) h->own_dft = h->own_dft && atoi(getenv("BLUES_B200_DFT")) != 0;
+            const bool small = d.gx <= PME_DFT_MAX && d.gy <= PME_DFT_MAX && d.gz <= PME_DFT_MAX;
+            h->own_dft = small ? 2 : 0;
+            if (getenv("BLUES_B200_DFT")) h->own_dft = small ? atoi(getenv("BLUES_B200_DFT")) : 0;
+            {
+                const int Zc2 = d.gz / 2 + 1, P = cdiv(d.gx, PME_CL);
+                h->dft_smem = sizeof(float2) * ((size_t)P * d.gy * Zc2 + d.gy * Zc2 + d.gz + d.gy + d.gx + (PME_CL_THREADS / 32) * 2 * d.gx) +
+                              sizeof(float) * ((d.gy * d.gz + 1) & ~1);
+                if (h->dft_smem > 200 * 1024 && h->own_dft == 2) h->own_dft = 1;
+                cudaFuncSetAttribute(k_pme_dft_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dft_smem);
+                cudaFuncSetAttribute(k_pme_dft_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dft_smem);
+            }
             const int Zc = d.gz / 2 + 1;
             const size_t sm = std::max(sizeof(float) * ((d.gy * d.gz + 1) & ~1) + sizeof(float2) * (d.gy * Zc + d.gz + d.gy),
                                        sizeof(float2) * (2 * d.gy * Zc + d.gz + d.gy));
@@ -1430,6 +1462,33 @@ int bl_copy_state(bl_handle* dst, const bl_handle* src, int flags) {
     if (flags & 1) CK(cudaMemcpyAsync(dst->d.pos, src->d.pos, n, cudaMemcpyDeviceToDevice, h->stream));
     if (flags & 2) { CK(cudaMemcpyAsync(dst->d.vel, src->d.vel, n, cudaMemcpyDeviceToDevice, h->stream)); h->vel_dirty = true; }
     if (flags & 5) positions_changed(h, (flags & 1) ? -1 : -2);
+    return BL_OK;
+}
+
+int bl_copy_state_masked(bl_handle* dst, const bl_handle* src, int flags, const int32_t* mask) {
+    if (!dst || !src) return BL_ERR_INVALID;
+    if (!mask) return bl_copy_state(dst, src, flags);
+    bl_handle* h = dst;
+    if (dst->d.N != src->d.N || dst->device != src->device || dst->d.R != src->d.R) { h->error = "handles are not compatible"; return BL_ERR_INVALID; }
+    cudaSetDevice(h->device);
+    CK(cudaStreamSynchronize(src->stream));
+    const size_t n = sizeof(double4) * (size_t)dst->d.N;
+    bool any = false;
+    for (int r = 0; r < dst->d.R; ++r) {
+        if (!mask[r]) continue;
+        any = true;
+        if (flags & 1) CK(cudaMemcpyAsync(dst->d.pos + (size_t)r * dst->d.N, src->d.pos + (size_t)r * dst->d.N, n, cudaMemcpyDeviceToDevice, h->stream));
+        if (flags & 2) { CK(cudaMemcpyAsync(dst->d.vel + (size_t)r * dst->d.N, src->d.vel + (size_t)r * dst->d.N, n, cudaMemcpyDeviceToDevice, h->stream)); h->vel_dirty = true; }
+    }
+    if (any && (flags & 1)) {
+        // clear the latches of the walkers that received coordinates; all mirrors are refreshed
+        positions_changed(h, -2);
+        std::vector<Globals> g(dst->d.R);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(g.data(), dst->d.g, sizeof(Globals) * dst->d.R, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < dst->d.R; ++r) if (mask[r]) { g[r].nan_flag = 0; g[r].item_overflow = 0; }
+        CK(cudaMemcpy(dst->d.g, g.data(), sizeof(Globals) * dst->d.R, cudaMemcpyHostToDevice));
+    }
     return BL_OK;
 }
 

@@ -87,6 +87,7 @@ struct Dev {
     long long* cm_acc;                      // [R][3] sum of m v
     long long* heat_acc;                    // [R]
     Globals* g;                             // [R]
+    int* cta_done;                          // [R] k_integrate CTAs of the walker that have finished (pre-evaluation launches)
     double* noise;                          // [R][MAX_NOISE_SETS][N][3] standard normals for the next INTEGRATE launch
     // neighbour structures: Morton-ranked cells (edge >= list cutoff / 2), sorted mirrors, Verlet lists
     int ncell[3]; int ncells;

@@ -138,6 +138,11 @@ struct IntegrateArgs {
     int energy_valid;   // the preceding force evaluation produced energies (for OP_STEP_END bookkeeping)
     int noise_offset;   // O / MD ops executed by INTEGRATE launches since the last k_begin_eval
     int md_offset;
+    // the launch is followed by a force evaluation (step programs only): every thread clears the force accumulators of its
+    // own atoms once it has used them, and the last CTA of a walker to finish does what k_sort_atoms' latch and
+    // k_begin_eval's first CTA otherwise do (rebuild latch, energy accumulators, noise counters, momentum parity) — one
+    // kernel less on the critical path and a latch-free early exit for the sort kernel
+    int pre_eval, pre_cm_mode, pre_adv_noise, pre_adv_md;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -426,6 +431,16 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
         }
     }
     const float lim = d.skin_half2;
+    if (args.pre_eval) {
+#pragma unroll
+        for (int k = 0; k < NA; ++k)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                d.f_env[(size_t)r * 3 * N + q * N + atom[k]] = 0;
+                if (d.n_alch > 0)
+                    for (int sl = 0; sl < ALCH_SLOTS; ++sl) d.f_alch[((size_t)sl * d.R + r) * 3 * N + q * N + atom[k]] = 0;
+            }
+    }
     if (!x_changed) {
         // velocity-only launch (e.g. the trailing "V H" of a pass): positions, mirrors and the displacement test are
         // untouched
@@ -573,6 +588,13 @@ __device__ __forceinline__ void run_cluster_generic(const Dev& d, const Integrat
         }
     }
     const float lim = d.skin_half2;
+    if (args.pre_eval)
+        for (int k = 0; k < c.natoms; ++k)
+            for (int q = 0; q < 3; ++q) {
+                d.f_env[(size_t)r * 3 * N + q * N + c.atom[k]] = 0;
+                if (d.n_alch > 0)
+                    for (int sl = 0; sl < ALCH_SLOTS; ++sl) d.f_alch[((size_t)sl * d.R + r) * 3 * N + q * N + c.atom[k]] = 0;
+            }
     for (int k = 0; k < c.natoms; ++k) {
         const int a = c.atom[k];
         pos[a] = make_double4(s.x[k][0], s.x[k][1], s.x[k][2], 0.0);
@@ -658,6 +680,30 @@ __global__ void __launch_bounds__(64) k_integrate(Dev d, IntegratorConsts ic, In
                 g.prop = 1;
                 if (g.nan_flag) g.protocol_work = __longlong_as_double(0x7ff8000000000000LL);   // rejected by the Metropolis test
             }
+        }
+    }
+    if (args.pre_eval) {
+        // last CTA of this walker to get here: every flag, momentum sum and energy read of the launch is complete
+        __shared__ int s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(&d.cta_done[r], 1) == (int)gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (threadIdx.x == 0) {
+                d.cta_done[r] = 0;
+                g.do_rebuild = g.rebuild_request == 2 || g.prune_request;
+                g.do_prune = g.do_rebuild;
+                g.rebuild_request = 0;
+                g.prune_request = 0;
+                g.noise_counter += args.pre_adv_noise;
+                g.md_counter += args.pre_adv_md;
+            }
+            for (int i = threadIdx.x; i < N_ETERMS; i += blockDim.x) d.eacc[r * N_ETERMS + i] = 0;
+            for (int i = threadIdx.x; i < ALCH_SLOTS * 3; i += blockDim.x) d.alch_acc[r * ALCH_SLOTS * 3 + i] = 0;
         }
     }
 }

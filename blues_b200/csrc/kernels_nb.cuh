@@ -50,7 +50,10 @@ __device__ __forceinline__ void atom_cell_coords(const Dev& d, float4 p, int& cx
 
 #define SORT_CTAS 8
 #define BUILD_GROUP 8          /* atoms per k_build_list work group */
-__global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort_atoms(Dev d) {
+// latched = 1: the preceding k_integrate launch (IntegrateArgs::pre_eval) has latched do_rebuild and cleared the energy
+// accumulators; this kernel then only handles the momentum parity (cm_mode as in k_begin_eval) and exits without a
+// cluster barrier unless a rebuild is due
+__global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort_atoms(Dev d, int latched, int cm_mode, int* cm_parity) {
     // one thread-block cluster (8 CTAs, hardware cluster barrier) per walker
     namespace cg = cooperative_groups;
     cudaGridDependencySynchronize();       // programmatic dependent launch: no-op when launched without the attribute
@@ -58,16 +61,26 @@ __global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort
     const int r = blockIdx.y;
     Globals& g = d.g[r];
     const int cta = (int)cluster.block_rank();
-    if (cta == 0 && threadIdx.x == 0) {
-        // latch: the Verlet list is rebuilt (cell sort + search) when some atom moved > skin / 2 since the last build,
-        // or on request (host wrote coordinates, box changed); the alchemical pair list follows the same schedule
-        g.do_rebuild = g.rebuild_request == 2 || g.prune_request;
-        g.do_prune = g.do_rebuild;
-        g.rebuild_request = 0;
-        g.prune_request = 0;
+    if (latched) {
+        if (cm_mode && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 32) {
+            const int p = *cm_parity;
+            for (int i = threadIdx.x; i < d.R * 3; i += 32) d.cm_acc[(size_t)p * d.R * 3 + i] = 0;
+            __syncwarp();
+            if (cm_mode == 2 && threadIdx.x == 0) *cm_parity = p ^ 1;
+        }
+        if (!g.do_rebuild) return;             // uniform over the cluster, no barrier needed
+    } else {
+        if (cta == 0 && threadIdx.x == 0) {
+            // latch: the Verlet list is rebuilt (cell sort + search) when some atom moved > skin / 2 since the last build,
+            // or on request (host wrote coordinates, box changed); the alchemical pair list follows the same schedule
+            g.do_rebuild = g.rebuild_request == 2 || g.prune_request;
+            g.do_prune = g.do_rebuild;
+            g.rebuild_request = 0;
+            g.prune_request = 0;
+        }
+        cluster.sync();
+        if (!g.do_rebuild) return;                 // uniform over the cluster
     }
-    cluster.sync();
-    if (!g.do_rebuild) return;                 // uniform over the cluster
     const int tid = cta * blockDim.x + threadIdx.x, nt = SORT_CTAS * blockDim.x;
     const int lane = threadIdx.x & 31, warp = tid >> 5, nwarps = nt >> 5;
     const int N = d.N, Npad = d.Npad, ncells = d.ncells;

@@ -1,6 +1,7 @@
 // Smooth particle-mesh Ewald reciprocal space (K4 spread, K5 convolution, K6 gather) around cuFFT.
 // Order-5 cardinal B-splines; weight of grid point base+k is M5(frac + 4 - k) (same convention as the oracle).
 #pragma once
+#include <cooperative_groups.h>
 #include "engine.cuh"
 
 // M5 weights and derivatives at fractional offset w in [0,1): out[k] = M5(w + 4 - k), dout[k] = M5'(w + 4 - k)
@@ -333,6 +334,144 @@ __global__ void __launch_bounds__(PME_DFT_THREADS) k_pme_idft_yz(Dev d) {
         }
         if (even) acc += (z & 1) ? -c[Zc - 1].x : c[Zc - 1].x;
         dst[o] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_pme_dft_cluster: the whole reciprocal-space transform chain — forward z, y, x, influence function (+ energy), inverse
+// x, y, z — as ONE kernel on one thread-block cluster per walker.  The timeline (gpurun_out/r2_timeline.log) shows why:
+// while the pair kernel fills the SMs each of the short transform kernels is stretched 4 x (k_pme_dft_zy 10 -> 43 us) and
+// every kernel boundary adds a launch + dependency gap, so the chain, not the pair kernel, is the critical path of the
+// ~5 of 6 steps without a list rebuild.  Here CTA c of the cluster owns the x-planes c P .. c P + P - 1 in shared memory
+// (P = ceil(X / PME_CL)); the z and y passes are local, the x pass reads the lines through distributed shared memory
+// (one warp per (ky, kz) line, staged locally), applies the influence function, transforms back and returns the line to
+// its owners; two cluster barriers in total, no global round trip between the passes.
+// ---------------------------------------------------------------------------------------------------------
+#define PME_CL 8
+#define PME_CL_THREADS 384
+template <bool ENERGY>
+__global__ void __cluster_dims__(PME_CL, 1, 1) __launch_bounds__(PME_CL_THREADS) k_pme_dft_cluster(Dev d, int P) {
+    namespace cg = cooperative_groups;
+    extern __shared__ float s_dft[];
+    cudaGridDependencySynchronize();
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int r = blockIdx.y;
+    const int X = d.gx, Y = d.gy, Z = d.gz, Zc = Z / 2 + 1, YZc = Y * Zc;
+    // shared layout: cplane [P][Y][Zc] float2 | tmp [Y][Zc] float2 | rplane [Y][Z] float | twz, twy, twx | line staging
+    float2* cplane = reinterpret_cast<float2*>(s_dft);
+    float2* tmp = cplane + (size_t)P * YZc;
+    float* rplane = reinterpret_cast<float*>(tmp + YZc);
+    float2* twz = reinterpret_cast<float2*>(rplane + ((Y * Z + 1) & ~1));
+    float2* twy = twz + Z;
+    float2* twx = twy + Y;
+    float2* sline = twx + X;                                   // [warps][2][X]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = tid; k < Z; k += nt) twz[k] = d.tw_z[k];
+    for (int k = tid; k < Y; k += nt) twy[k] = d.tw_y[k];
+    for (int k = tid; k < X; k += nt) twx[k] = d.tw_x[k];
+    // ---- forward z and y passes on the planes this CTA owns
+    for (int p = 0; p < P; ++p) {
+        const int x = rank * P + p;
+        if (x >= X) break;                                      // uniform over the CTA
+        const float* src = d.grid_r + (size_t)r * d.gsize + (size_t)x * Y * Z;
+        __syncthreads();                                        // rplane / tmp of the previous plane are free (and twiddles loaded)
+        for (int k = tid; k < Y * Z; k += nt) rplane[k] = src[k];
+        __syncthreads();
+        for (int o = tid; o < YZc; o += nt) {
+            const int y = o / Zc, kz = o - y * Zc;
+            const float* in = rplane + y * Z;
+            float re = 0.f, im = 0.f;
+            int m = 0;
+            for (int z = 0; z < Z; ++z) {
+                const float v = in[z];
+                const float2 w = twz[m];
+                re = fmaf(v, w.x, re); im = fmaf(-v, w.y, im);
+                m += kz; m -= m >= Z ? Z : 0;
+            }
+            tmp[o] = make_float2(re, im);
+        }
+        __syncthreads();
+        for (int o = tid; o < YZc; o += nt) {
+            const int ky = o / Zc, kz = o - ky * Zc;
+            cplane[(size_t)p * YZc + o] = dft_line_c(tmp + kz, Zc, Y, ky, twy, -1.f);
+        }
+    }
+    cluster.sync();
+    // ---- x pass: line l = ky Zc + kz is handled by CTA l mod PME_CL, one warp per line
+    {
+        const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+        float2* lin = sline + (size_t)warp * 2 * X;
+        float2* lout = lin + X;
+        const float V = d.boxf[0] * d.boxf[1] * d.boxf[2];
+        const float pi2_over_a2 = 9.8696044010893586f / (d.alpha * d.alpha);
+        double e = 0.0;
+        for (int l = rank + PME_CL * warp; l < YZc; l += PME_CL * nwarps) {
+            for (int x = lane; x < X; x += 32) {
+                const float2* owner = cluster.map_shared_rank(cplane, x / P);
+                lin[x] = owner[(size_t)(x % P) * YZc + l];
+            }
+            __syncwarp();
+            const int ky = l / Zc, kz = l - ky * Zc;
+            const int my = ky <= Y / 2 ? ky : ky - Y;
+            const float fy = my * d.boxf[4], fz = kz * d.boxf[5];
+            for (int kx = lane; kx < X; kx += 32) {
+                float2 c = dft_line_c(lin, 1, X, kx, twx, -1.f);
+                float eterm = 0.f;
+                if (kx != 0 || l != 0) {
+                    const int mx = kx <= X / 2 ? kx : kx - X;
+                    const float fx = mx * d.boxf[3];
+                    const float m2 = fx * fx + fy * fy + fz * fz;
+                    const float denom = m2 * d.bmod_x[kx] * d.bmod_y[ky] * d.bmod_z[kz] * 3.14159265358979f * V;
+                    eterm = (float)ONE_4PI_EPS0 * expf(-pi2_over_a2 * m2) / denom;
+                }
+                if (ENERGY) {
+                    const double w = (kz == 0 || (2 * kz == Z)) ? 1.0 : 2.0;
+                    e += 0.5 * w * (double)eterm * ((double)c.x * c.x + (double)c.y * c.y);
+                }
+                lout[kx] = make_float2(c.x * eterm, c.y * eterm);
+            }
+            __syncwarp();
+            for (int x = lane; x < X; x += 32) {
+                float2* owner = cluster.map_shared_rank(cplane, x / P);
+                owner[(size_t)(x % P) * YZc + l] = dft_line_c(lout, 1, X, x, twx, 1.f);
+            }
+            __syncwarp();
+        }
+        if (ENERGY) {
+            e = warp_sum(e);
+            if (lane == 0 && e != 0.0) fx_add(&d.eacc[r * N_ETERMS + E_PME], e, ENERGY_SCALE);
+        }
+    }
+    cluster.sync();
+    // ---- inverse y and z passes, real grid back to global memory
+    const bool even = (Z & 1) == 0;
+    for (int p = 0; p < P; ++p) {
+        const int x = rank * P + p;
+        if (x >= X) break;
+        const float2* in = cplane + (size_t)p * YZc;
+        __syncthreads();
+        for (int o = tid; o < YZc; o += nt) {
+            const int y = o / Zc, kz = o - y * Zc;
+            tmp[o] = dft_line_c(in + kz, Zc, Y, y, twy, 1.f);
+        }
+        __syncthreads();
+        float* dst = d.grid_r + (size_t)r * d.gsize + (size_t)x * Y * Z;
+        for (int o = tid; o < Y * Z; o += nt) {
+            const int y = o / Z, z = o - y * Z;
+            const float2* c = tmp + y * Zc;
+            float acc = c[0].x;
+            int m = z;
+            const int last = even ? Zc - 1 : Zc;
+            for (int kz = 1; kz < last; ++kz) {
+                const float2 w = twz[m];
+                acc = fmaf(2.f * c[kz].x, w.x, acc);
+                acc = fmaf(-2.f * c[kz].y, w.y, acc);
+                m += z; m -= m >= Z ? Z : 0;
+            }
+            if (even) acc += (z & 1) ? -c[Zc - 1].x : c[Zc - 1].x;
+            dst[o] = acc;
+        }
     }
 }
 

@@ -187,7 +187,26 @@ class SimulationFactory(object):
     @classmethod
     def generateSimFromStruct(cls, structure, system, integrator, platform=None, properties={}, **kwargs):
         """Simulation with box, positions and Maxwell–Boltzmann velocities set (``blues/simulation.py:707-745``)."""
+        # `nReplicas` (an addition: YAML `simulation: nReplicas:`) is the number of independent walkers of the JOB; under
+        # torchrun each rank (one per GPU) holds its round-robin share (parallel.shard_walkers) on device LOCAL_RANK, or on
+        # `devices[LOCAL_RANK]` when a device list is given.  Walkers never communicate (SURVEY.md §8e).
         n_replicas = kwargs.get('nReplicas', None)
+        if n_replicas:
+            from . import parallel
+            rank, world = parallel.rank_world()
+            n_replicas = len(parallel.shard_walkers(int(n_replicas), rank, world))
+            if n_replicas == 0:
+                raise ValueError('nReplicas (%s) is smaller than the number of ranks (%d)' % (kwargs.get('nReplicas'), world))
+            devices = kwargs.get('devices', None)
+            local_rank = int(__import__('os').environ.get('LOCAL_RANK', '0'))
+            properties = dict(properties)
+            if devices:
+                devices = devices if isinstance(devices, (list, tuple)) else [devices]
+                properties.setdefault('DeviceIndex', int(devices[local_rank % len(devices)]))
+            elif world > 1:
+                properties.setdefault('DeviceIndex', local_rank)
+            if platform is None:
+                platform = 'CUDA'
         if platform is None:
             simulation = openmm.Simulation(structure.topology, system, integrator, n_replicas=n_replicas)
         else:
@@ -210,6 +229,13 @@ class SimulationFactory(object):
     def generateSimulationSet(self, config=None):
         """md, alch (MD system, energy only) and ncmc Simulations (``blues/simulation.py:768-809``)."""
         cfg = config or self.config
+        if cfg.get('seed'):
+            # one Philox key per rank (walkers of a rank are subsequences of its key): ranks must not share noise
+            from . import parallel
+            rank, world = parallel.rank_world()
+            if world > 1 and not cfg.get('_seed_is_per_rank'):
+                cfg['seed'] = parallel.walker_seed(cfg['seed'], rank)
+                cfg['_seed_is_per_rank'] = True
         if 'pressure' in cfg:
             self._system = self.addBarostat(self._system, **cfg)
             logger.warning('NCMC simulation will NOT have pressure control. NCMC will use pressure from last MD state.')
@@ -449,6 +475,96 @@ class BLUESSimulation(object):
                 pass
             sys.exit(1)
 
+    # -- many walkers ----------------------------------------------------------------------------------------
+    def _iterateWalkers(self, nstepsNC, moveStep, nstepsMD, temperature):
+        """One BLUES iteration of every walker held by this rank (``simulation: nReplicas``), the steps of
+        ``blues/simulation.py:1028-1213`` per walker with the state resident on the device: MD -> NCMC copy
+        (``bl_copy_state``), NCMC protocol with the move on the device, alchemical correction from per-walker energies of
+        the three contexts, Metropolis test (``bl_accept_reject``), accepted walkers' positions NCMC -> MD
+        (``bl_copy_state_masked``), reset + velocity redraw, MD.  Returns the per-walker record of the iteration."""
+        md, alch, ncmc = (s.context._engine for s in (self._md_sim, self._alch_sim, self._ncmc_sim))
+        integrator = self._ncmc_sim.integrator
+        kT = integrator.kT.value_in_unit(unit.kilojoules_per_mole)
+        self._move_engine.selectMove()
+        move = self._move_engine.selected_move
+        device_move = move.device_move() if hasattr(move, 'device_move') else None
+        if device_move is None:
+            raise NotImplementedError('many-walker runs need a move with an on-device descriptor '
+                                      '(RandomLigandRotationMove, WaterTranslationMove)')
+        # _syncStatesMDtoNCMC
+        e_md0 = md.get_energy(True, False)[0]
+        ncmc.copy_state_from(md)
+        e_nc0 = ncmc.get_energy(True, False)[0]
+        # _stepNCMC
+        self._ncmc_sim.currentIter = self.currentIter
+        failed = False
+        try:
+            self._ncmc_sim.context = move.beforeMove(self._ncmc_sim.context)
+            if 0 <= moveStep < nstepsNC:
+                self._run_with_device_move(int(nstepsNC), int(moveStep), device_move)
+            else:
+                self._ncmc_sim.step(int(nstepsNC))
+            self._ncmc_sim.context = move.afterMove(self._ncmc_sim.context)
+        except openmm.OpenMMException as err:      # a walker blew up: its work reads NaN and it is rejected below
+            logger.error(err)
+            failed = True
+        finally:
+            integrator._scheduled_move = None
+        R = ncmc.n_replicas
+        work = np.array([ncmc.get_global('protocol_work', r) for r in range(R)])
+        e_nc1 = ncmc.get_energy(True, False)[0]
+        # _computeAlchemicalCorrection: E_alch(x1) on the MD system
+        alch.copy_state_from(ncmc, positions=True, velocities=False, box=True)
+        e_alch1 = alch.get_energy(True, False)[0]
+        correction = -(e_nc0 - e_md0 + e_alch1 - e_nc1) / kT
+        correction = np.where(np.isfinite(work) & np.isfinite(correction), correction, 0.0)
+        # _acceptRejectMove
+        accepted, logp, logu = ncmc.accept_reject(correction)
+        accepted = accepted.astype(bool) & np.isfinite(work)
+        if accepted.any():
+            md.copy_state_from(ncmc, positions=True, velocities=False, box=False, mask=accepted.astype(np.int32))
+        self.accept += int(accepted.sum())
+        self.reject += int(R - accepted.sum())
+        # _resetSimulations, _stepMD
+        self._ncmc_sim.currentStep = 0
+        integrator.reset()
+        self._md_sim.context.setVelocitiesToTemperature(temperature)
+        self._md_sim.currentIter = self.currentIter
+        self._md_sim.step(int(nstepsMD))
+        return {'work_kT': work / kT, 'correction': correction, 'log_accept': logp, 'log_u': logu, 'accepted': accepted,
+                'failed': failed}
+
+    def _runWalkers(self, nIter, nstepsNC, moveStep, nstepsMD, temperature):
+        """``run`` for contexts that hold several walkers; one all-gather of the per-walker statistics per iteration
+        (NCCL when the job runs under torchrun with GPUs, none in a single process)."""
+        from . import parallel
+        import torch.distributed as dist
+        rank, world = parallel.rank_world()
+        R = self._ncmc_sim.context.getNumReplicas()
+        distributed = world > 1 and dist.is_available() and dist.is_initialized()
+        device = None
+        if distributed and dist.get_backend() == 'nccl':
+            device = 'cuda'
+        local_ids = [rank + world * r for r in range(R)]
+        temperature = temperature if unit.is_quantity(temperature) else temperature * unit.kelvin
+        self.walker_history = []
+        n_total = 0
+        for it in range(int(nIter)):
+            self.currentIter = it
+            logger.info('BLUES Iteration: %s (%d walkers on this rank)' % (it, R))
+            rec = self._iterateWalkers(nstepsNC, moveStep, nstepsMD, temperature)
+            stats = parallel.gather_walker_stats(local_ids, rec['work_kT'], rec['log_accept'], rec['accepted'], device=device) \
+                if distributed else {'walker': np.asarray(local_ids), 'work_kT': rec['work_kT'],
+                                     'log_accept': rec['log_accept'], 'accepted': rec['accepted'].astype(int)}
+            self.walker_history.append(stats)
+            n_total += len(stats['walker'])
+            logger.info('Iteration %d: %d / %d walkers accepted, mean work %.3f kT' % (
+                it, int(np.sum(stats['accepted'])), len(stats['walker']), float(np.nanmean(stats['work_kT']))))
+        total_acc = sum(int(np.sum(s['accepted'])) for s in self.walker_history)
+        self.acceptRatio = total_acc / float(max(n_total, 1))
+        logger.info('Acceptance Ratio: %s' % self.acceptRatio)
+        logger.info('nIter: %s ' % nIter)
+
     def run(self, nIter=0, nstepsNC=0, moveStep=0, nstepsMD=0, temperature=300, write_move=False, **config):
         """NCMC → accept/reject → MD, ``nIter`` times (``blues/simulation.py:1215-1257``); arguments left at 0 come
         from the configuration."""
@@ -456,6 +572,8 @@ class BLUESSimulation(object):
         nIter, nstepsNC, nstepsMD, moveStep = (given or cfg[key] for given, key in (
             (nIter, 'nIter'), (nstepsNC, 'nstepsNC'), (nstepsMD, 'nstepsMD'), (moveStep, 'moveStep')))
         logger.info('Running %i BLUES iterations...' % (nIter))
+        if self._ncmc_sim.context.getNumReplicas() > 1:
+            return self._runWalkers(nIter, nstepsNC, moveStep, nstepsMD, temperature)
         for it in range(int(nIter)):
             self.currentIter = it
             logger.info('BLUES Iteration: %s' % it)

@@ -142,6 +142,9 @@ int bl_get_energy_terms(bl_handle* h, int replica, double terms[BL_NUM_ENERGY_TE
 /* device-to-device copy of box/positions/velocities between two handles on the same device
  * replaces: _syncStatesMDtoNCMC — blues/simulation.py:1028-1037 (flags: 1 positions, 2 velocities, 4 box) */
 int bl_copy_state(bl_handle* dst, const bl_handle* src, int flags);
+/* the same for the walkers r with mask[r] != 0 only (mask NULL: all) — the accepted walkers of a many-walker
+ * _acceptRejectMove take the NCMC end positions, blues/simulation.py:1142-1146 */
+int bl_copy_state_masked(bl_handle* dst, const bl_handle* src, int flags, const int32_t* mask /*[R]*/);
 /* replaces: context.setVelocitiesToTemperature(T) — blues/simulation.py:743,1187 */
 int bl_velocities_to_temperature(bl_handle* h, double temperature);
 

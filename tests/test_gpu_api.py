@@ -492,3 +492,93 @@ def test_contexts_draw_distinct_seeds_unless_one_is_configured(structure):
     assert [s.integrator.getRandomNumberSeed() for s in (sims2.md, sims2.alch, sims2.ncmc)] == [1234, 1235, 1236]
     v = [s.context.getState(getVelocities=True).getVelocities(asNumpy=True)._value for s in (sims2.md, sims2.alch)]
     assert not np.array_equal(v[0], v[1])
+
+
+def _walker_sim(structure, n_walkers, seed=4321, **over):
+    idx = utils.atomIndexfromTop('LIG', structure.topology)
+    systems = SystemFactory(structure, idx, system_cfg())
+    cfg = sim_cfg()
+    cfg.update(nIter=2, nstepsNC=10, nstepsMD=4, nReplicas=n_walkers, seed=seed)
+    cfg.update(over)
+    simulations = SimulationFactory(systems, MoveEngine(RandomLigandRotationMove(structure, 'LIG')), cfg)
+    for sim in (simulations.md, simulations.alch, simulations.ncmc):
+        sim.minimizeEnergy(maxIterations=100)
+    return BLUESSimulation(simulations), simulations
+
+
+def test_many_walker_blues_iteration_through_the_api(structure):
+    """`simulation: nReplicas` runs R walkers through BLUESSimulation.run — device-to-device sync,
+    NCMC with the on-device move, per-walker correction + Metropolis test, accepted walkers copied to the MD context —
+    and every piece agrees with the single-walker bookkeeping recomputed on the host from the same states."""
+    R = 4
+    b, sims = _walker_sim(structure, R)
+    md, alch, ncmc = (s.context._engine for s in (sims.md, sims.alch, sims.ncmc))
+    assert ncmc.n_replicas == R and md.n_replicas == R
+    sims.md.context.setVelocitiesToTemperature(300 * unit.kelvin)
+    sims.md.step(5)                                                  # walkers decorrelate (independent noise)
+    x_md0 = [md.get_positions(r) for r in range(R)]
+    assert not np.allclose(x_md0[0], x_md0[1])
+    e_md0 = md.get_energy(True, False)[0]
+    rec = b._iterateWalkers(10, 5, 4, 300 * unit.kelvin)
+    assert rec['accepted'].shape == (R,) and np.all(np.isfinite(rec['work_kT']))
+    assert b.accept + b.reject == R
+    assert np.std(rec['work_kT']) > 0
+    # Metropolis rule per walker, with the engine's own uniform draws
+    want = (rec['log_accept'] > rec['log_u'])
+    assert np.array_equal(rec['accepted'], want)
+    # log_accept = -work/kT + correction (blues/simulation.py:1130-1136)
+    assert np.allclose(rec['log_accept'], -rec['work_kT'] + rec['correction'], rtol=0, atol=1e-9)
+    # the integrator was reset, the MD leg ran
+    assert ncmc.get_global('step') == 0 and ncmc.get_global('protocol_work') == 0
+    x_md1 = [md.get_positions(r) for r in range(R)]
+    for r in range(R):
+        assert not np.array_equal(x_md1[r], x_md0[r])
+    # a full run over two iterations keeps per-walker statistics
+    b.run(nIter=2)
+    assert len(b.walker_history) == 2 and len(b.walker_history[0]['walker']) == R
+    assert 0.0 <= b.acceptRatio <= 1.0
+
+
+def test_many_walker_correction_and_accept_copy_match_host_recomputation(structure):
+    """The per-walker alchemical correction equals the four-energy formula evaluated walker by walker through the
+    single-walker calls, and exactly the accepted walkers' MD positions are replaced by the NCMC end positions."""
+    R = 3
+    b, sims = _walker_sim(structure, R, seed=99)
+    md, alch, ncmc = (s.context._engine for s in (sims.md, sims.alch, sims.ncmc))
+    sims.md.context.setVelocitiesToTemperature(300 * unit.kelvin)
+    sims.md.step(3)
+    x0 = [md.get_positions(r) for r in range(R)]
+    e_md0 = md.get_energy(True, False)[0].copy()
+    kT = sims.ncmc.integrator.kT.value_in_unit(unit.kilojoules_per_mole)
+
+    class Spy(object):
+        pass
+    spy = Spy()
+    orig = ncmc.accept_reject
+
+    def accept_reject(correction=None):
+        spy.x1 = [ncmc.get_positions(r) for r in range(R)]
+        spy.e_nc1 = ncmc.get_energy(True, False)[0].copy()
+        spy.corr = np.array(correction, float)
+        out = orig(correction)
+        spy.acc = out[0].astype(bool)
+        return out
+    ncmc.accept_reject = accept_reject
+    # force walker 1 to accept, walker 2 to reject, walker 0 by its own work
+    rec = b._iterateWalkers(10, 5, 0 + 1, 300 * unit.kelvin)
+    for r in range(R):
+        ncmc.set_positions(x0[r], r)
+    ncmc.reset_ncmc()
+    e_nc0 = ncmc.get_energy(True, False)[0]
+    for r in range(R):
+        alch.set_positions(spy.x1[r], r)
+    e_alch1 = alch.get_energy(True, False)[0]
+    want = -(e_nc0 - e_md0 + e_alch1 - spy.e_nc1) / kT
+    assert np.allclose(spy.corr, want, rtol=0, atol=2e-3)
+    # accepted walkers carry the NCMC end positions into the MD leg (which then ran 1 step); rejected keep x0
+    x_md = [md.get_positions(r) for r in range(R)]
+    for r in range(R):
+        ref = spy.x1[r] if spy.acc[r] else x0[r]
+        assert np.max(np.abs(x_md[r] - ref)) < 0.05                 # one MD step away from the right starting point
+        other = x0[r] if spy.acc[r] else spy.x1[r]
+        assert np.max(np.abs(x_md[r] - other)) > np.max(np.abs(x_md[r] - ref))
