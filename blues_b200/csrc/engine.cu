@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -19,6 +20,20 @@
 #include "kernels_integrate.cuh"
 
 static std::string g_create_error;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the function on a device, shared by every handle of the
+// process: a later handle with a smaller need must not lower it under an earlier handle's launches (BASELINE configs[2]
+// next to configs[1] in one process: the 64-walker builder uses smaller write-combining buffers than the 1-walker one)
+template <class F> static void raise_dyn_smem(F* func, int device, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> cur;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& c = cur[{device, (const void*)func}];
+    if (bytes > c) {
+        cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        c = bytes;
+    }
+}
 
 struct TimedLaunch { int kid; cudaEvent_t e0, e1; };
 
@@ -1122,10 +1137,10 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         int per_sm = 0, n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         if (d.nl_u16) {
-            cudaFuncSetAttribute(k_build_list<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            raise_dyn_smem(k_build_list<unsigned short>, device, smem);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_build_list<unsigned short>, 32, smem);
         } else {
-            cudaFuncSetAttribute(k_build_list<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            raise_dyn_smem(k_build_list<int>, device, smem);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_build_list<int>, 32, smem);
         }
         per_sm = std::max(1, per_sm);
@@ -1153,8 +1168,8 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
             if (plane_bytes > 200 * 1024) return fail(BL_ERR_INVALID, "PME grid plane does not fit in shared memory");
             if (plane_bytes > 48 * 1024)
             {
-                cudaFuncSetAttribute(k_pme_spread<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes);
-                cudaFuncSetAttribute(k_pme_spread<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_bytes);
+                raise_dyn_smem(k_pme_spread<4, 256>, device, plane_bytes);
+                raise_dyn_smem(k_pme_spread<8, 512>, device, plane_bytes);
             }
         }
         d.grid_r = dalloc<float>(h, (size_t)R * d.gsize);
@@ -1177,15 +1192,15 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
                 h->dft_smem = sizeof(float2) * ((size_t)P * d.gy * Zc2 + d.gy * Zc2 + d.gz + d.gy + d.gx + (PME_CL_THREADS / 32) * 2 * d.gx) +
                               sizeof(float) * ((d.gy * d.gz + 1) & ~1);
                 if (h->dft_smem > 200 * 1024 && h->own_dft == 2) h->own_dft = 1;
-                cudaFuncSetAttribute(k_pme_dft_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dft_smem);
-                cudaFuncSetAttribute(k_pme_dft_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dft_smem);
+                raise_dyn_smem(k_pme_dft_cluster<true>, device, h->dft_smem);
+                raise_dyn_smem(k_pme_dft_cluster<false>, device, h->dft_smem);
             }
             const int Zc = d.gz / 2 + 1;
             const size_t sm = std::max(sizeof(float) * ((d.gy * d.gz + 1) & ~1) + sizeof(float2) * (d.gy * Zc + d.gz + d.gy),
                                        sizeof(float2) * (2 * d.gy * Zc + d.gz + d.gy));
             if (h->own_dft && sm > 48 * 1024) {
-                cudaFuncSetAttribute(k_pme_dft_zy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                cudaFuncSetAttribute(k_pme_idft_yz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                raise_dyn_smem(k_pme_dft_zy, device, sm);
+                raise_dyn_smem(k_pme_idft_yz, device, sm);
             }
         }
         int n[3] = {d.gx, d.gy, d.gz};
