@@ -91,9 +91,12 @@ struct bl_handle {
     int build_cq = 0, build_ctas = 0;
     bool builder2 = false; int build2_ctas = 0;  // BLUES_B200_BUILDER=2: ballot-compaction list builder (measured 10 % slower than
                                                  // the shared-memory sub-list builder, gpurun_out/r2_builder.log: kept for reference)
+    int int_block = 32;          // BLUES_B200_INT_BLOCK: threads per k_integrate CTA (one constraint cluster per thread)
     bool fold_zero = true;       // step programs: force zeroing + rebuild latch inside the INTEGRATE launch before an evaluation
     int own_dft = 0;             // reciprocal space: 0 cuFFT, 1 three fused direct-DFT kernels, 2 one cluster kernel (small grids)
     size_t dft_smem = 0;
+    int pair_lanes = 8;          // BLUES_B200_PAIR_LANES: lanes per i-atom in k_pair4 (8, 16, 32)
+    int pair_x2 = 2;             // BLUES_B200_PAIR_X2: 0 off, 2 / 4 = k_pair4 (packed FFMA2 arithmetic) with that many entries per trip
     int pair_variant = 132;      // BLUES_B200_PAIR: 0 = k_pair (round 1), else k_pair2 <ewald, lanes, U> (see enqueue_eval); measured: gpurun_out/pair_sweep.log
     int graph_steps = 4;         // plain NCMC steps captured per CUDA graph
     bool pdl = true;             // programmatic dependent launch on the B -> flip -> A -> sort edges (BLUES_B200_PDL=0: off)
@@ -355,6 +358,21 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
 #undef P3A
 #undef P30
 #undef P3E
+    } else if (h->pair_x2 && !energy && d.nb_method == 4 && d.ewk_ok && d.ewk2_deg <= 12) {
+        LaunchTimer t(h, BL_K_PAIR);
+        // packed-pair FP32 kernel (FFMA2): PME force-only evaluations, i.e. every evaluation of a plain NCMC / MD step
+        const int U = h->pair_x2 == 4 ? 4 : 2;
+        const int lanes = h->pair_lanes;
+        dim3 grid(cdiv((long long)d.Npad * lanes, NL_BLOCK), R);
+#define PX3(T, L, UU, DG) k_pair4<T, L, UU, DG><<<grid, NL_BLOCK, 0, st>>>(d)
+#define PX2(T, UU, DG) if (lanes == 16) PX3(T, 16, UU, DG); else if (lanes == 32) PX3(T, 32, UU, DG); else PX3(T, 8, UU, DG)
+#define PX1(T, UU) if (d.ewk2_deg == 10) { PX2(T, UU, 10); } else { PX2(T, UU, 12); }
+#define PX0(T) if (U == 4) { PX1(T, 4) } else { PX1(T, 2) }
+        if (d.nl_u16) { PX0(unsigned short) } else { PX0(int) }
+#undef PX3
+#undef PX2
+#undef PX1
+#undef PX0
     } else if (h->pair_variant > 0) {
         LaunchTimer t(h, BL_K_PAIR);
         // variant = 100 * ewald + 10 * log2(lanes) + U  (BLUES_B200_PAIR; 0 = the round-1 kernel)
@@ -414,7 +432,7 @@ static void enqueue_integrate(bl_handle* h, const IntegrateArgs& a, bool noise_p
     }
     LaunchTimer t(h, BL_K_INTEGRATE);
     // + 1: the last CTA holds no clusters (n_clusters is passed to the bounds check) and does the scalar bookkeeping
-    launch_pdl(h, k_integrate, dim3(cdiv(h->d.n_clusters, 64) + 1, h->d.R), dim3(64), h->stream, h->d, h->ic, a,
+    launch_pdl(h, k_integrate, dim3(cdiv(h->d.n_clusters, h->int_block) + 1, h->d.R), dim3(h->int_block), h->stream, h->d, h->ic, a,
                (const int*)h->cm_parity);
     tl_mark(h, h->stream, TL_INT0 + std::min(h->tl_int++, 2));
 }
@@ -767,11 +785,11 @@ static double ewald_k(double z) {
     const double s = sqrt(z);
     return (erf(s) / s - 2.0 / sqrt(M_PI) * exp(-z)) / z;
 }
-// Chebyshev interpolant of k on [0, zmax] of degree EWK_DEG, returned as monomial coefficients in t = 2 z / zmax - 1
+// Chebyshev interpolant of k on [0, zmax] of degree `deg` (<= 15), returned as monomial coefficients in t = 2 z / zmax - 1
 // (sum of |c| ~ 0.75: a Horner evaluation in float is accurate to ~2e-7 absolute; interpolation error 1e-8 at zmax 11.5)
-static void fit_ewald_k(double zmax, float out[16]) {
-    const int n = EWK_DEG + 1;
-    double f[n], c[n];
+static void fit_ewald_k(double zmax, float out[16], int deg = EWK_DEG) {
+    const int n = deg + 1;
+    double f[17], c[17];
     for (int j = 0; j < n; ++j) f[j] = ewald_k(0.5 * zmax * (cos(M_PI * (j + 0.5) / n) + 1.0));
     for (int m = 0; m < n; ++m) {
         double acc = 0;
@@ -779,13 +797,13 @@ static void fit_ewald_k(double zmax, float out[16]) {
         c[m] = acc * 2.0 / n;
     }
     c[0] *= 0.5;
-    double mono[n] = {0}, tm1[n] = {0}, tm[n] = {0};     // T_{m-1}, T_m as monomial coefficient arrays
+    double mono[17] = {0}, tm1[17] = {0}, tm[17] = {0};     // T_{m-1}, T_m as monomial coefficient arrays
     tm1[0] = 1.0;                                         // T_0
     tm[1] = 1.0;                                          // T_1
     mono[0] += c[0];
     mono[1] += c[1];
     for (int m = 2; m < n; ++m) {
-        double tn[n] = {0};
+        double tn[17] = {0};
         for (int k = 0; k + 1 < n; ++k) tn[k + 1] += 2.0 * tm[k];
         for (int k = 0; k < n; ++k) tn[k] -= tm1[k];
         for (int k = 0; k < n; ++k) { mono[k] += c[m] * tn[k]; tm1[k] = tm[k]; tm[k] = tn[k]; }
@@ -912,7 +930,10 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_PDL")) h->pdl = atoi(getenv("BLUES_B200_PDL")) != 0;
     if (getenv("BLUES_B200_GRAPH_STEPS")) h->graph_steps = std::max(1, atoi(getenv("BLUES_B200_GRAPH_STEPS")));
     if (getenv("BLUES_B200_TIMELINE")) { h->timeline = true; h->graph_steps = 1; }
+    if (getenv("BLUES_B200_PAIR_LANES")) { const int l = atoi(getenv("BLUES_B200_PAIR_LANES")); h->pair_lanes = l == 16 || l == 32 ? l : 8; }
+    if (getenv("BLUES_B200_PAIR_X2")) h->pair_x2 = atoi(getenv("BLUES_B200_PAIR_X2"));
     if (getenv("BLUES_B200_PAIR")) h->pair_variant = atoi(getenv("BLUES_B200_PAIR"));
+    if (getenv("BLUES_B200_INT_BLOCK")) h->int_block = std::max(32, std::min(256, atoi(getenv("BLUES_B200_INT_BLOCK")) / 32 * 32));
     if (getenv("BLUES_B200_FOLD_ZERO")) h->fold_zero = atoi(getenv("BLUES_B200_FOLD_ZERO")) != 0;
     counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping
     auto fail = [&](int code, const std::string& msg) { g_create_error = msg; bl_destroy(h); return code; };
@@ -958,6 +979,8 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         const double zmax = 1.02 * t->ewald_alpha * t->ewald_alpha * t->cutoff * t->cutoff;
         d.ewk_ok = zmax <= 11.5;          // beyond that (ewaldErrorTolerance < 5e-6) the erfc form is used
         fit_ewald_k(std::min(zmax, 11.5), d.ewk);
+        d.ewk2_deg = zmax <= 4.8 ? 10 : (zmax <= 11.5 ? 12 : EWK_DEG);
+        fit_ewald_k(std::min(zmax, 11.5), d.ewk2, d.ewk2_deg);
         d.ewk_scale = (float)(2.0 * t->ewald_alpha * t->ewald_alpha / std::min(zmax, 11.5));
         d.alpha3 = (float)(t->ewald_alpha * t->ewald_alpha * t->ewald_alpha);
     }

@@ -68,6 +68,7 @@ struct Dev {
     // Ewald real-space force without exp / erfc: F = qq (1/r^3 - alpha^3 k(alpha^2 r^2)), k(z) = (erf(sqrt z)/sqrt z -
     // 2/sqrt(pi) exp(-z)) / z as a degree-EWK_DEG polynomial in t = ewk_scale r^2 - 1 on [0, (alpha rc)^2] (fitted at bl_create)
     float ewk[16]; float ewk_scale, alpha3; int ewk_ok;
+    float ewk2[16]; int ewk2_deg;           // the same fit at the lowest degree float rounding allows (k_pair4)
     double cutoffd, alphad;
     // static per-atom data (original order)
     double* mass; double* invmass;

@@ -616,7 +616,7 @@ __device__ __forceinline__ void run_cluster_generic(const Dev& d, const Integrat
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_integrate(Dev d, IntegratorConsts ic, IntegrateArgs args, const int* cm_parity) {
+__global__ void __launch_bounds__(256) k_integrate(Dev d, IntegratorConsts ic, IntegrateArgs args, const int* cm_parity) {
     cudaGridDependencySynchronize();       // (see k_cm_flip)
     const int r = blockIdx.y;
     const int cid = blockIdx.x * blockDim.x + threadIdx.x;

@@ -990,6 +990,134 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair2(Dev d) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// k_pair4: k_pair2's pipeline with the arithmetic of TWO list entries per instruction — Blackwell's packed FP32 pair
+// operations (PTX add/mul/fma .f32x2 → SASS FADD2 / FMUL2 / FFMA2 on 64-bit register pairs).  ncu on k_pair2
+// (profiles/r02a_*): 71 issue slots per entry, 52 of them FP32, issue-bound at 72 % of the slots; the packed form needs
+// ~26 FP32 slots per entry, so the loop becomes bound by the FP32 pipe itself.  The two entries of a trip sit in the
+// low / high halves; the scalar results that feed a pair (coordinate differences, rsqrt, per-atom parameters) are
+// written by scalar instructions into adjacent registers, which ptxas pairs without moves.  PME, forces only, polynomial
+// Ewald kernel of degree DEG (Dev::ewk2, fitted at bl_create: 10 up to (alpha rc)^2 = 4.8, 12 beyond — float rounding,
+// not the fit, limits both).  Energy steps and the other methods use k_pair2.
+// ---------------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_dup(float v) { return f2_pack(v, v); }
+
+struct PairAcc2 { f32x2 fx, fy, fz; };
+
+// two entries (p0, e0), (p1, e1) of one i-atom; in0 / in1: the entry lies inside the row
+template <int DEG>
+__device__ __forceinline__ void pair_trip_x2(const Dev& d, const float4 p0, const float2 e0, const float4 p1, const float2 e1,
+                                             bool in0, bool in1, const float4 pi, const float2 se_i, float qi, float cut2,
+                                             PairAcc2& acc) {
+    const f32x2 magic = f2_dup(12582912.0f), nmagic = f2_dup(-12582912.0f);
+    f32x2 dx = f2_pack(pi.x - p0.x, pi.x - p1.x);
+    f32x2 dy = f2_pack(pi.y - p0.y, pi.y - p1.y);
+    f32x2 dz = f2_pack(pi.z - p0.z, pi.z - p1.z);
+    // minimum image: n = rint(d / L) by the 1.5 * 2^23 trick (the product and the first add fused), d -= L n
+    dx = f2_fma(f2_dup(-d.boxf[0]), f2_add(f2_fma(dx, f2_dup(d.boxf[3]), magic), nmagic), dx);
+    dy = f2_fma(f2_dup(-d.boxf[1]), f2_add(f2_fma(dy, f2_dup(d.boxf[4]), magic), nmagic), dy);
+    dz = f2_fma(f2_dup(-d.boxf[2]), f2_add(f2_fma(dz, f2_dup(d.boxf[5]), magic), nmagic), dz);
+    const f32x2 r2 = f2_fma(dz, dz, f2_fma(dy, dy, f2_mul(dx, dx)));
+    float r2a, r2b;
+    f2_unpack(r2, r2a, r2b);
+    in0 = in0 && (r2a < cut2);
+    in1 = in1 && (r2b < cut2);
+    const f32x2 invr = f2_pack(rsqrtf(r2a), rsqrtf(r2b));
+    const f32x2 invr2 = f2_mul(invr, invr);
+    const f32x2 sig = f2_pack(se_i.x + e0.x, se_i.x + e1.x);
+    const f32x2 s2 = f2_mul(f2_mul(sig, sig), invr2);
+    const f32x2 s6 = f2_mul(f2_mul(s2, s2), s2);
+    const f32x2 eps4 = f2_pack(se_i.y * e0.y, se_i.y * e1.y);
+    // eps4 (12 s6^2 - 6 s6) / r^2
+    f32x2 de = f2_mul(f2_mul(eps4, f2_mul(s6, f2_fma(s6, f2_dup(12.0f), f2_dup(-6.0f)))), invr2);
+    const f32x2 qq = f2_pack(qi * p0.w, qi * p1.w);
+    const f32x2 tt = f2_fma(r2, f2_dup(d.ewk_scale), f2_dup(-1.0f));
+    f32x2 k = f2_dup(d.ewk2[DEG]);
+#pragma unroll
+    for (int c = DEG - 1; c >= 0; --c) k = f2_fma(k, tt, f2_dup(d.ewk2[c]));
+    de = f2_fma(qq, f2_fma(f2_dup(-d.alpha3), k, f2_mul(invr, invr2)), de);
+    float dea, deb;
+    f2_unpack(de, dea, deb);
+    // select, not a mask multiply: entries past the end of the row or in the skin shell may be anything
+    de = f2_pack(in0 ? dea : 0.f, in1 ? deb : 0.f);
+    acc.fx = f2_fma(dx, de, acc.fx);
+    acc.fy = f2_fma(dy, de, acc.fy);
+    acc.fz = f2_fma(dz, de, acc.fz);
+}
+
+template <typename IDX, int LANES, int U, int DEG>
+__global__ void __launch_bounds__(NL_BLOCK) k_pair4(Dev d) {
+    static_assert(U % 2 == 0, "entries are processed in packed pairs");
+    const int r = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int part = lane & (LANES - 1);
+    const int i = (blockIdx.x * NL_BLOCK + threadIdx.x) / LANES;
+    const int N = d.N, Npad = d.Npad;
+    if (i >= Npad) return;
+    const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
+    const float2* __restrict__ sigeps_s = d.sigeps_s + (size_t)r * Npad;
+    const IDX* __restrict__ lp = reinterpret_cast<const IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M + part;
+    const int cnt = d.nl_count[(size_t)r * Npad + i];
+    const int nm = cnt > part ? (cnt - part + LANES - 1) / LANES : 0;        // entries owned by this lane
+    const int ntrip = (nm + U - 1) / U;
+    const float cut2 = d.cutoff2;
+    const float4 pi = posq_s[i];
+    const float2 se_i = sigeps_s[i];
+    const float qi = pi.w * (float)ONE_4PI_EPS0;
+    PairAcc2 acc;
+    acc.fx = acc.fy = acc.fz = f2_dup(0.f);
+    // the same two-deep software pipeline as k_pair2: gathers of trip t + 1 and index loads of trips t + 2, t + 3 in flight
+    int iA[U], iB[U];
+    float4 pA[U], pB[U];
+    float2 eA[U], eB[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { iA[u] = ldg_nc_idx(lp + LANES * u); iB[u] = ldg_nc_idx(lp + LANES * (U + u)); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { pA[u] = ldg_nc_f4(posq_s + iA[u]); eA[u] = ldg_nc_f2(sigeps_s + iA[u]); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { pB[u] = ldg_nc_f4(posq_s + iB[u]); eB[u] = ldg_nc_f2(sigeps_s + iB[u]); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { iA[u] = ldg_nc_idx(lp + LANES * (2 * U + u)); iB[u] = ldg_nc_idx(lp + LANES * (3 * U + u)); }
+    for (int t = 0; t < ntrip; t += 2) {
+#pragma unroll
+        for (int u = 0; u < U; u += 2)
+            pair_trip_x2<DEG>(d, pA[u], eA[u], pA[u + 1], eA[u + 1], t * U + u < nm, t * U + u + 1 < nm, pi, se_i, qi, cut2, acc);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { pA[u] = ldg_nc_f4(posq_s + iA[u]); eA[u] = ldg_nc_f2(sigeps_s + iA[u]); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) iA[u] = ldg_nc_idx(lp + LANES * ((t + 4) * U + u));
+#pragma unroll
+        for (int u = 0; u < U; u += 2)
+            pair_trip_x2<DEG>(d, pB[u], eB[u], pB[u + 1], eB[u + 1], (t + 1) * U + u < nm, (t + 1) * U + u + 1 < nm, pi, se_i, qi, cut2, acc);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { pB[u] = ldg_nc_f4(posq_s + iB[u]); eB[u] = ldg_nc_f2(sigeps_s + iB[u]); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) iB[u] = ldg_nc_idx(lp + LANES * ((t + 5) * U + u));
+    }
+    float fx, fy, fz, hx, hy, hz;
+    f2_unpack(acc.fx, fx, hx); f2_unpack(acc.fy, fy, hy); f2_unpack(acc.fz, fz, hz);
+    fx += hx; fy += hy; fz += hz;
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, o);
+        fy += __shfl_xor_sync(0xffffffffu, fy, o);
+        fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    }
+    if (part == 0 && i < N) {
+        const int oi = d.orig_s[(size_t)r * Npad + i];
+        long long* fenv = d.f_env + (size_t)r * 3 * N;
+        fx_addf(&fenv[oi], fx, (float)FORCE_SCALE);
+        fx_addf(&fenv[N + oi], fy, (float)FORCE_SCALE);
+        fx_addf(&fenv[2 * N + oi], fz, (float)FORCE_SCALE);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // k_pair3: the pair sum with asynchronous gathers (cp.async → shared memory ring).  ptxas schedules plain loads next to
 // their consumers whatever the source order (k_pair2's software pipeline ends up with every load at the bottom of the loop
 // body), so the prefetch is made explicit: a lane owns the entry PAIRS (2 part, 2 part + 1) + 2 LANES m of its atom's row.
