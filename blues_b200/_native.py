@@ -190,6 +190,8 @@ def measure_fp32_peak(device=0):
 class Engine(object):
     """One native handle: R independent walkers of one flattened system on one GPU."""
 
+    created = 0          # native handles created by this process (bl_create calls that succeeded)
+
     def __init__(self, topo, device=0, n_replicas=1, seed=0):
         self.lib = load_library()
         self.topo = topo
@@ -201,6 +203,7 @@ class Engine(object):
         if rc != 0:
             raise EngineError('bl_create failed (%d): %s' % (rc, (self.lib.bl_last_error(None) or b'').decode()))
         self.h = h
+        Engine.created += 1
 
     # -- plumbing -----------------------------------------------------------------------------------
     def _check(self, rc):

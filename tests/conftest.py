@@ -6,6 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+# fixtures, not tests of this suite: the reference's own test files are run by tests/test_gpu_reference_suite.py
+collect_ignore_glob = ['golden/*']
 
 
 def pytest_configure(config):

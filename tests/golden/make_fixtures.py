@@ -401,7 +401,23 @@ def ethylene_fixture():
     print('ethylene fixture:', len(out['mass']), 'particles')
 
 
+def reference_tests():
+    """Verbatim copies of the reference's own test files and the data they read (tests/golden/reference_checkout/):
+    fixtures of tests/test_gpu_reference_suite.py, which runs them unmodified against the CUDA engine on the GPU box."""
+    import shutil
+    root = os.path.dirname(os.path.dirname(REF))          # <checkout>/blues
+    dst = os.path.join(HERE, 'reference_checkout', 'blues', 'tests')
+    os.makedirs(os.path.join(dst, 'data'), exist_ok=True)
+    for name in ('test_simulation.py', 'test_randomrotation.py'):
+        shutil.copyfile(os.path.join(root, 'tests', name), os.path.join(dst, name))
+    for name in ('TOL-parm.prmtop', 'TOL-parm.inpcrd'):
+        shutil.copyfile(os.path.join(REF, name), os.path.join(dst, 'data', name))
+    print('reference test fixtures refreshed under', dst)
+
+
 def main():
+    if '--reference-tests' in sys.argv:
+        return reference_tests()
     reference_bookkeeping()
     ethylene_fixture()
     structs = {}

@@ -90,3 +90,13 @@ def test_reference_tests_pass_on_the_host_layer_over_the_oracle_engine(tmp_path)
     passed = set(re.findall(r'^PASSED (\S+)', out, re.M))
     assert run.returncode == 0 and len(passed) == 26, out[-4000:]
     assert any('test_randomrotation.py' in p for p in passed)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, 'blues', 'tests')),
+                    reason='reference checkout not mounted (it is absent on the GPU box)')
+def test_fixture_copies_are_verbatim():
+    """tests/golden/reference_checkout/ (input of tests/test_gpu_reference_suite.py) equals the checkout byte for byte."""
+    base = os.path.join(ROOT, 'tests', 'golden', 'reference_checkout', 'blues', 'tests')
+    for rel in ('test_simulation.py', 'test_randomrotation.py', 'data/TOL-parm.prmtop', 'data/TOL-parm.inpcrd'):
+        with open(os.path.join(base, rel), 'rb') as a, open(os.path.join(REFERENCE, 'blues', 'tests', rel), 'rb') as b:
+            assert a.read() == b.read(), rel
