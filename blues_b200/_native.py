@@ -39,6 +39,11 @@ class BlTopology(C.Structure):
         ('alch_exc_eps', _dp),
         ('softcore_alpha', C.c_double), ('softcore_a', C.c_double), ('softcore_b', C.c_double),
         ('softcore_c', C.c_double), ('annihilate_sterics', C.c_int32), ('annihilate_electrostatics', C.c_int32),
+        ('n_custom_terms', C.c_int32), ('custom_term', _ip), ('custom_cutoff', _dp),
+        ('custom_n_params', C.c_int32), ('custom_params', _dp),
+        ('n_custom_groups', C.c_int32), ('custom_group_start', _ip), ('custom_group_atoms', _ip),
+        ('custom_group_weights', _dp),
+        ('n_custom_progs', C.c_int32), ('custom_prog_start', _ip), ('custom_code_op', _ip), ('custom_code_arg', _dp),
     ]
 
 
@@ -175,6 +180,19 @@ def build_topology(topo):
     t.softcore_b, t.softcore_c = float(topo['softcore_b']), float(topo['softcore_c'])
     t.annihilate_sterics = int(topo['annihilate_sterics'])
     t.annihilate_electrostatics = int(topo['annihilate_electrostatics'])
+    # generic Custom*Force terms (absent from flat dictionaries written before they existed)
+    n_custom = len(topo.get('custom_term', ()))
+    t.n_custom_terms = n_custom
+    if n_custom:
+        t.custom_term, t.custom_cutoff = dp('custom_term', np.int32), dp('custom_cutoff')
+        t.custom_n_params = int(topo['custom_n_params'])
+        t.custom_params = dp('custom_params')
+        t.n_custom_groups = len(topo['custom_group_start']) - 1
+        t.custom_group_start, t.custom_group_atoms = dp('custom_group_start', np.int32), dp('custom_group_atoms', np.int32)
+        t.custom_group_weights = dp('custom_group_weights')
+        t.n_custom_progs = len(topo['custom_prog_start']) - 1
+        t.custom_prog_start, t.custom_code_op = dp('custom_prog_start', np.int32), dp('custom_code_op', np.int32)
+        t.custom_code_arg = dp('custom_code_arg')
     return t, keep
 
 

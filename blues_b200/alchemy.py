@@ -48,7 +48,9 @@ class AbsoluteAlchemicalFactory(object):
         system = copy.deepcopy(reference_system)
         nb = system._force(NonbondedForce)
         if nb is None:
-            raise ValueError('reference system has no NonbondedForce')
+            # openmmtools copies every force it has no alchemical rule for: a system whose lambda dependence lives in
+            # its own Custom*Force global parameters (blues/tests/test_ethylene.py:76) comes back unchanged
+            return system
         atoms = np.asarray(region.alchemical_atoms, np.int32)
         if len(atoms) == 0:
             raise ValueError('alchemical region is empty')

@@ -45,7 +45,7 @@ def install(data_root=None, force=False):
     mods = {}
     # --- simtk ----------------------------------------------------------------------------------------------------
     openmm_attrs = {k: getattr(system, k) for k in dir(system) if k.endswith('Force') or k in ('System', 'CMMotionRemover',
-                                                                                            'MonteCarloBarostat')}
+                                                                                            'MonteCarloBarostat', 'XmlSerializer')}
     for k in ('Context', 'State', 'Platform', 'LangevinIntegrator', 'Vec3', 'OpenMMException'):
         openmm_attrs[k] = getattr(mm, k)
     app = _module('simtk.openmm.app', Simulation=mm.Simulation, StateDataReporter=reporters.StateDataReporter,

@@ -243,7 +243,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     cudaEventRecord(h->ev_fork, st);
     if (!pre_zeroed) {
         LaunchTimer t(h, -1);
-        long long nf = (long long)R * 3 * N * (d.n_alch > 0 ? 1 + ALCH_SLOTS : 1);
+        long long nf = (long long)R * 3 * N * (d.alch_on ? 1 + ALCH_SLOTS : 1);
         int blocks = std::max(1, std::min(cdiv(nf, 256 * 4), 148 * 8));
         k_begin_eval<<<blocks, 256, 0, st>>>(d, adv_noise, adv_md, cm_mode, h->cm_parity);
     }
@@ -316,14 +316,17 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         tl_mark(h, s3, TL_BONDED);
         cudaEventRecord(h->ev_join3, s3);
     }
-    if (d.n_alch > 0) {
+    if (d.alch_on) {
         cudaStream_t s4 = h->profiling ? st : h->stream4;
         cudaStreamWaitEvent(s4, h->ev_fork2, 0);
-        { LaunchTimer t(h, BL_K_NEIGHBOR, s4); k_alch_reset<<<cdiv(R * d.n_alch, 128), 128, 0, s4>>>(d); }
-        { LaunchTimer t(h, BL_K_NEIGHBOR, s4);
-          k_alch_list<<<dim3(cdiv(N, 128), R), 128, d.n_alch * sizeof(float4), s4>>>(d); }
-        { LaunchTimer t(h, BL_K_NEIGHBOR, s4); k_alch_sort<<<dim3(d.n_alch, R), 512, 0, s4>>>(d); }
-        { LaunchTimer t(h, BL_K_ALCH, s4); k_alch<<<dim3(cdiv(d.alch_cap, 128), d.n_alch, R), 128, 0, s4>>>(d); }
+        if (d.n_alch > 0) {
+            { LaunchTimer t(h, BL_K_NEIGHBOR, s4); k_alch_reset<<<cdiv(R * d.n_alch, 128), 128, 0, s4>>>(d); }
+            { LaunchTimer t(h, BL_K_NEIGHBOR, s4);
+              k_alch_list<<<dim3(cdiv(N, 128), R), 128, d.n_alch * sizeof(float4), s4>>>(d); }
+            { LaunchTimer t(h, BL_K_NEIGHBOR, s4); k_alch_sort<<<dim3(d.n_alch, R), 512, 0, s4>>>(d); }
+            { LaunchTimer t(h, BL_K_ALCH, s4); k_alch<<<dim3(cdiv(d.alch_cap, 128), d.n_alch, R), 128, 0, s4>>>(d); }
+        }
+        if (d.n_custom > 0) { LaunchTimer t(h, BL_K_ALCH, s4); k_custom<<<dim3(cdiv(d.n_custom, 64), R), 64, 0, s4>>>(d); }
         tl_mark(h, s4, TL_ALCH);
         cudaEventRecord(h->ev_join4, s4);
     }
@@ -410,7 +413,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
     tl_mark(h, st, TL_PAIR);
     if (pme) cudaStreamWaitEvent(st, h->ev_join, 0);
     if (nterms > 0 || prefetch_noise > 0) cudaStreamWaitEvent(st, h->ev_join3, 0);
-    if (d.n_alch > 0) cudaStreamWaitEvent(st, h->ev_join4, 0);
+    if (d.alch_on) cudaStreamWaitEvent(st, h->ev_join4, 0);
     tl_mark(h, st, TL_JOINED);
 }
 
@@ -1090,6 +1093,54 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         }
         d.alch_exc = dupload(h, ix); d.alch_exc_p = dupload(h, pe);
     }
+    // generic Custom*Force terms
+    d.n_custom = t->n_custom_terms; d.custom_np = std::max(1, t->custom_n_params);
+    if (d.n_custom > 0) {
+        if (!t->custom_term || !t->custom_cutoff || !t->custom_group_start || !t->custom_group_atoms || !t->custom_group_weights ||
+            !t->custom_prog_start || !t->custom_code_op || !t->custom_code_arg || t->n_custom_groups < 1 || t->n_custom_progs < 1)
+            return fail(BL_ERR_INVALID, "incomplete custom force tables");
+        std::vector<int4> ct(d.n_custom);
+        for (int k = 0; k < d.n_custom; ++k) {
+            ct[k] = make_int4(t->custom_term[4 * k], t->custom_term[4 * k + 1], t->custom_term[4 * k + 2], t->custom_term[4 * k + 3]);
+            if (ct[k].x < 0 || ct[k].x >= t->n_custom_groups || ct[k].y < 0 || ct[k].y >= t->n_custom_groups || ct[k].z < 0 ||
+                ct[k].z >= t->n_custom_progs)
+                return fail(BL_ERR_INVALID, "custom force term refers to a missing group or program");
+        }
+        const int n_ga = t->custom_group_start[t->n_custom_groups], n_code = t->custom_prog_start[t->n_custom_progs];
+        for (int k = 0; k < n_ga; ++k)
+            if (t->custom_group_atoms[k] < 0 || t->custom_group_atoms[k] >= N) return fail(BL_ERR_INVALID, "custom force group atom out of range");
+        // stack discipline of every program, checked once here so that the device interpreter needs no guards
+        for (int p = 0; p < t->n_custom_progs; ++p) {
+            int sp = 0;
+            for (int pc = t->custom_prog_start[p]; pc < t->custom_prog_start[p + 1]; ++pc) {
+                const int op = t->custom_code_op[pc];
+                int pops = 1, pushes = 1;
+                if (op <= BL_OP_GLOBAL) pops = 0;
+                else if (op == BL_OP_ADD || op == BL_OP_SUB || op == BL_OP_MUL || op == BL_OP_DIV || op == BL_OP_POW ||
+                         op == BL_OP_MIN || op == BL_OP_MAX) pops = 2;
+                else if (op == BL_OP_SELECT) pops = 3;
+                else if (op > BL_OP_ATAN) return fail(BL_ERR_INVALID, "unknown opcode in a custom force program");
+                if (op == BL_OP_PARAM && ((int)t->custom_code_arg[pc] < 0 || (int)t->custom_code_arg[pc] >= d.custom_np))
+                    return fail(BL_ERR_INVALID, "custom force program reads a missing parameter");
+                if (sp < pops) return fail(BL_ERR_INVALID, "custom force program underflows its stack");
+                sp += pushes - pops;
+                if (sp > BL_CUSTOM_STACK) return fail(BL_ERR_INVALID, "custom force expression too deep");
+            }
+            if (sp != 1) return fail(BL_ERR_INVALID, "custom force program must leave one value");
+        }
+        d.custom_term = dupload(h, ct);
+        d.custom_cutoff = dupload(h, std::vector<double>(t->custom_cutoff, t->custom_cutoff + d.n_custom));
+        d.custom_params = dupload(h, t->custom_params && t->custom_n_params > 0
+                                         ? std::vector<double>(t->custom_params, t->custom_params + (size_t)d.n_custom * t->custom_n_params)
+                                         : std::vector<double>((size_t)d.n_custom, 0.0));
+        d.custom_gstart = dupload(h, std::vector<int>(t->custom_group_start, t->custom_group_start + t->n_custom_groups + 1));
+        d.custom_gatoms = dupload(h, std::vector<int>(t->custom_group_atoms, t->custom_group_atoms + n_ga));
+        d.custom_gweights = dupload(h, std::vector<double>(t->custom_group_weights, t->custom_group_weights + n_ga));
+        d.custom_pstart = dupload(h, std::vector<int>(t->custom_prog_start, t->custom_prog_start + t->n_custom_progs + 1));
+        d.custom_op = dupload(h, std::vector<int>(t->custom_code_op, t->custom_code_op + n_code));
+        d.custom_arg = dupload(h, std::vector<double>(t->custom_code_arg, t->custom_code_arg + n_code));
+    }
+    d.alch_on = (d.n_alch > 0 || d.n_custom > 0) ? 1 : 0;
     d.alch_cap = std::min(N, 2048);
     d.alch_count = dalloc<int>(h, (size_t)R * std::max(1, d.n_alch));
     d.alch_list = dalloc<int>(h, (size_t)R * std::max(1, d.n_alch) * d.alch_cap);
@@ -1114,7 +1165,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     d.pos = dalloc<double4>(h, RN); d.vel = dalloc<double4>(h, RN);
     d.posq = dalloc<float4>(h, RN); d.pos_ref = dalloc<float4>(h, RN);
     d.f_env = dalloc<long long>(h, RN * 3);
-    d.f_alch = dalloc<long long>(h, d.n_alch > 0 ? RN * 3 * ALCH_SLOTS : 1);
+    d.f_alch = dalloc<long long>(h, d.alch_on ? RN * 3 * ALCH_SLOTS : 1);
     d.eacc = dalloc<long long>(h, (size_t)R * N_ETERMS);
     d.alch_acc = dalloc<long long>(h, (size_t)R * ALCH_SLOTS * 3);
     d.cm_acc = dalloc<long long>(h, (size_t)2 * R * 3);

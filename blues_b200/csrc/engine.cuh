@@ -119,6 +119,12 @@ struct Dev {
     double sc_alpha, sc_a, sc_b, sc_c;
     int annihilate_sterics, annihilate_elec;
     double* lam_s; double* lam_e; int n_lambda;       // tables indexed by lambda_step
+    // generic Custom*Force terms (bl_topology::custom_*): evaluated per alchemical slot by k_custom
+    int n_custom, custom_np;
+    int4* custom_term; double* custom_cutoff; double* custom_params;
+    int* custom_gstart; int* custom_gatoms; double* custom_gweights;
+    int* custom_pstart; int* custom_op; double* custom_arg;
+    int alch_on;                            // lambda-dependent force slots in use: n_alch > 0 or n_custom > 0
     // PME
     int gx, gy, gz; int gsize; int csize;   // real grid size, complex grid size (gx*gy*(gz/2+1))
     float* grid_r;                          // [R][gsize]

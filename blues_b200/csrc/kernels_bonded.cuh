@@ -366,3 +366,123 @@ __global__ void __launch_bounds__(128) k_alch(Dev d) {
         }
     }
 }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// k_custom: generic Custom*Force terms (bl_topology::custom_*).  One thread per (term, walker): r = distance between the
+// weighted centroids of two atom groups, E(r) and dE/dr from the host-compiled stack program by forward-mode dual
+// numbers, at the ALCH_SLOTS consecutive lambda_step values exactly like k_alch (energies into the slot accumulators
+// for Enew - Eold, forces into the slot force buffers for the following V steps).  Double precision throughout; the
+// terms are few (the reference's use: 12 pairs + 1 centroid bond, blues/tests/data/ethylene_system.xml:52-114).
+// ---------------------------------------------------------------------------------------------------------
+struct Dual { double v, d; };
+
+__device__ __noinline__ Dual custom_eval(const Dev& d, int prog, double r, const double* par, double g0, double g1) {
+    double sv[BL_CUSTOM_STACK], sd[BL_CUSTOM_STACK];
+    int sp = 0;
+    const int end = d.custom_pstart[prog + 1];
+    for (int pc = d.custom_pstart[prog]; pc < end; ++pc) {
+        const int op = d.custom_op[pc];
+        const double arg = d.custom_arg[pc];
+        switch (op) {
+        case BL_OP_CONST: sv[sp] = arg; sd[sp] = 0.0; ++sp; break;
+        case BL_OP_R: sv[sp] = r; sd[sp] = 1.0; ++sp; break;
+        case BL_OP_PARAM: sv[sp] = par[(int)arg]; sd[sp] = 0.0; ++sp; break;
+        case BL_OP_GLOBAL: sv[sp] = ((int)arg == 0) ? g0 : g1; sd[sp] = 0.0; ++sp; break;
+        case BL_OP_ADD: --sp; sv[sp - 1] += sv[sp]; sd[sp - 1] += sd[sp]; break;
+        case BL_OP_SUB: --sp; sv[sp - 1] -= sv[sp]; sd[sp - 1] -= sd[sp]; break;
+        case BL_OP_MUL: --sp; sd[sp - 1] = sd[sp - 1] * sv[sp] + sv[sp - 1] * sd[sp]; sv[sp - 1] *= sv[sp]; break;
+        case BL_OP_DIV: {
+            --sp;
+            const double inv = 1.0 / sv[sp], q = sv[sp - 1] * inv;
+            sd[sp - 1] = (sd[sp - 1] - q * sd[sp]) * inv;
+            sv[sp - 1] = q;
+        } break;
+        case BL_OP_NEG: sv[sp - 1] = -sv[sp - 1]; sd[sp - 1] = -sd[sp - 1]; break;
+        case BL_OP_POWI: {
+            const int n = (int)arg;
+            const double x = sv[sp - 1];
+            double pw = 1.0;                                      // x^(|n| - 1)
+            for (int k = 1; k < abs(n); ++k) pw *= x;
+            if (n == 0) { sv[sp - 1] = 1.0; sd[sp - 1] = 0.0; }
+            else if (n > 0) { sd[sp - 1] *= n * pw; sv[sp - 1] = pw * x; }
+            else { const double v = 1.0 / (pw * x); sd[sp - 1] *= n * v / x; sv[sp - 1] = v; }
+        } break;
+        case BL_OP_POW: {
+            --sp;
+            const double a = sv[sp - 1], b = sv[sp], v = pow(a, b);
+            double dv = 0.0;
+            if (sd[sp - 1] != 0.0) dv += b * pow(a, b - 1.0) * sd[sp - 1];
+            if (sd[sp] != 0.0) dv += v * log(a) * sd[sp];
+            sv[sp - 1] = v; sd[sp - 1] = dv;
+        } break;
+        case BL_OP_SQRT: { const double v = sqrt(sv[sp - 1]); sd[sp - 1] = sd[sp - 1] != 0.0 ? 0.5 * sd[sp - 1] / v : 0.0; sv[sp - 1] = v; } break;
+        case BL_OP_EXP: { const double v = exp(sv[sp - 1]); sd[sp - 1] *= v; sv[sp - 1] = v; } break;
+        case BL_OP_LOG: sd[sp - 1] /= sv[sp - 1]; sv[sp - 1] = log(sv[sp - 1]); break;
+        case BL_OP_SIN: sd[sp - 1] *= cos(sv[sp - 1]); sv[sp - 1] = sin(sv[sp - 1]); break;
+        case BL_OP_COS: sd[sp - 1] *= -sin(sv[sp - 1]); sv[sp - 1] = cos(sv[sp - 1]); break;
+        case BL_OP_TAN: { const double t = tan(sv[sp - 1]); sd[sp - 1] *= 1.0 + t * t; sv[sp - 1] = t; } break;
+        case BL_OP_ABS: if (sv[sp - 1] < 0.0) { sv[sp - 1] = -sv[sp - 1]; sd[sp - 1] = -sd[sp - 1]; } break;
+        case BL_OP_MIN: --sp; if (sv[sp] < sv[sp - 1]) { sv[sp - 1] = sv[sp]; sd[sp - 1] = sd[sp]; } break;
+        case BL_OP_MAX: --sp; if (sv[sp] > sv[sp - 1]) { sv[sp - 1] = sv[sp]; sd[sp - 1] = sd[sp]; } break;
+        case BL_OP_STEP: sv[sp - 1] = sv[sp - 1] >= 0.0 ? 1.0 : 0.0; sd[sp - 1] = 0.0; break;
+        case BL_OP_DELTA: sv[sp - 1] = sv[sp - 1] == 0.0 ? 1.0 : 0.0; sd[sp - 1] = 0.0; break;
+        case BL_OP_SELECT: sp -= 2; if (sv[sp - 1] != 0.0) { sv[sp - 1] = sv[sp]; sd[sp - 1] = sd[sp]; } else { sv[sp - 1] = sv[sp + 1]; sd[sp - 1] = sd[sp + 1]; } break;
+        case BL_OP_ERF: sd[sp - 1] *= TWO_OVER_SQRT_PI * exp(-sv[sp - 1] * sv[sp - 1]); sv[sp - 1] = erf(sv[sp - 1]); break;
+        case BL_OP_ERFC: sd[sp - 1] *= -TWO_OVER_SQRT_PI * exp(-sv[sp - 1] * sv[sp - 1]); sv[sp - 1] = erfc(sv[sp - 1]); break;
+        case BL_OP_TANH: { const double t = tanh(sv[sp - 1]); sd[sp - 1] *= 1.0 - t * t; sv[sp - 1] = t; } break;
+        case BL_OP_SINH: sd[sp - 1] *= cosh(sv[sp - 1]); sv[sp - 1] = sinh(sv[sp - 1]); break;
+        case BL_OP_COSH: sd[sp - 1] *= sinh(sv[sp - 1]); sv[sp - 1] = cosh(sv[sp - 1]); break;
+        case BL_OP_ATAN: sd[sp - 1] /= 1.0 + sv[sp - 1] * sv[sp - 1]; sv[sp - 1] = atan(sv[sp - 1]); break;
+        default: break;
+        }
+    }
+    Dual out;
+    out.v = sp > 0 ? sv[0] : 0.0;
+    out.d = sp > 0 ? sd[0] : 0.0;
+    return out;
+}
+
+__global__ void __launch_bounds__(64) k_custom(Dev d) {
+    const int r = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.n_custom) return;
+    const int N = d.N;
+    const double4* pos = d.pos + (size_t)r * N;
+    const int4 term = d.custom_term[t];
+    double3 ca = make_double3(0, 0, 0), cb = make_double3(0, 0, 0);
+    for (int k = d.custom_gstart[term.x]; k < d.custom_gstart[term.x + 1]; ++k) {
+        const double4 p = pos[d.custom_gatoms[k]];
+        const double w = d.custom_gweights[k];
+        ca.x += w * p.x; ca.y += w * p.y; ca.z += w * p.z;
+    }
+    for (int k = d.custom_gstart[term.y]; k < d.custom_gstart[term.y + 1]; ++k) {
+        const double4 p = pos[d.custom_gatoms[k]];
+        const double w = d.custom_gweights[k];
+        cb.x += w * p.x; cb.y += w * p.y; cb.z += w * p.z;
+    }
+    double3 dv = make_double3(ca.x - cb.x, ca.y - cb.y, ca.z - cb.z);
+    if (term.w & 1) min_image(d, dv);
+    const double rr = sqrt(d3dot(dv, dv));
+    const double cut = d.custom_cutoff[t];
+    if (cut > 0.0 && rr >= cut) return;
+    const double* par = d.custom_params + (size_t)t * d.custom_np;
+    const int base = d.g[r].lambda_step;
+    for (int s = 0; s < ALCH_SLOTS; ++s) {
+        const int li = min(base + s, d.n_lambda - 1);
+        const Dual e = custom_eval(d, term.z, rr, par, d.lam_s[li], d.lam_e[li]);
+        if (e.v != 0.0) fx_add(&d.alch_acc[(r * ALCH_SLOTS + s) * 3 + 0], e.v, ENERGY_SCALE);
+        const double fr = rr > 0.0 ? -e.d / rr : 0.0;          // F_A = -dE/dr * (cA - cB) / r, shared out by the weights
+        if (fr != 0.0) {
+            long long* fa = d.f_alch + ((size_t)s * d.R + r) * 3 * N;
+            for (int k = d.custom_gstart[term.x]; k < d.custom_gstart[term.x + 1]; ++k) {
+                const double w = d.custom_gweights[k] * fr;
+                add_force(fa, N, d.custom_gatoms[k], make_double3(w * dv.x, w * dv.y, w * dv.z));
+            }
+            for (int k = d.custom_gstart[term.y]; k < d.custom_gstart[term.y + 1]; ++k) {
+                const double w = -d.custom_gweights[k] * fr;
+                add_force(fa, N, d.custom_gatoms[k], make_double3(w * dv.x, w * dv.y, w * dv.z));
+            }
+        }
+    }
+}

@@ -304,7 +304,7 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     prefetch_l1(&fenv[q * N + atom[k]]);
-                    if (d.n_alch > 0) prefetch_l1(&d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + atom[k]]);
+                    if (d.alch_on) prefetch_l1(&d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + atom[k]]);
                 }
             break;
         }
@@ -335,7 +335,7 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                     if (s.im[k] > 0.0) { s.v[k][0] -= vx; s.v[k][1] -= vy; s.v[k][2] -= vz; }
             }
         } else if (op.kind == OP_V) {
-            const long long* fa = d.n_alch > 0 ? d.f_alch + ((size_t)op.slot * d.R + r) * 3 * N : nullptr;
+            const long long* fa = d.alch_on ? d.f_alch + ((size_t)op.slot * d.R + r) * 3 * N : nullptr;
 #pragma unroll
             for (int k = 0; k < NA; ++k) {
                 const double sc = ic.hV * s.im[k] * (1.0 / FORCE_SCALE);
@@ -387,7 +387,7 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
                     xref[k][q] = s.x[k][q];
                     if (s.im[k] > 0.0) {
                         long long fi = fenv[q * N + atom[k]];
-                        if (d.n_alch > 0) fi += d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + atom[k]];
+                        if (d.alch_on) fi += d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + atom[k]];
                         const double f = (double)fi * (1.0 / FORCE_SCALE);
                         s.v[k][q] = ic.md_vscale * s.v[k][q] + ic.md_fscale * s.im[k] * f + n[q];   // pre-scaled kick
                         s.x[k][q] += ic.dt * s.v[k][q];
@@ -437,7 +437,7 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 d.f_env[(size_t)r * 3 * N + q * N + atom[k]] = 0;
-                if (d.n_alch > 0)
+                if (d.alch_on)
                     for (int sl = 0; sl < ALCH_SLOTS; ++sl) d.f_alch[((size_t)sl * d.R + r) * 3 * N + q * N + atom[k]] = 0;
             }
     }
@@ -506,7 +506,7 @@ __device__ __forceinline__ void run_cluster_generic(const Dev& d, const Integrat
             }
         } break;
         case OP_V: {
-            const long long* fa = d.n_alch > 0 ? d.f_alch + ((size_t)op.slot * d.R + r) * 3 * N : nullptr;
+            const long long* fa = d.alch_on ? d.f_alch + ((size_t)op.slot * d.R + r) * 3 * N : nullptr;
             for (int k = 0; k < c.natoms; ++k) {
                 const int a = c.atom[k];
                 const double sc = ic.hV * s.im[k] * (1.0 / FORCE_SCALE);
@@ -563,7 +563,7 @@ __device__ __forceinline__ void run_cluster_generic(const Dev& d, const Integrat
                     xref[k][q] = s.x[k][q];
                     if (s.im[k] > 0.0) {
                         long long fi = fenv[q * N + a];
-                        if (d.n_alch > 0) fi += d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + a];
+                        if (d.alch_on) fi += d.f_alch[((size_t)op.slot * d.R + r) * 3 * N + q * N + a];
                         const double f = (double)fi * (1.0 / FORCE_SCALE);
                         s.v[k][q] = ic.md_vscale * s.v[k][q] + ic.md_fscale * s.im[k] * f + sq * n[q];
                         s.x[k][q] += ic.dt * s.v[k][q];
@@ -592,7 +592,7 @@ __device__ __forceinline__ void run_cluster_generic(const Dev& d, const Integrat
         for (int k = 0; k < c.natoms; ++k)
             for (int q = 0; q < 3; ++q) {
                 d.f_env[(size_t)r * 3 * N + q * N + c.atom[k]] = 0;
-                if (d.n_alch > 0)
+                if (d.alch_on)
                     for (int sl = 0; sl < ALCH_SLOTS; ++sl) d.f_alch[((size_t)sl * d.R + r) * 3 * N + q * N + c.atom[k]] = 0;
             }
     for (int k = 0; k < c.natoms; ++k) {
@@ -804,14 +804,14 @@ __global__ void k_export_forces(Dev d, int r, int slot, double* out) {
     if (a >= d.N) return;
     for (int q = 0; q < 3; ++q) {
         long long f = d.f_env[(size_t)r * 3 * d.N + q * d.N + a];
-        if (d.n_alch > 0) f += d.f_alch[((size_t)slot * d.R + r) * 3 * d.N + q * d.N + a];
+        if (d.alch_on) f += d.f_alch[((size_t)slot * d.R + r) * 3 * d.N + q * d.N + a];
         out[a * 3 + q] = (double)f * (1.0 / FORCE_SCALE);
     }
 }
 __global__ void k_export_energy(Dev d, int slot, double* out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= d.R) return;
-    out[r] = env_energy(d, r) + (d.n_alch > 0 ? alch_energy(d, r, slot) : 0.0);
+    out[r] = env_energy(d, r) + (d.alch_on ? alch_energy(d, r, slot) : 0.0);
 }
 
 __global__ void k_zero_ll(long long* p, size_t n) {
@@ -1092,7 +1092,7 @@ __global__ void __launch_bounds__(128) k_minimize_step(Dev d, double step, doubl
         s.im[k] = d.invmass[a];
         double f[3];
         for (int q = 0; q < 3; ++q) f[q] = (double)fenv[q * N + a] * (1.0 / FORCE_SCALE);
-        if (d.n_alch > 0) {
+        if (d.alch_on) {
             const long long* fa = d.f_alch + (size_t)r * 3 * N;
             for (int q = 0; q < 3; ++q) f[q] += (double)fa[q * N + a] * (1.0 / FORCE_SCALE);
         }
@@ -1125,7 +1125,7 @@ __global__ void k_max_force(Dev d, double* out) {
         const long long* fenv = d.f_env + (size_t)r * 3 * d.N;
         for (int q = 0; q < 3; ++q) {
             double f = (double)fenv[q * d.N + a] * (1.0 / FORCE_SCALE);
-            if (d.n_alch > 0) f += (double)d.f_alch[(size_t)r * 3 * d.N + q * d.N + a] * (1.0 / FORCE_SCALE);
+            if (d.alch_on) f += (double)d.f_alch[(size_t)r * 3 * d.N + q * d.N + a] * (1.0 / FORCE_SCALE);
             f2 += f * f;
         }
     }

@@ -14,7 +14,7 @@ __global__ void k_begin_eval(Dev d, int advance_noise, int advance_md, int cm_mo
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     const long long nf = (long long)d.R * 3 * d.N;
     for (long long i = tid; i < nf; i += nthreads) d.f_env[i] = 0;
-    if (d.n_alch > 0)
+    if (d.alch_on)
         for (long long i = tid; i < nf * ALCH_SLOTS; i += nthreads) d.f_alch[i] = 0;
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < d.R * N_ETERMS; i += blockDim.x) d.eacc[i] = 0;

@@ -227,20 +227,228 @@ class CustomExternalForce(Force):
         return len(self.atoms)
 
 
-class CustomNonbondedForce(Force):
-    """Parameter record for one softcore interaction class of the alchemical system (see alchemy.py)."""
+class _CustomForce(Force):
+    """Shared part of the generic ``Custom*Force`` classes: energy expression, global parameters, role.
 
-    def __init__(self, energy, role):
+    ``role`` is set on the parameter RECORDS that ``alchemy.AbsoluteAlchemicalFactory`` adds for API parity with
+    openmmtools (their arithmetic is the engine's softcore kernel); forces built by a user or read from a serialized
+    System (``XmlSerializer.deserialize``) have no role and are lowered by ``System.flatten`` to stack programs for the
+    engine's custom-force evaluator."""
+
+    def __init__(self, energy, role=None):
         Force.__init__(self)
-        self.energy = energy
+        self.energy = str(energy)
         self.role = role
+        self.global_params = {}
+        self.periodic = False
 
     def getEnergyFunction(self):
         return self.energy
 
+    def setEnergyFunction(self, energy):
+        self.energy = str(energy)
 
-class CustomBondForce(CustomNonbondedForce):
-    """Parameter record for alchemically-modified exceptions (see alchemy.py)."""
+    def addGlobalParameter(self, name, default):
+        self.global_params[str(name)] = float(_val(default, None) if u.is_quantity(default) else default)
+        return len(self.global_params) - 1
+
+    def getNumGlobalParameters(self):
+        return len(self.global_params)
+
+    def getGlobalParameterName(self, k):
+        return list(self.global_params)[k]
+
+    def getGlobalParameterDefaultValue(self, k):
+        return list(self.global_params.values())[k]
+
+    def usesPeriodicBoundaryConditions(self):
+        return bool(self.periodic)
+
+    def _constants(self):
+        return {k: v for k, v in self.global_params.items() if k not in ('lambda_sterics', 'lambda_electrostatics')}
+
+
+class CustomNonbondedForce(_CustomForce):
+    """OpenMM ``CustomNonbondedForce``: pair energy ``f(r; p1, p2, globals)`` over interaction groups or all pairs."""
+    NoCutoff, CutoffNonPeriodic, CutoffPeriodic = 0, 1, 2
+
+    def __init__(self, energy, role=None):
+        _CustomForce.__init__(self, energy, role)
+        self.per_particle_names = []
+        self.particles = []
+        self.exclusions = []
+        self.groups = []
+        self.method = 0
+        self.cutoff = 1.0
+
+    def addPerParticleParameter(self, name):
+        self.per_particle_names.append(str(name))
+        return len(self.per_particle_names) - 1
+
+    def getNumPerParticleParameters(self):
+        return len(self.per_particle_names)
+
+    def addParticle(self, params=()):
+        self.particles.append([float(v) for v in params])
+        return len(self.particles) - 1
+
+    def getNumParticles(self):
+        return len(self.particles)
+
+    def getParticleParameters(self, i):
+        return tuple(self.particles[i])
+
+    def setParticleParameters(self, i, params):
+        self.particles[i] = [float(v) for v in params]
+
+    def addExclusion(self, i, j):
+        self.exclusions.append((int(i), int(j)))
+        return len(self.exclusions) - 1
+
+    def getNumExclusions(self):
+        return len(self.exclusions)
+
+    def addInteractionGroup(self, set1, set2):
+        self.groups.append((sorted(int(a) for a in set1), sorted(int(a) for a in set2)))
+        return len(self.groups) - 1
+
+    def getNumInteractionGroups(self):
+        return len(self.groups)
+
+    def getInteractionGroupParameters(self, k):
+        return self.groups[k]
+
+    def setNonbondedMethod(self, m):
+        self.method = int(m)
+        self.periodic = self.method == self.CutoffPeriodic
+
+    def getNonbondedMethod(self):
+        return self.method
+
+    def setCutoffDistance(self, c):
+        self.cutoff = float(_val(c, u.nanometers))
+
+    def getCutoffDistance(self):
+        return self.cutoff * u.nanometers
+
+    def _terms(self, n_atoms):
+        """[(atoms A, weights A, atoms B, weights B, params)], parameter-name map of the expression."""
+        if self.role is not None or not self.particles:
+            return [], {}
+        if len(self.particles) != n_atoms:
+            raise ValueError('CustomNonbondedForce must have one particle per System particle')
+        excl = set((min(a, b), max(a, b)) for a, b in self.exclusions)
+        pairs, seen = [], set()
+        if self.groups:
+            for s1, s2 in self.groups:
+                for i in s1:
+                    for j in s2:
+                        key = (min(i, j), max(i, j))
+                        if i != j and key not in seen and key not in excl:
+                            seen.add(key)
+                            pairs.append((i, j))
+        else:
+            if n_atoms > 2000:
+                raise NotImplementedError('a CustomNonbondedForce over all pairs of %d particles needs interaction groups '
+                                          '(the custom-force evaluator enumerates its pairs explicitly)' % n_atoms)
+            pairs = [(i, j) for i in range(n_atoms) for j in range(i + 1, n_atoms) if (i, j) not in excl]
+        P = len(self.per_particle_names)
+        names = {}
+        for k, nm in enumerate(self.per_particle_names):
+            names[nm + '1'] = k
+            names[nm + '2'] = P + k
+        return [([i], [1.0], [j], [1.0], self.particles[i] + self.particles[j]) for i, j in pairs], names
+
+
+class CustomBondForce(_CustomForce):
+    """OpenMM ``CustomBondForce``: ``f(r; per-bond parameters, globals)`` for listed particle pairs."""
+
+    def __init__(self, energy, role=None):
+        _CustomForce.__init__(self, energy, role)
+        self.per_bond_names = []
+        self.bonds = []
+
+    def addPerBondParameter(self, name):
+        self.per_bond_names.append(str(name))
+        return len(self.per_bond_names) - 1
+
+    def addBond(self, i, j, params=()):
+        self.bonds.append((int(i), int(j), [float(v) for v in params]))
+        return len(self.bonds) - 1
+
+    def getNumBonds(self):
+        return len(self.bonds)
+
+    def getBondParameters(self, k):
+        return self.bonds[k]
+
+    def setUsesPeriodicBoundaryConditions(self, flag):
+        self.periodic = bool(flag)
+
+    def _terms(self, n_atoms):
+        if self.role is not None:
+            return [], {}
+        return ([([i], [1.0], [j], [1.0], list(p)) for i, j, p in self.bonds],
+                {nm: k for k, nm in enumerate(self.per_bond_names)})
+
+
+class CustomCentroidBondForce(_CustomForce):
+    """OpenMM ``CustomCentroidBondForce`` restricted to two groups per bond and energies in ``distance(g1,g2)``
+    (``blues/tests/data/ethylene_system.xml:96-113``)."""
+
+    def __init__(self, num_groups, energy):
+        _CustomForce.__init__(self, energy, None)
+        self.num_groups = int(num_groups)
+        self.per_bond_names = []
+        self.group_defs = []
+        self.bonds = []
+
+    def getNumGroupsPerBond(self):
+        return self.num_groups
+
+    def addPerBondParameter(self, name):
+        self.per_bond_names.append(str(name))
+        return len(self.per_bond_names) - 1
+
+    def addGroup(self, particles, weights=None):
+        self.group_defs.append(([int(a) for a in particles], None if weights is None or len(weights) == 0
+                                else [float(w) for w in weights]))
+        return len(self.group_defs) - 1
+
+    def getNumGroups(self):
+        return len(self.group_defs)
+
+    def getGroupParameters(self, k):
+        return self.group_defs[k]
+
+    def addBond(self, groups, params=()):
+        self.bonds.append(([int(g) for g in groups], [float(v) for v in params]))
+        return len(self.bonds) - 1
+
+    def getNumBonds(self):
+        return len(self.bonds)
+
+    def getBondParameters(self, k):
+        return self.bonds[k]
+
+    def setUsesPeriodicBoundaryConditions(self, flag):
+        self.periodic = bool(flag)
+
+    def _terms(self, n_atoms, masses=None):
+        if self.num_groups != 2:
+            raise NotImplementedError('CustomCentroidBondForce with %d groups per bond (only distance(g1,g2) between two '
+                                      'groups is supported)' % self.num_groups)
+        out = []
+        for groups, params in self.bonds:
+            sides = []
+            for gi in groups:
+                atoms, w = self.group_defs[gi]
+                w = np.asarray([masses[a] for a in atoms] if w is None else w, float)     # OpenMM: default weights = masses
+                if w.sum() <= 0:
+                    raise ValueError('CustomCentroidBondForce group %d has zero total weight' % gi)
+                sides.append((list(atoms), list(w / w.sum())))
+            out.append((sides[0][0], sides[0][1], sides[1][0], sides[1][1], list(params)))
+        return out, {nm: k for k, nm in enumerate(self.per_bond_names)}
 
 
 class System(object):
@@ -404,7 +612,58 @@ class System(object):
             t[k_] = float(al.get(k_, d))
         t['annihilate_sterics'] = int(al.get('annihilate_sterics', False))
         t['annihilate_electrostatics'] = int(al.get('annihilate_electrostatics', True))
+        t.update(self._flatten_custom())
         return t
+
+    def _flatten_custom(self):
+        """Generic Custom*Force objects → the ``custom_*`` tables of ``bl_topology`` (stack programs + term lists)."""
+        from . import lepton
+        n = self.getNumParticles()
+        terms, cutoffs, params, progs_op, progs_arg, pstart = [], [], [], [], [], [0]
+        gstart, gatoms, gweights, gindex = [0], [], [], {}
+
+        def group_id(atoms, weights):
+            key = (tuple(atoms), tuple(round(w, 15) for w in weights))
+            if key not in gindex:
+                gindex[key] = len(gstart) - 1
+                gatoms.extend(atoms)
+                gweights.extend(weights)
+                gstart.append(len(gatoms))
+            return gindex[key]
+
+        for f in self.forces:
+            if not isinstance(f, _CustomForce) or f.role is not None:
+                continue
+            if isinstance(f, CustomCentroidBondForce):
+                tl, names = f._terms(n, self.masses)
+                dist = ['distance(g1,g2)', 'distance(g2,g1)']
+            else:
+                tl, names = f._terms(n)
+                dist = []
+            if not tl:
+                continue
+            ops, args = lepton.compile_program(f.energy, names, f._constants(), dist)
+            prog = len(pstart) - 1
+            progs_op.extend(ops)
+            progs_arg.extend(args)
+            pstart.append(len(progs_op))
+            cut = -1.0
+            if isinstance(f, CustomNonbondedForce) and f.method != CustomNonbondedForce.NoCutoff:
+                cut = float(f.cutoff)
+            for a, wa, b, wb, par in tl:
+                terms.append([group_id(a, wa), group_id(b, wb), prog, 1 if f.periodic else 0])
+                cutoffs.append(cut)
+                params.append(list(par))
+        npar = max([len(p) for p in params] + [0])
+        ptab = np.zeros((len(terms), max(npar, 1)))
+        for k, p in enumerate(params):
+            ptab[k, :len(p)] = p
+        return {'custom_term': np.asarray(terms, np.int32).reshape(-1, 4), 'custom_cutoff': np.asarray(cutoffs, np.float64),
+                'custom_n_params': int(max(npar, 1)) if terms else 0, 'custom_params': ptab,
+                'custom_group_start': np.asarray(gstart, np.int32), 'custom_group_atoms': np.asarray(gatoms, np.int32),
+                'custom_group_weights': np.asarray(gweights, np.float64),
+                'custom_prog_start': np.asarray(pstart, np.int32), 'custom_code_op': np.asarray(progs_op, np.int32),
+                'custom_code_arg': np.asarray(progs_arg, np.float64)}
 
 
 # =========================================================================================================
@@ -629,3 +888,106 @@ def create_system(struct, nonbondedMethod=None, nonbondedCutoff=8.0 * u.angstrom
     if removeCMMotion:
         system.addForce(CMMotionRemover(1))
     return system
+
+
+# =========================================================================================================
+# serialized systems
+# =========================================================================================================
+class XmlSerializer(object):
+    """``openmm.XmlSerializer.deserialize`` for serialized ``System`` objects (``blues/tests/test_ethylene.py:64-67``
+    reads ``tests/data/ethylene_system.xml``).  Orthorhombic boxes; the force classes of this module."""
+
+    @staticmethod
+    def deserialize(xml):
+        import xml.etree.ElementTree as ET
+        root = ET.fromstring(xml)
+        if root.tag != 'System':
+            raise ValueError('XmlSerializer.deserialize: only <System> documents are supported (got <%s>)' % root.tag)
+        masses = [float(p.get('mass')) for p in root.find('Particles')]
+        system = System(len(masses))
+        system.masses = np.asarray(masses, float)
+        box = root.find('PeriodicBoxVectors')
+        if box is not None:
+            a, b, c = box.find('A'), box.find('B'), box.find('C')
+            off = [a.get('y'), a.get('z'), b.get('x'), b.get('z'), c.get('x'), c.get('y')]
+            if any(abs(float(v)) > 1e-12 for v in off):
+                raise NotImplementedError('triclinic boxes are not supported')
+            system.box = np.array([float(a.get('x')), float(b.get('y')), float(c.get('z'))])
+        cons = root.find('Constraints')
+        if cons is not None and len(cons):
+            system.constraints = np.asarray([[int(c.get('p1')), int(c.get('p2'))] for c in cons], np.int32)
+            system.constraint_d = np.asarray([float(c.get('d')) for c in cons], float)
+
+        def params_of(el):
+            out, k = [], 1
+            while el.get('param%d' % k) is not None:
+                out.append(float(el.get('param%d' % k)))
+                k += 1
+            return out
+
+        def globals_into(force, el):
+            gp = el.find('GlobalParameters')
+            for p in (gp if gp is not None else []):
+                force.addGlobalParameter(p.get('name'), float(p.get('default')))
+
+        for el in (root.find('Forces') if root.find('Forces') is not None else []):
+            kind = el.get('type')
+            if kind == 'HarmonicBondForce':
+                b = list(el.find('Bonds'))
+                f = HarmonicBondForce([[int(x.get('p1')), int(x.get('p2'))] for x in b], [float(x.get('d')) for x in b],
+                                      [float(x.get('k')) for x in b])
+            elif kind == 'HarmonicAngleForce':
+                a = list(el.find('Angles'))
+                f = HarmonicAngleForce([[int(x.get('p1')), int(x.get('p2')), int(x.get('p3'))] for x in a],
+                                       [float(x.get('a')) for x in a], [float(x.get('k')) for x in a])
+            elif kind == 'PeriodicTorsionForce':
+                tt = list(el.find('Torsions'))
+                f = PeriodicTorsionForce([[int(x.get('p%d' % q)) for q in (1, 2, 3, 4)] for x in tt],
+                                         [int(x.get('periodicity')) for x in tt], [float(x.get('phase')) for x in tt],
+                                         [float(x.get('k')) for x in tt])
+            elif kind == 'CustomNonbondedForce':
+                f = CustomNonbondedForce(el.get('energy'))
+                for p in el.find('PerParticleParameters'):
+                    f.addPerParticleParameter(p.get('name'))
+                globals_into(f, el)
+                for p in el.find('Particles'):
+                    f.addParticle(params_of(p))
+                for x in (el.find('Exclusions') if el.find('Exclusions') is not None else []):
+                    f.addExclusion(int(x.get('p1')), int(x.get('p2')))
+                for g in (el.find('InteractionGroups') if el.find('InteractionGroups') is not None else []):
+                    f.addInteractionGroup([int(x.get('index')) for x in g.find('Set1')], [int(x.get('index')) for x in g.find('Set2')])
+                f.setNonbondedMethod(int(el.get('method', 0)))
+                f.setCutoffDistance(float(el.get('cutoff', 1.0)))
+            elif kind == 'CustomBondForce':
+                f = CustomBondForce(el.get('energy'))
+                for p in el.find('PerBondParameters'):
+                    f.addPerBondParameter(p.get('name'))
+                globals_into(f, el)
+                for x in el.find('Bonds'):
+                    f.addBond(int(x.get('p1')), int(x.get('p2')), params_of(x))
+                f.setUsesPeriodicBoundaryConditions(el.get('usesPeriodic', '0') == '1')
+            elif kind == 'CustomCentroidBondForce':
+                f = CustomCentroidBondForce(int(el.get('groups')), el.get('energy'))
+                for p in el.find('PerBondParameters'):
+                    f.addPerBondParameter(p.get('name'))
+                globals_into(f, el)
+                for g in el.find('Groups'):
+                    parts = list(g)
+                    w = [x.get('weight') for x in parts]
+                    if any(v is not None for v in w) and not all(v is not None for v in w):
+                        raise ValueError('CustomCentroidBondForce group mixes explicit and default weights')
+                    f.addGroup([int(x.get('p')) for x in parts], None if w[0] is None else [float(v) for v in w])
+                for x in el.find('Bonds'):
+                    gs, k = [], 1
+                    while x.get('g%d' % k) is not None:
+                        gs.append(int(x.get('g%d' % k)))
+                        k += 1
+                    f.addBond(gs, params_of(x))
+                f.setUsesPeriodicBoundaryConditions(el.get('usesPeriodic', '0') == '1')
+            elif kind == 'CMMotionRemover':
+                f = CMMotionRemover(int(el.get('frequency', 1)))
+            else:
+                raise NotImplementedError('XmlSerializer.deserialize: force type %s is not supported' % kind)
+            f.setForceGroup(int(el.get('forceGroup', 0)))
+            system.addForce(f)
+        return system

@@ -66,7 +66,58 @@ typedef struct bl_topology {
     const double* alch_exc_eps;
     double  softcore_alpha, softcore_a, softcore_b, softcore_c;
     int32_t annihilate_sterics, annihilate_electrostatics;
+    /* Generic Custom*Force terms (OpenMM CustomNonbondedForce over interaction groups or all pairs, CustomBondForce,
+       two-group CustomCentroidBondForce — blues/tests/data/ethylene_system.xml:52-114 is the reference's use):
+       E = f(r; per-term parameters, lambda_sterics, lambda_electrostatics), r = distance between the weighted
+       centroids of two atom groups.  f arrives as a stack program compiled by the host from the Lepton expression
+       (blues_b200/lepton.py::compile_program); the device evaluates value and d/dr with forward-mode dual numbers.
+       The two lambdas follow the integrator's tables exactly like the softcore terms. */
+    int32_t n_custom_terms;
+    const int32_t* custom_term;          /* [n_custom_terms][4]: group A, group B, program, flags (bit 0: minimum image) */
+    const double*  custom_cutoff;        /* [n_custom_terms] nm; <= 0: no cutoff                                        */
+    int32_t custom_n_params;             /* parameters per term                                                         */
+    const double*  custom_params;        /* [n_custom_terms][custom_n_params]                                           */
+    int32_t n_custom_groups;
+    const int32_t* custom_group_start;   /* [n_custom_groups + 1] offsets into the two arrays below                     */
+    const int32_t* custom_group_atoms;
+    const double*  custom_group_weights; /* normalised (sum 1 per group)                                                */
+    int32_t n_custom_progs;
+    const int32_t* custom_prog_start;    /* [n_custom_progs + 1] offsets into the code arrays                           */
+    const int32_t* custom_code_op;       /* BL_OP_* */
+    const double*  custom_code_arg;      /* immediate: constant, parameter / global index, integer exponent             */
 } bl_topology;
+
+/* stack-program opcodes of the custom-force evaluator */
+#define BL_OP_CONST   0
+#define BL_OP_R       1   /* the distance */
+#define BL_OP_PARAM   2   /* per-term parameter arg */
+#define BL_OP_GLOBAL  3   /* 0 lambda_sterics, 1 lambda_electrostatics */
+#define BL_OP_ADD     4
+#define BL_OP_SUB     5
+#define BL_OP_MUL     6
+#define BL_OP_DIV     7
+#define BL_OP_NEG     8
+#define BL_OP_POWI    9   /* x^arg, arg integer */
+#define BL_OP_POW    10   /* a^b, both from the stack */
+#define BL_OP_SQRT   11
+#define BL_OP_EXP    12
+#define BL_OP_LOG    13
+#define BL_OP_SIN    14
+#define BL_OP_COS    15
+#define BL_OP_TAN    16
+#define BL_OP_ABS    17
+#define BL_OP_MIN    18
+#define BL_OP_MAX    19
+#define BL_OP_STEP   20
+#define BL_OP_DELTA  21
+#define BL_OP_SELECT 22   /* select(c, a, b): a if c != 0 else b */
+#define BL_OP_ERF    23
+#define BL_OP_ERFC   24
+#define BL_OP_TANH   25
+#define BL_OP_SINH   26
+#define BL_OP_COSH   27
+#define BL_OP_ATAN   28
+#define BL_CUSTOM_STACK 24
 
 /* Integrator kinds */
 #define BL_INTEGRATOR_NCMC      1   /* AlchemicalExternalLangevinIntegrator (blues/integrators.py:8-249)      */

@@ -410,7 +410,7 @@ def reference_tests():
     os.makedirs(os.path.join(dst, 'data'), exist_ok=True)
     for name in ('test_simulation.py', 'test_randomrotation.py'):
         shutil.copyfile(os.path.join(root, 'tests', name), os.path.join(dst, name))
-    for name in ('TOL-parm.prmtop', 'TOL-parm.inpcrd'):
+    for name in ('TOL-parm.prmtop', 'TOL-parm.inpcrd', 'ethylene_system.xml', 'ethylene_structure.pdb'):
         shutil.copyfile(os.path.join(REF, name), os.path.join(dst, 'data', name))
     print('reference test fixtures refreshed under', dst)
 

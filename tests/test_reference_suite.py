@@ -97,6 +97,7 @@ def test_reference_tests_pass_on_the_host_layer_over_the_oracle_engine(tmp_path)
 def test_fixture_copies_are_verbatim():
     """tests/golden/reference_checkout/ (input of tests/test_gpu_reference_suite.py) equals the checkout byte for byte."""
     base = os.path.join(ROOT, 'tests', 'golden', 'reference_checkout', 'blues', 'tests')
-    for rel in ('test_simulation.py', 'test_randomrotation.py', 'data/TOL-parm.prmtop', 'data/TOL-parm.inpcrd'):
+    for rel in ('test_simulation.py', 'test_randomrotation.py', 'data/TOL-parm.prmtop', 'data/TOL-parm.inpcrd',
+                'data/ethylene_system.xml', 'data/ethylene_structure.pdb'):
         with open(os.path.join(base, rel), 'rb') as a, open(os.path.join(REFERENCE, 'blues', 'tests', rel), 'rb') as b:
             assert a.read() == b.read(), rel
