@@ -304,13 +304,178 @@ class SmartDartMove(RandomLigandRotationMove):
 
 
 class SideChainMove(Move):
-    """Placeholder for ``blues/moves.py:413-843``: upstream needs the OpenEye toolkits (a licensed dependency) for its
-    rotor perception and prints "SideChainMove class will be unavailable" without them; here the class exists so that
-    ``from blues.moves import SideChainMove`` resolves, and constructing it says why it cannot run."""
+    """Rotation of a side chain about one of its rotatable heavy-atom bonds (``blues/moves.py:418-843``).
 
-    def __init__(self, *args, **kwargs):
-        raise ImportError('SideChainMove needs the OpenEye toolkits (openeye.oechem), which are not available; '
-                          'it is outside the NCMC hot path this package covers (DESIGN.md)')
+    Upstream needs the OpenEye toolkits for three graph queries — backbone atoms (``OEIsBackboneAtom``), ring membership
+    (``OEFindRingAtomsAndBonds``) and ``bond.IsRotor()`` — and is unavailable without a licence.  The same queries are
+    answered here from the structure's own bond graph: backbone = atoms named N, CA, C, O; a rotor is a bond between two
+    heavy atoms that is not in a ring, whose ends both carry another heavy neighbour (terminal groups such as methyls,
+    hydroxyls, carbonyl oxygens do not define a torsion) and that does not join two three-coordinate C/N atoms (amide,
+    guanidinium and other conjugated bonds, which OpenEye perceives as non-single from the geometry).  Everything else —
+    the dictionaries ``rot_atoms`` / ``rot_bonds`` / ``qry_atoms``, the atom walk of ``getRotAtoms``, the random choice of
+    bond and angle with Python's ``random`` module, the rotation matrix and ``move`` — follows the reference, whose test
+    (``blues/tests/test_sidechain.py:64-68``: one rotor, 11 listed atoms for valine) this class reproduces.
+
+    Bonds are identified by ``(index of first atom, index of second atom)`` tuples instead of OpenEye bond pointers.
+    Like upstream, ``atom_indices`` is the ``rot_atoms`` dictionary itself (``blues/moves.py:473``).
+    """
+    BACKBONE_NAMES = ('N', 'CA', 'C', 'O')
+
+    def __init__(self, structure, residue_list, verbose=False, write_move=False):
+        self.structure = structure
+        self.molecule = self._bondGraph()
+        self.residue_list = residue_list
+        self.all_atoms = [atom.index for atom in self.structure.topology.atoms()]
+        self.rot_atoms, self.rot_bonds, self.qry_atoms = self.getRotBondAtoms()
+        self.atom_indices = self.rot_atoms
+        self.verbose = verbose
+        self.write_move = write_move
+
+    # -- graph perception (the OpenEye part of the reference) ------------------------------------------------------
+    def _bondGraph(self):
+        """Adjacency lists, atomic numbers, residue numbers / names and ring-bond flags of the structure."""
+        s = self.structure
+        n = len(s.atoms)
+        adj = [[] for _ in range(n)]
+        for i, j in numpy.asarray(s.bonds, int).reshape(-1, 2):
+            adj[int(i)].append(int(j))
+            adj[int(j)].append(int(i))
+        z = [int(a.atomic_number) for a in s.atoms]
+        resnum, resname = [0] * n, [''] * n
+        for res in s.topology.residues():
+            for a in res.atoms():
+                resnum[a.index] = int(res.id)
+                resname[a.index] = res.name
+        names = [a.name for a in s.atoms]
+        return {'adj': adj, 'z': z, 'resnum': resnum, 'resname': resname, 'names': names}
+
+    def _bondInRing(self, a, b):
+        """True if a path from a to b exists that does not use the bond a-b (depth-first search)."""
+        adj = self.molecule['adj']
+        seen, stack = {a}, [x for x in adj[a] if x != b]
+        while stack:
+            x = stack.pop()
+            if x == b:
+                return True
+            if x not in seen:
+                seen.add(x)
+                stack.extend(y for y in adj[x] if y not in seen)
+        return False
+
+    def _isRotor(self, a, b):
+        m = self.molecule
+        if m['z'][a] <= 1 or m['z'][b] <= 1:
+            return False
+        heavy = lambda x: sum(1 for y in m['adj'][x] if m['z'][y] > 1)
+        if heavy(a) < 2 or heavy(b) < 2:
+            return False
+        planar = lambda x: m['z'][x] in (6, 7) and len(m['adj'][x]) == 3
+        if planar(a) and planar(b):
+            return False
+        return not self._bondInRing(a, b)
+
+    def getBackboneAtoms(self, molecule):
+        """Indices of the backbone atoms (``blues/moves.py:485-508``)."""
+        return [i for i, nm in enumerate(molecule['names']) if nm in self.BACKBONE_NAMES]
+
+    def getTargetAtoms(self, molecule, backbone_atoms, residue_list):
+        """Non-backbone atoms of the target residues as ``{atom index: atom index}`` (``blues/moves.py:510-550``)."""
+        bb = set(backbone_atoms)
+        qry_atoms = {}
+        for i in range(len(molecule['names'])):
+            if i not in bb and molecule['resnum'][i] in residue_list and molecule['resname'][i] != 'HOH':
+                qry_atoms[i] = i
+        return qry_atoms, backbone_atoms
+
+    def findHeavyRotBonds(self, pdb_OEMol, qry_atoms):
+        """``{(a, b): residue number}`` of the rotatable heavy-atom bonds of the query atoms (``blues/moves.py:552-586``)."""
+        rot_bonds = {}
+        for atom in qry_atoms.keys():
+            for nb in pdb_OEMol['adj'][atom]:
+                bond = (min(atom, nb), max(atom, nb))
+                if bond not in rot_bonds and self._isRotor(atom, nb):
+                    rot_bonds[bond] = pdb_OEMol['resnum'][atom]
+        return rot_bonds
+
+    def getRotAtoms(self, rotbonds, molecule, backbone_atoms):
+        """``{residue: {bond: [axis1, axis2, atoms downstream of the bond]}}`` — the walk of ``blues/moves.py:588-651``."""
+        backbone = set(backbone_atoms)
+        adj, z = molecule['adj'], molecule['z']
+        rot_atom_dict = {}
+        for bond, resnum in rotbonds.items():
+            ax1, ax2 = bond
+            rot_atom_dict.setdefault(resnum, {})[bond] = []
+            idx_list = [ax1, ax2]
+            query_list = []
+            if ax1 not in backbone:
+                query_list.append(ax1)
+            if ax2 not in query_list and ax2 not in backbone:
+                query_list.append(ax2)
+            for atom in query_list:                       # grows while it is walked, as upstream
+                for candidate in adj[atom]:
+                    if candidate not in query_list and candidate not in backbone and candidate != ax2:
+                        query_list.append(candidate)
+                        if z[candidate] > 1:
+                            for can_nbor in adj[candidate]:
+                                if can_nbor not in query_list and candidate not in backbone and candidate != ax2:
+                                    query_list.append(can_nbor)
+            for y in query_list:
+                if y not in idx_list:
+                    idx_list.append(y)
+            rot_atom_dict[resnum][bond] = list(idx_list)
+        return rot_atom_dict
+
+    def getRotBondAtoms(self):
+        backbone_atoms = self.getBackboneAtoms(self.molecule)
+        qry_atoms, backbone_atoms = self.getTargetAtoms(self.molecule, backbone_atoms, self.residue_list)
+        rot_bonds = self.findHeavyRotBonds(self.molecule, qry_atoms)
+        rot_atoms = self.getRotAtoms(rot_bonds, self.molecule, backbone_atoms)
+        return rot_atoms, rot_bonds, qry_atoms
+
+    # -- the move ----------------------------------------------------------------------------------------------------
+    def chooseBondandTheta(self):
+        """Random residue, bond and angle in [0, 2 pi) from Python's ``random`` module (``blues/moves.py:683-708``)."""
+        import math
+        import random
+        res_choice = random.choice(list(self.rot_atoms.keys()))
+        bond_choice = random.choice(list(self.rot_atoms[res_choice].keys()))
+        targetatoms = self.rot_atoms[res_choice][bond_choice]
+        theta_ran = random.random() * 2 * math.pi
+        return theta_ran, targetatoms, res_choice, bond_choice
+
+    def rotation_matrix(self, axis, theta):
+        """Counter-clockwise rotation about ``axis`` by ``theta`` radians (``blues/moves.py:710-730``)."""
+        import math
+        axis = numpy.asarray(axis, float)
+        axis = axis / math.sqrt(numpy.dot(axis, axis))
+        a = math.cos(theta / 2.0)
+        b, c, d = -axis * math.sin(theta / 2.0)
+        aa, bb, cc, dd = a * a, b * b, c * c, d * d
+        bc, ad, ac, ab, bd, cd = b * c, a * d, a * c, a * b, b * d, c * d
+        return numpy.array([[aa + bb - cc - dd, 2 * (bc + ad), 2 * (bd - ac)],
+                            [2 * (bc - ad), aa + cc - bb - dd, 2 * (cd + ab)],
+                            [2 * (bd + ac), 2 * (cd - ab), aa + dd - bb - cc]])
+
+    def move(self, context, verbose=False):
+        """Rotate the atoms listed for a randomly chosen bond about it (``blues/moves.py:732-843``): the two axis atoms
+        stay where they are, the structure's coordinates follow the context's."""
+        theta, target_atoms, res, bond = self.chooseBondandTheta()
+        print('Rotating bond: %s in resnum: %s by %.2f radians' % (bond, res, theta))
+        state = context.getState(getPositions=True)
+        nc_positions = copy.deepcopy(state.getPositions(asNumpy=True))
+        x = numpy.array(nc_positions.value_in_unit(unit.nanometers), float)
+        axis1, axis2 = target_atoms[0], target_atoms[1]
+        rot_matrix = self.rotation_matrix(x[axis1] - x[axis2], theta)
+        for atom in target_atoms:
+            before = x[atom].copy()
+            x[atom] = numpy.dot(rot_matrix, x[atom] - x[axis2]) + x[axis2]
+            if self.verbose or verbose:
+                print('atom %d: %s -> %s' % (atom, before, x[atom]))
+        context.setPositions(x * unit.nanometers)
+        self.structure.positions = x * unit.nanometers
+        if self.write_move:
+            self.structure.save('sc_move_%s_%s_%s.pdb' % (res, axis1, axis2), overwrite=True)
+        return context
 
 
 class CombinationMove(Move):

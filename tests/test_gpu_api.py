@@ -582,3 +582,42 @@ def test_many_walker_correction_and_accept_copy_match_host_recomputation(structu
         assert np.max(np.abs(x_md[r] - ref)) < 0.05                 # one MD step away from the right starting point
         other = x0[r] if spy.acc[r] else spy.x1[r]
         assert np.max(np.abs(x_md[r] - other)) > np.max(np.abs(x_md[r] - ref))
+
+
+def sidechain_move_contract(golden_dir=GOLDEN):
+    """``blues/tests/test_sidechain.py:30-88`` (which upstream can only run with an OpenEye licence): divaline in vacuum,
+    one rotatable bond in valine with 11 listed atoms, and a move that displaces everything but the two axis atoms."""
+    from blues_b200.simulation import SystemFactory, SimulationFactory
+    from blues_b200.moves import SideChainMove, MoveEngine
+    from blues_b200 import system as sysmod
+    struct = Structure.load_npz(os.path.join(golden_dir, 'vac_divaline.npz'))
+    sidechain = SideChainMove(struct, [1])
+    engine = MoveEngine(sidechain)
+    engine.selectMove()
+    vals = [v for v in sidechain.rot_atoms[1].values()][0]
+    assert len(vals) == 11
+    assert len(sidechain.rot_bonds) == 1
+    systems = SystemFactory(struct, sidechain.atom_indices, {'nonbondedMethod': sysmod.NoCutoff, 'constraints': sysmod.HBonds})
+    cfg = {'dt': 0.002 * unit.picoseconds, 'friction': 1 / unit.picoseconds, 'temperature': 300 * unit.kelvin,
+           'nIter': 1, 'nstepsMD': 1, 'nstepsNC': 4, 'platform': 'CUDA',
+           'alchemical_functions': {
+               'lambda_sterics': 'step(0.199999-lambda) + step(lambda-0.2)*step(0.8-lambda)*abs(lambda-0.5)*1/0.3 + step(lambda-0.800001)',
+               'lambda_electrostatics': 'step(0.2-lambda)- 1/0.2*lambda*step(0.2-lambda) + 1/0.2*(lambda-0.8)*step(lambda-0.8)'}}
+    simulations = SimulationFactory(systems, engine, cfg)
+    atom_indices = vals
+    before = simulations.ncmc.context.getState(getPositions=True).getPositions(asNumpy=True)[atom_indices, :]
+    simulations.ncmc.context = engine.runEngine(simulations.ncmc.context)
+    after = simulations.ncmc.context.getState(getPositions=True).getPositions(asNumpy=True)[atom_indices, :]
+    b, a = np.asarray(before._value), np.asarray(after._value)
+    assert np.not_equal(b, a)[2:, :].all()                 # every rotated atom moved ...
+    assert np.allclose(b[:2], a[:2], atol=1e-12)           # ... the two axis atoms did not
+    d0 = np.linalg.norm(b[2:] - b[1], axis=1)
+    d1 = np.linalg.norm(a[2:] - a[1], axis=1)
+    assert np.allclose(d0, d1, atol=1e-9)                  # a rigid rotation about the bond
+    ax = (b[0] - b[1]) / np.linalg.norm(b[0] - b[1])
+    assert np.allclose((b[2:] - b[1]) @ ax, (a[2:] - a[1]) @ ax, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_sidechain_move():
+    sidechain_move_contract()

@@ -131,3 +131,7 @@ def test_water_move_device_predicate_follows_all_three_hooks(structure):
     kw = dict(protein_selection='(index 0) or (index 1)', radius=0.9 * unit.nanometers)
     assert WaterTranslationMove(structure, **kw).device_move() is not None
     assert Custom(structure, **kw).device_move() is None
+
+
+def test_sidechain_move():
+    api.sidechain_move_contract()
