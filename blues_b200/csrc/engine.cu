@@ -91,6 +91,7 @@ struct bl_handle {
     int build_cq = 0, build_ctas = 0;
     bool builder2 = false; int build2_ctas = 0;  // BLUES_B200_BUILDER=2: ballot-compaction list builder (measured 10 % slower than
                                                  // the shared-memory sub-list builder, gpurun_out/r2_builder.log: kept for reference)
+    bool debug_sync = false, debug_reported = false;   // BLUES_B200_DEBUG_SYNC
     int int_block = 32;          // BLUES_B200_INT_BLOCK: threads per k_integrate CTA (one constraint cluster per thread)
     bool fold_zero = true;       // step programs: force zeroing + rebuild latch inside the INTEGRATE launch before an evaluation
     int own_dft = 0;             // reciprocal space: 0 cuFFT, 1 three fused direct-DFT kernels, 2 one cluster kernel (small grids)
@@ -140,8 +141,9 @@ static T* dupload(bl_handle* h, const std::vector<T>& v) {
 
 // ---- launch helper with optional per-kernel event timing -------------------------------------------------
 struct LaunchTimer {
-    bl_handle* h; int kid; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
-    LaunchTimer(bl_handle* h_, int kid_, cudaStream_t st_ = nullptr) : h(h_), kid(kid_), st(st_ ? st_ : h_->stream) {
+    bl_handle* h; int kid; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; int line;
+    LaunchTimer(bl_handle* h_, int kid_, cudaStream_t st_ = nullptr, int line_ = __builtin_LINE())
+        : h(h_), kid(kid_), st(st_ ? st_ : h_->stream), line(line_) {
         if (h->capturing) h->capture_launches++; else h->launches++;
         if (h->profiling && !h->capturing && kid >= 0) {
             cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -150,6 +152,16 @@ struct LaunchTimer {
     }
     ~LaunchTimer() {
         if (e0) { cudaEventRecord(e1, st); h->timed.push_back({kid, e0, e1}); }
+        if (h->debug_sync && !h->capturing) {
+            // BLUES_B200_DEBUG_SYNC=1 (diagnostic): direct launches, every one followed by a synchronisation, so that a
+            // device fault is reported at the launch that caused it
+            const cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess && !h->debug_reported) {
+                h->debug_reported = true;
+                fprintf(stderr, "[blues_b200 debug] launch at engine.cu:%d (timer id %d, launch #%llu, step %d) failed: %s\n", line,
+                        kid, h->launches, h->step, cudaGetErrorString(e));
+            }
+        }
     }
 };
 static void collect_timings(bl_handle* h) {
@@ -647,7 +659,8 @@ static int check_flags(bl_handle* h, bool nan_is_error = true) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->profiling) collect_timings(h);
     for (int r = 0; r < d.R; ++r) {
-        if (g[r].item_overflow) {
+        // a walker that blew up also overflows its list rows (its runaway atoms are parked at the origin): report the cause
+        if (g[r].item_overflow && !g[r].nan_flag) {
             h->error = "neighbour work-item list overflow";
             return BL_ERR_CAPACITY;
         }
@@ -936,6 +949,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_PAIR_LANES")) { const int l = atoi(getenv("BLUES_B200_PAIR_LANES")); h->pair_lanes = l == 16 || l == 32 ? l : 8; }
     if (getenv("BLUES_B200_PAIR_X2")) h->pair_x2 = atoi(getenv("BLUES_B200_PAIR_X2"));
     if (getenv("BLUES_B200_PAIR")) h->pair_variant = atoi(getenv("BLUES_B200_PAIR"));
+    if (getenv("BLUES_B200_DEBUG_SYNC") && atoi(getenv("BLUES_B200_DEBUG_SYNC"))) { h->debug_sync = true; h->use_graphs = false; h->pdl = false; }
     if (getenv("BLUES_B200_INT_BLOCK")) h->int_block = std::max(32, std::min(256, atoi(getenv("BLUES_B200_INT_BLOCK")) / 32 * 32));
     if (getenv("BLUES_B200_FOLD_ZERO")) h->fold_zero = atoi(getenv("BLUES_B200_FOLD_ZERO")) != 0;
     counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping
@@ -1626,6 +1640,7 @@ int bl_get_global(bl_handle* h, int replica, const char* name, double* value) {
     else if (n == "nsteps") *value = h->ic.nsteps;
     else if (n == "kT") *value = h->ic.kT;
     else if (n == "n_rebuilds") *value = (double)g.n_rebuilds;
+    else if (n == "noise_counter") *value = (double)g.noise_counter;       // diagnostic: position in the thermostat's Philox stream
     else { h->error = "unknown global variable '" + n + "'"; return BL_ERR_INVALID; }
     return BL_OK;
 }
@@ -1653,6 +1668,7 @@ int bl_set_global(bl_handle* h, int replica, const char* name, double value) {
         else if (n == "Eold") x.Eold = value;
         else if (n == "Enew") x.Enew = value;
         else if (n == "debug") x.debug = (int)value;
+        else if (n == "noise_counter") { x.noise_counter = (unsigned int)value; counters(h).noise_ready = 0; }   // diagnostic: replay a run from a later point of its noise stream
         else if (n == "nprop") { h->ic.nprop = std::max(1, (int)value); invalidate_graphs(h); }
         else if (n == "prop_lambda_min") h->prop_lambda_min = value;
         else if (n == "prop_lambda_max") h->prop_lambda_max = value;

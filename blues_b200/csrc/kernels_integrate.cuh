@@ -9,9 +9,18 @@ __device__ __forceinline__ float4 wrapped_mirror(const Dev& d, double x, double 
         x -= d.boxd[0] * floor(x * d.boxd[3]);
         y -= d.boxd[1] * floor(y * d.boxd[4]);
         z -= d.boxd[2] * floor(z * d.boxd[5]);
+        // a coordinate beyond ~1e15 box lengths (a walker that blew up; it is flagged like a NaN, see BLOWUP_LIMIT) no
+        // longer wraps into the cell: park it at the origin so that every index derived from the mirror stays in range
+        if (!(x >= 0.0 && x <= d.boxd[0])) x = 0.0;
+        if (!(y >= 0.0 && y <= d.boxd[1])) y = 0.0;
+        if (!(z >= 0.0 && z <= d.boxd[2])) z = 0.0;
     }
     return make_float4((float)x, (float)y, (float)z, q);
 }
+
+// A coordinate of this magnitude (nm) is a walker that blew up: OpenMM's "Particle coordinate is nan" follows within a
+// step or two; here it raises the same per-walker flag at once (NaN compares false, so NaN is covered too).
+#define BLOWUP_LIMIT 1.0e6
 
 struct ClusterState {
     double x[MAX_CLUSTER_ATOMS][3];
@@ -468,7 +477,7 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
             ddz -= d.boxf[2] * rintf(ddz * d.boxf[5]);
         }
         moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
-        bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
+        bad = bad || !(fabs(s.x[k][0]) < BLOWUP_LIMIT && fabs(s.x[k][1]) < BLOWUP_LIMIT && fabs(s.x[k][2]) < BLOWUP_LIMIT);
 #pragma unroll
         for (int q = 0; q < 3; ++q) mom[q] += s.mass[k] * s.v[k][q];
     }
@@ -610,7 +619,7 @@ __device__ __forceinline__ void run_cluster_generic(const Dev& d, const Integrat
             ddz -= d.boxf[2] * rintf(ddz * d.boxf[5]);
         }
         moved = moved || (ddx * ddx + ddy * ddy + ddz * ddz > lim);
-        bad = bad || !(isfinite(s.x[k][0]) && isfinite(s.x[k][1]) && isfinite(s.x[k][2]));
+        bad = bad || !(fabs(s.x[k][0]) < BLOWUP_LIMIT && fabs(s.x[k][1]) < BLOWUP_LIMIT && fabs(s.x[k][2]) < BLOWUP_LIMIT);
         for (int q = 0; q < 3; ++q) mom[q] += mass[k] * s.v[k][q];
     }
 }

@@ -285,9 +285,11 @@ __device__ __forceinline__ int build_group_runs(const Dev& d, const int* __restr
         if (rem2 > 0.f) {                                                     // else: column out of reach
             int z0 = 0, z1 = ncz - 1;
             if (!rz) {
+                // both ends clamped to [za - 2, zb + 2]: a walker that blew up has coordinates of any magnitude, the
+                // float -> int conversion then saturates and `z0 + ncz` below would wrap around
                 const float zr = sqrtf(rem2);
-                z0 = max(za - 2, (int)floorf((loz - zr) / ez));
-                z1 = min(zb + 2, (int)floorf((hiz + zr) / ez));
+                z0 = min(zb + 2, max(za - 2, (int)floorf((loz - zr) / ez)));
+                z1 = max(za - 2, min(zb + 2, (int)floorf((hiz + zr) / ez)));
             }
             const int row = (ax * ncy + ay) * ncz;
             // at most two of the three segments exist (the z range is no longer than the column)

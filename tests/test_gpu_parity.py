@@ -507,4 +507,37 @@ def test_energy_query_between_host_move_and_step_keeps_the_external_work():
     eng.ncmc_run(2)
     o.step(2)
     assert eng.get_global('protocol_work') == pytest.approx(o.g['protocol_work'], rel=1e-4, abs=1e-4)
+    eng.close()@pytest.mark.gpu
+@pytest.mark.parametrize('what', ['huge_velocity', 'huge_coordinate'])
+def test_blown_up_walker_is_flagged_like_nan_and_stays_memory_safe(what):
+    """Found by tests/gpu_stress_probe.py on the T4L surrogate (one blow-up in ~2e5 steps): coordinates of ~1e33 nm are
+    finite, so the isfinite latch stayed silent, the float -> int conversions of the list builder saturated and
+    `z0 + ncz` wrapped around into an out-of-bounds read (compute-sanitizer: build_group_runs).  A walker whose
+    coordinates leave +-1e6 nm now raises the NaN flag at once, its mirror is parked inside the box, and the builder
+    clamps its scan range; periodic PME system, many steps after the blow-up, neighbour rebuilds included."""
+    from blues_b200 import _native
+    eng, o, topo = gc.make_ncmc_pair('tol_parm', nsteps=400, seed=4, dt=0.002, minimize=True)
+    good = eng.get_positions(0)
+    eng.ncmc_run(5)
+    if what == 'huge_velocity':
+        v = eng.get_velocities(0)
+        v[17] = [3.0e33, -2.0e33, 1.0e33]
+        v[400:420] *= 1.0e30
+        eng.set_velocities(v, 0)
+    else:
+        x = eng.get_positions(0)
+        x[17] = [4.0e33, 1.0e17, -2.0e33]
+        x[500] = [1.0e9, 2.0, 3.0]
+        eng.set_positions(x)
+    with pytest.raises(_native.EngineError, match='nan'):
+        eng.ncmc_run(60)                                      # keeps stepping the dead walker: must not fault
+    assert np.isnan(eng.get_global('protocol_work'))
+    eng.reset_ncmc()
+    eng.set_positions(good)
+    eng.velocities_to_temperature(300.0)
+    eng.ncmc_run(20)
+    assert np.isfinite(eng.get_global('protocol_work')) and eng.get_global('step') == 20
     eng.close()
+
+
+
