@@ -35,7 +35,8 @@ rank = dist.get_rank()
 out = {'rank': rank, 'local': sims.ncmc.context.getNumReplicas(), 'seed': sims.ncmc.integrator.getRandomNumberSeed(),
        'walkers': [h['walker'].tolist() for h in b.walker_history], 'work': [h['work_kT'].tolist() for h in b.walker_history],
        'ratio': b.acceptRatio}
-print('RESULT ' + json.dumps(out))
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'result_%d.json' % rank), 'w') as fh:
+    json.dump(out, fh)          # one file per rank: two ranks printing to one pipe interleave their lines
 dist.destroy_process_group()
 '''
 
@@ -49,7 +50,7 @@ def test_walkers_shard_over_two_ranks_and_statistics_are_gathered(tmp_path):
                         '127.0.0.1', '--master-port', '29731', str(script)], capture_output=True, text=True, timeout=600,
                        env=env, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-3000:]
-    res = sorted((json.loads(l[7:]) for l in p.stdout.splitlines() if l.startswith('RESULT ')), key=lambda r: r['rank'])
+    res = sorted((json.load(open(str(f))) for f in tmp_path.glob('result_*.json')), key=lambda r: r['rank'])
     assert len(res) == 2
     assert [r['local'] for r in res] == [3, 2]                      # 5 walkers round-robin over 2 ranks
     assert res[0]['seed'] != res[1]['seed']
