@@ -58,6 +58,8 @@ struct bl_handle {
     int step = 0, lambda_step = 0, first_step = 0;
     int cursor = 0;               // alchemical slot holding the energy/forces of the current lambda_step
     bool forces_valid = false;    // f_env / slots match the current positions
+    bool forces_partial = false;  // ... but the last evaluation skipped the rows of the frozen atoms (enqueue_eval)
+    bool skip_frozen = true;
     bool work_pending = false;    // coordinates changed outside the integrator since the last external-work evaluation
     bool vel_dirty = true;        // cm_acc must be recomputed
     int* cm_parity = nullptr;     // device int
@@ -241,10 +243,14 @@ static void launch_pdl_smem(bl_handle* h, void (*kernel)(KArgs...), dim3 grid, d
 // pre_zeroed: the preceding INTEGRATE launch ran with IntegrateArgs::pre_eval (forces cleared, rebuild latched, counters
 // advanced): no k_begin_eval
 static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, int cm_mode, int prefetch_noise = 0,
-                         bool pre_zeroed = false) {
+                         bool pre_zeroed = false, bool in_program = false) {
     Dev& d = h->d;
     cudaStream_t st = h->stream;
     const int R = d.R, N = d.N;
+    // frozen atoms (mass 0): force-only evaluations inside a step program leave their rows out (BLUES_B200_SKIP_FROZEN=0:
+    // off).  The forces then cover the mobile atoms only; a host force query re-evaluates in full (forces_partial).
+    const int skip = (in_program && !energy && h->skip_frozen && d.n_frozen > 0 && h->pair_variant > 0) ? 1 : 0;
+    h->forces_partial = skip != 0;
     {
         // latches the rebuild request (unless the integrator did), then (only if due) the cell sort
         LaunchTimer t(h, BL_K_NEIGHBOR);
@@ -379,7 +385,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         const int U = h->pair_x2 == 4 ? 4 : 2;
         const int lanes = h->pair_lanes;
         dim3 grid(cdiv((long long)d.Npad * lanes, NL_BLOCK), R);
-#define PX3(T, L, UU, DG) k_pair4<T, L, UU, DG><<<grid, NL_BLOCK, 0, st>>>(d)
+#define PX3(T, L, UU, DG) k_pair4<T, L, UU, DG><<<grid, NL_BLOCK, 0, st>>>(d, skip)
 #define PX2(T, UU, DG) if (lanes == 16) PX3(T, 16, UU, DG); else if (lanes == 32) PX3(T, 32, UU, DG); else PX3(T, 8, UU, DG)
 #define PX1(T, UU) if (d.ewk2_deg == 10) { PX2(T, UU, 10); } else { PX2(T, UU, 12); }
 #define PX0(T) if (U == 4) { PX1(T, 4) } else { PX1(T, 2) }
@@ -394,7 +400,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         const int ew = (h->pair_variant / 100) && d.ewk_ok && d.nb_method == 4 ? 1 : 0;
         const int lanes = 1 << ((h->pair_variant / 10) % 10), U = h->pair_variant % 10;
         dim3 grid(cdiv((long long)d.Npad * lanes, NL_BLOCK), R);
-#define PV3(M, E, T, L, UU, W) k_pair2<M, E, T, L, UU, W><<<grid, NL_BLOCK, 0, st>>>(d)
+#define PV3(M, E, T, L, UU, W) k_pair2<M, E, T, L, UU, W><<<grid, NL_BLOCK, 0, st>>>(d, skip)
 #define PV2(M, E, T, L, UU) if (ew) PV3(M, E, T, L, UU, 1); else PV3(M, E, T, L, UU, 0)
 #define PV1(M, E, T) if (lanes == 8 && U == 2) { PV2(M, E, T, 8, 2); } else if (lanes == 8 && U == 4) { PV2(M, E, T, 8, 4); } \
                      else if (lanes == 16 && U == 2) { PV2(M, E, T, 16, 2); } else if (lanes == 4 && U == 4) { PV2(M, E, T, 4, 4); } \
@@ -582,7 +588,8 @@ static void issue(bl_handle* h, const std::vector<Launch>& ls, HostCounters& hc,
             if (hc.pending_noise != 0 || hc.pending_md != 0) hc.noise_ready = 0;    // counters move: stale
             const int prefetch = hc.noise_ready > 0 ? 0 : noise_lookahead(ls, k);
             const bool pre_zeroed = h->fold_zero && k > 0 && !ls[k - 1].is_eval;
-            if (!dry) enqueue_eval(h, l.energy, hc.pending_noise, hc.pending_md, l.cm_mode, prefetch, pre_zeroed);
+            if (!dry) enqueue_eval(h, l.energy, hc.pending_noise, hc.pending_md, l.cm_mode, prefetch, pre_zeroed, true);
+            else h->forces_partial = !l.energy && h->skip_frozen && h->d.n_frozen > 0 && h->pair_variant > 0;
             if (prefetch > 0) hc.noise_ready = prefetch;
             hc.pending_noise = 0;
             hc.pending_md = 0;
@@ -950,6 +957,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_PAIR_X2")) h->pair_x2 = atoi(getenv("BLUES_B200_PAIR_X2"));
     if (getenv("BLUES_B200_PAIR")) h->pair_variant = atoi(getenv("BLUES_B200_PAIR"));
     if (getenv("BLUES_B200_DEBUG_SYNC") && atoi(getenv("BLUES_B200_DEBUG_SYNC"))) { h->debug_sync = true; h->use_graphs = false; h->pdl = false; }
+    if (getenv("BLUES_B200_SKIP_FROZEN")) h->skip_frozen = atoi(getenv("BLUES_B200_SKIP_FROZEN")) != 0;
     if (getenv("BLUES_B200_INT_BLOCK")) h->int_block = std::max(32, std::min(256, atoi(getenv("BLUES_B200_INT_BLOCK")) / 32 * 32));
     if (getenv("BLUES_B200_FOLD_ZERO")) h->fold_zero = atoi(getenv("BLUES_B200_FOLD_ZERO")) != 0;
     counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping
@@ -1212,6 +1220,9 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     }
     d.nl_u16 = d.Npad < 65536 ? 1 : 0;
     d.nl_count = dalloc<int>(h, (size_t)R * d.Npad);
+    d.mobile_s = dalloc<unsigned char>(h, (size_t)R * d.Npad);
+    d.n_frozen = 0;
+    for (int i = 0; i < N; ++i) d.n_frozen += t->mass[i] == 0.0 ? 1 : 0;
     d.nl_list = dalloc<unsigned char>(h, ((size_t)R * d.Npad * d.nl_M + PAIR_SLACK_ENTRIES) * (d.nl_u16 ? 2 : 4));
     {
         // k_build_list: per-lane sub-lists in shared memory are write-combining buffers flushed to the rows whenever one
@@ -1501,7 +1512,7 @@ int bl_get_forces(bl_handle* h, int replica, double* f) {
     if (!h || !f || replica < 0 || replica >= h->d.R) return BL_ERR_INVALID;
     cudaSetDevice(h->device);
     Dev& d = h->d;
-    if (!h->forces_valid) eval_now(h, true);
+    if (!h->forces_valid || h->forces_partial) eval_now(h, true);
     { LaunchTimer t(h, -1); k_export_forces<<<cdiv(d.N, 128), 128, 0, h->stream>>>(d, replica, h->cursor, h->d_scratch); }
     CK(cudaMemcpyAsync(f, h->d_scratch, sizeof(double) * 3 * d.N, cudaMemcpyDeviceToHost, h->stream));
     return check_flags(h, false);

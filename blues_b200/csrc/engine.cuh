@@ -103,6 +103,8 @@ struct Dev {
     int* nl_count;                          // [R*Npad]
     void* nl_list;                          // [R*Npad][nl_M] sorted indices of the neighbours within cutoff + skin
     int nl_u16;                             // indices stored as uint16 (Npad < 65536) to halve the list traffic
+    unsigned char* mobile_s;                // [R*Npad] sorted atom has a mass (frozen rows are skipped by force-only pair launches)
+    int n_frozen;                           // atoms with mass 0 (freeze_radius / freeze_atoms, blues/simulation.py:364-480)
     // bonded tables
     int n_bonds, n_angles, n_torsions, n_excl, n_restraints, n_alch_exc;
     int2* bonds; double2* bond_p;           // (k, r0)

@@ -301,6 +301,26 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
         s.im[k] = d.invmass[a];
         s.mass[k] = d.mass[a];
     }
+    {
+        // a cluster of frozen atoms (mass 0: freeze_radius / freeze_atoms) is never moved by any op: all that is left of
+        // the launch for it is the clearing of its force accumulators before an evaluation
+        bool any_mobile = false;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) any_mobile = any_mobile || s.im[k] > 0.0;
+        if (!any_mobile) {
+            if (args.pre_eval) {
+#pragma unroll
+                for (int k = 0; k < NA; ++k)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        d.f_env[(size_t)r * 3 * N + q * N + atom[k]] = 0;
+                        if (d.alch_on)
+                            for (int sl = 0; sl < ALCH_SLOTS; ++sl) d.f_alch[((size_t)sl * d.R + r) * 3 * N + q * N + atom[k]] = 0;
+                    }
+            }
+            return;
+        }
+    }
 #pragma unroll
     for (int a = 0; a < NC; ++a) s.d2[a] = c.d2[a];
     // the forces of the first V step and the kicks of the first O step are needed a few hundred dependent instructions

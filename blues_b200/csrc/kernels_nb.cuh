@@ -164,6 +164,7 @@ __global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort
         const float2 se = d.sigeps[a];
         posq_s[s] = p;
         sigeps_s[s] = se;
+        d.mobile_s[(size_t)r * Npad + s] = d.invmass[a] > 0.0 ? 1 : 0;
         d.rec_s[2 * ((size_t)r * Npad + s)] = p;
         d.rec_s[2 * ((size_t)r * Npad + s) + 1] = make_float4(se.x, se.y, 0.f, 0.f);
         pos_ref[a] = p;
@@ -172,6 +173,7 @@ __global__ void __cluster_dims__(SORT_CTAS, 1, 1) __launch_bounds__(1024) k_sort
     for (int s = N + tid; s < Npad; s += nt) {
         posq_s[s] = make_float4(qnan, qnan, qnan, 0.f);
         sigeps_s[s] = make_float2(0.f, 0.f);
+        d.mobile_s[(size_t)r * Npad + s] = 0;
         d.rec_s[2 * ((size_t)r * Npad + s)] = make_float4(qnan, qnan, qnan, 0.f);
         d.rec_s[2 * ((size_t)r * Npad + s) + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         orig_s[s] = -1;
@@ -930,13 +932,16 @@ __device__ __forceinline__ void pair_trip(const Dev& d, const float4 (&pc)[U], c
 }
 
 template <int METHOD, bool ENERGY, typename IDX, int LANES, int U, int EWALD>
-__global__ void __launch_bounds__(NL_BLOCK) k_pair2(Dev d) {
+__global__ void __launch_bounds__(NL_BLOCK) k_pair2(Dev d, int skip_frozen) {
     const int r = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int part = lane & (LANES - 1);
     const int i = (blockIdx.x * NL_BLOCK + threadIdx.x) / LANES;
     const int N = d.N, Npad = d.Npad;
     if (i >= Npad) return;
+    // the force on an atom without mass moves nothing: inside a step program its row is not evaluated (full lists: the
+    // forces it exerts on its mobile neighbours come from THEIR rows); host force queries and energy launches pass 0
+    if (skip_frozen && !d.mobile_s[(size_t)r * Npad + i]) return;
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
     const float2* __restrict__ sigeps_s = d.sigeps_s + (size_t)r * Npad;
     const IDX* __restrict__ lp = reinterpret_cast<const IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M + part;
@@ -1053,7 +1058,7 @@ __device__ __forceinline__ void pair_trip_x2(const Dev& d, const float4 p0, cons
 }
 
 template <typename IDX, int LANES, int U, int DEG>
-__global__ void __launch_bounds__(NL_BLOCK) k_pair4(Dev d) {
+__global__ void __launch_bounds__(NL_BLOCK) k_pair4(Dev d, int skip_frozen) {
     static_assert(U % 2 == 0, "entries are processed in packed pairs");
     const int r = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -1061,6 +1066,7 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair4(Dev d) {
     const int i = (blockIdx.x * NL_BLOCK + threadIdx.x) / LANES;
     const int N = d.N, Npad = d.Npad;
     if (i >= Npad) return;
+    if (skip_frozen && !d.mobile_s[(size_t)r * Npad + i]) return;      // (see k_pair2)
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
     const float2* __restrict__ sigeps_s = d.sigeps_s + (size_t)r * Npad;
     const IDX* __restrict__ lp = reinterpret_cast<const IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M + part;
