@@ -507,7 +507,9 @@ def test_energy_query_between_host_move_and_step_keeps_the_external_work():
     eng.ncmc_run(2)
     o.step(2)
     assert eng.get_global('protocol_work') == pytest.approx(o.g['protocol_work'], rel=1e-4, abs=1e-4)
-    eng.close()@pytest.mark.gpu
+    eng.close()
+
+
 @pytest.mark.parametrize('what', ['huge_velocity', 'huge_coordinate'])
 def test_blown_up_walker_is_flagged_like_nan_and_stays_memory_safe(what):
     """Found by tests/gpu_stress_probe.py on the T4L surrogate (one blow-up in ~2e5 steps): coordinates of ~1e33 nm are
@@ -538,6 +540,3 @@ def test_blown_up_walker_is_flagged_like_nan_and_stays_memory_safe(what):
     eng.ncmc_run(20)
     assert np.isfinite(eng.get_global('protocol_work')) and eng.get_global('step') == 20
     eng.close()
-
-
-
