@@ -496,7 +496,8 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
     except Exception:
         pass
-    roofline = {'kernel': 'k_pair (direct-space LJ + Ewald over the Verlet list)', 'bound': 'fp32',
+    roofline = {'kernel': 'k_pair4 (direct-space LJ + polynomial Ewald over the full Verlet list, packed FP32 FFMA2/FMUL2/'
+                          'FADD2; the one energy evaluation per call uses k_pair2)', 'bound': 'fp32',
                 'achieved': achieved_tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved_tflops / fp32_peak,
                 'traffic': traffic.get('k_pair', {}).get('dram_bytes_per_launch'),
                 'traffic_source': traffic.get('source'), 'peak_source': fp32_src,
