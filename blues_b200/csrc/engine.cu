@@ -98,6 +98,7 @@ struct bl_handle {
     bool fold_zero = true;       // step programs: force zeroing + rebuild latch inside the INTEGRATE launch before an evaluation
     int own_dft = 0;             // reciprocal space: 0 cuFFT, 1 three fused direct-DFT kernels, 2 one cluster kernel (small grids)
     size_t dft_smem = 0;
+    int pair_per_sm = 0, n_sm = 148;   // BLUES_B200_PAIR_PER_SM: resident k_pair4 CTAs per SM (0: one CTA per row block)
     int pair_lanes = 8;          // BLUES_B200_PAIR_LANES: lanes per i-atom in k_pair4 (8, 16, 32)
     int pair_x2 = 2;             // BLUES_B200_PAIR_X2: 0 off, 2 / 4 = k_pair4 (packed FFMA2 arithmetic) with that many entries per trip
     int pair_variant = 132;      // BLUES_B200_PAIR: 0 = k_pair (round 1), else k_pair2 <ewald, lanes, U> (see enqueue_eval); measured: gpurun_out/pair_sweep.log
@@ -385,6 +386,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         const int U = h->pair_x2 == 4 ? 4 : 2;
         const int lanes = h->pair_lanes;
         dim3 grid(cdiv((long long)d.Npad * lanes, NL_BLOCK), R);
+        if (h->pair_per_sm > 0) grid.x = std::min<unsigned>(grid.x, (unsigned)std::max(1, h->pair_per_sm * h->n_sm / R));
 #define PX3(T, L, UU, DG) k_pair4<T, L, UU, DG><<<grid, NL_BLOCK, 0, st>>>(d, skip)
 #define PX2(T, UU, DG) if (lanes == 16) PX3(T, 16, UU, DG); else if (lanes == 32) PX3(T, 32, UU, DG); else PX3(T, 8, UU, DG)
 #define PX1(T, UU) if (d.ewk2_deg == 10) { PX2(T, UU, 10); } else { PX2(T, UU, 12); }
@@ -953,6 +955,8 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_PDL")) h->pdl = atoi(getenv("BLUES_B200_PDL")) != 0;
     if (getenv("BLUES_B200_GRAPH_STEPS")) h->graph_steps = std::max(1, atoi(getenv("BLUES_B200_GRAPH_STEPS")));
     if (getenv("BLUES_B200_TIMELINE")) { h->timeline = true; h->graph_steps = 1; }
+    if (getenv("BLUES_B200_PAIR_PER_SM")) h->pair_per_sm = std::max(0, atoi(getenv("BLUES_B200_PAIR_PER_SM")));
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (getenv("BLUES_B200_PAIR_LANES")) { const int l = atoi(getenv("BLUES_B200_PAIR_LANES")); h->pair_lanes = l == 16 || l == 32 ? l : 8; }
     if (getenv("BLUES_B200_PAIR_X2")) h->pair_x2 = atoi(getenv("BLUES_B200_PAIR_X2"));
     if (getenv("BLUES_B200_PAIR")) h->pair_variant = atoi(getenv("BLUES_B200_PAIR"));

@@ -1063,10 +1063,13 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair4(Dev d, int skip_frozen) {
     const int r = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int part = lane & (LANES - 1);
-    const int i = (blockIdx.x * NL_BLOCK + threadIdx.x) / LANES;
     const int N = d.N, Npad = d.Npad;
-    if (i >= Npad) return;
-    if (skip_frozen && !d.mobile_s[(size_t)r * Npad + i]) return;      // (see k_pair2)
+    // a launch with fewer CTAs than row blocks (BLUES_B200_PAIR_PER_SM: a bounded number of resident CTAs per SM, so that
+    // the short kernels of the reciprocal-space chain find room beside it) walks the blocks with a grid stride
+    for (int blk = blockIdx.x; blk * (NL_BLOCK / LANES) < Npad; blk += gridDim.x) {
+    const int i = (blk * NL_BLOCK + threadIdx.x) / LANES;
+    if (i >= Npad) continue;
+    if (skip_frozen && !d.mobile_s[(size_t)r * Npad + i]) continue;      // (see k_pair2)
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * Npad;
     const float2* __restrict__ sigeps_s = d.sigeps_s + (size_t)r * Npad;
     const IDX* __restrict__ lp = reinterpret_cast<const IDX*>(d.nl_list) + ((size_t)r * Npad + i) * d.nl_M + part;
@@ -1122,6 +1125,7 @@ __global__ void __launch_bounds__(NL_BLOCK) k_pair4(Dev d, int skip_frozen) {
         fx_addf(&fenv[oi], fx, (float)FORCE_SCALE);
         fx_addf(&fenv[N + oi], fy, (float)FORCE_SCALE);
         fx_addf(&fenv[2 * N + oi], fz, (float)FORCE_SCALE);
+    }
     }
 }
 
