@@ -297,6 +297,9 @@ def main():
             if 'nan' not in str(e).lower():
                 raise
             nan_events[0] += 1
+            if os.environ.get('BLUES_BENCH_VERBOSE'):
+                sys.stderr.write('[bench] blown-up walker in a %d-step call (engine step now %s): %s\n'
+                                 % (n, integ._context._engine.get_global('step'), str(e)[:80]))
             return False
 
     def timed_windows(ctx, integ, n_rep, warm, k, n_windows, budget_s=25.0):
@@ -365,10 +368,14 @@ def main():
             ok = step_or_flag(integ, min(50, max(1, NSTEPS_NC // 8)))
             eng.synchronize()
             if not ok or eng.get_global('step') + 120 >= NSTEPS_NC:
+                # positions AND velocities: resetting only the coordinates to the minimised structure would turn its
+                # relaxation into kinetic energy once per cycle and hand the timed windows a walker at thousands of K
                 integ.reset()
                 ctx.setPositions(x_relaxed * unit.nanometers)
+                ctx.setVelocitiesToTemperature(300 * unit.kelvin)
         integ.reset()
         ctx.setPositions(x_relaxed * unit.nanometers)
+        ctx.setVelocitiesToTemperature(300 * unit.kelvin)
         times, launches, restart = timed_windows(ctx, integ, R, W, K, args.windows)
     if launches <= 0:
         raise SystemExit('bench: the timed region launched no kernels')

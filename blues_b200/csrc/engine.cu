@@ -1287,7 +1287,11 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
                 return dupload(h, tw);
             };
             d.tw_x = twiddles(d.gx); d.tw_y = twiddles(d.gy); d.tw_z = twiddles(d.gz);
-            const bool small = d.gx <= PME_DFT_MAX && d.gy <= PME_DFT_MAX && d.gz <= PME_DFT_MAX;
+            // direct DFTs cost O(points x (X + Y + Z)): they beat cuFFT's seven launches up to ~32 points per dimension
+            // (24 x 25 x 28: 33 us against 45); beyond that cuFFT wins by far (45 x 48 x 54: 264 us against ~40)
+            const int dft_limit = getenv("BLUES_B200_DFT_LIMIT") ? atoi(getenv("BLUES_B200_DFT_LIMIT")) : 32;
+            const bool small = d.gx <= PME_DFT_MAX && d.gy <= PME_DFT_MAX && d.gz <= PME_DFT_MAX &&
+                               d.gx <= dft_limit && d.gy <= dft_limit && d.gz <= dft_limit;
             h->own_dft = small ? 2 : 0;
             if (getenv("BLUES_B200_DFT")) h->own_dft = small ? atoi(getenv("BLUES_B200_DFT")) : 0;
             {
