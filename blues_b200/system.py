@@ -126,8 +126,32 @@ class NonbondedForce(Force):
     def getNumParticles(self):
         return len(self.charge)
 
+    def addParticle(self, charge, sigma, epsilon):
+        self.charge = np.append(self.charge, _val(charge, u.elementary_charge))
+        self.sigma = np.append(self.sigma, _val(sigma, u.nanometers))
+        self.epsilon = np.append(self.epsilon, _val(epsilon, u.kilojoules_per_mole))
+        return len(self.charge) - 1
+
     def getNumExceptions(self):
         return len(self.exc_idx)
+
+    def addException(self, i, j, chargeProd, sigma, epsilon, replace=False):
+        """Exception (chargeProd, sigma, epsilon) for the pair; all zero = plain exclusion."""
+        self.exc_idx = np.vstack([self.exc_idx, [[int(i), int(j)]]]).astype(np.int32)
+        self.exc_qq = np.append(self.exc_qq, _val(chargeProd, u.elementary_charge ** 2))
+        self.exc_sigma = np.append(self.exc_sigma, _val(sigma, u.nanometers))
+        self.exc_eps = np.append(self.exc_eps, _val(epsilon, u.kilojoules_per_mole))
+        return len(self.exc_idx) - 1
+
+    def setNonbondedMethod(self, method):
+        names = {0: NoCutoff, 1: CutoffNonPeriodic, 2: CutoffPeriodic, 3: Ewald, 4: PME}
+        self.method = names.get(method, method)
+
+    def setCutoffDistance(self, cutoff):
+        self.cutoff = float(_val(cutoff, u.nanometers))
+
+    def setEwaldErrorTolerance(self, tol):
+        self.ewald_tol = float(tol)
 
     def getParticleParameters(self, i):
         return [self.charge[i] * u.elementary_charge, self.sigma[i] * u.nanometers,
