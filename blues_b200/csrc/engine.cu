@@ -96,6 +96,9 @@ struct bl_handle {
     bool debug_sync = false, debug_reported = false;   // BLUES_B200_DEBUG_SYNC
     int int_block = 32;          // BLUES_B200_INT_BLOCK: threads per k_integrate CTA (one constraint cluster per thread)
     bool fold_zero = true;       // step programs: force zeroing + rebuild latch inside the INTEGRATE launch before an evaluation
+    int spread_split = 0;        // BLUES_B200_SPREAD_SPLIT: y-bands per x-plane of k_pme_spread at <= 2 walkers (0: one wave, see bl_create)
+    int spread_threads = 1024;   // BLUES_B200_SPREAD_THREADS: 512 or 1024
+    int pme_cl = 16;             // BLUES_B200_PME_CL: CTAs of the reciprocal-space cluster kernel (8 or 16)
     int own_dft = 0;             // reciprocal space: 0 cuFFT, 1 three fused direct-DFT kernels, 2 one cluster kernel (small grids)
     size_t dft_smem = 0;
     int pair_per_sm = 0, n_sm = 148;   // BLUES_B200_PAIR_PER_SM: resident k_pair4 CTAs per SM (0: one CTA per row block)
@@ -280,15 +283,23 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         cudaStreamWaitEvent(s2, h->ev_fork, 0);
         { LaunchTimer t(h, BL_K_PME_SPREAD, s2);
           // few walkers: latency bound, many wide CTAs; many walkers: throughput bound, fewer duplicate B-splines
-          if (R <= 2) k_pme_spread<8, 512><<<dim3(d.gx, 8, R), 512, (d.gy / 8 + 1) * d.gz * sizeof(int), s2>>>(d);
-          else k_pme_spread<4, 256><<<dim3(d.gx, 4, R), 256, (d.gy / 4 + 1) * d.gz * sizeof(int), s2>>>(d); }
+          if (R <= 2) {
+              const int ys = h->spread_split;
+              if (h->spread_threads == 1024) k_pme_spread<1024><<<dim3(d.gx, ys, R), 1024, (d.gy / ys + 1) * d.gz * sizeof(int), s2>>>(d);
+              else k_pme_spread<512><<<dim3(d.gx, ys, R), 512, (d.gy / ys + 1) * d.gz * sizeof(int), s2>>>(d);
+          } else k_pme_spread<256><<<dim3(d.gx, 4, R), 256, (d.gy / 4 + 1) * d.gz * sizeof(int), s2>>>(d); }
         tl_mark(h, s2, TL_SPREAD);
         if (h->own_dft == 2) {
             // one cluster kernel for the whole transform chain
             LaunchTimer t(h, BL_K_FFT, s2);
-            const int P = cdiv(d.gx, PME_CL);
-            if (energy) launch_pdl_smem(h, k_pme_dft_cluster<true>, dim3(PME_CL, R), dim3(PME_CL_THREADS), h->dft_smem, s2, d, P);
-            else launch_pdl_smem(h, k_pme_dft_cluster<false>, dim3(PME_CL, R), dim3(PME_CL_THREADS), h->dft_smem, s2, d, P);
+            const int P = cdiv(d.gx, h->pme_cl);
+            if (h->pme_cl == 16) {
+                if (energy) launch_pdl_smem(h, k_pme_dft_cluster<true, 16>, dim3(16, R), dim3(PME_CL_THREADS), h->dft_smem, s2, d, P);
+                else launch_pdl_smem(h, k_pme_dft_cluster<false, 16>, dim3(16, R), dim3(PME_CL_THREADS), h->dft_smem, s2, d, P);
+            } else {
+                if (energy) launch_pdl_smem(h, k_pme_dft_cluster<true, PME_CL>, dim3(PME_CL, R), dim3(PME_CL_THREADS), h->dft_smem, s2, d, P);
+                else launch_pdl_smem(h, k_pme_dft_cluster<false, PME_CL>, dim3(PME_CL, R), dim3(PME_CL_THREADS), h->dft_smem, s2, d, P);
+            }
             tl_mark(h, s2, TL_C2R);
         } else if (h->own_dft) {
             const int Zc = d.gz / 2 + 1;
@@ -961,6 +972,8 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_PAIR_X2")) h->pair_x2 = atoi(getenv("BLUES_B200_PAIR_X2"));
     if (getenv("BLUES_B200_PAIR")) h->pair_variant = atoi(getenv("BLUES_B200_PAIR"));
     if (getenv("BLUES_B200_DEBUG_SYNC") && atoi(getenv("BLUES_B200_DEBUG_SYNC"))) { h->debug_sync = true; h->use_graphs = false; h->pdl = false; }
+    if (getenv("BLUES_B200_SPREAD_SPLIT")) h->spread_split = atoi(getenv("BLUES_B200_SPREAD_SPLIT"));
+    if (getenv("BLUES_B200_SPREAD_THREADS")) h->spread_threads = atoi(getenv("BLUES_B200_SPREAD_THREADS")) == 1024 ? 1024 : 512;
     if (getenv("BLUES_B200_SKIP_FROZEN")) h->skip_frozen = atoi(getenv("BLUES_B200_SKIP_FROZEN")) != 0;
     if (getenv("BLUES_B200_INT_BLOCK")) h->int_block = std::max(32, std::min(256, atoi(getenv("BLUES_B200_INT_BLOCK")) / 32 * 32));
     if (getenv("BLUES_B200_FOLD_ZERO")) h->fold_zero = atoi(getenv("BLUES_B200_FOLD_ZERO")) != 0;
@@ -1265,14 +1278,18 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         d.gx = t->pme_grid[0]; d.gy = t->pme_grid[1]; d.gz = t->pme_grid[2];
         if (d.gx < PME_ORDER || d.gy < PME_ORDER || d.gz < PME_ORDER) return fail(BL_ERR_INVALID, "PME grid too small");
         d.gsize = d.gx * d.gy * d.gz;
+        // k_pme_spread at <= 2 walkers: as many y-bands per x-plane as keep the launch within one wave of one CTA per SM
+        if (h->spread_split <= 0) h->spread_split = std::max(1, std::min(12, h->n_sm / std::max(1, d.gx * std::min(R, 2))));
+        h->spread_split = std::max(1, std::min(h->spread_split, d.gy / 2));
         d.csize = d.gx * d.gy * (d.gz / 2 + 1);
         {
-            const size_t plane_bytes = (size_t)(d.gy / 4 + 1) * d.gz * sizeof(int);
+            const size_t plane_bytes = (size_t)(d.gy / std::min(4, h->spread_split) + 1) * d.gz * sizeof(int);
             if (plane_bytes > 200 * 1024) return fail(BL_ERR_INVALID, "PME grid plane does not fit in shared memory");
             if (plane_bytes > 48 * 1024)
             {
-                raise_dyn_smem(k_pme_spread<4, 256>, device, plane_bytes);
-                raise_dyn_smem(k_pme_spread<8, 512>, device, plane_bytes);
+                raise_dyn_smem(k_pme_spread<256>, device, plane_bytes);
+                raise_dyn_smem(k_pme_spread<512>, device, plane_bytes);
+                raise_dyn_smem(k_pme_spread<1024>, device, plane_bytes);
             }
         }
         d.grid_r = dalloc<float>(h, (size_t)R * d.gsize);
@@ -1292,15 +1309,27 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
             const int dft_limit = getenv("BLUES_B200_DFT_LIMIT") ? atoi(getenv("BLUES_B200_DFT_LIMIT")) : 32;
             const bool small = d.gx <= PME_DFT_MAX && d.gy <= PME_DFT_MAX && d.gz <= PME_DFT_MAX &&
                                d.gx <= dft_limit && d.gy <= dft_limit && d.gz <= dft_limit;
-            h->own_dft = small ? 2 : 0;
+            // measured again in round 2 (bench.py, same box): cuFFT 7 632 steps/s at one walker and 13 086 walker-steps/s at
+            // eight, the cluster kernel (16 CTAs, packed complex arithmetic) 7 554 and 12 625 — inside the four-stream
+            // evaluation cuFFT's seven small kernels spread over the idle SMs while one cluster waits for sixteen free SMs of
+            // one GPC.  cuFFT (the library call the north star allows) is the default; BLUES_B200_DFT=2 / 1 select the own kernels.
+            h->own_dft = 0;
+            (void)small;
             if (getenv("BLUES_B200_DFT")) h->own_dft = small ? atoi(getenv("BLUES_B200_DFT")) : 0;
             {
-                const int Zc2 = d.gz / 2 + 1, P = cdiv(d.gx, PME_CL);
-                h->dft_smem = sizeof(float2) * ((size_t)P * d.gy * Zc2 + d.gy * Zc2 + d.gz + d.gy + d.gx + (PME_CL_THREADS / 32) * 2 * d.gx) +
-                              sizeof(float) * ((d.gy * d.gz + 1) & ~1);
+                h->pme_cl = getenv("BLUES_B200_PME_CL") ? (atoi(getenv("BLUES_B200_PME_CL")) == 16 ? 16 : PME_CL) : h->pme_cl;
+                if (d.gx < 16) h->pme_cl = PME_CL;
+                const int Zc2 = d.gz / 2 + 1, P = cdiv(d.gx, h->pme_cl);
+                h->dft_smem = sizeof(float4) * (2 * (size_t)d.gy + 2 * d.gx) +
+                              sizeof(float2) * (2 * (size_t)P * d.gy * Zc2 + d.gz + (PME_CL_THREADS / 32) * 2 * d.gx) +
+                              sizeof(float) * ((size_t)P * d.gy * d.gz + 4);
                 if (h->dft_smem > 200 * 1024 && h->own_dft == 2) h->own_dft = 1;
-                raise_dyn_smem(k_pme_dft_cluster<true>, device, h->dft_smem);
-                raise_dyn_smem(k_pme_dft_cluster<false>, device, h->dft_smem);
+                raise_dyn_smem(k_pme_dft_cluster<true, PME_CL>, device, h->dft_smem);
+                raise_dyn_smem(k_pme_dft_cluster<false, PME_CL>, device, h->dft_smem);
+                raise_dyn_smem(k_pme_dft_cluster<true, 16>, device, h->dft_smem);
+                raise_dyn_smem(k_pme_dft_cluster<false, 16>, device, h->dft_smem);
+                cudaFuncSetAttribute(k_pme_dft_cluster<true, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                cudaFuncSetAttribute(k_pme_dft_cluster<false, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             }
             const int Zc = d.gz / 2 + 1;
             const size_t sm = std::max(sizeof(float) * ((d.gy * d.gz + 1) & ~1) + sizeof(float2) * (d.gy * Zc + d.gz + d.gy),

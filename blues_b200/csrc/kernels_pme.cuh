@@ -54,14 +54,17 @@ __device__ __forceinline__ void pme_atom_setup(const Dev& d, float4 p, int* base
 // no separate conversion pass.
 #define SPREAD_SCALE 8388608.0f            /* 2^23 */
 #define SPREAD_MAX_RUNS 64
-// YSPLIT: CTAs per x-plane, each owning a band of y-rows.  More, smaller bands shorten the kernel when one walker
-// leaves the device mostly idle (latency bound); fewer bands recompute fewer B-splines when many walkers fill it.
-template <int SPREAD_YSPLIT, int SPREAD_THREADS>
+// gridDim.y = CTAs per x-plane, each owning a band of y-rows.  More, smaller bands shorten the kernel when one walker
+// leaves the device mostly idle (latency bound); fewer bands recompute fewer B-splines when many walkers fill it.  At
+// <= 2 walkers the host picks the band count that makes the launch ONE wave of one CTA per SM (24 planes x 6 bands = 144
+// CTAs on 148 SMs: 21 us; 8 bands = 192 CTAs ran as two unequal waves: 27 us).
+template <int SPREAD_THREADS>
 __global__ void __launch_bounds__(SPREAD_THREADS) k_pme_spread(Dev d) {
     extern __shared__ int s_plane[];            // [rows * gz]
     __shared__ int s_run0[SPREAD_MAX_RUNS], s_runoff[SPREAD_MAX_RUNS + 1];
     const int r = blockIdx.z, plane = blockIdx.x, part = blockIdx.y;
-    const int ya = part * d.gy / SPREAD_YSPLIT, yb = (part + 1) * d.gy / SPREAD_YSPLIT;   // rows [ya, yb)
+    const int ysplit = (int)gridDim.y;                          // CTAs per x-plane, each owning a band of y-rows
+    const int ya = part * d.gy / ysplit, yb = (part + 1) * d.gy / ysplit;   // rows [ya, yb)
     const int npts = (yb - ya) * d.gz;
     for (int k = threadIdx.x; k < npts; k += blockDim.x) s_plane[k] = 0;
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * d.Npad;
@@ -348,57 +351,106 @@ __global__ void __launch_bounds__(PME_DFT_THREADS) k_pme_idft_yz(Dev d) {
 // its owners; two cluster barriers in total, no global round trip between the passes.
 // ---------------------------------------------------------------------------------------------------------
 #define PME_CL 8
-#define PME_CL_THREADS 384
-template <bool ENERGY>
-__global__ void __cluster_dims__(PME_CL, 1, 1) __launch_bounds__(PME_CL_THREADS) k_pme_dft_cluster(Dev d, int P) {
+#define PME_CL_THREADS 768
+// CL: CTAs of the cluster — 8 (portable) or 16 (B200 allows it with cudaFuncAttributeNonPortableClusterSizeAllowed): the kernel
+// is instruction bound on the SMs of its one cluster (ncu: 864 k warp instructions on 8 SMs, 47 % issue), twice the SMs
+// halve the lines and planes per CTA.  The planes a CTA owns are transformed together (one barrier per pass, not per plane),
+// the complex multiply-adds are packed FP32 pairs (re, im) against twiddle quadruples (c, -s, s, c) / (c, s, -s, c).
+__device__ __forceinline__ unsigned long long pme_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long pme_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// out = sum_n in[n * stride] * w^(+-k n); tq[m] = (c, -s, s, c) for the forward sign, (c, s, -s, c) for the inverse
+__device__ __forceinline__ float2 dft_line_q(const float2* in, int stride, int L, int k, const float4* tq) {
+    unsigned long long acc0 = pme_pack(0.f, 0.f), acc1 = acc0;          // two chains: even / odd terms
+    int m = 0;
+    int n = 0;
+    for (; n + 1 < L; n += 2) {
+        const float2 v0 = in[n * stride];
+        const float4 t0 = tq[m];
+        m += k; m -= m >= L ? L : 0;
+        const float2 v1 = in[(n + 1) * stride];
+        const float4 t1 = tq[m];
+        m += k; m -= m >= L ? L : 0;
+        acc0 = pme_fma2(pme_pack(v0.x, v0.x), pme_pack(t0.x, t0.y), acc0);
+        acc1 = pme_fma2(pme_pack(v1.x, v1.x), pme_pack(t1.x, t1.y), acc1);
+        acc0 = pme_fma2(pme_pack(v0.y, v0.y), pme_pack(t0.z, t0.w), acc0);
+        acc1 = pme_fma2(pme_pack(v1.y, v1.y), pme_pack(t1.z, t1.w), acc1);
+    }
+    if (n < L) {
+        const float2 v0 = in[n * stride];
+        const float4 t0 = tq[m];
+        acc0 = pme_fma2(pme_pack(v0.x, v0.x), pme_pack(t0.x, t0.y), acc0);
+        acc0 = pme_fma2(pme_pack(v0.y, v0.y), pme_pack(t0.z, t0.w), acc0);
+    }
+    float r0, i0, r1, i1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(i0) : "l"(acc0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r1), "=f"(i1) : "l"(acc1));
+    return make_float2(r0 + r1, i0 + i1);
+}
+
+template <bool ENERGY, int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PME_CL_THREADS) k_pme_dft_cluster(Dev d, int P) {
     namespace cg = cooperative_groups;
     extern __shared__ float s_dft[];
     cudaGridDependencySynchronize();
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int r = blockIdx.y;
-    const int X = d.gx, Y = d.gy, Z = d.gz, Zc = Z / 2 + 1, YZc = Y * Zc;
-    // shared layout: cplane [P][Y][Zc] float2 | tmp [Y][Zc] float2 | rplane [Y][Z] float | twz, twy, twx | line staging
-    float2* cplane = reinterpret_cast<float2*>(s_dft);
+    const int X = d.gx, Y = d.gy, Z = d.gz, Zc = Z / 2 + 1, YZc = Y * Zc, YZ = Y * Z;
+    // shared layout (float4-aligned pieces first): twiddle quadruples fwd / inv for y, x and fwd for z | cplane [P][Y][Zc] float2 |
+    // tmp [P][Y][Zc] float2 | twz (c, s) float2 [Z] | line staging [warps][2][X] float2 | rplane [P][Y][Z] float
+    float4* tqyf = reinterpret_cast<float4*>(s_dft);
+    float4* tqyi = tqyf + Y;
+    float4* tqxf = tqyi + Y;
+    float4* tqxi = tqxf + X;
+    float2* cplane = reinterpret_cast<float2*>(tqxi + X);
     float2* tmp = cplane + (size_t)P * YZc;
-    float* rplane = reinterpret_cast<float*>(tmp + YZc);
-    float2* twz = reinterpret_cast<float2*>(rplane + ((Y * Z + 1) & ~1));
-    float2* twy = twz + Z;
-    float2* twx = twy + Y;
-    float2* sline = twx + X;                                   // [warps][2][X]
+    float2* twz = tmp + (size_t)P * YZc;
+    float2* sline = twz + Z;                                   // [warps][2][X]
+    float* rplane = reinterpret_cast<float*>(sline + (size_t)(PME_CL_THREADS / 32) * 2 * X);
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int k = tid; k < Z; k += nt) twz[k] = d.tw_z[k];
-    for (int k = tid; k < Y; k += nt) twy[k] = d.tw_y[k];
-    for (int k = tid; k < X; k += nt) twx[k] = d.tw_x[k];
-    // ---- forward z and y passes on the planes this CTA owns
-    for (int p = 0; p < P; ++p) {
-        const int x = rank * P + p;
-        if (x >= X) break;                                      // uniform over the CTA
-        const float* src = d.grid_r + (size_t)r * d.gsize + (size_t)x * Y * Z;
-        __syncthreads();                                        // rplane / tmp of the previous plane are free (and twiddles loaded)
-        for (int k = tid; k < Y * Z; k += nt) rplane[k] = src[k];
-        __syncthreads();
-        for (int o = tid; o < YZc; o += nt) {
-            const int y = o / Zc, kz = o - y * Zc;
-            const float* in = rplane + y * Z;
-            float re = 0.f, im = 0.f;
-            int m = 0;
-            for (int z = 0; z < Z; ++z) {
-                const float v = in[z];
-                const float2 w = twz[m];
-                re = fmaf(v, w.x, re); im = fmaf(-v, w.y, im);
-                m += kz; m -= m >= Z ? Z : 0;
-            }
-            tmp[o] = make_float2(re, im);
+    for (int k = tid; k < Y; k += nt) { const float2 w = d.tw_y[k]; tqyf[k] = make_float4(w.x, -w.y, w.y, w.x); tqyi[k] = make_float4(w.x, w.y, -w.y, w.x); }
+    for (int k = tid; k < X; k += nt) { const float2 w = d.tw_x[k]; tqxf[k] = make_float4(w.x, -w.y, w.y, w.x); tqxi[k] = make_float4(w.x, w.y, -w.y, w.x); }
+    const int x_first = rank * P;
+    const int np = max(0, min(P, X - x_first));                // planes this CTA owns (the last ranks may own none)
+    // ---- forward z and y passes on all owned planes at once (they are contiguous in the x-major grid)
+    {
+        const float* src = d.grid_r + (size_t)r * d.gsize + (size_t)x_first * YZ;
+        for (int k = tid; k < np * YZ; k += nt) rplane[k] = src[k];
+    }
+    __syncthreads();
+    for (int o = tid; o < np * YZc; o += nt) {
+        const int pl = o / YZc, oo = o - pl * YZc;
+        const int y = oo / Zc, kz = oo - y * Zc;
+        const float* in = rplane + pl * YZ + y * Z;
+        unsigned long long acc = pme_pack(0.f, 0.f);
+        int m = 0;
+        for (int z = 0; z < Z; ++z) {
+            const float v = in[z];
+            const float2 w = twz[m];
+            acc = pme_fma2(pme_pack(v, v), pme_pack(w.x, -w.y), acc);
+            m += kz; m -= m >= Z ? Z : 0;
         }
-        __syncthreads();
-        for (int o = tid; o < YZc; o += nt) {
-            const int ky = o / Zc, kz = o - ky * Zc;
-            cplane[(size_t)p * YZc + o] = dft_line_c(tmp + kz, Zc, Y, ky, twy, -1.f);
-        }
+        float re, im;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(acc));
+        tmp[o] = make_float2(re, im);
+    }
+    __syncthreads();
+    for (int o = tid; o < np * YZc; o += nt) {
+        const int pl = o / YZc, oo = o - pl * YZc;
+        const int ky = oo / Zc, kz = oo - ky * Zc;
+        cplane[o] = dft_line_q(tmp + pl * YZc + kz, Zc, Y, ky, tqyf);
     }
     cluster.sync();
-    // ---- x pass: line l = ky Zc + kz is handled by CTA l mod PME_CL, one warp per line
+    // ---- x pass: line l = ky Zc + kz is handled by CTA l mod CL, one warp per line
     {
         const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
         float2* lin = sline + (size_t)warp * 2 * X;
@@ -406,7 +458,7 @@ __global__ void __cluster_dims__(PME_CL, 1, 1) __launch_bounds__(PME_CL_THREADS)
         const float V = d.boxf[0] * d.boxf[1] * d.boxf[2];
         const float pi2_over_a2 = 9.8696044010893586f / (d.alpha * d.alpha);
         double e = 0.0;
-        for (int l = rank + PME_CL * warp; l < YZc; l += PME_CL * nwarps) {
+        for (int l = rank + CL * warp; l < YZc; l += CL * nwarps) {
             for (int x = lane; x < X; x += 32) {
                 const float2* owner = cluster.map_shared_rank(cplane, x / P);
                 lin[x] = owner[(size_t)(x % P) * YZc + l];
@@ -416,7 +468,7 @@ __global__ void __cluster_dims__(PME_CL, 1, 1) __launch_bounds__(PME_CL_THREADS)
             const int my = ky <= Y / 2 ? ky : ky - Y;
             const float fy = my * d.boxf[4], fz = kz * d.boxf[5];
             for (int kx = lane; kx < X; kx += 32) {
-                float2 c = dft_line_c(lin, 1, X, kx, twx, -1.f);
+                float2 c = dft_line_q(lin, 1, X, kx, tqxf);
                 float eterm = 0.f;
                 if (kx != 0 || l != 0) {
                     const int mx = kx <= X / 2 ? kx : kx - X;
@@ -434,7 +486,7 @@ __global__ void __cluster_dims__(PME_CL, 1, 1) __launch_bounds__(PME_CL_THREADS)
             __syncwarp();
             for (int x = lane; x < X; x += 32) {
                 float2* owner = cluster.map_shared_rank(cplane, x / P);
-                owner[(size_t)(x % P) * YZc + l] = dft_line_c(lout, 1, X, x, twx, 1.f);
+                owner[(size_t)(x % P) * YZc + l] = dft_line_q(lout, 1, X, x, tqxi);
             }
             __syncwarp();
         }
@@ -446,32 +498,28 @@ __global__ void __cluster_dims__(PME_CL, 1, 1) __launch_bounds__(PME_CL_THREADS)
     cluster.sync();
     // ---- inverse y and z passes, real grid back to global memory
     const bool even = (Z & 1) == 0;
-    for (int p = 0; p < P; ++p) {
-        const int x = rank * P + p;
-        if (x >= X) break;
-        const float2* in = cplane + (size_t)p * YZc;
-        __syncthreads();
-        for (int o = tid; o < YZc; o += nt) {
-            const int y = o / Zc, kz = o - y * Zc;
-            tmp[o] = dft_line_c(in + kz, Zc, Y, y, twy, 1.f);
+    for (int o = tid; o < np * YZc; o += nt) {
+        const int pl = o / YZc, oo = o - pl * YZc;
+        const int y = oo / Zc, kz = oo - y * Zc;
+        tmp[o] = dft_line_q(cplane + pl * YZc + kz, Zc, Y, y, tqyi);
+    }
+    __syncthreads();
+    float* dst = d.grid_r + (size_t)r * d.gsize + (size_t)x_first * YZ;
+    for (int o = tid; o < np * YZ; o += nt) {
+        const int pl = o / YZ, oo = o - pl * YZ;
+        const int y = oo / Z, z = oo - y * Z;
+        const float2* c = tmp + pl * YZc + y * Zc;
+        float acc = c[0].x;
+        int m = z;
+        const int last = even ? Zc - 1 : Zc;
+        for (int kz = 1; kz < last; ++kz) {
+            const float2 w = twz[m];
+            acc = fmaf(2.f * c[kz].x, w.x, acc);
+            acc = fmaf(-2.f * c[kz].y, w.y, acc);
+            m += z; m -= m >= Z ? Z : 0;
         }
-        __syncthreads();
-        float* dst = d.grid_r + (size_t)r * d.gsize + (size_t)x * Y * Z;
-        for (int o = tid; o < Y * Z; o += nt) {
-            const int y = o / Z, z = o - y * Z;
-            const float2* c = tmp + y * Zc;
-            float acc = c[0].x;
-            int m = z;
-            const int last = even ? Zc - 1 : Zc;
-            for (int kz = 1; kz < last; ++kz) {
-                const float2 w = twz[m];
-                acc = fmaf(2.f * c[kz].x, w.x, acc);
-                acc = fmaf(-2.f * c[kz].y, w.y, acc);
-                m += z; m -= m >= Z ? Z : 0;
-            }
-            if (even) acc += (z & 1) ? -c[Zc - 1].x : c[Zc - 1].x;
-            dst[o] = acc;
-        }
+        if (even) acc += (z & 1) ? -c[Zc - 1].x : c[Zc - 1].x;
+        dst[o] = acc;
     }
 }
 

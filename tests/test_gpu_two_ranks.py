@@ -35,7 +35,7 @@ rank = dist.get_rank()
 out = {'rank': rank, 'local': sims.ncmc.context.getNumReplicas(), 'seed': sims.ncmc.integrator.getRandomNumberSeed(),
        'walkers': [h['walker'].tolist() for h in b.walker_history], 'work': [h['work_kT'].tolist() for h in b.walker_history],
        'ratio': b.acceptRatio}
-with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'result_%d.json' % rank), 'w') as fh:
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'result_%%d.json' %% rank), 'w') as fh:
     json.dump(out, fh)          # one file per rank: two ranks printing to one pipe interleave their lines
 dist.destroy_process_group()
 '''
