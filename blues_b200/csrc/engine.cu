@@ -128,7 +128,12 @@ static T* dalloc(bl_handle* h, size_t n) {
     void* p = nullptr;
     if (n == 0) n = 1;
     if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) return nullptr;
+    // cudaMemset on device memory is asynchronous and runs in the legacy stream, with which the handle's non-blocking
+    // streams are NOT ordered: without the synchronisation a buffer allocated lazily (move staging, water state, grown
+    // cell tables) could be zeroed AFTER the first asynchronous upload into it.  Seen as NaN work of every walker of a rank
+    // in the first iteration when two processes shared one GPU (tests/test_gpu_two_ranks.py).
     cudaMemset(p, 0, n * sizeof(T));
+    cudaStreamSynchronize(cudaStreamLegacy);
     h->allocs.push_back(p);
     return static_cast<T*>(p);
 }
@@ -1601,6 +1606,7 @@ int bl_copy_state(bl_handle* dst, const bl_handle* src, int flags) {
     if (dst->d.N != src->d.N || dst->device != src->device) { h->error = "handles are not compatible"; return BL_ERR_INVALID; }
     cudaSetDevice(h->device);
     CK(cudaStreamSynchronize(src->stream));
+    CK(cudaStreamSynchronize(dst->stream));            // the box / cell tables below are rewritten with blocking copies
     const int R = std::min(dst->d.R, src->d.R);
     const size_t n = sizeof(double4) * (size_t)R * dst->d.N;
     if (flags & 4) {

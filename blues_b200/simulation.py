@@ -532,7 +532,7 @@ class BLUESSimulation(object):
         self._md_sim.currentIter = self.currentIter
         self._md_sim.step(int(nstepsMD))
         return {'work_kT': work / kT, 'correction': correction, 'log_accept': logp, 'log_u': logu, 'accepted': accepted,
-                'failed': failed}
+                'failed': failed, 'energies': {'md0': e_md0, 'ncmc0': e_nc0, 'ncmc1': e_nc1, 'alch1': e_alch1}}
 
     def _runWalkers(self, nIter, nstepsNC, moveStep, nstepsMD, temperature):
         """``run`` for contexts that hold several walkers; one all-gather of the per-walker statistics per iteration
@@ -548,11 +548,13 @@ class BLUESSimulation(object):
         local_ids = [rank + world * r for r in range(R)]
         temperature = temperature if unit.is_quantity(temperature) else temperature * unit.kelvin
         self.walker_history = []
+        self.walker_records = []          # this rank's own per-walker records (work, correction, energies, flags)
         n_total = 0
         for it in range(int(nIter)):
             self.currentIter = it
             logger.info('BLUES Iteration: %s (%d walkers on this rank)' % (it, R))
             rec = self._iterateWalkers(nstepsNC, moveStep, nstepsMD, temperature)
+            self.walker_records.append(rec)
             stats = parallel.gather_walker_stats(local_ids, rec['work_kT'], rec['log_accept'], rec['accepted'], device=device) \
                 if distributed else {'walker': np.asarray(local_ids), 'work_kT': rec['work_kT'],
                                      'log_accept': rec['log_accept'], 'accepted': rec['accepted'].astype(int)}
