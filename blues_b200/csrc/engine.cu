@@ -404,7 +404,7 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         dim3 grid(cdiv((long long)d.Npad * lanes, NL_BLOCK), R);
         if (h->pair_per_sm > 0) grid.x = std::min<unsigned>(grid.x, (unsigned)std::max(1, h->pair_per_sm * h->n_sm / R));
 #define PX3(T, L, UU, DG) k_pair4<T, L, UU, DG><<<grid, NL_BLOCK, 0, st>>>(d, skip)
-#define PX2(T, UU, DG) if (lanes == 16) PX3(T, 16, UU, DG); else if (lanes == 32) PX3(T, 32, UU, DG); else PX3(T, 8, UU, DG)
+#define PX2(T, UU, DG) if (lanes == 16) PX3(T, 16, UU, DG); else if (lanes == 32) PX3(T, 32, UU, DG); else if (lanes == 4) PX3(T, 4, UU, DG); else PX3(T, 8, UU, DG)
 #define PX1(T, UU) if (d.ewk2_deg == 10) { PX2(T, UU, 10); } else { PX2(T, UU, 12); }
 #define PX0(T) if (U == 4) { PX1(T, 4) } else { PX1(T, 2) }
         if (d.nl_u16) { PX0(unsigned short) } else { PX0(int) }
@@ -874,6 +874,7 @@ static int setup_box(bl_handle* h, const double box[3]) {
         bf[k] = (float)bd[k];
         bf[3 + k] = (float)bd[3 + k];
     }
+    if (h->stream) CK(cudaStreamSynchronize(h->stream));     // blocking copies are not ordered with the non-blocking streams
     CK(cudaMemcpy(d.boxd, bd, sizeof bd, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d.boxf, bf, sizeof bf, cudaMemcpyHostToDevice));
     return BL_OK;
@@ -973,7 +974,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_TIMELINE")) { h->timeline = true; h->graph_steps = 1; }
     if (getenv("BLUES_B200_PAIR_PER_SM")) h->pair_per_sm = std::max(0, atoi(getenv("BLUES_B200_PAIR_PER_SM")));
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
-    if (getenv("BLUES_B200_PAIR_LANES")) { const int l = atoi(getenv("BLUES_B200_PAIR_LANES")); h->pair_lanes = l == 16 || l == 32 ? l : 8; }
+    if (getenv("BLUES_B200_PAIR_LANES")) { const int l = atoi(getenv("BLUES_B200_PAIR_LANES")); h->pair_lanes = l == 16 || l == 32 || l == 4 ? l : 8; }
     if (getenv("BLUES_B200_PAIR_X2")) h->pair_x2 = atoi(getenv("BLUES_B200_PAIR_X2"));
     if (getenv("BLUES_B200_PAIR")) h->pair_variant = atoi(getenv("BLUES_B200_PAIR"));
     if (getenv("BLUES_B200_DEBUG_SYNC") && atoi(getenv("BLUES_B200_DEBUG_SYNC"))) { h->debug_sync = true; h->use_graphs = false; h->pdl = false; }
@@ -2022,6 +2023,7 @@ int bl_minimize(bl_handle* h, int max_iterations, double tolerance) {
     }
     // clear a NaN flag possibly raised by rejected trial steps
     std::vector<Globals> g(d.R);
+    CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(g.data(), d.g, sizeof(Globals) * d.R, cudaMemcpyDeviceToHost));
     for (auto& x : g) x.nan_flag = 0;
     CK(cudaMemcpy(d.g, g.data(), sizeof(Globals) * d.R, cudaMemcpyHostToDevice));
