@@ -1243,6 +1243,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     }
     d.nl_u16 = d.Npad < 65536 ? 1 : 0;
     d.nl_count = dalloc<int>(h, (size_t)R * d.Npad);
+    if (SORT_CTAS > 8) cudaFuncSetAttribute(k_sort_atoms, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     d.mobile_s = dalloc<unsigned char>(h, (size_t)R * d.Npad);
     d.n_frozen = 0;
     for (int i = 0; i < N; ++i) d.n_frozen += t->mass[i] == 0.0 ? 1 : 0;

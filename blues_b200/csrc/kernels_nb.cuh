@@ -48,7 +48,9 @@ __device__ __forceinline__ void atom_cell_coords(const Dev& d, float4 p, int& cx
     cz = max(0, min((int)(wrap01(p.z * d.boxf[5]) * d.ncell[2]), d.ncell[2] - 1));
 }
 
-#define SORT_CTAS 8
+#ifndef SORT_CTAS
+#define SORT_CTAS 16        /* CTAs of the sort cluster: 16 needs cudaFuncAttributeNonPortableClusterSizeAllowed (set at bl_create) */
+#endif
 #define BUILD_GROUP 8          /* atoms per k_build_list work group */
 // latched = 1: the preceding k_integrate launch (IntegrateArgs::pre_eval) has latched do_rebuild and cleared the energy
 // accumulators; this kernel then only handles the momentum parity (cm_mode as in k_begin_eval) and exits without a
