@@ -44,6 +44,9 @@ struct bl_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // reciprocal-space branch, forked from / joined to `stream` inside every evaluation
     cudaStream_t stream3 = nullptr, stream4 = nullptr;   // bonded branch, alchemical branch
+    cudaStream_t stream5 = nullptr; cudaEvent_t ev_join5 = nullptr;   // pair kernel of the walkers that do not rebuild (many walkers)
+    int pair_split = 0;          // BLUES_B200_PAIR_SPLIT=1: > 2 walkers: pair kernel of the non-rebuilding walkers beside the builder
+                                 // (measured: 617 vs 610 us per 8-walker step — both kernels are issue bound, the overlap buys nothing)
     cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
     std::string error;
     std::vector<void*> allocs;
@@ -365,6 +368,32 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         tl_mark(h, s4, TL_ALCH);
         cudaEventRecord(h->ev_join4, s4);
     }
+    // packed-pair FP32 kernel (FFMA2): PME force-only evaluations, i.e. every evaluation of a plain NCMC / MD step
+    const bool use_x2 = h->pair_x2 && !energy && d.nb_method == 4 && d.ewk_ok && d.ewk2_deg <= 12;
+    auto launch_pair4 = [&](cudaStream_t ps, int phase) {
+        LaunchTimer t(h, BL_K_PAIR, ps);
+        const int U = h->pair_x2 == 4 ? 4 : 2;
+        const int lanes = h->pair_lanes;
+        dim3 grid(cdiv((long long)d.Npad * lanes, NL_BLOCK), R);
+        if (h->pair_per_sm > 0) grid.x = std::min<unsigned>(grid.x, (unsigned)std::max(1, h->pair_per_sm * h->n_sm / R));
+#define PX3(T, L, UU, DG) k_pair4<T, L, UU, DG><<<grid, NL_BLOCK, 0, ps>>>(d, skip, phase)
+#define PX2(T, UU, DG) if (lanes == 16) PX3(T, 16, UU, DG); else if (lanes == 32) PX3(T, 32, UU, DG); else if (lanes == 4) PX3(T, 4, UU, DG); else PX3(T, 8, UU, DG)
+#define PX1(T, UU) if (d.ewk2_deg == 10) { PX2(T, UU, 10); } else { PX2(T, UU, 12); }
+#define PX0(T) if (U == 4) { PX1(T, 4) } else { PX1(T, 2) }
+        if (d.nl_u16) { PX0(unsigned short) } else { PX0(int) }
+#undef PX3
+#undef PX2
+#undef PX1
+#undef PX0
+    };
+    // many walkers: each rebuilds its list on its own schedule (every ~4 steps), so in a typical evaluation a quarter of the
+    // walkers wait for the builder and the others do not — their pair kernel runs beside the builder on its own stream
+    const bool split = use_x2 && R > 2 && h->pair_split && !h->profiling;
+    if (split) {
+        cudaStreamWaitEvent(h->stream5, h->ev_fork2, 0);
+        launch_pair4(h->stream5, 1);
+        cudaEventRecord(h->ev_join5, h->stream5);
+    }
     {
         LaunchTimer t(h, BL_K_NEIGHBOR);
         dim3 grid(h->build_ctas);                          // persistent single-warp CTAs shared by all walkers
@@ -396,22 +425,9 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
 #undef P3A
 #undef P30
 #undef P3E
-    } else if (h->pair_x2 && !energy && d.nb_method == 4 && d.ewk_ok && d.ewk2_deg <= 12) {
-        LaunchTimer t(h, BL_K_PAIR);
-        // packed-pair FP32 kernel (FFMA2): PME force-only evaluations, i.e. every evaluation of a plain NCMC / MD step
-        const int U = h->pair_x2 == 4 ? 4 : 2;
-        const int lanes = h->pair_lanes;
-        dim3 grid(cdiv((long long)d.Npad * lanes, NL_BLOCK), R);
-        if (h->pair_per_sm > 0) grid.x = std::min<unsigned>(grid.x, (unsigned)std::max(1, h->pair_per_sm * h->n_sm / R));
-#define PX3(T, L, UU, DG) k_pair4<T, L, UU, DG><<<grid, NL_BLOCK, 0, st>>>(d, skip)
-#define PX2(T, UU, DG) if (lanes == 16) PX3(T, 16, UU, DG); else if (lanes == 32) PX3(T, 32, UU, DG); else if (lanes == 4) PX3(T, 4, UU, DG); else PX3(T, 8, UU, DG)
-#define PX1(T, UU) if (d.ewk2_deg == 10) { PX2(T, UU, 10); } else { PX2(T, UU, 12); }
-#define PX0(T) if (U == 4) { PX1(T, 4) } else { PX1(T, 2) }
-        if (d.nl_u16) { PX0(unsigned short) } else { PX0(int) }
-#undef PX3
-#undef PX2
-#undef PX1
-#undef PX0
+    } else if (use_x2) {
+        launch_pair4(st, split ? 2 : 0);
+        if (split) cudaStreamWaitEvent(st, h->ev_join5, 0);
     } else if (h->pair_variant > 0) {
         LaunchTimer t(h, BL_K_PAIR);
         // variant = 100 * ewald + 10 * log2(lanes) + U  (BLUES_B200_PAIR; 0 = the round-1 kernel)
@@ -949,6 +965,8 @@ int bl_destroy(bl_handle* h) {
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream3) cudaStreamDestroy(h->stream3);
     if (h->stream4) cudaStreamDestroy(h->stream4);
+    if (h->stream5) cudaStreamDestroy(h->stream5);
+    if (h->ev_join5) cudaEventDestroy(h->ev_join5);
     if (h->ev_join3) cudaEventDestroy(h->ev_join3);
     if (h->ev_join4) cudaEventDestroy(h->ev_join4);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -972,6 +990,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_PDL")) h->pdl = atoi(getenv("BLUES_B200_PDL")) != 0;
     if (getenv("BLUES_B200_GRAPH_STEPS")) h->graph_steps = std::max(1, atoi(getenv("BLUES_B200_GRAPH_STEPS")));
     if (getenv("BLUES_B200_TIMELINE")) { h->timeline = true; h->graph_steps = 1; }
+    if (getenv("BLUES_B200_PAIR_SPLIT")) h->pair_split = atoi(getenv("BLUES_B200_PAIR_SPLIT"));
     if (getenv("BLUES_B200_PAIR_PER_SM")) h->pair_per_sm = std::max(0, atoi(getenv("BLUES_B200_PAIR_PER_SM")));
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
     if (getenv("BLUES_B200_PAIR_LANES")) { const int l = atoi(getenv("BLUES_B200_PAIR_LANES")); h->pair_lanes = l == 16 || l == 32 || l == 4 ? l : 8; }
@@ -996,6 +1015,8 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream5, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join5, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||

@@ -1060,9 +1060,12 @@ __device__ __forceinline__ void pair_trip_x2(const Dev& d, const float4 p0, cons
 }
 
 template <typename IDX, int LANES, int U, int DEG>
-__global__ void __launch_bounds__(NL_BLOCK) k_pair4(Dev d, int skip_frozen) {
+__global__ void __launch_bounds__(NL_BLOCK) k_pair4(Dev d, int skip_frozen, int phase) {
     static_assert(U % 2 == 0, "entries are processed in packed pairs");
     const int r = blockIdx.y;
+    // phase 1: only the walkers whose list is NOT being rebuilt in this evaluation (launched beside the builder, on its own
+    // stream); phase 2: only the walkers whose list has just been rebuilt; 0: all
+    if (phase != 0 && (d.g[r].do_rebuild != 0) != (phase == 2)) return;
     const int lane = threadIdx.x & 31;
     const int part = lane & (LANES - 1);
     const int N = d.N, Npad = d.Npad;
