@@ -397,3 +397,90 @@ def test_committed_bench_line_keeps_the_contract():
     assert cpu['kind'] in ('port', 'reference') and cpu['cores'] >= 1 and cpu['value'] > 0 and cpu['sample']
     assert not {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'} & set(line['clocks']['reasons'])
     assert line['clocks']['sm_mhz'] >= 0.9 * line['clocks']['sm_max_mhz']
+
+
+def test_sidechain_rotor_perception_gives_the_chi_bonds_of_every_residue_type():
+    """`SideChainMove` without OpenEye (blues/moves.py:418-843): backbone / ring / rotor perception from the bond graph
+    must find exactly the side-chain torsion (chi) bonds of the standard residues — checked on one residue of each of the
+    20 types of the T4 lysozyme surrogate topology (OpenEye's `IsRotor` on heavy-atom bonds gives the same set)."""
+    from blues_b200.moves import SideChainMove
+    s = Structure.load_npz(os.path.join(GOLDEN, 't4l_surrogate.npz'))
+    chi = {'ALA': [], 'GLY': [], 'PRO': [], 'VAL': ['CA-CB'], 'SER': ['CA-CB'], 'THR': ['CA-CB'], 'CYS': ['CA-CB'],
+           'LEU': ['CA-CB', 'CB-CG'], 'ILE': ['CA-CB', 'CB-CG1'], 'PHE': ['CA-CB', 'CB-CG'], 'TYR': ['CA-CB', 'CB-CG'],
+           'TRP': ['CA-CB', 'CB-CG'], 'HIS': ['CA-CB', 'CB-CG'], 'ASP': ['CA-CB', 'CB-CG'], 'ASN': ['CA-CB', 'CB-CG'],
+           'GLU': ['CA-CB', 'CB-CG', 'CG-CD'], 'GLN': ['CA-CB', 'CB-CG', 'CG-CD'], 'MET': ['CA-CB', 'CB-CG', 'CG-SD'],
+           'LYS': ['CA-CB', 'CB-CG', 'CG-CD', 'CD-CE'], 'ARG': ['CA-CB', 'CB-CG', 'CG-CD', 'CD-NE']}
+    names = [a.name for a in s.atoms]
+    first = {}
+    for r in list(s.topology.residues())[:164]:
+        first.setdefault(r.name, int(r.id))
+    assert set(first) == set(chi)
+    for resname, rid in first.items():
+        mv = SideChainMove(s, [rid])
+        found = sorted('%s-%s' % (names[a], names[b]) for a, b in mv.rot_bonds)
+        assert found == sorted(chi[resname]), (resname, rid, found)
+        for bond, atoms in (mv.rot_atoms.get(rid) or {}).items():
+            assert atoms[:2] == list(bond) and len(set(atoms)) == len(atoms)
+            assert all(names[a] not in ('N', 'C', 'O') for a in atoms[2:])       # nothing of the backbone is rotated
+
+
+def test_lepton_compiler_values_and_derivatives():
+    """Custom*Force energy expressions -> stack programs (blues_b200/lepton.py): value and d/dr of the host twin of the
+    device interpreter against direct evaluation and central differences, for every supported function."""
+    import math
+    from blues_b200 import lepton
+    cases = [
+        ('0.5*k*(r-r0)^2', {'k': 0, 'r0': 1}, {}, [250.0, 0.3], lambda r, p, g: 0.5 * p[0] * (r - p[1]) ** 2),
+        ('4*eps*((s/r)^12-(s/r)^6); s=0.5*(s1+s2)*lambda_sterics; eps=sqrt(e1*e2)*lambda_electrostatics',
+         {'s1': 0, 'e1': 1, 's2': 2, 'e2': 3}, {}, [0.3, 0.5, 0.34, 0.7],
+         lambda r, p, g: 4 * math.sqrt(p[1] * p[3]) * g[1] * ((0.5 * (p[0] + p[2]) * g[0] / r) ** 12 - (0.5 * (p[0] + p[2]) * g[0] / r) ** 6)),
+        ('A*exp(-b*r) - c/r^6 + step(r-0.4)*delta(0)*min(r, 0.5)*max(r, 0.1)', {'b': 0}, {'A': 1000.0, 'c': 0.002}, [12.0],
+         lambda r, p, g: 1000.0 * math.exp(-p[0] * r) - 0.002 / r ** 6 + (1.0 if r >= 0.4 else 0.0) * min(r, 0.5) * max(r, 0.1)),
+        ('q*erfc(a*r)/r + erf(r)*tanh(r) + sin(r)*cos(r)/tan(r+0.3) + log(r+1) + abs(r-0.5)^1.5 + select(r-0.2, sinh(r), cosh(r)) + atan(r)',
+         {'q': 0}, {'a': 2.5}, [138.9],
+         lambda r, p, g: p[0] * math.erfc(2.5 * r) / r + math.erf(r) * math.tanh(r) + math.sin(r) * math.cos(r) / math.tan(r + 0.3)
+         + math.log(r + 1) + abs(r - 0.5) ** 1.5 + (math.sinh(r) if r - 0.2 != 0 else math.cosh(r)) + math.atan(r)),
+        ('0.5*kc*distance(g1,g2)^2 + recip(distance(g1, g2)+1) + square(distance(g1,g2)) - cube(distance(g1,g2))', {'kc': 0}, {}, [1.0e5],
+         lambda r, p, g: 0.5 * p[0] * r ** 2 + 1.0 / (r + 1) + r * r - r ** 3),
+    ]
+    for text, params, consts, par, ref in cases:
+        ops, args = lepton.compile_program(text, params, consts, ['distance(g1,g2)'])
+        for r in (0.27, 0.41, 0.66):
+            for g in ((1.0, 1.0), (0.35, 0.8)):
+                v, d = lepton.evaluate_program(ops, args, r, par, g)
+                want = ref(r, par, g)
+                fd = (ref(r + 1e-6, par, g) - ref(r - 1e-6, par, g)) / 2e-6
+                assert abs(v - want) <= 1e-12 * max(1.0, abs(want)), (text, r, v, want)
+                assert abs(d - fd) <= 2e-6 * max(1.0, abs(fd)), (text, r, d, fd)
+    with pytest.raises(ValueError):
+        lepton.compile_program('k*r + undefined_name', {'k': 0})
+    with pytest.raises(ValueError):
+        lepton.compile_program('a*r; a = b; b = a', {})
+    with pytest.raises(NotImplementedError):
+        lepton.compile_program('k*angle(g1,g2,g3)', {'k': 0})
+
+
+def test_xml_system_round_trip_of_the_ethylene_known_answer_system():
+    """XmlSerializer.deserialize on the reference's serialized System (verbatim fixture): particles, constraints, forces and
+    the custom-force tables the engine receives."""
+    from blues_b200.system import (XmlSerializer, CustomNonbondedForce, CustomCentroidBondForce, HarmonicBondForce,
+                                   HarmonicAngleForce, PeriodicTorsionForce)
+    xml = open(os.path.join(GOLDEN, 'reference_checkout', 'blues', 'tests', 'data', 'ethylene_system.xml')).read()
+    system = XmlSerializer.deserialize(xml)
+    assert system.getNumParticles() == 8 and system.getNumConstraints() == 4
+    assert [system.getParticleMass(i)._value for i in range(3)] == [0.0, 0.0, 12.01]
+    kinds = [type(f) for f in system.getForces()]
+    assert kinds == [HarmonicBondForce, HarmonicAngleForce, PeriodicTorsionForce, CustomNonbondedForce, CustomCentroidBondForce]
+    cn = system.getForces()[3]
+    assert cn.getNumParticles() == 8 and cn.getNumInteractionGroups() == 1 and cn.getNumPerParticleParameters() == 4
+    assert cn.global_params == {'lambda_sterics': 1.0, 'lambda_electrostatics': 1.0, 'lambda_charge': 1.0}
+    cb = system.getForces()[4]
+    assert cb.getNumGroups() == 2 and cb.getGroupParameters(0) == ([0, 1], [1.0, 1.0]) and cb.getGroupParameters(1) == ([2, 3], None)
+    t = system.flatten()
+    assert t['custom_term'].shape == (13, 4) and t['custom_n_params'] == 8 and len(t['custom_prog_start']) == 3
+    assert list(t['custom_term'][-1][:2]) != list(t['custom_term'][0][:2])
+    w = t['custom_group_weights']
+    gs = t['custom_group_start']
+    for k in range(len(gs) - 1):
+        assert abs(w[gs[k]:gs[k + 1]].sum() - 1.0) < 1e-12                          # normalised group weights
+    assert t['nb_method'] == 0 and np.allclose(t['box'], [2.0, 2.0, 2.0])
