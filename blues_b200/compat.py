@@ -8,6 +8,7 @@ already), limited to the surface the reference's NCMC path touches (SURVEY.md §
     simtk.openmm (System, Context, Platform, LangevinIntegrator, the Force classes …), simtk.openmm.app
     parmed (load_file, Structure, amber.AmberMask / Rst7, geometry.center_of_mass)
     openmmtools.alchemy (AbsoluteAlchemicalFactory, AlchemicalRegion)
+    mdtraj (load, load_netcdf, compute_distances, compute_dihedrals, utils.uniform_quaternion …) -> blues_b200.trajectory
 
 so that a user script or the reference's own test files (``blues/tests/test_simulation.py`` …) import unchanged.
 With ``data_root`` given, ``blues.utils.get_data_filename('blues', 'tests/data/…')`` resolves inside that checkout
@@ -40,6 +41,7 @@ def _module(name, **attrs):
 def install(data_root=None, force=False):
     """Register the aliases; returns the list of module names that were installed."""
     from . import unit, mm, system, structure, alchemy, utils, simulation, moves, integrators, reporters, settings
+    from . import trajectory
     import blues_b200
 
     mods = {}
@@ -70,6 +72,15 @@ def install(data_root=None, force=False):
     omt = _module('openmmtools', alchemy=omt_alchemy)
     omt.__path__ = []
     mods.update({'openmmtools': omt, 'openmmtools.alchemy': omt_alchemy})
+    # --- mdtraj: reading back the trajectories the reporters write (blues/tests/test_ethylene.py:113-163) -------------
+    md_utils = _module('mdtraj.utils', uniform_quaternion=lambda size=None, random_state=None:
+                       moves.uniform_quaternion(random_state),
+                       rotation_matrix_from_quaternion=moves.rotation_matrix_from_quaternion)
+    mdtraj = _module('mdtraj', load=trajectory.load, load_netcdf=trajectory.load_netcdf, Trajectory=trajectory.Trajectory,
+                     compute_distances=trajectory.compute_distances, compute_dihedrals=trajectory.compute_dihedrals,
+                     utils=md_utils)
+    mdtraj.__path__ = []
+    mods.update({'mdtraj': mdtraj, 'mdtraj.utils': md_utils})
     # --- blues --------------------------------------------------------------------------------------------------------
     blues_utils = utils
     if data_root is not None:

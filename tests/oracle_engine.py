@@ -31,7 +31,39 @@ class _FastForceField(object):
         return self._c
 
     def energy_forces(self, x, box, lam_s=1.0, lam_e=1.0):
-        return self._oracle(box).energy_forces(x, lam_s, lam_e)
+        out = self._oracle(box).energy_forces(x, lam_s, lam_e)
+        if len(self.topo.get('custom_term', ())):
+            ec, fc = self._custom(np.asarray(x, float), np.asarray(box, float).reshape(-1)[:3], lam_s, lam_e)
+            out = (out[0] + ec, out[1] + fc) + tuple(out[2:])
+        return out
+
+    def _custom(self, x, box, lam_s, lam_e):
+        """Generic Custom*Force terms (the ``custom_*`` tables of ``bl_topology``): E(r) between the weighted centroids
+        of two atom groups from the stack program, by the host interpreter of ``blues_b200/lepton.py``."""
+        from blues_b200.lepton import evaluate_program
+        t = self.topo
+        gs, ga, gw = t['custom_group_start'], t['custom_group_atoms'], t['custom_group_weights']
+        ps, op, arg = t['custom_prog_start'], t['custom_code_op'], t['custom_code_arg']
+        par = np.asarray(t['custom_params'], float).reshape(len(t['custom_term']), -1)
+        e, f = 0.0, np.zeros_like(x)
+        for k, (a, b, prog, flags) in enumerate(np.asarray(t['custom_term']).reshape(-1, 4)):
+            ia, wa = ga[gs[a]:gs[a + 1]], np.asarray(gw[gs[a]:gs[a + 1]], float)
+            ib, wb = ga[gs[b]:gs[b + 1]], np.asarray(gw[gs[b]:gs[b + 1]], float)
+            dv = wa @ x[ia] - wb @ x[ib]
+            if flags & 1:
+                dv -= box * np.round(dv / box)
+            r = math.sqrt(float(dv @ dv))
+            cut = float(t['custom_cutoff'][k])
+            if cut > 0.0 and r >= cut:
+                continue
+            v, d = evaluate_program(list(op[ps[prog]:ps[prog + 1]]), list(arg[ps[prog]:ps[prog + 1]]), r, par[k],
+                                    (lam_s, lam_e))
+            e += v
+            if r > 0.0 and d != 0.0:
+                g = -d / r * dv
+                np.add.at(f, ia, wa[:, None] * g)
+                np.add.at(f, ib, -wb[:, None] * g)
+        return e, f
 
     def energy(self, x, box, lam_s=1.0, lam_e=1.0):
         return self.energy_forces(x, box, lam_s, lam_e)[0]

@@ -484,3 +484,38 @@ def test_xml_system_round_trip_of_the_ethylene_known_answer_system():
     for k in range(len(gs) - 1):
         assert abs(w[gs[k]:gs[k + 1]].sum() - 1.0) < 1e-12                          # normalised group weights
     assert t['nb_method'] == 0 and np.allclose(t['box'], [2.0, 2.0, 2.0])
+
+
+def test_trajectory_reader_distances_and_dihedrals(tmp_path):
+    """blues_b200/trajectory.py (the ``mdtraj`` alias of compat): AMBER NetCDF in ångström → nm frames; distances with
+    the minimum image; dihedral sign convention (IUPAC: trans = pi, right-handed twist positive)."""
+    import math
+    from scipy.io import netcdf_file
+    from blues_b200 import trajectory
+    x = np.array([[[0, 1, 0], [0, 0, 0], [1, 0, 0], [1, 0, 1]],
+                  [[0, 1, 0], [0, 0, 0], [1, 0, 0], [1, -1, 0]],
+                  [[0, 1, 0], [0, 0, 0], [19, 0, 0], [1, 1, 0]]], float)           # Å
+    fn = str(tmp_path / 't.nc')
+    nc = netcdf_file(fn, 'w', version=2)
+    nc.createDimension('frame', None); nc.createDimension('spatial', 3); nc.createDimension('atom', 4)
+    nc.createDimension('cell_spatial', 3); nc.createDimension('cell_angular', 3)
+    nc.createVariable('time', 'f', ('frame',))
+    nc.createVariable('coordinates', 'f', ('frame', 'atom', 'spatial'))
+    nc.createVariable('cell_lengths', 'd', ('frame', 'cell_spatial'))
+    nc.createVariable('cell_angles', 'd', ('frame', 'cell_angular'))
+    for k in range(3):
+        nc.variables['time'][k] = k
+        nc.variables['coordinates'][k] = x[k]
+        nc.variables['cell_lengths'][k] = [20.0, 20.0, 20.0]
+        nc.variables['cell_angles'][k] = [90.0, 90.0, 90.0]
+    nc.close()
+    t = trajectory.load(fn)
+    assert t.n_frames == 3 and t.n_atoms == 4 and len(t[1:]) == 2
+    np.testing.assert_allclose(t.xyz, x * 0.1, atol=1e-6)
+    d = trajectory.compute_distances(t, [[1, 2], [0, 3]])
+    assert d.shape == (3, 2)
+    np.testing.assert_allclose(d[:, 0], [0.1, 0.1, 0.1], atol=1e-6)                # frame 2: 1.9 nm wraps to 0.1 nm
+    np.testing.assert_allclose(trajectory.compute_distances(t, [[1, 2]], periodic=False)[2, 0], 1.9, atol=1e-6)
+    phi = trajectory.compute_dihedrals(t[:2], [[0, 1, 2, 3]])
+    np.testing.assert_allclose(np.abs(phi[:, 0]), [math.pi / 2, math.pi], atol=1e-6)
+    assert phi[0, 0] > 0            # seen along 1 -> 2 the front bond turns clockwise onto the back bond: +90 degrees

@@ -60,6 +60,8 @@ ORACLE_RUNNER = r'''
 import sys
 sys.dont_write_bytecode = True
 sys.path.insert(0, %(root)r)
+import numpy
+numpy.random.seed(1)                 # test_ethylene.py draws its integrator seeds from numpy's global generator
 import blues_b200.compat as compat
 compat.install(data_root=%(ref)r)
 import blues_b200._native as native
@@ -77,10 +79,11 @@ def test_reference_tests_pass_on_the_host_layer_over_the_oracle_engine(tmp_path)
     layer (SystemFactory … BLUESSimulation.run, YAML settings, reporters, the rotation move, state sync, accept/reject)
     with ``tests/oracle_engine.OracleEngine`` standing in for the CUDA engine below the C ABI.  Together with the
     ``-m gpu`` tests (CUDA engine == oracle on the same inputs) this is the reference's own acceptance test for the
-    drop-in.  Not run: ``test_watertranslation.py`` (its ``eqToluene.prmtop`` is missing upstream), ``test_ethylene.py``
-    (generic ``Custom*Force`` system; its populations are reproduced by ``tests/test_oracle_ethylene.py``),
-    ``test_sidechain.py`` (OpenEye)."""
-    for name in ('test_simulation.py', 'test_randomrotation.py'):
+    drop-in.  ``test_ethylene.py`` (the known-answer test: XML system of generic ``Custom*Force`` terms, NetCDF
+    trajectories read back through the ``mdtraj`` alias, populations 0.25 / 0.75) runs the same way, the stand-in
+    evaluating the ``custom_*`` tables with the host interpreter.  Not run: ``test_watertranslation.py`` (its
+    ``eqToluene.prmtop`` is missing upstream), ``test_sidechain.py`` (OpenEye)."""
+    for name in ('test_simulation.py', 'test_randomrotation.py', 'test_ethylene.py'):
         shutil.copy(os.path.join(REFERENCE, 'blues', 'tests', name), str(tmp_path))
     code = ORACLE_RUNNER % {'root': ROOT, 'ref': REFERENCE, 'tmp': str(tmp_path)}
     env = dict(os.environ, COLUMNS='400', PYTHONDONTWRITEBYTECODE='1')
@@ -88,7 +91,8 @@ def test_reference_tests_pass_on_the_host_layer_over_the_oracle_engine(tmp_path)
                          timeout=1500)
     out = run.stdout
     passed = set(re.findall(r'^PASSED (\S+)', out, re.M))
-    assert run.returncode == 0 and len(passed) == 26, out[-4000:]
+    assert run.returncode == 0 and len(passed) == 28, out[-4000:]
+    assert any('test_ethylene.py::test_runAnalysis' in p for p in passed)
     assert any('test_randomrotation.py' in p for p in passed)
 
 
@@ -97,7 +101,7 @@ def test_reference_tests_pass_on_the_host_layer_over_the_oracle_engine(tmp_path)
 def test_fixture_copies_are_verbatim():
     """tests/golden/reference_checkout/ (input of tests/test_gpu_reference_suite.py) equals the checkout byte for byte."""
     base = os.path.join(ROOT, 'tests', 'golden', 'reference_checkout', 'blues', 'tests')
-    for rel in ('test_simulation.py', 'test_randomrotation.py', 'data/TOL-parm.prmtop', 'data/TOL-parm.inpcrd',
+    for rel in ('test_simulation.py', 'test_randomrotation.py', 'test_ethylene.py', 'data/TOL-parm.prmtop', 'data/TOL-parm.inpcrd',
                 'data/ethylene_system.xml', 'data/ethylene_structure.pdb'):
         with open(os.path.join(base, rel), 'rb') as a, open(os.path.join(REFERENCE, 'blues', 'tests', rel), 'rb') as b:
             assert a.read() == b.read(), rel
