@@ -1059,8 +1059,13 @@ __device__ __forceinline__ void pair_trip_x2(const Dev& d, const float4 p0, cons
     acc.fz = f2_fma(dz, de, acc.fz);
 }
 
+#ifdef PAIR4_MIN_CTAS            /* experiment hook: cap the registers for more resident warps (measured: see DESIGN.md §11) */
+#define PAIR4_BOUNDS __launch_bounds__(NL_BLOCK, PAIR4_MIN_CTAS)
+#else
+#define PAIR4_BOUNDS __launch_bounds__(NL_BLOCK)
+#endif
 template <typename IDX, int LANES, int U, int DEG>
-__global__ void __launch_bounds__(NL_BLOCK) k_pair4(Dev d, int skip_frozen, int phase) {
+__global__ void PAIR4_BOUNDS k_pair4(Dev d, int skip_frozen, int phase) {
     static_assert(U % 2 == 0, "entries are processed in packed pairs");
     const int r = blockIdx.y;
     // phase 1: only the walkers whose list is NOT being rebuilt in this evaluation (launched beside the builder, on its own
