@@ -284,7 +284,7 @@ struct FixedCluster {
 template <int NA, int NC, int SHAPE>
 __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts& ic, const IntegrateArgs& args,
                                             const Cluster& c, int r, int parity, unsigned int noise0, unsigned int md0,
-                                            double (&mom)[3], double& dheat, bool& moved, bool& bad, bool& moved_outer) {
+                                            double (&mom)[3], double& dheat, bool& moved, bool& bad) {
     const int N = d.N;
     double4* pos = d.pos + (size_t)r * N;
     double4* vel = d.vel + (size_t)r * N;
@@ -506,7 +506,7 @@ __device__ __forceinline__ void run_cluster(const Dev& d, const IntegratorConsts
 // generic fallback (dynamic indexing, local memory): clusters that are neither stars nor water triangles
 __device__ __forceinline__ void run_cluster_generic(const Dev& d, const IntegratorConsts& ic, const IntegrateArgs& args,
                                                  const Cluster& c, int r, int parity, unsigned int noise0,
-                                                 unsigned int md0, double (&mom)[3], double& dheat, bool& moved, bool& bad, bool& moved_outer) {
+                                                 unsigned int md0, double (&mom)[3], double& dheat, bool& moved, bool& bad) {
     const int N = d.N;
     double4* pos = d.pos + (size_t)r * N;
     double4* vel = d.vel + (size_t)r * N;
@@ -653,17 +653,17 @@ __global__ void __launch_bounds__(256) k_integrate(Dev d, IntegratorConsts ic, I
     const int parity = *cm_parity;
     double mom[3] = {0.0, 0.0, 0.0};
     double dheat = 0.0;
-    bool moved = false, bad = false, moved_outer = false;
+    bool moved = false, bad = false;
     if (cid < d.n_clusters) {
         const Cluster c = d.clusters[cid];
         const unsigned int noise0 = g.noise_counter + args.noise_offset, md0 = g.md_counter + args.md_offset;
         const int key = c.shape * 16 + c.ncons;
         switch (key) {
-        case SHAPE_STAR * 16 + 0: run_cluster<1, 0, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
-        case SHAPE_STAR * 16 + 1: run_cluster<2, 1, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
-        case SHAPE_STAR * 16 + 2: run_cluster<3, 2, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
-        case SHAPE_STAR * 16 + 3: run_cluster<4, 3, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
-        case SHAPE_TRI * 16 + 3: run_cluster<3, 3, SHAPE_TRI>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer); break;
+        case SHAPE_STAR * 16 + 0: run_cluster<1, 0, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_STAR * 16 + 1: run_cluster<2, 1, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_STAR * 16 + 2: run_cluster<3, 2, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_STAR * 16 + 3: run_cluster<4, 3, SHAPE_STAR>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
+        case SHAPE_TRI * 16 + 3: run_cluster<3, 3, SHAPE_TRI>(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad); break;
         default: break;      // generic clusters are integrated by k_integrate_generic
         }
         if (moved) g.prune_request = 1;
@@ -747,11 +747,11 @@ __global__ void __launch_bounds__(64) k_integrate_generic(Dev d, IntegratorConst
     const int parity = *cm_parity;
     double mom[3] = {0.0, 0.0, 0.0};
     double dheat = 0.0;
-    bool moved = false, bad = false, moved_outer = false;
+    bool moved = false, bad = false;
     if (cid < n_generic) {
         const Cluster c = d.clusters[cid];
         const unsigned int noise0 = g.noise_counter + args.noise_offset, md0 = g.md_counter + args.md_offset;
-        run_cluster_generic(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad, moved_outer);
+        run_cluster_generic(d, ic, args, c, r, parity, noise0, md0, mom, dheat, moved, bad);
         if (moved) g.prune_request = 1;
         if (bad) g.nan_flag = 1;
     }
