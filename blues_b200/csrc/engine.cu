@@ -289,13 +289,15 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         cufftSetStream(h->plan_r2c, s2);
         cufftSetStream(h->plan_c2r, s2);
         cudaStreamWaitEvent(s2, h->ev_fork, 0);
+        const int fcache = d.grid_frozen ? 1 : 0;      // frozen atoms' share of the charge grid is kept (k_pme_spread)
         { LaunchTimer t(h, BL_K_PME_SPREAD, s2);
           // few walkers: latency bound, many wide CTAs; many walkers: throughput bound, fewer duplicate B-splines
           if (R <= 2) {
               const int ys = h->spread_split;
-              if (h->spread_threads == 1024) k_pme_spread<1024><<<dim3(d.gx, ys, R), 1024, (d.gy / ys + 1) * d.gz * sizeof(int), s2>>>(d);
-              else k_pme_spread<512><<<dim3(d.gx, ys, R), 512, (d.gy / ys + 1) * d.gz * sizeof(int), s2>>>(d);
-          } else k_pme_spread<256><<<dim3(d.gx, 4, R), 256, (d.gy / 4 + 1) * d.gz * sizeof(int), s2>>>(d); }
+              const size_t sm = (size_t)(d.gy / ys + 1) * d.gz * sizeof(int) * (fcache ? 2 : 1);
+              if (h->spread_threads == 1024) k_pme_spread<1024><<<dim3(d.gx, ys, R), 1024, sm, s2>>>(d, fcache);
+              else k_pme_spread<512><<<dim3(d.gx, ys, R), 512, sm, s2>>>(d, fcache);
+          } else k_pme_spread<256><<<dim3(d.gx, 4, R), 256, (size_t)(d.gy / 4 + 1) * d.gz * sizeof(int) * (fcache ? 2 : 1), s2>>>(d, fcache); }
         tl_mark(h, s2, TL_SPREAD);
         if (h->own_dft == 2) {
             // one cluster kernel for the whole transform chain
@@ -336,8 +338,8 @@ static void enqueue_eval(bl_handle* h, bool energy, int adv_noise, int adv_md, i
         }
         if (!h->profiling) cudaStreamWaitEvent(s2, h->ev_fork2, 0);      // the gather adds to the cleared force accumulators
         { LaunchTimer t(h, BL_K_PME_GATHER, s2);
-          if (R <= 2) k_pme_gather5<<<dim3(cdiv(cdiv(N, 6) * 32, 128), R), 128, 0, s2>>>(d);
-          else k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d); }
+          if (R <= 2) k_pme_gather5<<<dim3(cdiv(cdiv(N, 6) * 32, 128), R), 128, 0, s2>>>(d, skip);
+          else k_pme_gather<<<dim3(cdiv(N, 128), R), 128, 0, s2>>>(d, skip); }
         tl_mark(h, s2, TL_GATHER);
         cudaEventRecord(h->ev_join, s2);
     }
@@ -1311,7 +1313,8 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
         h->spread_split = std::max(1, std::min(h->spread_split, d.gy / 2));
         d.csize = d.gx * d.gy * (d.gz / 2 + 1);
         {
-            const size_t plane_bytes = (size_t)(d.gy / std::min(4, h->spread_split) + 1) * d.gz * sizeof(int);
+            const bool fcache = h->skip_frozen && d.n_frozen > 0;
+            const size_t plane_bytes = (size_t)(d.gy / std::min(4, h->spread_split) + 1) * d.gz * sizeof(int) * (fcache ? 2 : 1);
             if (plane_bytes > 200 * 1024) return fail(BL_ERR_INVALID, "PME grid plane does not fit in shared memory");
             if (plane_bytes > 48 * 1024)
             {
@@ -1321,6 +1324,10 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
             }
         }
         d.grid_r = dalloc<float>(h, (size_t)R * d.gsize);
+        if (h->skip_frozen && d.n_frozen > 0) {
+            d.grid_frozen = dalloc<int>(h, (size_t)R * d.gsize);
+            d.frozen_grid_state = dalloc<int>(h, R);             // zeroed: the first spread launch fills the cache
+        }
         d.grid_c = dalloc<float2>(h, (size_t)R * d.csize);
         std::vector<float> mx, my, mz;
         bspline_moduli_host(d.gx, mx); bspline_moduli_host(d.gy, my); bspline_moduli_host(d.gz, mz);
@@ -1522,6 +1529,9 @@ static void positions_changed(bl_handle* h, int replica = -2) {
     Dev& d = h->d;
     LaunchTimer t(h, -1);
     k_refresh_mirrors<<<dim3(cdiv(d.N, 128), d.R), 128, 0, h->stream>>>(d, 1, replica);
+    // any coordinate may have been written, frozen atoms included: their stored charge grid is recomputed by the next
+    // evaluation (stream order: the evaluation's reciprocal-space branch forks from this stream)
+    if (d.grid_frozen) cudaMemsetAsync(d.frozen_grid_state, 0, sizeof(int) * d.R, h->stream);
     h->forces_valid = false;
     h->work_pending = true;      // consumed by k_external_work only (blues/integrators.py:184-191)
 }

@@ -131,6 +131,10 @@ struct Dev {
     int gx, gy, gz; int gsize; int csize;   // real grid size, complex grid size (gx*gy*(gz/2+1))
     float* grid_r;                          // [R][gsize]
     float2* grid_c;                         // [R][csize]
+    // charge grid of the frozen atoms (mass 0) in k_pme_spread's fixed point: they never move, so their share of every
+    // plane is computed once per coordinate upload and the later launches start from it instead of from zero
+    int* grid_frozen;                       // [R][gsize], null when nothing is frozen
+    int* frozen_grid_state;                 // [R] 0: rebuild in the next spread launch, 1: valid
     float* bmod_x; float* bmod_y; float* bmod_z;
     float2* tw_x; float2* tw_y; float2* tw_z;       // (cos, sin)(2 pi m / L) of the direct-DFT reciprocal-space kernels
     double self_energy_coeff;               // -k_e alpha/sqrt(pi) sum q^2  (constant)

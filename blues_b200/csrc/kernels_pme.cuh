@@ -58,15 +58,25 @@ __device__ __forceinline__ void pme_atom_setup(const Dev& d, float4 p, int* base
 // leaves the device mostly idle (latency bound); fewer bands recompute fewer B-splines when many walkers fill it.  At
 // <= 2 walkers the host picks the band count that makes the launch ONE wave of one CTA per SM (24 planes x 6 bands = 144
 // CTAs on 148 SMs: 21 us; 8 bands = 192 CTAs ran as two unequal waves: 27 us).
+//
+// Frozen atoms (use_cache, Dev::grid_frozen): the sums are integers, so "frozen share + mobile share" is bit for bit the
+// plane a launch over all atoms produces.  State 0 of the walker: this launch accumulates the two shares separately
+// (second shared plane), stores the frozen one and k_pme_gather* flips the state once the whole grid is done; state 1:
+// the plane starts from the stored share and frozen atoms are skipped after a one-byte load.
 template <int SPREAD_THREADS>
-__global__ void __launch_bounds__(SPREAD_THREADS) k_pme_spread(Dev d) {
-    extern __shared__ int s_plane[];            // [rows * gz]
+__global__ void __launch_bounds__(SPREAD_THREADS) k_pme_spread(Dev d, int use_cache) {
+    extern __shared__ int s_plane[];            // [rows * gz] (+ the same again for the frozen share in state 0)
     __shared__ int s_run0[SPREAD_MAX_RUNS], s_runoff[SPREAD_MAX_RUNS + 1];
     const int r = blockIdx.z, plane = blockIdx.x, part = blockIdx.y;
     const int ysplit = (int)gridDim.y;                          // CTAs per x-plane, each owning a band of y-rows
     const int ya = part * d.gy / ysplit, yb = (part + 1) * d.gy / ysplit;   // rows [ya, yb)
     const int npts = (yb - ya) * d.gz;
-    for (int k = threadIdx.x; k < npts; k += blockDim.x) s_plane[k] = 0;
+    const int cstate = use_cache ? d.frozen_grid_state[r] : -1;            // -1: no cache, 0: fill it, 1: use it
+    int* s_frozen = s_plane + npts;
+    int* cache = use_cache ? d.grid_frozen + (size_t)r * d.gsize + ((size_t)plane * d.gy + ya) * d.gz : nullptr;
+    const unsigned char* __restrict__ mobile_s = d.mobile_s + (size_t)r * d.Npad;
+    if (cstate == 1) for (int k = threadIdx.x; k < npts; k += blockDim.x) s_plane[k] = cache[k];
+    else for (int k = threadIdx.x; k < npts; k += blockDim.x) { s_plane[k] = 0; if (cstate == 0) s_frozen[k] = 0; }
     const float4* __restrict__ posq_s = d.posq_s + (size_t)r * d.Npad;
     const int* __restrict__ start = d.cell_start + (size_t)r * (d.ncells + 1);
     const int ncx = d.ncell[0], ncy = d.ncell[1], ncz = d.ncell[2];
@@ -105,6 +115,11 @@ __global__ void __launch_bounds__(SPREAD_THREADS) k_pme_spread(Dev d) {
         for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
             while (idx >= s_runoff[run + 1]) ++run;
             const int s = s_run0[run] + (idx - s_runoff[run]);
+            int* dst = s_plane;
+            if (cstate >= 0 && !mobile_s[s]) {
+                if (cstate == 1) continue;
+                dst = s_frozen;
+            }
             const float4 p = posq_s[s];
             if (p.w == 0.f) continue;
             int base[3];
@@ -138,14 +153,21 @@ __global__ void __launch_bounds__(SPREAD_THREADS) k_pme_spread(Dev d) {
 #pragma unroll
                 for (int k = 0; k < PME_ORDER; ++k) {
                     int gz = base[2] + k; gz -= gz >= d.gz ? d.gz : 0;
-                    atomicAdd(&s_plane[jrow[j] * d.gz + gz], __float2int_rn(qxy * wz[k]));
+                    atomicAdd(&dst[jrow[j] * d.gz + gz], __float2int_rn(qxy * wz[k]));
                 }
             }
         }
     }
     __syncthreads();
     float* out = d.grid_r + (size_t)r * d.gsize + ((size_t)plane * d.gy + ya) * d.gz;
-    for (int k = threadIdx.x; k < npts; k += blockDim.x) out[k] = (float)s_plane[k] * (1.0f / SPREAD_SCALE);
+    if (cstate == 0) {
+        for (int k = threadIdx.x; k < npts; k += blockDim.x) {
+            cache[k] = s_frozen[k];
+            out[k] = (float)(s_plane[k] + s_frozen[k]) * (1.0f / SPREAD_SCALE);
+        }
+    } else {
+        for (int k = threadIdx.x; k < npts; k += blockDim.x) out[k] = (float)s_plane[k] * (1.0f / SPREAD_SCALE);
+    }
 }
 
 // multiply the transformed charge grid by the influence function; optional energy
@@ -523,10 +545,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(PME_CL_THREADS) k_p
     }
 }
 
-__global__ void __launch_bounds__(128) k_pme_gather(Dev d) {
+// skip_frozen: forces on atoms of mass 0 are not needed (an evaluation inside the integrator program; blues/simulation.py:
+// 364-480 freezes by zeroing masses).  The first thread also marks the frozen share of the charge grid as stored — the
+// whole spread launch that wrote it has finished by the time any gather thread runs.
+__global__ void __launch_bounds__(128) k_pme_gather(Dev d, int skip_frozen) {
     const int r = blockIdx.y;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a == 0 && d.grid_frozen) d.frozen_grid_state[r] = 1;
     if (a >= d.N) return;
+    if (skip_frozen && d.mass[a] == 0.0) return;
     const float4 p = d.posq[(size_t)r * d.N + a];
     if (p.w == 0.f) return;
     int base[3];
@@ -568,12 +595,13 @@ __global__ void __launch_bounds__(128) k_pme_gather(Dev d) {
 
 // Latency-oriented gather for contexts with one or two walkers: five lanes per atom, one stencil x-plane each (25 grid
 // loads per lane instead of 125), combined with shuffles.  Six atoms per warp (lanes 30, 31 idle).
-__global__ void __launch_bounds__(128) k_pme_gather5(Dev d) {
+__global__ void __launch_bounds__(128) k_pme_gather5(Dev d, int skip_frozen) {
     const int r = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int slot = lane / PME_ORDER, i = lane - slot * PME_ORDER;       // atom slot 0..5 (6 = idle), x-plane 0..4
     const int a = warp * 6 + slot;
-    const bool active = slot < 6 && a < d.N;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d.grid_frozen) d.frozen_grid_state[r] = 1;      // (see k_pme_gather)
+    const bool active = slot < 6 && a < d.N && !(skip_frozen && d.mass[min(a, d.N - 1)] == 0.0);
     float fx = 0.f, fy = 0.f, fz = 0.f, q = 0.f;
     if (active) {
         const float4 p = d.posq[(size_t)r * d.N + a];

@@ -349,6 +349,54 @@ def test_t4l_freeze_radius_variant_runs_with_frozen_atoms_untouched():
     eng.close()
 
 
+@pytest.mark.parametrize('name,frz,rotate', [('tol_parm', 0.6, True), ('wat_divaline', 0.5, False)])
+def test_frozen_fast_paths_do_not_change_a_single_bit(name, frz, rotate):
+    """Skipping frozen rows in the pair kernel, frozen clusters in the integrator, frozen atoms in the PME gather and
+    keeping the frozen atoms' share of the PME charge grid (fixed-point sums: share + share == sum over all) must leave
+    the mobile atoms' trajectory and the work bit for bit what the engine computes with all of that switched off
+    (BLUES_B200_SKIP_FROZEN=0) — across a rotation move, a host coordinate upload (which invalidates the stored grid)
+    and an energy query in between.  (No rotation for the dipeptide: re-coupling it on top of the water within 20 steps
+    blows the walker up whichever path computes it.)"""
+    import os
+    from blues_b200 import _native
+    s, system, topo, x = gc.load_case(name, True, freeze_beyond_nm=frz)
+    mass = np.asarray(topo['mass'], float)
+    alch = np.asarray(gc.CASES[name]['alch'], np.int32)
+    assert np.count_nonzero(mass == 0) > 0 and np.all(mass[alch] > 0)
+    ls, le = gc.lambda_tables(40)
+    res = {}
+    old = os.environ.get('BLUES_B200_SKIP_FROZEN')
+    try:
+        for flag in ('1', '0'):
+            os.environ['BLUES_B200_SKIP_FROZEN'] = flag
+            eng = _native.Engine(topo, n_replicas=2, seed=5)
+            eng.set_ncmc_integrator(300.0, 1.0, 0.002, 'H V R O R V H', 40, 1, 0.2, 0.8, ls, le)
+            eng.set_positions(x)
+            eng.minimize(40, 10.0)
+            eng.velocities_to_temperature(300.0)
+            # the rotation at lambda = 0.5, where the ligand is decoupled (blues/simulation.py:1039-1098)
+            eng.ncmc_run(24, move=dict(kind=_native.BL_MOVE_ROTATE, step=20, atoms=alch, masses=mass[alch]) if rotate else None)
+            e_mid = eng.get_energy()[0].copy()
+            xm = eng.get_positions(1)
+            xm[mass > 0] += 1e-3                      # host upload for one walker: every stored grid share is dropped
+            eng.set_positions(xm, replica=1)
+            eng.ncmc_run(16)
+            res[flag] = dict(x=[eng.get_positions(r) for r in range(2)], v=[eng.get_velocities(r) for r in range(2)],
+                             w=[eng.get_global('protocol_work', r) for r in range(2)], e=e_mid,
+                             e_end=eng.get_energy()[0].copy())
+            eng.close()
+    finally:
+        if old is None:
+            os.environ.pop('BLUES_B200_SKIP_FROZEN', None)
+        else:
+            os.environ['BLUES_B200_SKIP_FROZEN'] = old
+    a, b = res['1'], res['0']
+    for r in range(2):
+        assert np.array_equal(a['x'][r], b['x'][r]) and np.array_equal(a['v'][r], b['v'][r])
+        assert a['w'][r] == b['w'][r] and np.isfinite(a['w'][r])
+    assert np.array_equal(a['e'], b['e']) and np.array_equal(a['e_end'], b['e_end'])
+
+
 def test_m1_full_protocol_ensemble_work_and_acceptance():
     """North-star criterion 3 on M1 = BASELINE configs[0]: 64 walkers of toluene in TIP3P (TOL-parm, PME, HBonds),
     the full nstepsNC = 100 protocol with the rotation at moveStep = 50, the alchemical correction and the Metropolis
