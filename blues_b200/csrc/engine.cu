@@ -63,6 +63,7 @@ struct bl_handle {
     bool forces_valid = false;    // f_env / slots match the current positions
     bool forces_partial = false;  // ... but the last evaluation skipped the rows of the frozen atoms (enqueue_eval)
     bool skip_frozen = true;
+    int zfine = 2;               // BLUES_B200_ZFINE: z resolution of the search cells (plan_cells); 2 measured +2 % over 1, 3 = 2
     bool work_pending = false;    // coordinates changed outside the integrator since the last external-work evaluation
     bool vel_dirty = true;        // cm_acc must be recomputed
     int* cm_parity = nullptr;     // device int
@@ -898,11 +899,14 @@ static int setup_box(bl_handle* h, const double box[3]) {
     return BL_OK;
 }
 
-// cell grid for the neighbour search: cell edge >= list cutoff / 2 (so +-2 cells cover it), Morton rank per cell
-static void plan_cells(const double box[3], bool periodic, double list_cutoff, int nc[3], std::vector<int>& order) {
+// cell grid for the neighbour search: cell edge >= list cutoff / 2 in x and y (so +-2 columns cover it), row-major order
+// zfine: z cells finer by that factor (a cell column is one run of the sorted order whatever its z resolution; finer z
+// cells trim the scanned z range of a column, and the z extent of a build group, more tightly)
+static void plan_cells(const double box[3], bool periodic, double list_cutoff, int zfine, int nc[3], std::vector<int>& order) {
     nc[0] = nc[1] = nc[2] = 1;
     if (periodic && box[0] > 0)
-        for (int k = 0; k < 3; ++k) nc[k] = std::max(1, std::min(256, (int)floor(box[k] / (0.5 * list_cutoff))));
+        for (int k = 0; k < 3; ++k)
+            nc[k] = std::max(1, std::min(256, (int)floor(box[k] / (0.5 * list_cutoff / (k == 2 ? zfine : 1)))));
     const int n = nc[0] * nc[1] * nc[2];
     std::vector<std::pair<uint32_t, int>> keys(n);
     for (int x = 0; x < nc[0]; ++x)
@@ -921,7 +925,8 @@ static int setup_cells(bl_handle* h, const double box[3]) {
     Dev& d = h->d;
     std::vector<int> order;
     int nc[3];
-    plan_cells(box, d.periodic, d.cutoffd + h->skin, nc, order);
+    plan_cells(box, d.periodic, d.cutoffd + h->skin, h->zfine, nc, order);
+    d.zreach = 2 * h->zfine;
     const int n = nc[0] * nc[1] * nc[2];
     if (n > h->cell_capacity) {
         h->cell_capacity = n + n / 4 + 8;
@@ -1002,6 +1007,7 @@ int bl_create(const bl_topology* t, int device, int n_replicas, uint64_t seed, b
     if (getenv("BLUES_B200_SPREAD_SPLIT")) h->spread_split = atoi(getenv("BLUES_B200_SPREAD_SPLIT"));
     if (getenv("BLUES_B200_SPREAD_THREADS")) h->spread_threads = atoi(getenv("BLUES_B200_SPREAD_THREADS")) == 1024 ? 1024 : 512;
     if (getenv("BLUES_B200_SKIP_FROZEN")) h->skip_frozen = atoi(getenv("BLUES_B200_SKIP_FROZEN")) != 0;
+    if (getenv("BLUES_B200_ZFINE")) h->zfine = std::max(1, std::min(4, atoi(getenv("BLUES_B200_ZFINE"))));
     if (getenv("BLUES_B200_INT_BLOCK")) h->int_block = std::max(32, std::min(256, atoi(getenv("BLUES_B200_INT_BLOCK")) / 32 * 32));
     if (getenv("BLUES_B200_FOLD_ZERO")) h->fold_zero = atoi(getenv("BLUES_B200_FOLD_ZERO")) != 0;
     counter_map().erase(h);      // a recycled address must not inherit another handle's bookkeeping

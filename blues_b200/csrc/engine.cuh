@@ -92,6 +92,7 @@ struct Dev {
     double* noise;                          // [R][MAX_NOISE_SETS][N][3] standard normals for the next INTEGRATE launch
     // neighbour structures: Morton-ranked cells (edge >= list cutoff / 2), sorted mirrors, Verlet lists
     int ncell[3]; int ncells;
+    int zreach;                             // cells that cover the list cutoff along z: 2, or 2 k with k-times finer z cells
     int* cell_order;                        // [ncells] Morton rank of each cell
     int* cell_start; int* cell_cursor;      // [R][ncells+1] first sorted slot of every cell (+ scatter cursor)
     int* atom_cell;                         // [R*N]

@@ -289,11 +289,11 @@ __device__ __forceinline__ int build_group_runs(const Dev& d, const int* __restr
         if (rem2 > 0.f) {                                                     // else: column out of reach
             int z0 = 0, z1 = ncz - 1;
             if (!rz) {
-                // both ends clamped to [za - 2, zb + 2]: a walker that blew up has coordinates of any magnitude, the
+                // both ends clamped to [za - zreach, zb + zreach]: a walker that blew up has coordinates of any magnitude, the
                 // float -> int conversion then saturates and `z0 + ncz` below would wrap around
                 const float zr = sqrtf(rem2);
-                z0 = min(zb + 2, max(za - 2, (int)floorf((loz - zr) / ez)));
-                z1 = max(za - 2, min(zb + 2, (int)floorf((hiz + zr) / ez)));
+                z0 = min(zb + d.zreach, max(za - d.zreach, (int)floorf((loz - zr) / ez)));
+                z1 = max(za - d.zreach, min(zb + d.zreach, (int)floorf((hiz + zr) / ez)));
             }
             const int row = (ax * ncy + ay) * ncz;
             // at most two of the three segments exist (the z range is no longer than the column)
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(32) k_build_list(Dev d, int cq) {
             const float lox = warp_min(pa.x), hix = warp_max(pa.x), loy = warp_min(pa.y), hiy = warp_max(pa.y);
             const float loz = warp_min(pa.z), hiz = warp_max(pa.z);
             // a dimension whose scan range would cover a cell twice is scanned once, with the rint() minimum image
-            const bool rx = xb - xa + 5 > ncx, ry = yb - ya + 5 > ncy, rz = zb - za + 5 > ncz;
+            const bool rx = xb - xa + 5 > ncx, ry = yb - ya + 5 > ncy, rz = zb - za + 2 * d.zreach + 1 > ncz;
             const int x0 = rx ? 0 : xa - 2, x1 = rx ? ncx - 1 : xb + 2;
             const int y0 = ry ? 0 : ya - 2, y1 = ry ? ncy - 1 : yb + 2;
             const int nruns = build_group_runs(d, start, lane, rx, ry, rz, x0, x1, y0, y1, za, zb, lox, hix, loy, hiy, loz,
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(32, 24) k_build_list2(Dev d) {
             const int za = __reduce_min_sync(0xffffffffu, cz), zb = __reduce_max_sync(0xffffffffu, cz);
             const float lox = warp_min(pa.x), hix = warp_max(pa.x), loy = warp_min(pa.y), hiy = warp_max(pa.y);
             const float loz = warp_min(pa.z), hiz = warp_max(pa.z);
-            const bool rx = xb - xa + 5 > ncx, ry = yb - ya + 5 > ncy, rz = zb - za + 5 > ncz;
+            const bool rx = xb - xa + 5 > ncx, ry = yb - ya + 5 > ncy, rz = zb - za + 2 * d.zreach + 1 > ncz;
             const int x0 = rx ? 0 : xa - 2, x1 = rx ? ncx - 1 : xb + 2;
             const int y0 = ry ? 0 : ya - 2, y1 = ry ? ncy - 1 : yb + 2;
             const int nruns = build_group_runs(d, start, lane, rx, ry, rz, x0, x1, y0, y1, za, zb, lox, hix, loy, hiy, loz,

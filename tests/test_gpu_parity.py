@@ -383,7 +383,8 @@ def test_frozen_fast_paths_do_not_change_a_single_bit(name, frz, rotate):
             eng.ncmc_run(16)
             res[flag] = dict(x=[eng.get_positions(r) for r in range(2)], v=[eng.get_velocities(r) for r in range(2)],
                              w=[eng.get_global('protocol_work', r) for r in range(2)], e=e_mid,
-                             e_end=eng.get_energy()[0].copy())
+                             e_end=eng.get_energy()[0].copy(), f=eng.get_forces(0),
+                             pairs=np.sort(np.asarray(eng.neighbor_pairs(1))))
             eng.close()
     finally:
         if old is None:
@@ -395,6 +396,9 @@ def test_frozen_fast_paths_do_not_change_a_single_bit(name, frz, rotate):
         assert np.array_equal(a['x'][r], b['x'][r]) and np.array_equal(a['v'][r], b['v'][r])
         assert a['w'][r] == b['w'][r] and np.isfinite(a['w'][r])
     assert np.array_equal(a['e'], b['e']) and np.array_equal(a['e_end'], b['e_end'])
+    # a host force query after force-only launches re-evaluates every row (forces_partial): frozen atoms get their forces
+    assert np.array_equal(a['f'], b['f']) and np.any(a['f'][mass == 0] != 0.0)
+    assert len(a['pairs']) > 0 and np.array_equal(a['pairs'], b['pairs'])
 
 
 def test_m1_full_protocol_ensemble_work_and_acceptance():
