@@ -621,3 +621,24 @@ def sidechain_move_contract(golden_dir=GOLDEN):
 @pytest.mark.gpu
 def test_sidechain_move():
     sidechain_move_contract()
+
+
+def test_example_sidechain_script(tmp_path, monkeypatch):
+    """examples/example_sidechain.py on the CUDA engine (the reference's examples/example_sidechain.py:1-37 with its
+    analysis step): SideChainMove + NCMC on the valine dipeptide, MD frames into NetCDF, chi1 of every frame read back."""
+    import importlib.util
+    import shutil
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ex = tmp_path / 'examples'
+    shutil.copytree(os.path.join(root, 'examples'), str(ex))
+    os.makedirs(str(tmp_path / 'tests' / 'golden'))
+    shutil.copy(os.path.join(GOLDEN, 'vac_divaline.npz'), str(tmp_path / 'tests' / 'golden'))
+    monkeypatch.chdir(str(ex))
+    spec = importlib.util.spec_from_file_location('example_sidechain', str(ex / 'example_sidechain.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    blues = mod.sidechain('sidechain_b200.yml', nIter=3, nstepsNC=20, nstepsMD=500)
+    assert blues.accept + blues.reject == 3
+    chi = np.asarray(blues.dihedrals)
+    assert chi.shape == (6, 1) and np.all(np.isfinite(chi)) and np.all(np.abs(chi) <= np.pi + 1e-6)
+    assert os.path.exists(str(ex / 'divaline-b200-ncmc.nc'))

@@ -63,7 +63,8 @@ def test_md_leg_with_monte_carlo_barostat(structure):
     api.test_md_leg_with_monte_carlo_barostat(structure)
 
 
-def _run_example(name, func, tmp_path, monkeypatch):
+def _run_example(name, func, tmp_path, monkeypatch, yaml='rotmove_b200.yml', fixture='tol_parm.npz', out='toluene-b200',
+                 **overrides):
     """The scripts under examples/ with a short protocol, in a scratch directory (they write reporter files)."""
     import importlib.util
     import os
@@ -72,14 +73,16 @@ def _run_example(name, func, tmp_path, monkeypatch):
     ex = tmp_path / 'examples'
     shutil.copytree(os.path.join(root, 'examples'), str(ex))
     os.makedirs(str(tmp_path / 'tests' / 'golden'))
-    shutil.copy(os.path.join(api.GOLDEN, 'tol_parm.npz'), str(tmp_path / 'tests' / 'golden'))
+    shutil.copy(os.path.join(api.GOLDEN, fixture), str(tmp_path / 'tests' / 'golden'))
     monkeypatch.chdir(str(ex))
     spec = importlib.util.spec_from_file_location(name, str(ex / (name + '.py')))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    blues = getattr(mod, func)('rotmove_b200.yml', nIter=2, nstepsNC=6, nstepsMD=4)
-    assert blues.accept + blues.reject == 2
-    assert os.path.exists(str(ex / 'toluene-b200.log')) and os.path.exists(str(ex / 'toluene-b200-ncmc.nc'))
+    kw = dict(nIter=2, nstepsNC=6, nstepsMD=4)
+    kw.update(overrides)
+    blues = getattr(mod, func)(yaml, **kw)
+    assert blues.accept + blues.reject == kw['nIter']
+    assert os.path.exists(str(ex / (out + '.log'))) and os.path.exists(str(ex / (out + '-ncmc.nc')))
     return blues
 
 
@@ -89,6 +92,19 @@ def test_example_rotmove(tmp_path, monkeypatch):
 
 def test_example_water(tmp_path, monkeypatch):
     _run_example('example_water', 'watermove', tmp_path, monkeypatch)
+
+
+def test_example_sidechain(tmp_path, monkeypatch):
+    """examples/example_sidechain.py (the reference's examples/example_sidechain.py:1-37 with its analysis step): SideChainMove
+    on the valine dipeptide, MD frames into a NetCDF trajectory, chi1 of every frame read back through the trajectory
+    reader."""
+    import numpy as np
+    blues = _run_example('example_sidechain', 'sidechain', tmp_path, monkeypatch, yaml='sidechain_b200.yml',
+                         fixture='vac_divaline.npz', out='divaline-b200', nIter=3, nstepsNC=6, nstepsMD=500)
+    chi = np.asarray(blues.dihedrals)
+    assert chi.shape == (6, 1) and np.all(np.isfinite(chi)) and np.all(np.abs(chi) <= np.pi + 1e-6)
+    lines = open(str(tmp_path / 'examples' / 'divaline-b200-dihedrals.txt')).read().split()
+    assert len(lines) == 6 and abs(float(lines[0]) - float(chi[0, 0])) < 1e-6
 
 
 def test_monte_carlo_simulation_driver(structure):
