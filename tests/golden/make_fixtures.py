@@ -408,7 +408,7 @@ def reference_tests():
     root = os.path.dirname(os.path.dirname(REF))          # <checkout>/blues
     dst = os.path.join(HERE, 'reference_checkout', 'blues', 'tests')
     os.makedirs(os.path.join(dst, 'data'), exist_ok=True)
-    for name in ('test_simulation.py', 'test_randomrotation.py'):
+    for name in ('test_simulation.py', 'test_randomrotation.py', 'test_ethylene.py'):
         shutil.copyfile(os.path.join(root, 'tests', name), os.path.join(dst, name))
     for name in ('TOL-parm.prmtop', 'TOL-parm.inpcrd', 'ethylene_system.xml', 'ethylene_structure.pdb'):
         shutil.copyfile(os.path.join(REF, name), os.path.join(dst, 'data', name))
