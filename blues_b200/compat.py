@@ -50,15 +50,20 @@ def install(data_root=None, force=False):
                                                                                             'MonteCarloBarostat', 'XmlSerializer')}
     for k in ('Context', 'State', 'Platform', 'LangevinIntegrator', 'Vec3', 'OpenMMException'):
         openmm_attrs[k] = getattr(mm, k)
+    from . import lepton
+    openmm_attrs.update(Discrete1DFunction=lepton.Discrete1DFunction, Continuous1DFunction=lepton.Continuous1DFunction)
     app = _module('simtk.openmm.app', Simulation=mm.Simulation, StateDataReporter=reporters.StateDataReporter,
                   NoCutoff=system.NoCutoff, CutoffNonPeriodic=system.CutoffNonPeriodic,
                   CutoffPeriodic=system.CutoffPeriodic, Ewald=system.Ewald, PME=system.PME,
                   HBonds=system.HBonds, AllBonds=system.AllBonds, HAngles=system.HAngles)
     openmm = _module('simtk.openmm', app=app, unit=unit, **openmm_attrs)
+    openmm_inner = _module('simtk.openmm.openmm', **openmm_attrs)       # `from simtk.openmm.openmm import Discrete1DFunction`
+    openmm.openmm = openmm_inner
     simtk = _module('simtk', unit=unit, openmm=openmm)
     simtk.__path__ = []
     openmm.__path__ = []
-    mods.update({'simtk': simtk, 'simtk.unit': unit, 'simtk.openmm': openmm, 'simtk.openmm.app': app})
+    mods.update({'simtk': simtk, 'simtk.unit': unit, 'simtk.openmm': openmm, 'simtk.openmm.app': app,
+                 'simtk.openmm.openmm': openmm_inner})
     # --- parmed -----------------------------------------------------------------------------------------------------
     amber = _module('parmed.amber', AmberMask=structure.AmberMask, Rst7=structure.Rst7)
     geometry = _module('parmed.geometry', center_of_mass=structure.geometry.center_of_mass)

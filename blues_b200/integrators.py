@@ -89,10 +89,33 @@ class AlchemicalExternalLangevinIntegrator(object):
         return self._seed
 
     # -- binding to a context --------------------------------------------------------------------------
+    def addTabulatedFunction(self, name, function):
+        """``CustomIntegrator.addTabulatedFunction``: ``name(x)`` becomes callable from the alchemical functions, e.g.
+        ``{'lambda_sterics': 'sterics_tab(lambda*1000)'}`` with a ``Discrete1DFunction`` from
+        ``utils.spreadLambdaProtocol`` (``blues/utils.py:306-325``).  The tables handed to the engine are rebuilt; on a bound
+        integrator call it before the first step (the engine takes the tables when the Context is created)."""
+        if not callable(function):
+            raise TypeError('a tabulated function must be callable (Discrete1DFunction / Continuous1DFunction)')
+        self._tabulated = getattr(self, '_tabulated', {})
+        self._tabulated[str(name)] = function
+        if getattr(self, '_context', None) is not None:
+            self._bind(self._context)
+        return len(self._tabulated) - 1
+
+    def getNumTabulatedFunctions(self):
+        return len(getattr(self, '_tabulated', {}))
+
+    def getTabulatedFunctionName(self, index):
+        return list(getattr(self, '_tabulated', {}))[index]
+
+    def getTabulatedFunction(self, index):
+        return list(getattr(self, '_tabulated', {}).values())[index]
+
     def _tables(self):
         n = self._n_lambda_steps
-        ls = lepton.tabulate(self._alchemical_functions.get('lambda_sterics', '1'), n)
-        le = lepton.tabulate(self._alchemical_functions.get('lambda_electrostatics', '1'), n)
+        funcs = getattr(self, '_tabulated', None)
+        ls = lepton.tabulate(self._alchemical_functions.get('lambda_sterics', '1'), n, funcs)
+        le = lepton.tabulate(self._alchemical_functions.get('lambda_electrostatics', '1'), n, funcs)
         return np.asarray(ls, float), np.asarray(le, float)
 
     def _bind(self, context):

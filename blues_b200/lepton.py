@@ -22,9 +22,55 @@ _BINOPS = {ast.Add: lambda a, b: a + b, ast.Sub: lambda a, b: a - b, ast.Mult: l
 _VAR = '__lambda__'
 
 
+class Discrete1DFunction(object):
+    """OpenMM's tabulated function of an integer argument: f(x) = values[round(x)] (``CustomIntegrator.addTabulatedFunction``;
+    what ``blues/utils.py:276-369`` ``spreadLambdaProtocol`` returns)."""
+
+    def __init__(self, values):
+        self.values = [float(v) for v in values]
+        if not self.values:
+            raise ValueError('a tabulated function needs at least one value')
+
+    def getFunctionParameters(self):
+        return list(self.values)
+
+    def setFunctionParameters(self, values):
+        self.values = [float(v) for v in values]
+
+    def __call__(self, x):
+        i = int(round(x))
+        if i < 0 or i >= len(self.values):
+            return 0.0                       # OpenMM: zero outside the tabulated range
+        return self.values[i]
+
+
+class Continuous1DFunction(object):
+    """OpenMM's natural cubic spline through ``values`` at evenly spaced points of [min, max]; zero outside."""
+
+    def __init__(self, values, min, max):
+        import numpy as np
+        from scipy.interpolate import CubicSpline
+        self.values, self.min, self.max = [float(v) for v in values], float(min), float(max)
+        if len(self.values) < 2 or not self.max > self.min:
+            raise ValueError('a continuous tabulated function needs >= 2 values and max > min')
+        self._spline = CubicSpline(np.linspace(self.min, self.max, len(self.values)), self.values, bc_type='natural')
+
+    def getFunctionParameters(self):
+        return list(self.values), self.min, self.max
+
+    def __call__(self, x):
+        if x < self.min or x > self.max:
+            return 0.0
+        return float(self._spline(x))
+
+
 class Expression(object):
-    def __init__(self, text):
+    """``functions``: name -> callable of one argument (tabulated functions added to the integrator)."""
+
+    def __init__(self, text, functions=None):
         self.text = str(text)
+        self._funcs = dict(_FUNCS)
+        self._funcs.update(functions or {})
         src = self.text.split(';')[0].replace('^', '**')
         src = re.sub(r'\blambda\b', _VAR, src)
         self._tree = ast.parse(src.strip(), mode='eval').body
@@ -36,7 +82,7 @@ class Expression(object):
             self._check(node.right)
         elif isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
             self._check(node.operand)
-        elif isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in _FUNCS and not node.keywords:
+        elif isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in self._funcs and not node.keywords:
             for a in node.args:
                 self._check(a)
         elif isinstance(node, ast.Constant) and isinstance(node.value, (int, float)):
@@ -53,7 +99,7 @@ class Expression(object):
             v = self._eval(node.operand, lam)
             return -v if isinstance(node.op, ast.USub) else v
         if isinstance(node, ast.Call):
-            return _FUNCS[node.func.id](*[self._eval(a, lam) for a in node.args])
+            return self._funcs[node.func.id](*[self._eval(a, lam) for a in node.args])
         if isinstance(node, ast.Constant):
             return float(node.value)
         return lam
@@ -62,9 +108,9 @@ class Expression(object):
         return float(self._eval(self._tree, float(lam)))
 
 
-def tabulate(text, n_lambda_steps):
+def tabulate(text, n_lambda_steps, functions=None):
     """Values of the expression at lambda = k / n_lambda_steps, k = 0..n_lambda_steps."""
-    e = Expression(text)
+    e = Expression(text, functions)
     if n_lambda_steps <= 0:
         return [e(0.0)]
     return [e(k / float(n_lambda_steps)) for k in range(n_lambda_steps + 1)]

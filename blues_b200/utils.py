@@ -127,3 +127,44 @@ def get_data_filename(package_root, relative_path):
             return alt
         raise ValueError("Sorry! %s does not exist. If you just added it, you'll have to re-install" % fn)
     return fn
+
+
+def spreadLambdaProtocol(switching_values, steps, switching_types='auto', kind='cubic', return_tab_function=True):
+    """Stretch a one-way lambda schedule (1 -> 0, e.g. the windows of a free-energy protocol) over a symmetric NCMC
+    protocol of ``steps`` steps: off at the midpoint, back on at the end (``blues/utils.py:276-369``).
+
+    The schedule is mirrored about its last point, interpolated (``scipy.interpolate.interp1d(kind=kind)``) on the
+    ``steps + 1`` points k / steps, and the plateaus the interpolant may overshoot are restored: a ``'sterics'`` schedule
+    stays at exactly 1 before its last leading 1 and after the mirrored one, an ``'electrostatics'`` schedule at exactly 0
+    between its first 0 and the mirrored one (``'auto'``: sterics if the second value is still 1).  The second half is the
+    mirror image of the first.  Returns a ``Discrete1DFunction`` for ``integrator.addTabulatedFunction`` (use it as
+    ``'name(lambda*steps)'`` in ``alchemical_functions``), or the plain list with ``return_tab_function=False``.
+    """
+    import numpy as np
+    from scipy.interpolate import interp1d
+    values = [float(v) for v in switching_values]
+    n_ones = values.count(1.0)
+    first_zero = values.index(0.0)
+    both = values + values[-2::-1]                         # off state in the middle
+    x = np.arange(len(both)) / float(len(both) - 1)
+    xs = np.arange(0.0, 1.0 + 1.0 / float(steps), 1.0 / float(steps))
+    ys = interp1d(x, both, kind=kind)(xs)
+    if switching_types == 'auto':
+        switching_types = 'sterics' if both[1] == 1.0 else 'electrostatics'
+    if switching_types == 'sterics':
+        lo, hi = x[n_ones - 1], x[-n_ones]
+        tab = [1.0 if (t < lo or t > hi) else float(y) for t, y in zip(xs, ys)]
+    elif switching_types == 'electrostatics':
+        lo, hi = x[first_zero], x[-(first_zero + 1)]
+        tab = [0.0 if (lo < t < hi) else float(y) for t, y in zip(xs, ys)]
+    else:
+        raise ValueError('`switching_types` should be either sterics or electrostatics, currently ' + str(switching_types))
+    half = math.floor(len(tab) / 2.0)
+    tab = [v if i <= half else tab[-i - 1] for i, v in enumerate(tab)]
+    for i, v in enumerate(tab):
+        if v < 0.0 or v > 1.0:
+            raise ValueError('interpolated lambda %f at index %i is outside [0, 1]: check switching_types / kind' % (v, i))
+    if return_tab_function:
+        from .lepton import Discrete1DFunction
+        return Discrete1DFunction(tab)
+    return tab

@@ -519,3 +519,61 @@ def test_trajectory_reader_distances_and_dihedrals(tmp_path):
     phi = trajectory.compute_dihedrals(t[:2], [[0, 1, 2, 3]])
     np.testing.assert_allclose(np.abs(phi[:, 0]), [math.pi / 2, math.pi], atol=1e-6)
     assert phi[0, 0] > 0            # seen along 1 -> 2 the front bond turns clockwise onto the back bond: +90 degrees
+
+
+_STERICS = [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.95, 0.8848447462380346, 0.8428373352131427, 0.7928373352131427,
+            0.7490146003095886, 0.6934088361682191, 0.6515123083157823, 0.6088924298371354, 0.5588924298371354,
+            0.5088924298371353, 0.4649556683144045, 0.4298606804827029, 0.3798606804827029, 0.35019373288005945,
+            0.31648339779024653, 0.2780498882483276, 0.2521302239477468, 0.23139484523965026, 0.18729812232625365,
+            0.15427643961733822, 0.12153116162972155, 0.09632462702545555, 0.06463743549588846, 0.01463743549588846, 0.0]
+_STATICS = [1.0, 0.8519493439593149, 0.7142750443470669, 0.5385929179832776, 0.3891972949356391, 0.18820309596839535] + [0.0] * 26
+
+
+def test_spread_lambda_protocol_and_tabulated_functions_in_the_integrator():
+    """utils.spreadLambdaProtocol (blues/utils.py:276-369; the schedules are the ones of its docstring) and
+    CustomIntegrator.addTabulatedFunction on the NCMC integrator: a symmetric protocol, plateaus exact, and the tables the
+    engine receives are the tabulated functions sampled at every lambda step.  Where the checkout is mounted the values
+    are compared with the reference's own function, executed from its source text (its module cannot be imported here)."""
+    import ast
+    from blues_b200.lepton import Discrete1DFunction, Continuous1DFunction, Expression
+    steps = 100
+    st = utils.spreadLambdaProtocol(_STERICS, steps, switching_types='sterics', return_tab_function=False)
+    el = utils.spreadLambdaProtocol(_STATICS, steps, switching_types='auto', return_tab_function=False)
+    for tab in (st, el):
+        assert len(tab) == steps + 1 and tab[0] == 1.0 and tab[-1] == 1.0 and abs(tab[steps // 2]) < 1e-12
+        assert all(0.0 <= v <= 1.0 for v in tab)
+        np.testing.assert_allclose(tab, tab[::-1], atol=1e-12)                     # symmetric about the midpoint
+    assert st[:10] == [1.0] * 10 and el[12:50] == [0.0] * 38                       # plateaus restored exactly
+    assert el[1] < 1.0 and st[9] == 1.0 and st[10] < 1.0                           # electrostatics go first
+    with pytest.raises(ValueError):
+        utils.spreadLambdaProtocol(_STATICS, steps, switching_types='bogus')
+    ref_src = os.path.join(os.environ.get('BLUES_REFERENCE', '/root/reference'), 'blues', 'utils.py')
+    if os.path.exists(ref_src):
+        tree = ast.parse(open(ref_src).read())
+        fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'spreadLambdaProtocol'][0]
+        from math import floor
+        from scipy.interpolate import interp1d
+        ns = {'np': np, 'interp1d': interp1d, 'floor': floor}
+        exec(compile(ast.Module([fn], []), ref_src, 'exec'), ns)
+        for vals, kind in ((_STERICS, 'sterics'), (_STATICS, 'auto'), (_STATICS, 'electrostatics')):
+            for n in (100, 37, 1000):
+                want = ns['spreadLambdaProtocol'](list(vals), n, switching_types=kind, return_tab_function=False)
+                got = utils.spreadLambdaProtocol(list(vals), n, switching_types=kind, return_tab_function=False)
+                np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+    # tabulated functions
+    f = utils.spreadLambdaProtocol(_STERICS, steps, switching_types='sterics')
+    assert isinstance(f, Discrete1DFunction) and f(0) == 1.0 and f(50.4) == f(50) and f(-1) == 0.0 and f(101) == 0.0
+    c = Continuous1DFunction([0.0, 1.0, 4.0, 9.0], 0.0, 3.0)
+    assert abs(c(2.0) - 4.0) < 1e-12 and c(3.5) == 0.0 and 1.0 < c(1.5) < 4.0
+    assert Expression('2*tab(lambda*100)', {'tab': f})(0.5) == 2 * f(50)
+    with pytest.raises(ValueError):
+        Expression('tab(lambda)')                                                  # unknown function without the table
+    integ = AlchemicalExternalLangevinIntegrator(
+        alchemical_functions={'lambda_sterics': 'sterics_tab(lambda*100)', 'lambda_electrostatics': 'elec_tab(lambda*100)'},
+        splitting='H V R O R V H', nsteps_neq=50)
+    assert integ.addTabulatedFunction('sterics_tab', f) == 0
+    assert integ.addTabulatedFunction('elec_tab', Discrete1DFunction(el)) == 1
+    assert integ.getNumTabulatedFunctions() == 2 and integ.getTabulatedFunctionName(1) == 'elec_tab'
+    ls, le = integ._tables()                                                       # 2 H steps x 50 = 100 lambda steps
+    np.testing.assert_allclose(ls, st, atol=0)
+    np.testing.assert_allclose(le, el, atol=0)
